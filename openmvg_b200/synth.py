@@ -1,0 +1,166 @@
+"""Seeded synthetic inputs for the two hot paths.
+
+Shared by tests/ and bench.py so the CUDA path, the oracle and the compiled reference all see
+byte-identical inputs.  Nothing here is on the product path.
+
+* :func:`ba_scene` — the BA scene family of BASELINE.json configs 1/2/5: cameras on a radius-1.5
+  ring (0.2·sin 3θ wobble) looking at the origin (openMVG ``LookAt``, numeric/numeric.cpp:65-74),
+  points uniform in [-0.6,0.6]^3, each point seen by ``obs_per_point`` cameras of a strided window,
+  one shared pinhole intrinsic f=1000, pp=(500,500) (as in every reference BA test,
+  sfm/sfm_data_BA_test.cpp:361), pixel noise N(0,0.5), perturbed initial poses/points.
+* :func:`descriptors` — 128-D uint8 SIFT-like descriptors: bytes u·v/255 (right-skewed like
+  root-SIFT); image k re-uses 30 % of image k-1's rows ±8 noise so the ratio test passes for a
+  realistic fraction.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# cameras::EINTRINSIC (reference: cameras/Camera_Common.hpp:39-49)
+PINHOLE_CAMERA = 1
+PINHOLE_CAMERA_RADIAL1 = 2
+PINHOLE_CAMERA_RADIAL3 = 3
+PINHOLE_CAMERA_BROWN = 4
+PINHOLE_CAMERA_FISHEYE = 5
+INTR_NPARAMS = {1: 3, 2: 4, 3: 6, 4: 8, 5: 7}
+INTR_STRIDE = 8
+
+
+def _look_at(center: np.ndarray, up=np.array([0.0, 1.0, 0.0])) -> np.ndarray:
+    zc = center / np.linalg.norm(center)
+    xc = np.cross(up, zc)
+    xc /= np.linalg.norm(xc)
+    yc = np.cross(zc, xc)
+    return np.stack([xc, yc, zc])
+
+
+def _rodrigues(aa: np.ndarray) -> np.ndarray:
+    th = np.linalg.norm(aa)
+    if th < 1e-300:
+        return np.eye(3)
+    k = aa / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def _log_so3(R: np.ndarray) -> np.ndarray:
+    """Rotation matrix -> angle-axis (generic branch; scenes here never sit at theta≈pi)."""
+    c = np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)
+    th = np.arccos(c)
+    v = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    s = np.linalg.norm(v)
+    if s < 1e-300:
+        return np.zeros(3)
+    return v / s * th
+
+
+def ba_scene(n_cams: int, n_points: int, obs_per_point: int, seed: int = 42,
+             model: int = PINHOLE_CAMERA, n_intrinsics: int = 1, noise_px: float = 0.5,
+             outlier_frac: float = 0.0) -> dict:
+    """Flat BA problem in the include/omvg_b200.h layout (all float64 / int32, C-contiguous)."""
+    rng = np.random.default_rng(seed)
+    f, cx, cy = 1000.0, 500.0, 500.0
+    gtR = np.zeros((n_cams, 3, 3))
+    gtC = np.zeros((n_cams, 3))
+    poses = np.zeros((n_cams, 6))
+    for i in range(n_cams):
+        th = i * 2 * np.pi / n_cams
+        c = np.array([1.5 * np.sin(th), 0.2 * np.sin(3 * th), 1.5 * np.cos(th)])
+        R = _look_at(-c)
+        gtR[i], gtC[i] = R, c
+        dR = _rodrigues(rng.normal(0, 0.005, 3))
+        Ri = dR @ R
+        Ci = c + rng.normal(0, 0.005, 3)
+        poses[i, :3] = _log_so3(Ri)
+        poses[i, 3:] = -Ri @ Ci
+    intr = np.zeros((n_intrinsics, INTR_STRIDE))
+    intr[:, 0], intr[:, 1], intr[:, 2] = f, cx, cy
+    gt_dist = np.zeros(INTR_STRIDE)
+    if model == PINHOLE_CAMERA_RADIAL1:
+        gt_dist[3] = 0.05
+    elif model == PINHOLE_CAMERA_RADIAL3:
+        gt_dist[3:6] = [0.05, -0.01, 0.002]
+    elif model == PINHOLE_CAMERA_BROWN:
+        gt_dist[3:8] = [0.05, -0.01, 0.002, 0.001, -0.0005]
+    elif model == PINHOLE_CAMERA_FISHEYE:
+        gt_dist[3:7] = [0.02, -0.005, 0.001, 0.0]
+    intr_model = np.full(n_intrinsics, model, np.int32)
+    view_pose = np.arange(n_cams, dtype=np.int32)
+    view_intr = (np.arange(n_cams) % n_intrinsics).astype(np.int32)
+
+    X = rng.uniform(-0.6, 0.6, (n_points, 3))
+    s0 = rng.integers(0, n_cams, n_points)
+    k = np.arange(obs_per_point)
+    stride = 1 + (np.arange(n_points) % 3)
+    cam = (s0[:, None] + k[None, :] * stride[:, None]) % n_cams          # [P, K]
+    # a point cannot be observed twice by the same view (Observations is keyed by view id)
+    if obs_per_point * 3 > n_cams:
+        cam = (s0[:, None] + k[None, :]) % n_cams
+    assert obs_per_point <= n_cams
+    obs_point = np.repeat(np.arange(n_points, dtype=np.int32), obs_per_point)
+    obs_view = cam.reshape(-1).astype(np.int32)
+    Xc = np.einsum('oij,oj->oi', gtR[obs_view], X[obs_point] - gtC[obs_view])
+    u = Xc[:, :2] / Xc[:, 2:3]
+    u = _distort(u, model, gt_dist)
+    xy = np.stack([cx + f * u[:, 0], cy + f * u[:, 1]], 1) + rng.normal(0, noise_px, (len(obs_view), 2))
+    if outlier_frac > 0:
+        bad = rng.random(len(obs_view)) < outlier_frac
+        xy[bad] += rng.normal(0, 60.0, (int(bad.sum()), 2))
+    points = X + rng.normal(0, 0.01, X.shape)
+    return dict(
+        poses=np.ascontiguousarray(poses), intrinsics=np.ascontiguousarray(intr),
+        intr_model=intr_model, points=np.ascontiguousarray(points),
+        view_pose=view_pose, view_intr=view_intr,
+        obs_view=np.ascontiguousarray(obs_view), obs_point=np.ascontiguousarray(obs_point),
+        obs_xy=np.ascontiguousarray(xy), gt_dist=gt_dist)
+
+
+def _distort(u: np.ndarray, model: int, d: np.ndarray) -> np.ndarray:
+    """Forward distortion of normalised coordinates, per camera model
+    (sfm/sfm_data_BA_ceres_camera_functor.hpp:262-267, 372-379, 489-500, 609-626)."""
+    if model == PINHOLE_CAMERA:
+        return u
+    r2 = (u * u).sum(1, keepdims=True)
+    if model == PINHOLE_CAMERA_RADIAL1:
+        return u * (1 + d[3] * r2)
+    if model == PINHOLE_CAMERA_RADIAL3:
+        return u * (1 + d[3] * r2 + d[4] * r2 ** 2 + d[5] * r2 ** 3)
+    if model == PINHOLE_CAMERA_BROWN:
+        k1, k2, k3, t1, t2 = d[3:8]
+        rc = 1 + k1 * r2 + k2 * r2 ** 2 + k3 * r2 ** 3
+        x, y = u[:, :1], u[:, 1:]
+        tx = t2 * (r2 + 2 * x * x) + 2 * t1 * x * y
+        ty = t1 * (r2 + 2 * y * y) + 2 * t2 * x * y
+        return np.concatenate([x * rc + tx, y * rc + ty], 1)
+    if model == PINHOLE_CAMERA_FISHEYE:
+        r = np.sqrt(r2)
+        th = np.arctan(r)
+        thd = th * (1 + d[3] * th ** 2 + d[4] * th ** 4 + d[5] * th ** 6 + d[6] * th ** 8)
+        scale = np.where(r > 1e-8, thd / np.maximum(r, 1e-300), 1.0)
+        return u * scale
+    raise ValueError(model)
+
+
+def descriptors(n_images: int, n_desc, seed: int = 7, inlier_frac: float = 0.3) -> list:
+    """List of [n_k,128] uint8 arrays; ``n_desc`` is an int or a per-image sequence."""
+    rng = np.random.default_rng(seed)
+    counts = [int(n_desc)] * n_images if np.isscalar(n_desc) else [int(x) for x in n_desc]
+    out = []
+    for k, n in enumerate(counts):
+        u = rng.integers(0, 256, (n, 128), dtype=np.int32)
+        v = rng.integers(0, 256, (n, 128), dtype=np.int32)
+        d = (u * v // 255).astype(np.uint8)
+        if k > 0 and n > 0 and len(out[-1]) > 0:
+            m = min(n, len(out[-1]))
+            sel = rng.random(m) < inlier_frac
+            noise = rng.integers(-8, 9, (m, 128), dtype=np.int32)
+            base = out[-1][:m].astype(np.int32)
+            d[:m][sel] = np.clip(base[sel] + noise[sel], 0, 255).astype(np.uint8)
+        out.append(np.ascontiguousarray(d))
+    return out
+
+
+def exhaustive_pairs(n_images: int):
+    """Pair_Builder.hpp:25-33 — all (I,J) with I<J in lexicographic order."""
+    i, j = np.triu_indices(n_images, 1)
+    return np.ascontiguousarray(i.astype(np.uint32)), np.ascontiguousarray(j.astype(np.uint32))

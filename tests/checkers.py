@@ -1,0 +1,177 @@
+"""ctypes bindings for the CHECKERS: oracle/_build/liboracle.so (our CPU restatement) and
+oracle/_ref/libref_{match,ba}.so (the reference itself, compiled by oracle/Makefile).
+
+Test infrastructure only — imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference leg; never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+REF_MATCH_SO = os.path.join(ROOT, "oracle", "_ref", "libref_match.so")
+REF_BA_SO = os.path.join(ROOT, "oracle", "_ref", "libref_ba.so")
+
+_P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+
+# Ceres defaults as overridden by sfm_data_BA_ceres.cpp:477-493 (solver.h:62-138)
+BA_DEFAULT_OPTS = dict(
+    intrinsics_opt=14, extrinsics_opt=6, structure_opt=1, use_loss=1, huber_a=16.0,
+    max_num_iterations=50, function_tolerance=1e-6, gradient_tolerance=1e-10,
+    parameter_tolerance=1e-8, initial_radius=1e4, max_radius=1e16, min_radius=1e-32,
+    min_relative_decrease=1e-3, min_lm_diagonal=1e-6, max_lm_diagonal=1e32,
+    max_consecutive_invalid_steps=5)
+BA_OPT_ORDER = list(BA_DEFAULT_OPTS.keys())
+
+
+def build_oracle():
+    if not os.path.exists(ORACLE_SO):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    return ORACLE_SO
+
+
+_cache = {}
+
+
+def oracle():
+    if "o" not in _cache:
+        lib = ctypes.CDLL(build_oracle())
+        lib.oracle_match_pair.restype = ctypes.c_int64
+        lib.oracle_fnv1a_ij.restype = ctypes.c_uint64
+        lib.oracle_ba_cost.restype = ctypes.c_double
+        lib.oracle_ba_eval.restype = ctypes.c_double
+        _cache["o"] = lib
+    return _cache["o"]
+
+
+def have_ref_match():
+    return os.path.exists(REF_MATCH_SO)
+
+
+def have_ref_ba():
+    return os.path.exists(REF_BA_SO)
+
+
+def ref_match():
+    if "rm" not in _cache:
+        lib = ctypes.CDLL(REF_MATCH_SO)
+        lib.ref_match_pair.restype = ctypes.c_int64
+        lib.ref_match_collection.restype = ctypes.c_int64
+        _cache["rm"] = lib
+    return _cache["rm"]
+
+
+def ref_ba():
+    if "rb" not in _cache:
+        _cache["rb"] = ctypes.CDLL(REF_BA_SO)
+    return _cache["rb"]
+
+
+# ----------------------------------------------------------------------------- MATCH
+def oracle_match_pair(di, dj, ratio=0.8):
+    ni, nj = len(di), len(dj)
+    out = np.zeros(2 * max(nj, 1), np.uint32)
+    scratch = np.zeros(3 * max(nj, 1), np.int32)
+    n = oracle().oracle_match_pair(_P(di), ni, _P(dj), nj, ctypes.c_float(ratio), _P(out), _P(scratch))
+    return out[:2 * n].reshape(-1, 2).copy()
+
+
+def oracle_top2(di, dj):
+    nj = len(dj)
+    d1 = np.zeros(nj, np.int32); i1 = np.zeros(nj, np.uint32); d2 = np.zeros(nj, np.int32)
+    rc = oracle().oracle_top2(_P(di), len(di), _P(dj), nj, _P(d1), _P(i1), _P(d2))
+    return rc, d1, i1, d2
+
+
+def ref_match_pair(di, dj, ratio=0.8):
+    out = np.zeros(2 * max(len(dj), 1), np.uint32)
+    n = ref_match().ref_match_pair(_P(di), len(di), _P(dj), len(dj), ctypes.c_float(ratio), _P(out))
+    return out[:2 * n].reshape(-1, 2).copy()
+
+
+def ref_match_collection(descs, pi, pj, ratio=0.8):
+    counts = np.array([len(d) for d in descs], np.uint32)
+    row_start = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.uint64)
+    allrows = np.ascontiguousarray(np.concatenate([d.reshape(-1, 128) for d in descs]) if len(descs) else np.zeros((0, 128), np.uint8))
+    pi = np.ascontiguousarray(pi, np.uint32); pj = np.ascontiguousarray(pj, np.uint32)
+    offsets = np.zeros(len(pi) + 1, np.uint64)
+    cap = int(sum(int(counts[j]) for j in pj)) + 1
+    ij = np.zeros(2 * cap, np.uint32)
+    n = ref_match().ref_match_collection(_P(allrows), _P(row_start), _P(counts), len(descs), _P(pi), _P(pj),
+                                         ctypes.c_uint64(len(pi)), ctypes.c_float(ratio), _P(offsets), _P(ij),
+                                         ctypes.c_uint64(cap))
+    assert n >= 0
+    return offsets, ij[:2 * n].reshape(-1, 2).copy()
+
+
+def oracle_match_collection(descs, pi, pj, ratio=0.8):
+    """Matcher_Regions.cpp:32-107 over the oracle's pair routine; CSR in the order of (pi,pj)."""
+    offsets = [0]; rows = []
+    for i, j in zip(pi, pj):
+        m = oracle_match_pair(descs[int(i)], descs[int(j)], ratio)
+        rows.append(m); offsets.append(offsets[-1] + len(m))
+    ij = np.concatenate(rows) if rows else np.zeros((0, 2), np.uint32)
+    return np.array(offsets, np.uint64), ij.astype(np.uint32)
+
+
+# ----------------------------------------------------------------------------- BA
+def _ba_args(s, poses, intr, pts):
+    return (len(poses), _P(poses), len(intr), _P(intr), _P(s["intr_model"]), len(pts), _P(pts),
+            len(s["view_pose"]), _P(s["view_pose"]), _P(s["view_intr"]), ctypes.c_long(len(s["obs_view"])),
+            _P(s["obs_view"]), _P(s["obs_point"]), _P(s["obs_xy"]))
+
+
+def oracle_ba_cost(s, poses=None, intr=None, pts=None, use_loss=1, huber_a=16.0):
+    poses = s["poses"] if poses is None else poses
+    intr = s["intrinsics"] if intr is None else intr
+    pts = s["points"] if pts is None else pts
+    return oracle().oracle_ba_cost(*_ba_args(s, poses, intr, pts), int(use_loss), ctypes.c_double(huber_a))
+
+
+def oracle_ba_eval(s, use_loss=1, huber_a=16.0):
+    n = len(s["obs_view"])
+    r = np.zeros((n, 2)); Ji = np.zeros((n, 2, 8)); Jc = np.zeros((n, 2, 6)); Jp = np.zeros((n, 2, 3))
+    c = oracle().oracle_ba_eval(*_ba_args(s, s["poses"], s["intrinsics"], s["points"]), int(use_loss),
+                                ctypes.c_double(huber_a), _P(r), _P(Ji), _P(Jc), _P(Jp))
+    return c, r, Ji, Jc, Jp
+
+
+def oracle_ba_solve(s, **kw):
+    o = dict(BA_DEFAULT_OPTS); o.update(kw)
+    opts = np.array([float(o[k]) for k in BA_OPT_ORDER])
+    poses = s["poses"].copy(); intr = s["intrinsics"].copy(); pts = s["points"].copy()
+    summ = np.zeros(16); trace = np.zeros((128, 4))
+    rc = oracle().oracle_ba_solve(*_ba_args(s, poses, intr, pts), _P(opts), _P(summ), _P(trace), 128)
+    return dict(rc=rc, poses=poses, intrinsics=intr, points=pts, initial_cost=summ[0], final_cost=summ[1],
+                iterations=int(summ[2]), successful=int(summ[3]), unsuccessful=int(summ[4]),
+                termination=int(summ[5]), usable=bool(summ[6]), trace=trace[:int(summ[7])], lm_steps=int(summ[8]))
+
+
+def ref_ba_adjust(s, intrinsics_opt=14, extrinsics_opt=6, structure_opt=1, threads=0, use_loss=1):
+    opts = np.array([intrinsics_opt, extrinsics_opt, structure_opt, threads, use_loss], np.int32)
+    poses = s["poses"].copy(); intr = s["intrinsics"].copy(); pts = s["points"].copy()
+    out = np.zeros(4); rep = ctypes.create_string_buffer(1 << 16)
+    rc = ref_ba().ref_ba_adjust(*_ba_args(s, poses, intr, pts), _P(opts), _P(out), rep, 1 << 16)
+    text = rep.value.decode(errors="replace")
+
+    def grab(pat, cast=float, default=None):
+        m = re.search(pat, text)
+        return cast(m.group(1)) if m else default
+    return dict(rc=rc, ok=bool(out[0]), initial_cost=out[1], final_cost=out[2], wall_s=out[3], poses=poses,
+                intrinsics=intr, points=pts, report=text,
+                iterations=grab(r"Minimizer iterations\s+(\d+)", int),
+                successful=grab(r"Successful steps\s+(\d+)", int),
+                unsuccessful=grab(r"Unsuccessful steps\s+(\d+)", int),
+                minimizer_s=grab(r"\nMinimizer\s+([0-9.]+)"),
+                preprocessor_s=grab(r"Preprocessor\s+([0-9.]+)"),
+                linear_solver_s=grab(r"Linear solver\s+([0-9.]+)"),
+                jacobian_s=grab(r"Jacobian evaluation\s+([0-9.]+)"),
+                residual_s=grab(r"Residual evaluation\s+([0-9.]+)"),
+                threads=grab(r"\nThreads\s+\d+\s+(\d+)", int),
+                termination=grab(r"Termination:\s+(.*)", str))
