@@ -1,0 +1,734 @@
+// ba_kernels.cuh — device kernels of the bundle-adjustment hot path (FP64 throughout).
+//
+// What each kernel replaces in the reference (ceres = src/third_party/ceres-solver):
+//   cam_prep_kernel     ceres/include/ceres/rotation.h:563-622 (AngleAxisRotatePoint) hoisted per pose:
+//                       R(w) and dR/dw_k by forward-mode duals of the same expression
+//   eval_kernel         openMVG/sfm/sfm_data_BA_ceres_camera_functor.hpp (5 models) +
+//                       ceres autodiff (internal/autodiff.h:207-319) + HuberLoss (loss_function.cc:47-61)
+//                       + Corrector (corrector.cc:41-155) + ProgramEvaluator::Evaluate
+//                       (program_evaluator.h:138-285) + Jacobi column scaling
+//                       (trust_region_minimizer.cc:239-253)
+//   point_accum_kernel  SchurEliminator::ChunkDiagonalBlockAndGradient (schur_eliminator_impl.h:434-490)
+//   colsum_kernel       SquaredColumnNorm / gradient for the camera+intrinsic columns
+//   schur_kernel        SchurEliminator::Eliminate (schur_eliminator_impl.h:176-298, :374-410, :499-548)
+//   pcg_kernel          ConjugateGradientsSolver::Solve (conjugate_gradients_solver.cc:66-245) with a
+//                       block-Jacobi preconditioner, standing in for SimplicialLDLT (eigensparse.cc:45-143)
+//   backsub_kernel      SchurEliminator::BackSubstitute (schur_eliminator_impl.h:303-366)
+//   model_kernel        model_cost_change (trust_region_minimizer.cc:402-405)
+//   update_kernel       Program::Plus + SubsetParameterization::Plus (program.cc:115-127)
+#pragma once
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <cfloat>
+
+namespace omvg { namespace ba {
+
+namespace cg = cooperative_groups;
+constexpr int KI = OMVG_BA_INTR_STRIDE;   // 8
+
+// ------------------------------------------------------------------------------ small helpers
+template <int N> struct Dual { double a; double v[N]; };
+template <int N> __device__ __forceinline__ Dual<N> dconst(double s) { Dual<N> d; d.a = s; for (int i = 0; i < N; ++i) d.v[i] = 0; return d; }
+template <int N> __device__ __forceinline__ Dual<N> dvar(double s, int k) { Dual<N> d = dconst<N>(s); d.v[k] = 1.0; return d; }
+template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; h.a = f.a + g.a; for (int i = 0; i < N; ++i) h.v[i] = f.v[i] + g.v[i]; return h; }
+template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; h.a = f.a - g.a; for (int i = 0; i < N; ++i) h.v[i] = f.v[i] - g.v[i]; return h; }
+template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; h.a = f.a * g.a; for (int i = 0; i < N; ++i) h.v[i] = f.a * g.v[i] + f.v[i] * g.a; return h; }
+template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N> &f, const Dual<N> &g) { Dual<N> h; const double gi = 1.0 / g.a, q = f.a * gi; h.a = q; for (int i = 0; i < N; ++i) h.v[i] = (f.v[i] - q * g.v[i]) * gi; return h; }
+template <int N> __device__ __forceinline__ Dual<N> dsqrt(const Dual<N> &f) { Dual<N> h; h.a = sqrt(f.a); const double t = 1.0 / (2.0 * h.a); for (int i = 0; i < N; ++i) h.v[i] = t * f.v[i]; return h; }
+template <int N> __device__ __forceinline__ Dual<N> dcos(const Dual<N> &f) { Dual<N> h; h.a = cos(f.a); const double s = -sin(f.a); for (int i = 0; i < N; ++i) h.v[i] = s * f.v[i]; return h; }
+template <int N> __device__ __forceinline__ Dual<N> dsin(const Dual<N> &f) { Dual<N> h; h.a = sin(f.a); const double c = cos(f.a); for (int i = 0; i < N; ++i) h.v[i] = c * f.v[i]; return h; }
+
+// deterministic block sum (fixed tree); result valid in thread 0
+template <int THREADS> __device__ __forceinline__ double block_sum(double v, double *sh /* THREADS/32 */) {
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0;
+  if (threadIdx.x == 0) for (int i = 0; i < THREADS / 32; ++i) t += sh[i];
+  return t;
+}
+
+// 3x3 SPD inverse through LLT (invert_psd_matrix.h:56-59). m = {a00,a10,a11,a20,a21,a22}
+__device__ __forceinline__ bool inv3_spd(const double m[6], double inv[9]) {
+  const double l00 = sqrt(m[0]), l10 = m[1] / l00, l20 = m[3] / l00;
+  const double l11 = sqrt(m[2] - l10 * l10), l21 = (m[4] - l20 * l10) / l11;
+  const double l22 = sqrt(m[5] - l20 * l20 - l21 * l21);
+  if (!(l00 > 0.0 && l11 > 0.0 && l22 > 0.0) || !isfinite(l00) || !isfinite(l11) || !isfinite(l22)) return false;
+  #pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double b0 = c == 0 ? 1.0 : 0.0, b1 = c == 1 ? 1.0 : 0.0, b2 = c == 2 ? 1.0 : 0.0;
+    b0 /= l00; b1 = (b1 - l10 * b0) / l11; b2 = (b2 - l20 * b0 - l21 * b1) / l22;
+    b2 /= l22; b1 = (b1 - l21 * b2) / l11; b0 = (b0 - l10 * b1 - l20 * b2) / l00;
+    inv[0 * 3 + c] = b0; inv[1 * 3 + c] = b1; inv[2 * 3 + c] = b2;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------ per-pose rotation
+// camR[p][9] row-major R(w); camdR[p][k][9] = dR/dw_k.  Same expression as AngleAxisRotatePoint:
+// R = cos I + sin [w]x + (1-cos) w w^T with w = aa/theta;  theta^2 <= eps: R = I + [aa]x.
+__global__ void cam_prep_kernel(const double *__restrict__ poses, int n_poses, double *__restrict__ camR, double *__restrict__ camdR) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_poses) return;
+  typedef Dual<3> D;
+  D aa[3]; for (int k = 0; k < 3; ++k) aa[k] = dvar<3>(poses[6 * p + k], k);
+  const D theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  D R[9];
+  if (theta2.a > DBL_EPSILON) {
+    const D theta = dsqrt(theta2), c = dcos(theta), s = dsin(theta), ti = dconst<3>(1.0) / theta;
+    const D w[3] = {aa[0] * ti, aa[1] * ti, aa[2] * ti};
+    const D omc = dconst<3>(1.0) - c;
+    // column j of R = R e_j = e_j c + (w x e_j) s + w (w_j) (1-c)
+    for (int j = 0; j < 3; ++j) {
+      D e[3] = {dconst<3>(j == 0), dconst<3>(j == 1), dconst<3>(j == 2)};
+      const D wx[3] = {w[1] * e[2] - w[2] * e[1], w[2] * e[0] - w[0] * e[2], w[0] * e[1] - w[1] * e[0]};
+      const D tmp = (w[0] * e[0] + w[1] * e[1] + w[2] * e[2]) * omc;
+      for (int i = 0; i < 3; ++i) R[i * 3 + j] = e[i] * c + wx[i] * s + w[i] * tmp;
+    }
+  } else {
+    for (int j = 0; j < 3; ++j) {
+      D e[3] = {dconst<3>(j == 0), dconst<3>(j == 1), dconst<3>(j == 2)};
+      const D wx[3] = {aa[1] * e[2] - aa[2] * e[1], aa[2] * e[0] - aa[0] * e[2], aa[0] * e[1] - aa[1] * e[0]};
+      for (int i = 0; i < 3; ++i) R[i * 3 + j] = e[i] + wx[i];
+    }
+  }
+  for (int i = 0; i < 9; ++i) { camR[9 * p + i] = R[i].a; for (int k = 0; k < 3; ++k) camdR[27 * p + 9 * k + i] = R[i].v[k]; }
+}
+
+// ------------------------------------------------------------------------------ residual / Jacobian
+struct EvalArgs {
+  const double *poses, *intr, *pts, *camR, *camdR, *obs_xy;
+  const int *intr_model, *obs_pose, *obs_intr, *obs_pt;
+  long long n_obs;
+  int use_loss; double huber_a;
+  // outputs (component-major: comp * n_obs + obs)
+  double *r, *Jp, *Jc, *Ji;
+  double *cost_partial;
+  // scaling & masks
+  const double *sc_pt, *sc_cam, *sc_intr;   // null => unscaled
+  unsigned pose_mask;                       // bit k set => pose coordinate k is free
+  const unsigned *intr_mask;                // per intrinsic: bit k set => parameter k is free
+  int pts_free;
+};
+
+// distortion d(u; K) and its derivatives: dd[2][2] = d d/du, dk[2][5] = d d/dK[3..7]
+__device__ __forceinline__ void distort(int model, const double *K, double x, double y, double &dx, double &dy,
+                                        double dd[4], double dk[10], bool want_j) {
+  for (int i = 0; i < 10; ++i) dk[i] = 0.0;
+  if (model == OMVG_PINHOLE_CAMERA) { dx = x; dy = y; dd[0] = 1; dd[1] = 0; dd[2] = 0; dd[3] = 1; return; }
+  const double r2 = x * x + y * y;
+  if (model == OMVG_PINHOLE_CAMERA_RADIAL1 || model == OMVG_PINHOLE_CAMERA_RADIAL3 || model == OMVG_PINHOLE_CAMERA_BROWN) {
+    const double k1 = K[3], k2 = model == OMVG_PINHOLE_CAMERA_RADIAL1 ? 0.0 : K[4], k3 = model == OMVG_PINHOLE_CAMERA_RADIAL1 ? 0.0 : K[5];
+    const double r4 = r2 * r2, r6 = r4 * r2;
+    const double rc = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+    const double drc = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;      // d rc / d r2
+    dx = x * rc; dy = y * rc;
+    if (want_j) {
+      dd[0] = rc + x * drc * 2.0 * x; dd[1] = x * drc * 2.0 * y;
+      dd[2] = y * drc * 2.0 * x;      dd[3] = rc + y * drc * 2.0 * y;
+      dk[0] = x * r2; dk[5] = y * r2;
+      if (model != OMVG_PINHOLE_CAMERA_RADIAL1) { dk[1] = x * r4; dk[2] = x * r6; dk[6] = y * r4; dk[7] = y * r6; }
+    }
+    if (model == OMVG_PINHOLE_CAMERA_BROWN) {
+      const double t1 = K[6], t2 = K[7];
+      dx += t2 * (r2 + 2.0 * x * x) + 2.0 * t1 * x * y;
+      dy += t1 * (r2 + 2.0 * y * y) + 2.0 * t2 * x * y;
+      if (want_j) {
+        dd[0] += t2 * (2.0 * x + 4.0 * x) + 2.0 * t1 * y; dd[1] += t2 * 2.0 * y + 2.0 * t1 * x;
+        dd[2] += t1 * 2.0 * x + 2.0 * t2 * y;             dd[3] += t1 * (2.0 * y + 4.0 * y) + 2.0 * t2 * x;
+        dk[3] = 2.0 * x * y; dk[4] = r2 + 2.0 * x * x;
+        dk[8] = r2 + 2.0 * y * y; dk[9] = 2.0 * x * y;
+      }
+    }
+    return;
+  }
+  // fisheye (sfm_data_BA_ceres_camera_functor.hpp:609-626)
+  const double r = sqrt(r2);
+  if (r > 1e-8) {
+    const double th = atan(r), th2 = th * th, th3 = th2 * th, th4 = th2 * th2, th5 = th4 * th, th7 = th3 * th3 * th, th8 = th4 * th4, th9 = th8 * th;
+    const double thd = th + K[3] * th3 + K[4] * th5 + K[5] * th7 + K[6] * th9;
+    const double cd = thd / r;
+    dx = x * cd; dy = y * cd;
+    if (want_j) {
+      const double dthd_dth = 1.0 + 3.0 * K[3] * th2 + 5.0 * K[4] * th4 + 7.0 * K[5] * th3 * th3 + 9.0 * K[6] * th8;
+      const double dth_dr = 1.0 / (1.0 + r2);
+      const double dcd_dr = (dthd_dth * dth_dr - cd) / r;         // d(thd/r)/dr
+      const double gx = dcd_dr * x / r, gy = dcd_dr * y / r;      // d cd / dx, dy
+      dd[0] = cd + x * gx; dd[1] = x * gy; dd[2] = y * gx; dd[3] = cd + y * gy;
+      const double ir = 1.0 / r;
+      dk[0] = x * th3 * ir; dk[1] = x * th5 * ir; dk[2] = x * th7 * ir; dk[3] = x * th9 * ir;
+      dk[5] = y * th3 * ir; dk[6] = y * th5 * ir; dk[7] = y * th7 * ir; dk[8] = y * th9 * ir;
+    }
+  } else { dx = x; dy = y; dd[0] = 1; dd[1] = 0; dd[2] = 0; dd[3] = 1; }
+}
+
+constexpr int EVAL_THREADS = 128;
+template <bool WANT_J>
+__global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs A) {
+  __shared__ double sh[EVAL_THREADS / 32];
+  const long long o = (long long)blockIdx.x * EVAL_THREADS + threadIdx.x;
+  double cost = 0.0;
+  if (o < A.n_obs) {
+    const int ip = A.obs_pose[o], iq = A.obs_intr[o], j = A.obs_pt[o];
+    const double *R = A.camR + 9 * ip;
+    const double X0 = A.pts[3 * j], X1 = A.pts[3 * j + 1], X2 = A.pts[3 * j + 2];
+    const double *T = A.poses + 6 * ip + 3;
+    const double p0 = R[0] * X0 + R[1] * X1 + R[2] * X2 + T[0];
+    const double p1 = R[3] * X0 + R[4] * X1 + R[5] * X2 + T[1];
+    const double p2 = R[6] * X0 + R[7] * X1 + R[8] * X2 + T[2];
+    const double iz = 1.0 / p2, x = p0 * iz, y = p1 * iz;
+    const double *K = A.intr + KI * iq;
+    const int model = A.intr_model[iq];
+    double dx, dy, dd[4], dk[10];
+    distort(model, K, x, y, dx, dy, dd, dk, WANT_J);
+    const double f = K[0];
+    double r0 = K[1] + dx * f - A.obs_xy[2 * o], r1 = K[2] + dy * f - A.obs_xy[2 * o + 1];
+    const double s = r0 * r0 + r1 * r1;
+    double rho0 = s, rho1 = 1.0;
+    const double b = A.huber_a * A.huber_a;
+    if (A.use_loss && s > b) { const double rr = sqrt(s); rho0 = 2.0 * A.huber_a * rr - b; rho1 = fmax(DBL_MIN, A.huber_a / rr); }
+    cost = 0.5 * rho0;
+    if (WANT_J) {
+      const double w = sqrt(rho1);                              // Huber: rho'' <= 0 => r, J scaled by sqrt(rho')
+      const long long n = A.n_obs;
+      A.r[o] = w * r0; A.r[n + o] = w * r1;
+      // d r / d u = f * dd ; d u / d p = [[iz,0,-x iz],[0,iz,-y iz]]
+      const double a00 = w * f * dd[0], a01 = w * f * dd[1], a10 = w * f * dd[2], a11 = w * f * dd[3];
+      double g[6];                                              // d r / d p (2x3)
+      g[0] = a00 * iz; g[1] = a01 * iz; g[2] = -(a00 * x + a01 * y) * iz;
+      g[3] = a10 * iz; g[4] = a11 * iz; g[5] = -(a10 * x + a11 * y) * iz;
+      // point block: g * R
+      #pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double sc = A.pts_free ? (A.sc_pt ? A.sc_pt[3 * j + c] : 1.0) : 0.0;
+        A.Jp[(0 * 3 + c) * n + o] = sc * (g[0] * R[c] + g[1] * R[3 + c] + g[2] * R[6 + c]);
+        A.Jp[(1 * 3 + c) * n + o] = sc * (g[3] * R[c] + g[4] * R[3 + c] + g[5] * R[6 + c]);
+      }
+      // pose block: rotation columns g * (dR_k X), translation columns g
+      const double *dR = A.camdR + 27 * ip;
+      #pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double q0 = dR[9 * k + 0] * X0 + dR[9 * k + 1] * X1 + dR[9 * k + 2] * X2;
+        const double q1 = dR[9 * k + 3] * X0 + dR[9 * k + 4] * X1 + dR[9 * k + 5] * X2;
+        const double q2 = dR[9 * k + 6] * X0 + dR[9 * k + 7] * X1 + dR[9 * k + 8] * X2;
+        const double sc = ((A.pose_mask >> k) & 1) ? (A.sc_cam ? A.sc_cam[6 * ip + k] : 1.0) : 0.0;
+        A.Jc[(0 * 6 + k) * n + o] = sc * (g[0] * q0 + g[1] * q1 + g[2] * q2);
+        A.Jc[(1 * 6 + k) * n + o] = sc * (g[3] * q0 + g[4] * q1 + g[5] * q2);
+        const double st = ((A.pose_mask >> (3 + k)) & 1) ? (A.sc_cam ? A.sc_cam[6 * ip + 3 + k] : 1.0) : 0.0;
+        A.Jc[(0 * 6 + 3 + k) * n + o] = st * g[k];
+        A.Jc[(1 * 6 + 3 + k) * n + o] = st * g[3 + k];
+      }
+      // intrinsic block: [f, ppx, ppy, K3..K7]
+      const unsigned im = A.intr_mask[iq];
+      double ji0[KI], ji1[KI];
+      ji0[0] = w * dx; ji1[0] = w * dy; ji0[1] = w; ji1[1] = 0.0; ji0[2] = 0.0; ji1[2] = w;
+      #pragma unroll
+      for (int k = 0; k < 5; ++k) { ji0[3 + k] = w * f * dk[k]; ji1[3 + k] = w * f * dk[5 + k]; }
+      #pragma unroll
+      for (int k = 0; k < KI; ++k) {
+        const double sc = ((im >> k) & 1) ? (A.sc_intr ? A.sc_intr[KI * iq + k] : 1.0) : 0.0;
+        A.Ji[(0 * KI + k) * n + o] = sc * ji0[k];
+        A.Ji[(1 * KI + k) * n + o] = sc * ji1[k];
+      }
+    }
+  }
+  const double t = block_sum<EVAL_THREADS>(cost, sh);
+  if (threadIdx.x == 0) A.cost_partial[blockIdx.x] = t;
+}
+
+// fixed-order final reduction of per-block partials -> out[0]
+__global__ void reduce_partials_kernel(const double *__restrict__ part, int n, double *__restrict__ out) {
+  __shared__ double sh[32];
+  double v = 0; for (int i = threadIdx.x; i < n; i += 1024) v += part[i];
+  const double t = block_sum<1024>(v, sh);
+  if (threadIdx.x == 0) out[0] = t;
+}
+
+// ------------------------------------------------------------------------------ column sums
+// per point: EtE (6 unique: 00,10,11,20,21,22), Etb (3) from the (scaled) point blocks.
+__global__ void point_accum_kernel(const double *__restrict__ Jp, const double *__restrict__ r, const int *__restrict__ pt_start,
+                                   int n_points, long long n, double *__restrict__ EtE, double *__restrict__ Etb) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_points) return;
+  double e00 = 0, e10 = 0, e11 = 0, e20 = 0, e21 = 0, e22 = 0, b0 = 0, b1 = 0, b2 = 0;
+  for (long long o = pt_start[j]; o < pt_start[j + 1]; ++o) {
+    #pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      const double a = Jp[(row * 3 + 0) * n + o], b = Jp[(row * 3 + 1) * n + o], c = Jp[(row * 3 + 2) * n + o], rr = r[row * n + o];
+      e00 += a * a; e10 += b * a; e11 += b * b; e20 += c * a; e21 += c * b; e22 += c * c;
+      b0 += a * rr; b1 += b * rr; b2 += c * rr;
+    }
+  }
+  double *E = EtE + 6 * (size_t)j; E[0] = e00; E[1] = e10; E[2] = e11; E[3] = e20; E[4] = e21; E[5] = e22;
+  Etb[3 * (size_t)j] = b0; Etb[3 * (size_t)j + 1] = b1; Etb[3 * (size_t)j + 2] = b2;
+}
+
+// per pose (one warp): squared column norms and gradient over the pose's observation list.
+__global__ void cam_colsum_kernel(const double *__restrict__ Jc, const double *__restrict__ r, const int *__restrict__ cam_start,
+                                  const int *__restrict__ cam_obs, int n_poses, long long n, double *__restrict__ diag_cam,
+                                  double *__restrict__ g_cam) {
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (p >= n_poses) return;
+  double d[6] = {0, 0, 0, 0, 0, 0}, g[6] = {0, 0, 0, 0, 0, 0};
+  for (int t = cam_start[p] + lane; t < cam_start[p + 1]; t += 32) {
+    const long long o = cam_obs[t];
+    const double r0 = r[o], r1 = r[n + o];
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) { const double a = Jc[k * n + o], b = Jc[(6 + k) * n + o]; d[k] += a * a + b * b; g[k] += a * r0 + b * r1; }
+  }
+  #pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { d[k] += __shfl_down_sync(0xffffffffu, d[k], o); g[k] += __shfl_down_sync(0xffffffffu, g[k], o); }
+    if (lane == 0) { diag_cam[6 * p + k] = d[k]; g_cam[6 * p + k] = g[k]; }
+  }
+}
+
+// per intrinsic (one block): squared column norms and gradient over all observations using it.
+constexpr int ICS_THREADS = 256;
+__global__ void __launch_bounds__(ICS_THREADS) intr_colsum_kernel(const double *__restrict__ Ji, const double *__restrict__ r, const int *__restrict__ obs_intr,
+                                   long long n, int chunks, double *__restrict__ part /* [n_intr][chunks][16] */) {
+  __shared__ double sh[ICS_THREADS / 32];
+  const int q = blockIdx.y, chunk = blockIdx.x;
+  double d[KI], g[KI];
+  for (int k = 0; k < KI; ++k) { d[k] = 0; g[k] = 0; }
+  const long long per = (n + chunks - 1) / chunks, lo = per * chunk, hi = lo + per < n ? lo + per : n;
+  for (long long o = lo + threadIdx.x; o < hi; o += ICS_THREADS) {
+    if (obs_intr[o] != q) continue;
+    const double r0 = r[o], r1 = r[n + o];
+    #pragma unroll
+    for (int k = 0; k < KI; ++k) { const double a = Ji[k * n + o], b = Ji[(KI + k) * n + o]; d[k] += a * a + b * b; g[k] += a * r0 + b * r1; }
+  }
+  for (int k = 0; k < KI; ++k) {
+    const double td = block_sum<ICS_THREADS>(d[k], sh); const double tg = block_sum<ICS_THREADS>(g[k], sh);
+    if (threadIdx.x == 0) { part[((size_t)q * chunks + chunk) * 16 + k] = td; part[((size_t)q * chunks + chunk) * 16 + 8 + k] = tg; }
+  }
+}
+__global__ void intr_colsum_final_kernel(const double *__restrict__ part, int chunks, int n_intr, double *__restrict__ diag_intr, double *__restrict__ g_intr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_intr * KI) return;
+  const int q = t / KI, k = t % KI;
+  double d = 0, g = 0;
+  for (int c = 0; c < chunks; ++c) { d += part[((size_t)q * chunks + c) * 16 + k]; g += part[((size_t)q * chunks + c) * 16 + 8 + k]; }
+  diag_intr[t] = d; g_intr[t] = g;
+}
+
+// scale[i] = 1 / (1 + sqrt(colnorm2[i]))    (trust_region_minimizer.cc:239-250)
+__global__ void make_scale_kernel(const double *__restrict__ n2, int n, double *__restrict__ scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) scale[i] = 1.0 / (1.0 + sqrt(n2[i]));
+}
+__global__ void point_diag_from_EtE_kernel(const double *__restrict__ EtE, int n_points, double *__restrict__ diag_pt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n_points) return;
+  diag_pt[3 * j] = EtE[6 * (size_t)j]; diag_pt[3 * j + 1] = EtE[6 * (size_t)j + 2]; diag_pt[3 * j + 2] = EtE[6 * (size_t)j + 5];
+}
+// apply the just-computed column scaling to the unscaled J of iteration 0 (ScaleColumns, :253)
+__global__ void scale_J_kernel(double *__restrict__ Jp, double *__restrict__ Jc, double *__restrict__ Ji, const int *__restrict__ obs_pose,
+                               const int *__restrict__ obs_intr, const int *__restrict__ obs_pt, long long n,
+                               const double *__restrict__ sc_pt, const double *__restrict__ sc_cam, const double *__restrict__ sc_intr) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n) return;
+  const int ip = obs_pose[o], iq = obs_intr[o], j = obs_pt[o];
+  for (int row = 0; row < 2; ++row) {
+    for (int c = 0; c < 3; ++c) Jp[(row * 3 + c) * n + o] *= sc_pt[3 * j + c];
+    for (int c = 0; c < 6; ++c) Jc[(row * 6 + c) * n + o] *= sc_cam[6 * ip + c];
+    for (int c = 0; c < KI; ++c) Ji[(row * KI + c) * n + o] *= sc_intr[KI * iq + c];
+  }
+}
+// g_unscaled = g_scaled / scale ; then max |g| over free columns (gradient_max_norm)
+__global__ void grad_max_kernel(const double *__restrict__ g, const double *__restrict__ scale, int n, double *__restrict__ part) {
+  __shared__ double sh[8];
+  double m = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) m = fmax(m, fabs(g[i] / scale[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int i = 1; i < 8; ++i) m = fmax(m, sh[i]); part[blockIdx.x] = m; }
+}
+
+// lmD = sqrt(clamp(diag, lo, hi) / radius)   (levenberg_marquardt_strategy.cc:75-87)
+__global__ void lm_diag_kernel(const double *__restrict__ diag, int n, double lo, double hi, double radius, double *__restrict__ lmD) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) lmD[i] = sqrt(fmin(fmax(diag[i], lo), hi) / radius);
+}
+
+// ------------------------------------------------------------------------------ reduced system
+// Camera-pair structure: bitmap[nc][words] (bit b of row a set <=> S block (a,b) exists),
+// wprefix[nc][words] = #bits of the row before that word, rowptr[nc+1].
+struct Bsr { const unsigned *bitmap; const int *wprefix; const int *rowptr; int words; };
+__device__ __forceinline__ int bsr_find(const Bsr &B, int a, int b) {
+  const size_t w = (size_t)a * B.words + (b >> 5);
+  return B.rowptr[a] + B.wprefix[w] + __popc(B.bitmap[w] & ((1u << (b & 31)) - 1u));
+}
+__global__ void bitmap_mark_kernel(const int *__restrict__ obs_pose, const int *__restrict__ obs_pt, const int *__restrict__ pt_start,
+                                   long long n, unsigned *__restrict__ bitmap, int words) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n) return;
+  const int a = obs_pose[o], j = obs_pt[o];
+  for (long long u = pt_start[j]; u < pt_start[j + 1]; ++u) { const int b = obs_pose[u]; atomicOr(&bitmap[(size_t)a * words + (b >> 5)], 1u << (b & 31)); }
+}
+__global__ void bitmap_rowcount_kernel(const unsigned *__restrict__ bitmap, int nc, int words, int *__restrict__ wprefix, int *__restrict__ rowcount) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x; if (a >= nc) return;
+  int c = 0; for (int w = 0; w < words; ++w) { wprefix[(size_t)a * words + w] = c; c += __popc(bitmap[(size_t)a * words + w]); }
+  rowcount[a] = c;
+}
+__global__ void bitmap_cols_kernel(const unsigned *__restrict__ bitmap, const int *__restrict__ rowptr, int nc, int words, int *__restrict__ cols) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x; if (a >= nc) return;
+  int k = rowptr[a];
+  for (int w = 0; w < words; ++w) { unsigned m = bitmap[(size_t)a * words + w]; while (m) { const int b = __ffs(m) - 1; m &= m - 1; cols[k++] = w * 32 + b; } }
+}
+
+struct SchurArgs {
+  const double *r, *Jp, *Jc, *Ji, *EtE, *Etb, *lmD_pt;
+  const int *obs_pose, *obs_intr, *obs_pt, *pt_start;
+  long long n; int n_poses, n_intr, pts_free;
+  Bsr bsr;
+  double *Scc;      // [nnzb][36]
+  double *Sci;      // [KI*n_intr][6*n_poses]
+  double *Sii;      // [KI*n_intr][KI*n_intr]
+  double *rhs;      // [6*n_poses + KI*n_intr]
+  double *Einv;     // [n_points][9]  (written by the thread of the point's first observation)
+  int *fail;
+};
+
+// One thread per observation t; loops over all observations u of the same point.
+constexpr int SCHUR_THREADS = 128;
+__global__ void __launch_bounds__(SCHUR_THREADS) schur_kernel(SchurArgs A) {
+  const long long t = (long long)blockIdx.x * SCHUR_THREADS + threadIdx.x;
+  if (t >= A.n) return;
+  const long long n = A.n;
+  const int j = A.obs_pt[t], ct = A.obs_pose[t], qt = A.obs_intr[t];
+  const int nred_c = 6 * A.n_poses;
+  double jc[12], ji[2 * KI], jp[6];
+  #pragma unroll
+  for (int k = 0; k < 12; ++k) jc[k] = A.Jc[k * n + t];
+  #pragma unroll
+  for (int k = 0; k < 2 * KI; ++k) ji[k] = A.Ji[k * n + t];
+  #pragma unroll
+  for (int k = 0; k < 6; ++k) jp[k] = A.Jp[k * n + t];
+  const double r0 = A.r[t], r1 = A.r[n + t];
+  double inv[9], ie[3] = {0, 0, 0};
+  bool have_e = A.pts_free != 0;
+  if (have_e) {
+    double m[6];
+    const double *E = A.EtE + 6 * (size_t)j;
+    const double d0 = A.lmD_pt[3 * j], d1 = A.lmD_pt[3 * j + 1], d2 = A.lmD_pt[3 * j + 2];
+    m[0] = E[0] + d0 * d0; m[1] = E[1]; m[2] = E[2] + d1 * d1; m[3] = E[3]; m[4] = E[4]; m[5] = E[5] + d2 * d2;
+    if (!inv3_spd(m, inv)) { atomicExch(A.fail, 1); return; }
+    const double *b = A.Etb + 3 * (size_t)j;
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) ie[a] = inv[a * 3] * b[0] + inv[a * 3 + 1] * b[1] + inv[a * 3 + 2] * b[2];
+    if (t == A.pt_start[j]) { for (int a = 0; a < 9; ++a) A.Einv[9 * (size_t)j + a] = inv[a]; }
+  }
+  // EtFc_t (3x6), EtFi_t (3xKI)
+  double efc[18], efi[3 * KI];
+  #pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) efc[a * 6 + c] = jp[a] * jc[c] + jp[3 + a] * jc[6 + c];
+    #pragma unroll
+    for (int c = 0; c < KI; ++c) efi[a * KI + c] = jp[a] * ji[c] + jp[3 + a] * ji[KI + c];
+  }
+  // rhs_c += Fc'r - EtFc' (Einv Etb) ; rhs_i likewise
+  #pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    double v = jc[c] * r0 + jc[6 + c] * r1;
+    if (have_e) v -= efc[c] * ie[0] + efc[6 + c] * ie[1] + efc[12 + c] * ie[2];
+    atomicAdd(&A.rhs[6 * ct + c], v);
+  }
+  #pragma unroll
+  for (int c = 0; c < KI; ++c) {
+    double v = ji[c] * r0 + ji[KI + c] * r1;
+    if (have_e) v -= efi[c] * ie[0] + efi[KI + c] * ie[1] + efi[2 * KI + c] * ie[2];
+    if (v != 0.0) atomicAdd(&A.rhs[nred_c + KI * qt + c], v);
+  }
+  // same-observation terms: Fc'Fc, Fi'Fc, Fi'Fi
+  {
+    double *blk = A.Scc + 36 * (size_t)bsr_find(A.bsr, ct, ct);
+    #pragma unroll
+    for (int a = 0; a < 6; ++a)
+      #pragma unroll
+      for (int b = 0; b < 6; ++b) atomicAdd(&blk[a * 6 + b], jc[a] * jc[b] + jc[6 + a] * jc[6 + b]);
+    #pragma unroll
+    for (int a = 0; a < KI; ++a) {
+      if (ji[a] == 0.0 && ji[KI + a] == 0.0) continue;
+      #pragma unroll
+      for (int b = 0; b < 6; ++b) atomicAdd(&A.Sci[(size_t)(KI * qt + a) * nred_c + 6 * ct + b], ji[a] * jc[b] + ji[KI + a] * jc[6 + b]);
+      #pragma unroll
+      for (int b = 0; b < KI; ++b) { const double v = ji[a] * ji[b] + ji[KI + a] * ji[KI + b]; if (v != 0.0) atomicAdd(&A.Sii[(size_t)(KI * qt + a) * (KI * A.n_intr) + KI * qt + b], v); }
+    }
+  }
+  if (!have_e) return;
+  // cross terms with every observation u of the point:  -(EtF_t)' Einv (EtF_u)
+  double gt_c[18], gt_i[3 * KI];                              // Einv * EtF_t  (3x6, 3xKI)
+  #pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) gt_c[a * 6 + c] = inv[a * 3] * efc[c] + inv[a * 3 + 1] * efc[6 + c] + inv[a * 3 + 2] * efc[12 + c];
+    #pragma unroll
+    for (int c = 0; c < KI; ++c) gt_i[a * KI + c] = inv[a * 3] * efi[c] + inv[a * 3 + 1] * efi[KI + c] + inv[a * 3 + 2] * efi[2 * KI + c];
+  }
+  for (long long u = A.pt_start[j]; u < A.pt_start[j + 1]; ++u) {
+    const int cu = A.obs_pose[u], qu = A.obs_intr[u];
+    double up[6], uc[12];
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) up[k] = A.Jp[k * n + u];
+    #pragma unroll
+    for (int k = 0; k < 12; ++k) uc[k] = A.Jc[k * n + u];
+    double efu[18];
+    #pragma unroll
+    for (int a = 0; a < 3; ++a)
+      #pragma unroll
+      for (int c = 0; c < 6; ++c) efu[a * 6 + c] = up[a] * uc[c] + up[3 + a] * uc[6 + c];
+    // Scc(ct, cu) -= gt_c' efu          (6x6)
+    double *blk = A.Scc + 36 * (size_t)bsr_find(A.bsr, ct, cu);
+    #pragma unroll
+    for (int a = 0; a < 6; ++a)
+      #pragma unroll
+      for (int b = 0; b < 6; ++b) atomicAdd(&blk[a * 6 + b], -(gt_c[a] * efu[b] + gt_c[6 + a] * efu[6 + b] + gt_c[12 + a] * efu[12 + b]));
+    // Sci(qt ; cu) -= gt_i' efu         (KI x 6)
+    #pragma unroll
+    for (int a = 0; a < KI; ++a) {
+      if (gt_i[a] == 0.0 && gt_i[KI + a] == 0.0 && gt_i[2 * KI + a] == 0.0) continue;
+      #pragma unroll
+      for (int b = 0; b < 6; ++b) atomicAdd(&A.Sci[(size_t)(KI * qt + a) * nred_c + 6 * cu + b], -(gt_i[a] * efu[b] + gt_i[KI + a] * efu[6 + b] + gt_i[2 * KI + a] * efu[12 + b]));
+    }
+    // Sii(qt, qu) -= gt_i' EtFi_u       (KI x KI)
+    double ui[2 * KI];
+    #pragma unroll
+    for (int k = 0; k < 2 * KI; ++k) ui[k] = A.Ji[k * n + u];
+    #pragma unroll
+    for (int a = 0; a < KI; ++a) {
+      if (gt_i[a] == 0.0 && gt_i[KI + a] == 0.0 && gt_i[2 * KI + a] == 0.0) continue;
+      #pragma unroll
+      for (int b = 0; b < KI; ++b) {
+        const double e0 = up[0] * ui[b] + up[3] * ui[KI + b], e1 = up[1] * ui[b] + up[4] * ui[KI + b], e2 = up[2] * ui[b] + up[5] * ui[KI + b];
+        const double v = gt_i[a] * e0 + gt_i[KI + a] * e1 + gt_i[2 * KI + a] * e2;
+        if (v != 0.0) atomicAdd(&A.Sii[(size_t)(KI * qt + a) * (KI * A.n_intr) + KI * qu + b], -v);
+      }
+    }
+  }
+}
+
+// S diag += D^2 (free columns) / = 1 (masked columns); block-Jacobi preconditioner Minv_c = inv(diag block)
+__global__ void finish_cam_kernel(double *__restrict__ Scc, Bsr B, const double *__restrict__ lmD_cam, unsigned pose_mask, int n_poses,
+                                  double *__restrict__ Minv, int *__restrict__ fail) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x; if (p >= n_poses) return;
+  double *blk = Scc + 36 * (size_t)bsr_find(B, p, p);
+  double M[36];
+  for (int k = 0; k < 6; ++k) { if ((pose_mask >> k) & 1) blk[k * 6 + k] += lmD_cam[6 * p + k] * lmD_cam[6 * p + k]; else blk[k * 6 + k] = 1.0; }
+  for (int k = 0; k < 36; ++k) M[k] = blk[k];
+  // Cholesky 6x6 in place (lower), then inverse via forward/back substitution of unit vectors
+  for (int k = 0; k < 6; ++k) {
+    double d = M[k * 6 + k]; for (int q = 0; q < k; ++q) d -= M[k * 6 + q] * M[k * 6 + q];
+    if (!(d > 0.0) || !isfinite(d)) { atomicExch(fail, 2); return; }
+    d = sqrt(d); M[k * 6 + k] = d;
+    for (int i = k + 1; i < 6; ++i) { double s = M[i * 6 + k]; for (int q = 0; q < k; ++q) s -= M[i * 6 + q] * M[k * 6 + q]; M[i * 6 + k] = s / d; }
+  }
+  for (int c = 0; c < 6; ++c) {
+    double b[6]; for (int i = 0; i < 6; ++i) b[i] = i == c ? 1.0 : 0.0;
+    for (int i = 0; i < 6; ++i) { double s = b[i]; for (int q = 0; q < i; ++q) s -= M[i * 6 + q] * b[q]; b[i] = s / M[i * 6 + i]; }
+    for (int i = 5; i >= 0; --i) { double s = b[i]; for (int q = i + 1; q < 6; ++q) s -= M[q * 6 + i] * b[q]; b[i] = s / M[i * 6 + i]; }
+    for (int i = 0; i < 6; ++i) Minv[36 * (size_t)p + i * 6 + c] = b[i];
+  }
+}
+// intrinsics corner: add D^2 / identity, dense Cholesky inverse by one thread block (ni*8 <= 256)
+__global__ void finish_intr_kernel(double *__restrict__ Sii, const double *__restrict__ lmD_intr, const unsigned *__restrict__ intr_mask,
+                                   int ni8, double *__restrict__ Minv_i, double *__restrict__ work, int *__restrict__ fail) {
+  // single thread does the (tiny) factorisation; ni8 is typically 8
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int i = 0; i < ni8; ++i) {
+    const bool free_ = (intr_mask[i / KI] >> (i % KI)) & 1;
+    if (free_) Sii[(size_t)i * ni8 + i] += lmD_intr[i] * lmD_intr[i];
+    else { for (int k = 0; k < ni8; ++k) { Sii[(size_t)i * ni8 + k] = 0.0; Sii[(size_t)k * ni8 + i] = 0.0; } Sii[(size_t)i * ni8 + i] = 1.0; }
+  }
+  double *L = work;
+  for (int i = 0; i < ni8 * ni8; ++i) L[i] = Sii[i];
+  for (int k = 0; k < ni8; ++k) {
+    double d = L[k * ni8 + k]; for (int q = 0; q < k; ++q) d -= L[k * ni8 + q] * L[k * ni8 + q];
+    if (!(d > 0.0) || !isfinite(d)) { atomicExch(fail, 3); return; }
+    d = sqrt(d); L[k * ni8 + k] = d;
+    for (int i = k + 1; i < ni8; ++i) { double s = L[i * ni8 + k]; for (int q = 0; q < k; ++q) s -= L[i * ni8 + q] * L[k * ni8 + q]; L[i * ni8 + k] = s / d; }
+  }
+  for (int c = 0; c < ni8; ++c) {
+    double *b = work + (size_t)ni8 * ni8 + (size_t)c * 0;   // reuse one column buffer
+    double *col = work + (size_t)ni8 * ni8;
+    for (int i = 0; i < ni8; ++i) col[i] = i == c ? 1.0 : 0.0;
+    for (int i = 0; i < ni8; ++i) { double s = col[i]; for (int q = 0; q < i; ++q) s -= L[i * ni8 + q] * col[q]; col[i] = s / L[i * ni8 + i]; }
+    for (int i = ni8 - 1; i >= 0; --i) { double s = col[i]; for (int q = i + 1; q < ni8; ++q) s -= L[q * ni8 + i] * col[q]; col[i] = s / L[i * ni8 + i]; }
+    for (int i = 0; i < ni8; ++i) Minv_i[(size_t)i * ni8 + c] = col[i];
+    (void)b;
+  }
+}
+
+// ------------------------------------------------------------------------------ PCG (cooperative)
+struct PcgArgs {
+  const double *Scc; const int *rowptr, *cols; const double *Sci, *Sii, *rhs, *Minv_c, *Minv_i;
+  int n_poses, ni8;
+  double *z, *res, *p, *w, *zeta;          // length nred = 6 n_poses + ni8
+  double *part;                            // [3][gridDim.x] partial sums
+  double tol; int max_iter;
+  double *out;                             // [0]=iterations, [1]=final relative residual, [2]=|b|
+};
+
+__device__ __forceinline__ double grid_sum(cg::grid_group &grid, double v, double *part, double *sh) {
+  const double t = block_sum<256>(v, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+  grid.sync();
+  double s = 0;
+  for (int i = 0; i < (int)gridDim.x; ++i) s += part[i];     // same order in every thread: deterministic
+  return s;
+}
+
+// y = S x for the rows owned by this block; returns this thread's partial of x'y (lane 0 of each warp holds it)
+__device__ __forceinline__ double spmv_rows(const PcgArgs &A, const double *__restrict__ x, double *__restrict__ y) {
+  const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nc6 = 6 * A.n_poses;
+  double dot = 0;
+  for (int a = warp; a < A.n_poses; a += nwarps) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int e = A.rowptr[a] + lane; e < A.rowptr[a + 1]; e += 32) {
+      const double *blk = A.Scc + 36 * (size_t)e; const double *xb = x + 6 * A.cols[e];
+      #pragma unroll
+      for (int i = 0; i < 6; ++i)
+        #pragma unroll
+        for (int k = 0; k < 6; ++k) acc[i] += blk[i * 6 + k] * xb[k];
+    }
+    // border: + Sci' x_i   (column block of camera a)
+    for (int q = lane; q < A.ni8; q += 32) {
+      const double xi = x[nc6 + q]; const double *row = A.Sci + (size_t)q * nc6 + 6 * a;
+      #pragma unroll
+      for (int i = 0; i < 6; ++i) acc[i] += row[i] * xi;
+    }
+    #pragma unroll
+    for (int i = 0; i < 6; ++i) { for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o); }
+    if (lane == 0) { for (int i = 0; i < 6; ++i) { y[6 * a + i] = acc[i]; dot += acc[i] * x[6 * a + i]; } }
+  }
+  // intrinsic rows: y_i = Sci x_c + Sii x_i   (one warp per row)
+  for (int q = warp; q < A.ni8; q += nwarps) {
+    double acc = 0;
+    const double *row = A.Sci + (size_t)q * nc6;
+    for (int k = lane; k < nc6; k += 32) acc += row[k] * x[k];
+    for (int k = lane; k < A.ni8; k += 32) acc += A.Sii[(size_t)q * A.ni8 + k] * x[nc6 + k];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) { y[nc6 + q] = acc; dot += acc * x[nc6 + q]; }
+  }
+  return dot;
+}
+
+// zeta = Minv r for this block's rows; returns partial r'zeta
+__device__ __forceinline__ double precond_rows(const PcgArgs &A, const double *__restrict__ r, double *__restrict__ zeta) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int nc6 = 6 * A.n_poses;
+  double dot = 0;
+  for (int i = tid; i < nc6; i += nt) {
+    const int a = i / 6, k = i % 6; const double *M = A.Minv_c + 36 * (size_t)a + 6 * k; const double *rb = r + 6 * a;
+    const double v = M[0] * rb[0] + M[1] * rb[1] + M[2] * rb[2] + M[3] * rb[3] + M[4] * rb[4] + M[5] * rb[5];
+    zeta[i] = v; dot += v * r[i];
+  }
+  for (int q = tid; q < A.ni8; q += nt) {
+    double v = 0; for (int k = 0; k < A.ni8; ++k) v += A.Minv_i[(size_t)q * A.ni8 + k] * r[nc6 + k];
+    zeta[nc6 + q] = v; dot += v * r[nc6 + q];
+  }
+  return dot;
+}
+
+__global__ void __launch_bounds__(256) pcg_kernel(PcgArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[8];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int nred = 6 * A.n_poses + A.ni8;
+  double *P0 = A.part, *P1 = A.part + gridDim.x, *P2 = A.part + 2 * gridDim.x;
+  double bb = 0;
+  for (int i = tid; i < nred; i += nt) { A.z[i] = 0.0; const double b = A.rhs[i]; A.res[i] = b; bb += b * b; }
+  const double bnorm2 = grid_sum(grid, bb, P0, sh);
+  double rz = grid_sum(grid, precond_rows(A, A.res, A.zeta), P1, sh);
+  for (int i = tid; i < nred; i += nt) A.p[i] = A.zeta[i];
+  grid.sync();
+  int it = 0; double rr = bnorm2;
+  if (bnorm2 > 0.0) {
+    for (it = 1; it <= A.max_iter; ++it) {
+      const double pw = grid_sum(grid, spmv_rows(A, A.p, A.w), P0, sh);
+      const double alpha = rz / pw;
+      double rr_l = 0;
+      for (int i = tid; i < nred; i += nt) { A.z[i] += alpha * A.p[i]; const double rn = A.res[i] - alpha * A.w[i]; A.res[i] = rn; rr_l += rn * rn; }
+      rr = grid_sum(grid, rr_l, P2, sh);
+      if (!(rr > A.tol * A.tol * bnorm2)) break;
+      const double rz_new = grid_sum(grid, precond_rows(A, A.res, A.zeta), P1, sh);
+      const double beta = rz_new / rz; rz = rz_new;
+      for (int i = tid; i < nred; i += nt) A.p[i] = A.zeta[i] + beta * A.p[i];
+      grid.sync();
+    }
+  }
+  if (tid == 0) { A.out[0] = (double)(it > A.max_iter ? A.max_iter : it); A.out[1] = bnorm2 > 0 ? sqrt(rr / bnorm2) : 0.0; A.out[2] = sqrt(bnorm2); }
+}
+
+// ------------------------------------------------------------------------------ back substitution
+// y_pt = Einv (Etb - sum_obs EtFc z_c + EtFi z_i) ; step = -y  (levenberg_marquardt_strategy.cc:120)
+__global__ void backsub_kernel(const double *__restrict__ Jp, const double *__restrict__ Jc, const double *__restrict__ Ji,
+                               const double *__restrict__ Etb, const double *__restrict__ Einv, const int *__restrict__ obs_pose,
+                               const int *__restrict__ obs_intr, const int *__restrict__ pt_start, int n_points, int n_poses, long long n,
+                               const double *__restrict__ z, int pts_free, double *__restrict__ step_pt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n_points) return;
+  if (!pts_free) { step_pt[3 * j] = step_pt[3 * j + 1] = step_pt[3 * j + 2] = 0.0; return; }
+  double b0 = Etb[3 * (size_t)j], b1 = Etb[3 * (size_t)j + 1], b2 = Etb[3 * (size_t)j + 2];
+  for (long long o = pt_start[j]; o < pt_start[j + 1]; ++o) {
+    const double *zc = z + 6 * obs_pose[o]; const double *zi = z + 6 * n_poses + KI * obs_intr[o];
+    double f0 = 0, f1 = 0;                                    // F z for the two residual rows
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) { f0 += Jc[k * n + o] * zc[k]; f1 += Jc[(6 + k) * n + o] * zc[k]; }
+    #pragma unroll
+    for (int k = 0; k < KI; ++k) { f0 += Ji[k * n + o] * zi[k]; f1 += Ji[(KI + k) * n + o] * zi[k]; }
+    b0 -= Jp[0 * n + o] * f0 + Jp[3 * n + o] * f1; b1 -= Jp[1 * n + o] * f0 + Jp[4 * n + o] * f1; b2 -= Jp[2 * n + o] * f0 + Jp[5 * n + o] * f1;
+  }
+  const double *I = Einv + 9 * (size_t)j;
+  step_pt[3 * j] = -(I[0] * b0 + I[1] * b1 + I[2] * b2); step_pt[3 * j + 1] = -(I[3] * b0 + I[4] * b1 + I[5] * b2); step_pt[3 * j + 2] = -(I[6] * b0 + I[7] * b1 + I[8] * b2);
+}
+__global__ void negate_kernel(const double *__restrict__ z, int n, double *__restrict__ step) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) step[i] = -z[i]; }
+
+// model_cost_change partials: - m . (r + m/2), m = J step    (trust_region_minimizer.cc:402-405)
+constexpr int MODEL_THREADS = 128;
+__global__ void __launch_bounds__(MODEL_THREADS) model_kernel(const double *__restrict__ r, const double *__restrict__ Jp, const double *__restrict__ Jc, const double *__restrict__ Ji,
+                             const int *__restrict__ obs_pose, const int *__restrict__ obs_intr, const int *__restrict__ obs_pt, long long n, int n_poses,
+                             const double *__restrict__ step_pt, const double *__restrict__ step_red, double *__restrict__ part) {
+  __shared__ double sh[MODEL_THREADS / 32];
+  const long long o = (long long)blockIdx.x * MODEL_THREADS + threadIdx.x;
+  double v = 0;
+  if (o < n) {
+    const double *sp = step_pt + 3 * obs_pt[o], *sc = step_red + 6 * obs_pose[o], *si = step_red + 6 * n_poses + KI * obs_intr[o];
+    #pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      double m = 0;
+      #pragma unroll
+      for (int k = 0; k < 3; ++k) m += Jp[(row * 3 + k) * n + o] * sp[k];
+      #pragma unroll
+      for (int k = 0; k < 6; ++k) m += Jc[(row * 6 + k) * n + o] * sc[k];
+      #pragma unroll
+      for (int k = 0; k < KI; ++k) m += Ji[(row * KI + k) * n + o] * si[k];
+      v += -m * (r[row * n + o] + m / 2.0);
+    }
+  }
+  const double t = block_sum<MODEL_THREADS>(v, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+// candidate = x + step * scale on free coordinates; partials of |delta|^2 (ambient) and |x|^2
+__global__ void update_kernel(const double *__restrict__ x, const double *__restrict__ step, const double *__restrict__ scale, int n, int stride,
+                              unsigned uniform_mask, const unsigned *__restrict__ block_mask, int count_in_norm_all,
+                              double *__restrict__ cand, double *__restrict__ part_step, double *__restrict__ part_x) {
+  __shared__ double sh[8];
+  double ds = 0, xs = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int blk = i / stride, k = i % stride;
+    const unsigned m = block_mask ? block_mask[blk] : uniform_mask;
+    const double xv = x[i];
+    double d = 0;
+    if ((m >> k) & 1) d = step[i] * scale[i];
+    cand[i] = xv + d;
+    ds += d * d;
+    if (count_in_norm_all || m != 0) xs += xv * xv;           // constant blocks are not part of the reduced program
+  }
+  const double a = block_sum<256>(ds, sh); const double b = block_sum<256>(xs, sh);
+  if (threadIdx.x == 0) { part_step[blockIdx.x] = a; part_x[blockIdx.x] = b; }
+}
+
+}}  // namespace omvg::ba

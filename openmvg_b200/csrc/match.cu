@@ -1,0 +1,761 @@
+// match.cu — exhaustive putative matching of 128-D uint8 SIFT descriptors on sm_100a.
+//
+// Replaces (reference, /root/reference/src/openMVG):
+//   matching_image_collection/Matcher_Regions.cpp:32-107   pair loop (BRUTE_FORCE_L2)
+//   matching/regions_matcher.hpp:162-207                   MatchDistanceRatio
+//   matching/matcher_brute_force.hpp:100-200               2-NN scan (L2<uint8_t>, metric.hpp:55-93)
+//   matching/matching_filters.hpp:38-60                    NNdistanceRatio
+//
+// Design:
+//   |q - b|^2 = |q|^2 + |b|^2 - 2 q.b.   q.b for a 128-query x 256-database tile is ONE dense
+//   u8 x u8 -> s32 contraction with K = 128: four tcgen05.mma.kind::i8 (M128 N256 K32) fed by TMA
+//   (128-byte rows, SWIZZLE_128B), accumulators in TMEM (2 x 256 columns, double buffered).
+//   Epilogue (8 warps): key = 512*dot + ckey[b], ckey[b] = -256*|b|^2 + (b / G)  — one IMAD gives
+//   ((2 q.b - |b|^2) << 8) | group(b); the running MAX of the key over a 32-column chunk is one
+//   max per element, and a top-2 over chunk maxima costs 3 ops per 32 elements.  The kernel thus
+//   emits, per query, the exact best key (=> exact d1 and the 32..G-row group holding the nearest
+//   neighbour) and the best key of any OTHER chunk (=> an upper bound ub2 >= d2 that is exact
+//   whenever the second neighbour lies outside the best chunk).  A finalize kernel re-scans the one
+//   group exactly (dp4a) only for queries that can still pass the ratio test with ub2, recovers
+//   (i1, d2) exactly, applies  float(d1) < fratio*float(d2)  and compacts in ascending query order.
+//   All integer arithmetic is exact, so the output is bit-identical to the reference.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <vector>
+
+namespace omvg {
+
+constexpr int TILE_Q = 128;      // UMMA M  (queries  -> TMEM lanes)
+constexpr int TILE_DB = 256;     // UMMA N  (database -> TMEM columns)
+constexpr int ROW_PAD = 256;     // every image starts at a multiple of this many arena rows
+constexpr int A_STAGES = 2, B_STAGES = 4;
+constexpr int A_BYTES = TILE_Q * OMVG_DESC_LEN;                 // 16 KB
+constexpr int B_BYTES = TILE_DB * OMVG_DESC_LEN;                // 32 KB
+constexpr int CK_BYTES = TILE_DB * 4;                           //  1 KB of packed keys
+constexpr int B_STAGE_BYTES = B_BYTES + CK_BYTES;
+constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align slack*/ + 2048 /*merge*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2-5 / 6-9 epilogue for even / odd tiles
+constexpr int KEY_MIN = INT_MIN;
+
+struct Unit { uint32_t q_row, db_row, n_db_tiles, out_off; };   // one (pair, 128-query tile)
+
+// --------------------------------------------------------------------------------- prep kernel
+// norm[r] = |row r|^2 ; ckey[r] = -256*norm + (local_row / G) for real rows, INT_MIN for padding.
+__global__ void prep_rows_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ img_row0,
+                                 const uint32_t *__restrict__ img_count, const uint32_t *__restrict__ img_group,
+                                 const uint32_t *__restrict__ row_img, int32_t *__restrict__ norm,
+                                 int32_t *__restrict__ ckey, uint32_t total_rows) {
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;   // 8 threads per row, 16 B each
+  const uint32_t sub = threadIdx.x & 7;
+  if (gw >= total_rows) return;
+  const uint4 v = reinterpret_cast<const uint4 *>(desc + (size_t)gw * OMVG_DESC_LEN)[sub];
+  uint32_t s = __dp4a(v.x, v.x, 0u); s = __dp4a(v.y, v.y, s); s = __dp4a(v.z, v.z, s); s = __dp4a(v.w, v.w, s);
+  s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (sub == 0) {
+    const uint32_t img = row_img[gw >> 8];                      // ROW_PAD == 256 rows per slot
+    const uint32_t local = gw - img_row0[img];
+    norm[gw] = (int32_t)s;
+    ckey[gw] = local < img_count[img] ? (int32_t)(-(int32_t)(s << 8) + (int32_t)(local / img_group[img])) : KEY_MIN;
+  }
+}
+
+// --------------------------------------------------------------------------------- tcgen05 kernel
+__device__ __forceinline__ void tmem_ld_wait_dep(int32_t (&r)[32]) {
+  // tcgen05.wait::ld, with the 32 registers as in/out operands so that no use of them can be
+  // scheduled above the wait.
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+    : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+      "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+    :: "memory");
+}
+
+__device__ __forceinline__ int4 lds128(uint32_t saddr) {
+  int4 v;
+  asm("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+
+__device__ __forceinline__ void chunk_update(const int32_t (&r)[32], uint32_t ck, int &k1, int &k2) {
+  int gm = KEY_MIN;
+  #pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int4 c = lds128(ck + 16 * j);                          // LDS.128, same address for all lanes (broadcast)
+    const int a = r[4 * j + 0] * 512 + c.x, b = r[4 * j + 1] * 512 + c.y;
+    const int e = r[4 * j + 2] * 512 + c.z, f = r[4 * j + 3] * 512 + c.w;
+    gm = max(max(gm, a), b);
+    gm = max(max(gm, e), f);
+  }
+  k2 = max(k2, min(k1, gm));
+  k1 = max(k1, gm);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ ckey,
+                const Unit *__restrict__ units, uint32_t n_units, int2 *__restrict__ k12) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *a_smem = smem;                                        // [A_STAGES][16 KB]
+  uint8_t *b_smem = smem + A_STAGES * A_BYTES;                   // [B_STAGES][32 KB + 1 KB]
+  int2 *merge = reinterpret_cast<int2 *>(b_smem + B_STAGES * B_STAGE_BYTES);   // [2][128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(merge + 2 * TILE_Q);
+  uint64_t *full_a = bars, *empty_a = bars + 2, *full_b = bars + 4, *empty_b = bars + 8;
+  uint64_t *tmem_full = bars + 12, *tmem_empty = bars + 14;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap);
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1 + 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t g = 0, ul = 0;
+      for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+        const Unit un = units[u];
+        const uint32_t as = ul & 1;
+        mbar_wait(&empty_a[as], ((ul >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full_a[as], A_BYTES);
+        tma_load_2d(a_smem + as * A_BYTES, &tmap, 0, (int)un.q_row, &full_a[as]);
+        for (uint32_t t = 0; t < un.n_db_tiles; ++t, ++g) {
+          const uint32_t st = g % B_STAGES;
+          mbar_wait(&empty_b[st], ((g / B_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_b[st], B_STAGE_BYTES);
+          uint8_t *dst = b_smem + st * B_STAGE_BYTES;
+          const uint32_t row = un.db_row + t * TILE_DB;
+          tma_load_2d(dst, &tmap, 0, (int)row, &full_b[st]);
+          tma_load_2d(dst + A_BYTES, &tmap, 0, (int)(row + 128), &full_b[st]);
+          bulk_load_1d(dst + B_BYTES, ckey + row, CK_BYTES, &full_b[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_u8(TILE_Q, TILE_DB);
+      uint32_t g = 0, ul = 0;
+      for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+        const uint32_t n_tiles = units[u].n_db_tiles;
+        const uint32_t as = ul & 1;
+        mbar_wait(&full_a[as], (ul >> 1) & 1);
+        const uint32_t a_addr = smem_u32(a_smem + as * A_BYTES);
+        for (uint32_t t = 0; t < n_tiles; ++t, ++g) {
+          const uint32_t st = g % B_STAGES, acc = g & 1;
+          mbar_wait(&full_b[st], (g / B_STAGES) & 1);
+          mbar_wait(&tmem_empty[acc], ((g >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(b_smem + st * B_STAGE_BYTES);
+          const uint32_t d = tmem_base + acc * TILE_DB;
+          #pragma unroll
+          for (int k = 0; k < OMVG_DESC_LEN / 32; ++k)
+            umma_i8(d, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32), idesc, k > 0);
+          tc_commit(&empty_b[st]);
+          tc_commit(&tmem_full[acc]);
+        }
+        tc_commit(&empty_a[as]);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (8 warps)
+    const uint32_t wg = (warp - 2) >> 2;                 // 0: even tiles / acc 0, 1: odd tiles / acc 1
+    const uint32_t quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    uint32_t g = 0, ul = 0;
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+      const Unit un = units[u];
+      int k1 = KEY_MIN, k2 = KEY_MIN;
+      for (uint32_t t = 0; t < un.n_db_tiles; ++t, ++g) {
+        if ((g & 1) != wg) continue;
+        const uint32_t st = g % B_STAGES, acc = wg;
+        mbar_wait(&full_b[st], (g / B_STAGES) & 1);      // packed keys of this tile are in smem
+        mbar_wait(&tmem_full[acc], (g >> 1) & 1);        // accumulator complete
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + acc * TILE_DB;
+        const uint32_t ck = smem_u32(b_smem + st * B_STAGE_BYTES + B_BYTES);
+        int32_t ra[32], rb[32];
+        tmem_ld_32x32(taddr, ra);
+        #pragma unroll
+        for (int c = 0; c < TILE_DB / 32; c += 2) {
+          tmem_ld_wait_dep(ra);
+          tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+          chunk_update(ra, ck + c * 128, k1, k2);
+          tmem_ld_wait_dep(rb);
+          if (c + 2 < TILE_DB / 32) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+          chunk_update(rb, ck + (c + 1) * 128, k1, k2);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&tmem_empty[acc]); mbar_arrive(&empty_b[st]); }
+      }
+      // merge the two warpgroups' partial top-2 (disjoint chunks) and store
+      int2 *mb = merge + (ul & 1) * TILE_Q;
+      if (wg == 1) mb[row_in_tile] = make_int2(k1, k2);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (wg == 0) {
+        const int2 o = mb[row_in_tile];
+        const int K1 = max(k1, o.x);
+        const int K2 = max(min(k1, o.x), max(k2, o.y));
+        k12[(size_t)un.out_off + row_in_tile] = make_int2(K1, K2);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// --------------------------------------------------------------------------------- finalize
+struct PairInfo { uint32_t db_row0, db_count, db_group, q_row0, q_count; uint32_t pad; uint64_t out_off; };
+
+// exact top-2 of one query inside rows [r0, r1) of the database; whole warp cooperates.
+__device__ __forceinline__ void warp_rescan(const uint8_t *__restrict__ desc, const int32_t *__restrict__ norm,
+                                            uint32_t q_row, uint32_t r0, uint32_t r1, uint32_t db_row0,
+                                            int lane, int &bd1, uint32_t &bi1, int &bd2) {
+  const uint32_t qword = reinterpret_cast<const uint32_t *>(desc + (size_t)q_row * OMVG_DESC_LEN)[lane];
+  const int qn = norm[q_row];
+  int d1 = INT_MAX, d2 = INT_MAX; uint32_t i1 = 0xffffffffu;
+  for (uint32_t base = r0; base < r1; base += 32) {              // uniform trip count for the shuffles
+    const uint32_t r = base + lane;
+    const bool ok = r < r1;
+    const uint4 *rp = reinterpret_cast<const uint4 *>(desc + (size_t)(ok ? r : r0) * OMVG_DESC_LEN);
+    uint32_t dot = 0;
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint4 v = rp[k];
+      dot = __dp4a(v.x, __shfl_sync(0xffffffffu, qword, 4 * k + 0), dot);
+      dot = __dp4a(v.y, __shfl_sync(0xffffffffu, qword, 4 * k + 1), dot);
+      dot = __dp4a(v.z, __shfl_sync(0xffffffffu, qword, 4 * k + 2), dot);
+      dot = __dp4a(v.w, __shfl_sync(0xffffffffu, qword, 4 * k + 3), dot);
+    }
+    if (ok) {
+      const int d = qn + norm[r] - 2 * (int)dot;
+      if (d < d1) { d2 = d1; d1 = d; i1 = r - db_row0; } else if (d < d2) d2 = d;
+    }
+  }
+  #pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const int od1 = __shfl_xor_sync(0xffffffffu, d1, off), od2 = __shfl_xor_sync(0xffffffffu, d2, off);
+    const uint32_t oi1 = __shfl_xor_sync(0xffffffffu, i1, off);
+    if (od1 < d1 || (od1 == d1 && oi1 < i1)) { d2 = min(od2, d1); d1 = od1; i1 = oi1; }
+    else d2 = min(d2, od1);
+  }
+  bd1 = d1; bi1 = i1; bd2 = d2;
+}
+
+constexpr int FIN_THREADS = 256;
+__global__ void __launch_bounds__(FIN_THREADS)
+match_finalize_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ norm,
+                      const PairInfo *__restrict__ pairs, int2 *__restrict__ k12, uint32_t *__restrict__ counts,
+                      float fratio) {
+  __shared__ uint32_t warp_tot[FIN_THREADS / 32];
+  __shared__ uint32_t running;
+  const PairInfo P = pairs[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  int2 *io = k12 + P.out_off;
+  for (uint32_t q0 = 0; q0 < P.q_count; q0 += FIN_THREADS) {
+    const uint32_t q = q0 + threadIdx.x;
+    const bool valid = q < P.q_count;
+    int d1 = 0, ub2 = 0; uint32_t g1 = 0; bool cand = false;
+    if (valid) {
+      const int2 K = io[q];
+      const int qn = norm[P.q_row0 + q];
+      d1 = qn - (K.x >> 8);
+      g1 = (uint32_t)(K.x & 255);
+      ub2 = (K.y == KEY_MIN) ? INT_MAX : qn - (K.y >> 8);
+      cand = __int2float_rn(d1) < __fmul_rn(fratio, __int2float_rn(ub2));
+    }
+    bool keep = false; uint32_t idx = 0;
+    uint32_t m = __ballot_sync(0xffffffffu, cand);
+    while (m) {
+      const int src = __ffs(m) - 1; m &= m - 1;
+      const uint32_t qq = __shfl_sync(0xffffffffu, q, src);
+      const uint32_t gg = __shfl_sync(0xffffffffu, g1, src);
+      const uint32_t r0 = P.db_row0 + gg * P.db_group;
+      const uint32_t r1 = min(r0 + P.db_group, P.db_row0 + P.db_count);
+      int bd1, bd2; uint32_t bi1;
+      warp_rescan(desc, norm, P.q_row0 + qq, r0, r1, P.db_row0, lane, bd1, bi1, bd2);
+      if (lane == src) {
+        const int d2 = min(ub2, bd2);
+        keep = __int2float_rn(bd1) < __fmul_rn(fratio, __int2float_rn(d2));   // matching_filters.hpp:57
+        idx = bi1;
+      }
+    }
+    // ordered compaction (ascending q): block exclusive scan of keep
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    const uint32_t in_warp = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();                                   // all reads of io[q0..] done, warp totals visible
+    uint32_t before = running;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (keep) reinterpret_cast<uint2 *>(io)[before + in_warp] = make_uint2(idx, q);
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < FIN_THREADS / 32; ++w) t += warp_tot[w]; running += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[blockIdx.x] = running;
+}
+
+// exclusive scan of per-pair counts of one batch, offset by *total_io (running total over batches)
+__global__ void scan_counts_kernel(const uint32_t *__restrict__ counts, uint32_t n, uint64_t *__restrict__ offsets,
+                                   uint64_t *__restrict__ total_io) {
+  __shared__ uint64_t wsum[32];
+  __shared__ uint64_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = *total_io;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    uint64_t v = i < n ? counts[i] : 0, x = v;
+    #pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const uint64_t y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    uint64_t pre = carry;
+    for (int w = 0; w < warp; ++w) pre += wsum[w];
+    if (i < n) offsets[i] = pre + x - v;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint64_t t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w]; carry += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { offsets[n] = carry; *total_io = carry; }
+}
+
+__global__ void compact_kernel(const int2 *__restrict__ k12, const PairInfo *__restrict__ pairs,
+                               const uint32_t *__restrict__ counts, const uint64_t *__restrict__ offsets,
+                               uint2 *__restrict__ out) {
+  const uint32_t p = blockIdx.x, n = counts[p];
+  const uint2 *src = reinterpret_cast<const uint2 *>(k12 + pairs[p].out_off);
+  uint2 *dst = out + offsets[p];
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// --------------------------------------------------------------------------------- SIMT validation
+// Exact 2-NN by brute force with dp4a; one block per query.  Tests only.
+__global__ void __launch_bounds__(128)
+top2_simt_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ norm, uint32_t db_row0,
+                 uint32_t db_count, uint32_t q_row0, int32_t *__restrict__ od1, uint32_t *__restrict__ oi1,
+                 int32_t *__restrict__ od2) {
+  __shared__ uint32_t qs[32];
+  __shared__ int sd1[128], sd2[128]; __shared__ uint32_t si1[128];
+  const uint32_t q = blockIdx.x;
+  if (threadIdx.x < 32) qs[threadIdx.x] = reinterpret_cast<const uint32_t *>(desc + (size_t)(q_row0 + q) * OMVG_DESC_LEN)[threadIdx.x];
+  __syncthreads();
+  const int qn = norm[q_row0 + q];
+  int d1 = INT_MAX, d2 = INT_MAX; uint32_t i1 = 0xffffffffu;
+  for (uint32_t r = threadIdx.x; r < db_count; r += blockDim.x) {
+    const uint4 *rp = reinterpret_cast<const uint4 *>(desc + (size_t)(db_row0 + r) * OMVG_DESC_LEN);
+    uint32_t dot = 0;
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) { const uint4 v = rp[k];
+      dot = __dp4a(v.x, qs[4 * k], dot); dot = __dp4a(v.y, qs[4 * k + 1], dot);
+      dot = __dp4a(v.z, qs[4 * k + 2], dot); dot = __dp4a(v.w, qs[4 * k + 3], dot); }
+    const int d = qn + norm[db_row0 + r] - 2 * (int)dot;
+    if (d < d1) { d2 = d1; d1 = d; i1 = r; } else if (d < d2) d2 = d;
+  }
+  sd1[threadIdx.x] = d1; sd2[threadIdx.x] = d2; si1[threadIdx.x] = i1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int t = 1; t < 128; ++t) {
+      const int a1 = sd1[t], a2 = sd2[t]; const uint32_t ai = si1[t];
+      if (a1 < d1 || (a1 == d1 && ai < i1)) { d2 = min(a2, d1); d1 = a1; i1 = ai; } else d2 = min(d2, a1);
+    }
+    od1[q] = d1; oi1[q] = i1; od2[q] = d2;
+  }
+}
+
+__global__ void decode_k12_kernel(const int2 *__restrict__ k12, const int32_t *__restrict__ norm, uint32_t q_row0,
+                                  uint32_t n, int32_t *d1, uint32_t *g1, int32_t *ub2) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int2 K = k12[q]; const int qn = norm[q_row0 + q];
+  d1[q] = qn - (K.x >> 8); g1[q] = (uint32_t)(K.x & 255);
+  ub2[q] = (K.y == KEY_MIN) ? INT_MAX : qn - (K.y >> 8);
+}
+
+}  // namespace omvg
+
+// ===================================================================================== host side
+using namespace omvg;
+
+struct omvg_match_ctx {
+  int device = 0, n_sms = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t n_images = 0, total_rows = 0;
+  std::vector<uint32_t> counts, row0, group;
+  uint8_t *d_desc = nullptr; int32_t *d_norm = nullptr, *d_ckey = nullptr;
+  uint32_t *d_img_row0 = nullptr, *d_img_count = nullptr, *d_img_group = nullptr, *d_row_img = nullptr;
+  bool uploaded = false, prepared = false;
+  CUtensorMap tmap;
+  // run state
+  int2 *d_k12 = nullptr; size_t k12_cap = 0;           // in int2 elements
+  Unit *d_units = nullptr; size_t units_cap = 0;
+  PairInfo *d_pairs = nullptr; uint32_t *d_counts = nullptr; size_t pairs_cap = 0;
+  uint64_t *d_offsets = nullptr; size_t offsets_cap = 0;   // n_pairs + 1 (global)
+  uint64_t *d_total = nullptr;
+  uint2 *d_out = nullptr; size_t out_cap = 0;
+  uint64_t n_pairs_last = 0, total_last = 0; bool have_result = false;
+  uint64_t *h_offsets = nullptr; size_t h_offsets_cap = 0; uint32_t *h_ij = nullptr; size_t h_ij_cap = 0;
+  uint64_t launches = 0;
+  double tc_ms = 0; uint64_t tc_launches = 0; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t k12_budget_bytes = size_t(2) << 30;
+};
+
+namespace {
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap(omvg_match_ctx *c) {
+  void *fn = nullptr; cudaDriverEntryPointQueryResult qres;
+  OMVG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(OMVG_E_CUDA, "cuTensorMapEncodeTiled not available");
+  const cuuint64_t dims[2] = {OMVG_DESC_LEN, c->total_rows};
+  const cuuint64_t strides[1] = {OMVG_DESC_LEN};
+  const cuuint32_t box[2] = {OMVG_DESC_LEN, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = ((encode_tiled_fn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_desc, dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OMVG_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return OMVG_OK;
+}
+
+void free_images(omvg_match_ctx *c) {
+  cudaFree(c->d_desc); cudaFree(c->d_norm); cudaFree(c->d_ckey); cudaFree(c->d_img_row0); cudaFree(c->d_img_count);
+  cudaFree(c->d_img_group); cudaFree(c->d_row_img);
+  c->d_desc = nullptr; c->d_norm = c->d_ckey = nullptr; c->d_img_row0 = c->d_img_count = c->d_img_group = c->d_row_img = nullptr;
+}
+
+template <typename T> int ensure(T *&p, size_t &cap, size_t need) {
+  if (need <= cap) return OMVG_OK;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  OMVG_CUDA(cudaMalloc(&p, need * sizeof(T)));
+  cap = need; return OMVG_OK;
+}
+
+int drain_timers(omvg_match_ctx *c) {
+  for (auto &pr : c->pending) {
+    float ms = 0; OMVG_CUDA(cudaEventSynchronize(pr.second)); OMVG_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    c->tc_ms += ms; c->ev_pool.push_back(pr.first); c->ev_pool.push_back(pr.second);
+  }
+  c->pending.clear(); return OMVG_OK;
+}
+cudaEvent_t get_event(omvg_match_ctx *c) {
+  if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
+// one batch of pairs: tensor-core kernel + finalize + scan + compact
+int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_t p0, uint64_t p1, float fratio,
+              std::vector<Unit> &units, std::vector<PairInfo> &pinfo) {
+  units.clear(); pinfo.clear();
+  size_t out = 0;
+  for (uint64_t p = p0; p < p1; ++p) {
+    const uint32_t I = pi[p], J = pj[p];
+    PairInfo P{}; P.db_row0 = c->row0[I]; P.db_count = c->counts[I]; P.db_group = c->group[I];
+    P.q_row0 = c->row0[J]; P.q_count = c->counts[J]; P.out_off = out;
+    // Matcher_Regions.cpp:65-69,85-90 (empty regions) and matcher_brute_force.hpp:108-113 (NN > rows)
+    const bool active = P.db_count >= 2 && P.q_count >= 1;
+    if (!active) P.q_count = 0;
+    pinfo.push_back(P);
+    if (!active) continue;
+    const uint32_t qt = (P.q_count + TILE_Q - 1) / TILE_Q, dt = (P.db_count + TILE_DB - 1) / TILE_DB;
+    for (uint32_t t = 0; t < qt; ++t) units.push_back(Unit{P.q_row0 + t * TILE_Q, P.db_row0, dt, (uint32_t)(out + t * TILE_Q)});
+    out += size_t(qt) * TILE_Q;
+  }
+  if (out > 0xffffffffull) return fail(OMVG_E_ARG, "batch too large");
+  const uint32_t nb = (uint32_t)(p1 - p0);
+  int rc;
+  if ((rc = ensure(c->d_k12, c->k12_cap, std::max<size_t>(out, 1)))) return rc;
+  if ((rc = ensure(c->d_units, c->units_cap, std::max<size_t>(units.size(), 1)))) return rc;
+  if (nb > c->pairs_cap) {
+    if (c->d_pairs) cudaFree(c->d_pairs); if (c->d_counts) cudaFree(c->d_counts);
+    c->d_pairs = nullptr; c->d_counts = nullptr; c->pairs_cap = 0;
+    OMVG_CUDA(cudaMalloc(&c->d_pairs, nb * sizeof(PairInfo))); OMVG_CUDA(cudaMalloc(&c->d_counts, nb * sizeof(uint32_t)));
+    c->pairs_cap = nb;
+  }
+  OMVG_CUDA(cudaMemcpyAsync(c->d_pairs, pinfo.data(), nb * sizeof(PairInfo), cudaMemcpyHostToDevice, c->stream));
+  if (!units.empty()) {
+    OMVG_CUDA(cudaMemcpyAsync(c->d_units, units.data(), units.size() * sizeof(Unit), cudaMemcpyHostToDevice, c->stream));
+    const uint32_t grid = (uint32_t)std::min<size_t>(units.size(), (size_t)c->n_sms);
+    cudaEvent_t e0 = get_event(c), e1 = get_event(c);
+    OMVG_CUDA(cudaEventRecord(e0, c->stream));
+    match_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)units.size(), c->d_k12);
+    OMVG_CUDA(cudaGetLastError());
+    OMVG_CUDA(cudaEventRecord(e1, c->stream));
+    c->pending.emplace_back(e0, e1); c->tc_launches++; c->launches++;
+  }
+  match_finalize_kernel<<<nb, FIN_THREADS, 0, c->stream>>>(c->d_desc, c->d_norm, c->d_pairs, c->d_k12, c->d_counts, fratio);
+  OMVG_CUDA(cudaGetLastError());
+  scan_counts_kernel<<<1, 1024, 0, c->stream>>>(c->d_counts, nb, c->d_offsets + p0, c->d_total);
+  OMVG_CUDA(cudaGetLastError());
+  c->launches += 2;
+  // size the global output buffer: needs the running total (one small sync per batch)
+  uint64_t total = 0;
+  OMVG_CUDA(cudaMemcpyAsync(&total, c->d_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  if (total > c->out_cap) {
+    const size_t ncap = std::max<size_t>(total, c->out_cap * 2 + 1024);
+    uint2 *n = nullptr; OMVG_CUDA(cudaMalloc(&n, ncap * sizeof(uint2)));
+    if (c->d_out && c->total_last) OMVG_CUDA(cudaMemcpyAsync(n, c->d_out, c->total_last * sizeof(uint2), cudaMemcpyDeviceToDevice, c->stream));
+    OMVG_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d_out) cudaFree(c->d_out);
+    c->d_out = n; c->out_cap = ncap;
+  }
+  compact_kernel<<<nb, 128, 0, c->stream>>>(c->d_k12, c->d_pairs, c->d_counts, c->d_offsets + p0, c->d_out);
+  OMVG_CUDA(cudaGetLastError());
+  c->launches++;
+  c->total_last = total;
+  return OMVG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int omvg_version(void) { return 100; }
+const char *omvg_last_error(void) { return last_error().c_str(); }
+int omvg_device_count(void) {
+  int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  int ok = 0; for (int d = 0; d < n; ++d) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok; }
+  return ok;
+}
+
+int omvg_match_create(omvg_match_ctx **out, int device) {
+  if (!out) return fail(OMVG_E_ARG, "null ctx");
+  int n = 0; OMVG_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail(OMVG_E_CUDA, "no CUDA device %d (found %d)", device, n);
+  cudaDeviceProp prop; OMVG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(OMVG_E_CUDA, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  OMVG_CUDA(cudaSetDevice(device));
+  omvg_match_ctx *c = new omvg_match_ctx; c->device = device; c->n_sms = prop.multiProcessorCount;
+  OMVG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  OMVG_CUDA(cudaMalloc(&c->d_total, sizeof(uint64_t)));
+  if (const char *e = getenv("OMVG_MATCH_K12_MB")) c->k12_budget_bytes = size_t(atol(e)) << 20;
+  *out = c; return OMVG_OK;
+}
+
+int omvg_match_destroy(omvg_match_ctx *c) {
+  if (!c) return OMVG_OK;
+  cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
+  drain_timers(c); for (auto e : c->ev_pool) cudaEventDestroy(e);
+  free_images(c);
+  cudaFree(c->d_k12); cudaFree(c->d_units); cudaFree(c->d_pairs); cudaFree(c->d_counts); cudaFree(c->d_offsets);
+  cudaFree(c->d_total); cudaFree(c->d_out);
+  if (c->h_offsets) cudaFreeHost(c->h_offsets); if (c->h_ij) cudaFreeHost(c->h_ij);
+  cudaStreamDestroy(c->stream);
+  delete c; return OMVG_OK;
+}
+
+int omvg_match_set_images(omvg_match_ctx *c, uint32_t n_images, const uint32_t *counts) {
+  if (!c || (!counts && n_images)) return fail(OMVG_E_ARG, "bad arguments");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  free_images(c);
+  c->n_images = n_images; c->counts.assign(counts, counts + n_images); c->row0.resize(n_images); c->group.resize(n_images);
+  uint64_t rows = 0; std::vector<uint32_t> row_img;
+  for (uint32_t k = 0; k < n_images; ++k) {
+    c->row0[k] = (uint32_t)rows;
+    const uint32_t padded = (counts[k] + ROW_PAD - 1) / ROW_PAD * ROW_PAD;
+    c->group[k] = 32 * std::max<uint32_t>(1, (counts[k] + 8191) / 8192);      // rows/group <= 256 groups
+    for (uint32_t s = 0; s < padded / ROW_PAD; ++s) row_img.push_back(k);
+    rows += padded;
+    if (rows + 2 * ROW_PAD > 0xffffffffull) return fail(OMVG_E_ARG, "collection too large (%llu rows)", (unsigned long long)rows);
+  }
+  rows += ROW_PAD;                                      // tail slot: TMA boxes never leave the arena
+  row_img.push_back(n_images ? n_images - 1 : 0);
+  c->total_rows = (uint32_t)rows;
+  OMVG_CUDA(cudaMalloc(&c->d_desc, rows * OMVG_DESC_LEN));
+  OMVG_CUDA(cudaMemsetAsync(c->d_desc, 0, rows * OMVG_DESC_LEN, c->stream));
+  OMVG_CUDA(cudaMalloc(&c->d_norm, rows * 4)); OMVG_CUDA(cudaMalloc(&c->d_ckey, rows * 4));
+  OMVG_CUDA(cudaMalloc(&c->d_img_row0, std::max(1u, n_images) * 4)); OMVG_CUDA(cudaMalloc(&c->d_img_count, std::max(1u, n_images) * 4));
+  OMVG_CUDA(cudaMalloc(&c->d_img_group, std::max(1u, n_images) * 4)); OMVG_CUDA(cudaMalloc(&c->d_row_img, row_img.size() * 4));
+  if (n_images) {
+    OMVG_CUDA(cudaMemcpyAsync(c->d_img_row0, c->row0.data(), n_images * 4, cudaMemcpyHostToDevice, c->stream));
+    OMVG_CUDA(cudaMemcpyAsync(c->d_img_count, c->counts.data(), n_images * 4, cudaMemcpyHostToDevice, c->stream));
+    OMVG_CUDA(cudaMemcpyAsync(c->d_img_group, c->group.data(), n_images * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  OMVG_CUDA(cudaMemcpyAsync(c->d_row_img, row_img.data(), row_img.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  c->uploaded = false; c->prepared = false; c->have_result = false;
+  return make_tmap(c);
+}
+
+int omvg_match_upload_host(omvg_match_ctx *c, uint32_t image, const uint8_t *desc) {
+  if (!c || image >= c->n_images || (!desc && c->counts[image])) return fail(OMVG_E_ARG, "bad image %u", image);
+  OMVG_CUDA(cudaSetDevice(c->device));
+  if (c->counts[image])
+    OMVG_CUDA(cudaMemcpyAsync(c->d_desc + (size_t)c->row0[image] * OMVG_DESC_LEN, desc, (size_t)c->counts[image] * OMVG_DESC_LEN,
+                              cudaMemcpyHostToDevice, c->stream));
+  c->uploaded = true; c->prepared = false; return OMVG_OK;
+}
+
+int omvg_match_upload_device(omvg_match_ctx *c, uint32_t image, const void *desc_dev) {
+  if (!c || image >= c->n_images || (!desc_dev && c->counts[image])) return fail(OMVG_E_ARG, "bad image %u", image);
+  OMVG_CUDA(cudaSetDevice(c->device));
+  if (c->counts[image])
+    OMVG_CUDA(cudaMemcpyAsync(c->d_desc + (size_t)c->row0[image] * OMVG_DESC_LEN, desc_dev, (size_t)c->counts[image] * OMVG_DESC_LEN,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  c->uploaded = true; c->prepared = false; return OMVG_OK;
+}
+
+int omvg_match_upload_device_packed(omvg_match_ctx *c, const void *desc_dev) {
+  if (!c || !desc_dev) return fail(OMVG_E_ARG, "bad arguments");
+  size_t off = 0;
+  for (uint32_t k = 0; k < c->n_images; ++k) {
+    const int rc = omvg_match_upload_device(c, k, static_cast<const uint8_t *>(desc_dev) + off);
+    if (rc) return rc;
+    off += (size_t)c->counts[k] * OMVG_DESC_LEN;
+  }
+  c->uploaded = true; return OMVG_OK;
+}
+
+int omvg_match_prepare(omvg_match_ctx *c) {
+  if (!c || !c->d_desc) return fail(OMVG_E_STATE, "set_images first");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  const uint32_t threads = 256, rows_per_block = threads / 8;
+  prep_rows_kernel<<<(c->total_rows + rows_per_block - 1) / rows_per_block, threads, 0, c->stream>>>(
+      c->d_desc, c->d_img_row0, c->d_img_count, c->d_img_group, c->d_row_img, c->d_norm, c->d_ckey, c->total_rows);
+  OMVG_CUDA(cudaGetLastError());
+  c->launches++; c->prepared = true; return OMVG_OK;
+}
+
+int omvg_match_run(omvg_match_ctx *c, const uint32_t *pair_i, const uint32_t *pair_j, uint64_t n_pairs, float dist_ratio) {
+  if (!c || ((!pair_i || !pair_j) && n_pairs)) return fail(OMVG_E_ARG, "bad arguments");
+  if (!c->prepared) return fail(OMVG_E_STATE, "omvg_match_prepare must follow the uploads");
+  if (!(dist_ratio >= 0.f)) return fail(OMVG_E_ARG, "dist_ratio must be >= 0");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  for (uint64_t p = 0; p < n_pairs; ++p)
+    if (pair_i[p] >= c->n_images || pair_j[p] >= c->n_images) return fail(OMVG_E_ARG, "pair %llu out of range", (unsigned long long)p);
+  const float fratio = dist_ratio * dist_ratio;                   // numeric.h:56 Square<float>, regions_matcher.hpp:196
+  if (n_pairs + 1 > c->offsets_cap) {
+    if (c->d_offsets) cudaFree(c->d_offsets);
+    c->d_offsets = nullptr; c->offsets_cap = 0;
+    OMVG_CUDA(cudaMalloc(&c->d_offsets, (n_pairs + 1) * sizeof(uint64_t))); c->offsets_cap = n_pairs + 1;
+  }
+  OMVG_CUDA(cudaMemsetAsync(c->d_total, 0, sizeof(uint64_t), c->stream));
+  OMVG_CUDA(cudaMemsetAsync(c->d_offsets, 0, sizeof(uint64_t), c->stream));
+  c->total_last = 0; c->n_pairs_last = n_pairs; c->have_result = false;
+  std::vector<Unit> units; std::vector<PairInfo> pinfo;
+  const size_t budget = c->k12_budget_bytes / sizeof(int2);
+  uint64_t p0 = 0;
+  while (p0 < n_pairs) {
+    size_t acc = 0; uint64_t p1 = p0;
+    while (p1 < n_pairs) {
+      const size_t need = size_t((c->counts[pair_j[p1]] + TILE_Q - 1) / TILE_Q) * TILE_Q;
+      if (p1 > p0 && (acc + need > budget || p1 - p0 >= (1u << 20))) break;
+      acc += need; ++p1;
+    }
+    const int rc = run_batch(c, pair_i, pair_j, p0, p1, fratio, units, pinfo);
+    if (rc) return rc;
+    p0 = p1;
+  }
+  c->have_result = true; return OMVG_OK;
+}
+
+int omvg_match_sync(omvg_match_ctx *c) {
+  if (!c) return fail(OMVG_E_ARG, "null ctx");
+  OMVG_CUDA(cudaSetDevice(c->device)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  return drain_timers(c);
+}
+
+int omvg_match_fetch(omvg_match_ctx *c, const uint64_t **offsets, const uint32_t **ij, uint64_t *n_matches) {
+  if (!c || !offsets || !ij || !n_matches) return fail(OMVG_E_ARG, "bad arguments");
+  if (!c->have_result) return fail(OMVG_E_STATE, "no result: call omvg_match_run");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  const size_t no = c->n_pairs_last + 1;
+  if (no > c->h_offsets_cap) { if (c->h_offsets) cudaFreeHost(c->h_offsets); c->h_offsets = nullptr; c->h_offsets_cap = 0;
+    OMVG_CUDA(cudaMallocHost(&c->h_offsets, no * sizeof(uint64_t))); c->h_offsets_cap = no; }
+  OMVG_CUDA(cudaMemcpyAsync(c->h_offsets, c->d_offsets, no * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  if (c->n_pairs_last == 0) { OMVG_CUDA(cudaStreamSynchronize(c->stream)); c->h_offsets[0] = 0; }
+  const size_t nm = c->total_last;
+  if (nm > c->h_ij_cap) { if (c->h_ij) cudaFreeHost(c->h_ij); c->h_ij = nullptr; c->h_ij_cap = 0;
+    OMVG_CUDA(cudaMallocHost(&c->h_ij, std::max<size_t>(nm, 1) * 2 * sizeof(uint32_t))); c->h_ij_cap = std::max<size_t>(nm, 1); }
+  if (nm) OMVG_CUDA(cudaMemcpyAsync(c->h_ij, c->d_out, nm * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  drain_timers(c);
+  *offsets = c->h_offsets; *ij = c->h_ij; *n_matches = nm;
+  return OMVG_OK;
+}
+
+uint64_t omvg_match_launch_count(const omvg_match_ctx *c) { return c ? c->launches : 0; }
+
+int omvg_match_kernel_time(omvg_match_ctx *c, double *ms, uint64_t *launches, int reset) {
+  if (!c) return fail(OMVG_E_ARG, "null ctx");
+  OMVG_CUDA(cudaSetDevice(c->device)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  const int rc = drain_timers(c); if (rc) return rc;
+  if (ms) *ms = c->tc_ms; if (launches) *launches = c->tc_launches;
+  if (reset) { c->tc_ms = 0; c->tc_launches = 0; }
+  return OMVG_OK;
+}
+
+int omvg_match_debug_top2_simt(omvg_match_ctx *c, uint32_t I, uint32_t J, int32_t *d1, uint32_t *i1, int32_t *d2) {
+  if (!c || I >= c->n_images || J >= c->n_images) return fail(OMVG_E_ARG, "bad image");
+  if (!c->prepared) return fail(OMVG_E_STATE, "prepare first");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  const uint32_t nq = c->counts[J];
+  if (nq == 0 || c->counts[I] < 2) return fail(OMVG_E_ARG, "need >=2 database rows and >=1 query");
+  int32_t *dd1, *dd2; uint32_t *di1;
+  OMVG_CUDA(cudaMalloc(&dd1, nq * 4)); OMVG_CUDA(cudaMalloc(&dd2, nq * 4)); OMVG_CUDA(cudaMalloc(&di1, nq * 4));
+  top2_simt_kernel<<<nq, 128, 0, c->stream>>>(c->d_desc, c->d_norm, c->row0[I], c->counts[I], c->row0[J], dd1, di1, dd2);
+  OMVG_CUDA(cudaGetLastError()); c->launches++;
+  OMVG_CUDA(cudaMemcpyAsync(d1, dd1, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(i1, di1, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(d2, dd2, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(dd1); cudaFree(dd2); cudaFree(di1);
+  return OMVG_OK;
+}
+
+int omvg_match_debug_top2_tc(omvg_match_ctx *c, uint32_t I, uint32_t J, int32_t *d1, uint32_t *g1, int32_t *ub2) {
+  if (!c || I >= c->n_images || J >= c->n_images) return fail(OMVG_E_ARG, "bad image");
+  if (!c->prepared) return fail(OMVG_E_STATE, "prepare first");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  const uint32_t nq = c->counts[J], ndb = c->counts[I];
+  if (nq == 0 || ndb < 2) return fail(OMVG_E_ARG, "need >=2 database rows and >=1 query");
+  const uint32_t qt = (nq + TILE_Q - 1) / TILE_Q, dt = (ndb + TILE_DB - 1) / TILE_DB;
+  std::vector<Unit> units;
+  for (uint32_t t = 0; t < qt; ++t) units.push_back(Unit{c->row0[J] + t * TILE_Q, c->row0[I], dt, t * TILE_Q});
+  int rc;
+  if ((rc = ensure(c->d_k12, c->k12_cap, size_t(qt) * TILE_Q))) return rc;
+  if ((rc = ensure(c->d_units, c->units_cap, units.size()))) return rc;
+  OMVG_CUDA(cudaMemcpyAsync(c->d_units, units.data(), units.size() * sizeof(Unit), cudaMemcpyHostToDevice, c->stream));
+  match_tc_kernel<<<std::min<uint32_t>(qt, c->n_sms), TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, qt, c->d_k12);
+  OMVG_CUDA(cudaGetLastError()); c->launches++;
+  int32_t *dd1, *dd2; uint32_t *dg1;
+  OMVG_CUDA(cudaMalloc(&dd1, nq * 4)); OMVG_CUDA(cudaMalloc(&dd2, nq * 4)); OMVG_CUDA(cudaMalloc(&dg1, nq * 4));
+  decode_k12_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_k12, c->d_norm, c->row0[J], nq, dd1, dg1, dd2);
+  OMVG_CUDA(cudaGetLastError()); c->launches++;
+  OMVG_CUDA(cudaMemcpyAsync(d1, dd1, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(g1, dg1, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(ub2, dd2, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(dd1); cudaFree(dd2); cudaFree(dg1);
+  c->have_result = false;
+  return OMVG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""MATCH parity on the GPU: the CUDA path (through the C-ABI) against the oracle, bit-exact."""
+import numpy as np
+import pytest
+
+import checkers as ck
+from openmvg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def matching():
+    from openmvg_b200 import matching as m
+    return m
+
+
+def _csr_equal(off_a, ij_a, off_b, ij_b):
+    assert np.array_equal(np.asarray(off_a, np.uint64), np.asarray(off_b, np.uint64))
+    assert np.array_equal(ij_a, ij_b)
+
+
+def test_tc_top2_against_simt_and_oracle(matching):
+    """Raw tensor-core result: exact d1, the group of i1, and an upper bound of d2."""
+    descs = synth.descriptors(2, [700, 1000], seed=3)
+    ctx = matching.MatchContext(0)
+    ctx.load(descs)
+    sd1, si1, sd2 = ctx.debug_top2_simt(0, 1)
+    rc, od1, oi1, od2 = ck.oracle_top2(descs[0], descs[1])
+    assert rc == 0
+    assert np.array_equal(sd1, od1) and np.array_equal(sd2, od2)
+    uniq = od1 < od2
+    assert np.array_equal(si1[uniq], oi1[uniq])
+    td1, tg1, tub2 = ctx.debug_top2_tc(0, 1)
+    assert np.array_equal(td1, od1)
+    assert np.array_equal(tg1[uniq], (oi1 // 32)[uniq])
+    assert np.all(tub2 >= od2)
+    ctx.close()
+
+
+@pytest.mark.parametrize("counts", [[5000, 5000], [300, 129, 2, 257, 1000], [128, 256, 384]])
+def test_collection_bit_exact(matching, counts):
+    descs = synth.descriptors(len(counts), counts, seed=11)
+    pi, pj = synth.exhaustive_pairs(len(counts))
+    ctx = matching.MatchContext(0)
+    ctx.load(descs)
+    ctx.run(pi, pj, 0.8)
+    off, ij = ctx.fetch()
+    ooff, oij = ck.oracle_match_collection(descs, pi, pj, 0.8)
+    _csr_equal(off, ij, ooff, oij)
+    assert len(ij) > 0
+    ctx.close()
+
+
+def test_edge_cases(matching):
+    """Empty images, a 1-row database (NN=2 > rows => nothing), duplicates (d1 == d2), ratio 1.0 / 0.0."""
+    rng = np.random.default_rng(5)
+    base = synth.descriptors(1, 64, seed=9)[0]
+    dup = np.concatenate([base, base])                  # every row twice: d1 == d2 == 0 for queries = base
+    descs = [base, np.zeros((0, 128), np.uint8), base[:1].copy(), dup,
+             rng.integers(0, 256, (40, 128), dtype=np.int64).astype(np.uint8), np.full((33, 128), 255, np.uint8)]
+    n = len(descs)
+    pi, pj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    pi = pi.reshape(-1).astype(np.uint32); pj = pj.reshape(-1).astype(np.uint32)     # incl. I == J and I > J
+    ctx = matching.MatchContext(0)
+    ctx.load(descs)
+    for ratio in (0.8, 1.0, 0.0, 0.6):
+        ctx.run(pi, pj, ratio)
+        off, ij = ctx.fetch()
+        ooff, oij = ck.oracle_match_collection(descs, pi, pj, ratio)
+        _csr_equal(off, ij, ooff, oij)
+    ctx.close()
+
+
+def test_large_database_groups(matching):
+    """> 8192 rows in the database: group size 64 (re-scan spans two 32-row chunks)."""
+    descs = synth.descriptors(2, [9000, 600], seed=21)
+    ctx = matching.MatchContext(0)
+    ctx.load(descs)
+    pi = np.array([0, 1], np.uint32); pj = np.array([1, 0], np.uint32)
+    ctx.run(pi, pj, 0.8)
+    off, ij = ctx.fetch()
+    ooff, oij = ck.oracle_match_collection(descs, pi, pj, 0.8)
+    _csr_equal(off, ij, ooff, oij)
+    ctx.close()
+
+
+def test_batched_runs_match_single(matching, monkeypatch):
+    """Small k12 budget forces several batches; result must not change."""
+    import os
+    descs = synth.descriptors(6, [400, 500, 300, 450, 380, 410], seed=4)
+    pi, pj = synth.exhaustive_pairs(6)
+    ctx = matching.MatchContext(0)
+    ctx.load(descs); ctx.run(pi, pj, 0.8); off1, ij1 = ctx.fetch(); ctx.close()
+    monkeypatch.setenv("OMVG_MATCH_K12_MB", "0")        # 0 MB => one pair per batch
+    ctx = matching.MatchContext(0)
+    ctx.load(descs); ctx.run(pi, pj, 0.8); off2, ij2 = ctx.fetch(); ctx.close()
+    _csr_equal(off1, ij1, off2, ij2)
+
+
+def test_matcher_interface(matching):
+    """The Matcher::Match mirror: non-dense image ids, only non-empty pairs inserted."""
+    d = synth.descriptors(3, [300, 300, 0], seed=2)
+    provider = {10: d[0], 42: d[1], 7: d[2]}
+    pairs = {(10, 42), (7, 10), (7, 42)}
+    out = matching.Matcher_Regions_B200(0.8).Match(provider, pairs)
+    assert set(out.keys()) == {(10, 42)}
+    assert np.array_equal(out[(10, 42)], ck.oracle_match_pair(d[0], d[1], 0.8))
