@@ -1,0 +1,153 @@
+"""Python binding of the BA C-ABI (tests / bench plumbing; the drop-in host shim is the C++ class
+in openmvg_b200/host/Bundle_Adjustment_B200.hpp).
+
+Mirrors openMVG::sfm::Bundle_Adjustment_Ceres::Adjust (reference: sfm/sfm_data_BA_ceres.cpp:165-608)
+on the flat scene of include/omvg_b200.h: same options (Optimize_Options, sfm_data_BA.hpp:66-89),
+same outcome convention (returns the refined parameters iff the solution is usable).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from ._lib import OmvgError, check, lib
+
+_vp = ctypes.c_void_p
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+
+
+class Problem(ctypes.Structure):
+    _fields_ = [("n_poses", ctypes.c_int32), ("n_intrinsics", ctypes.c_int32), ("n_points", ctypes.c_int32),
+                ("n_views", ctypes.c_int32), ("n_obs", ctypes.c_int64), ("poses", _dp), ("intrinsics", _dp),
+                ("intr_model", _ip), ("points", _dp), ("view_pose", _ip), ("view_intr", _ip), ("obs_view", _ip),
+                ("obs_point", _ip), ("obs_xy", _dp)]
+
+
+class Options(ctypes.Structure):
+    _fields_ = [("intrinsics_opt", ctypes.c_int32), ("extrinsics_opt", ctypes.c_int32), ("structure_opt", ctypes.c_int32),
+                ("use_loss", ctypes.c_int32), ("huber_a", ctypes.c_double), ("max_num_iterations", ctypes.c_int32),
+                ("max_consecutive_invalid_steps", ctypes.c_int32), ("function_tolerance", ctypes.c_double),
+                ("gradient_tolerance", ctypes.c_double), ("parameter_tolerance", ctypes.c_double),
+                ("initial_radius", ctypes.c_double), ("max_radius", ctypes.c_double), ("min_radius", ctypes.c_double),
+                ("min_relative_decrease", ctypes.c_double), ("min_lm_diagonal", ctypes.c_double),
+                ("max_lm_diagonal", ctypes.c_double), ("pcg_tolerance", ctypes.c_double),
+                ("pcg_max_iterations", ctypes.c_int32), ("verbose", ctypes.c_int32)]
+
+
+class Summary(ctypes.Structure):
+    _fields_ = [("initial_cost", ctypes.c_double), ("final_cost", ctypes.c_double), ("iterations", ctypes.c_int32),
+                ("successful_steps", ctypes.c_int32), ("unsuccessful_steps", ctypes.c_int32), ("lm_steps", ctypes.c_int32),
+                ("termination", ctypes.c_int32), ("usable", ctypes.c_int32), ("pcg_iterations", ctypes.c_int64),
+                ("kernel_launches", ctypes.c_int64), ("device_ms", ctypes.c_double), ("jacobian_ms", ctypes.c_double),
+                ("jacobian_launches", ctypes.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def default_options(**kw) -> Options:
+    o = Options()
+    lib().omvg_ba_default_options(ctypes.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(f"unknown BA option {k}")
+        setattr(o, k, v)
+    return o
+
+
+def _problem(s, poses, intr, pts) -> Problem:
+    P = Problem()
+    P.n_poses, P.n_intrinsics, P.n_points = len(poses), len(intr), len(pts)
+    P.n_views, P.n_obs = len(s["view_pose"]), len(s["obs_view"])
+    d = lambda a: a.ctypes.data_as(_dp)   # noqa: E731
+    i = lambda a: a.ctypes.data_as(_ip)   # noqa: E731
+    P.poses, P.intrinsics, P.points = d(poses), d(intr), d(pts)
+    P.intr_model, P.view_pose, P.view_intr = i(s["intr_model"]), i(s["view_pose"]), i(s["view_intr"])
+    P.obs_view, P.obs_point, P.obs_xy = i(s["obs_view"]), i(s["obs_point"]), d(s["obs_xy"])
+    return P
+
+
+def solve(s: dict, **opts) -> dict:
+    """One-shot Adjust through omvg_ba_solve with HOST buffers (upload, solve, write-back)."""
+    poses = np.ascontiguousarray(s["poses"], np.float64).copy()
+    intr = np.ascontiguousarray(s["intrinsics"], np.float64).copy()
+    pts = np.ascontiguousarray(s["points"], np.float64).copy()
+    P = _problem(s, poses, intr, pts)
+    o = default_options(**opts)
+    sm = Summary()
+    rc = lib().omvg_ba_solve(ctypes.byref(P), ctypes.byref(o), ctypes.byref(sm))
+    if rc not in (0, -5):
+        check(rc)
+    out = sm.as_dict()
+    out.update(ok=(rc == 0), poses=poses, intrinsics=intr, points=pts)
+    return out
+
+
+class BAContext:
+    """Device-resident scene (omvg_ba_ctx): create once, reset/run many times."""
+
+    def __init__(self, s: dict, device: int = 0):
+        self._keep = (np.ascontiguousarray(s["poses"], np.float64).copy(),
+                      np.ascontiguousarray(s["intrinsics"], np.float64).copy(),
+                      np.ascontiguousarray(s["points"], np.float64).copy())
+        self._s = s
+        P = _problem(s, *self._keep)
+        self._h = _vp()
+        check(lib().omvg_ba_create(ctypes.byref(self._h), int(device), ctypes.byref(P)))
+
+    def close(self):
+        if self._h:
+            lib().omvg_ba_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        check(lib().omvg_ba_reset(self._h))
+
+    def run(self, **opts) -> dict:
+        o = default_options(**opts)
+        sm = Summary()
+        rc = lib().omvg_ba_run(self._h, ctypes.byref(o), ctypes.byref(sm))
+        if rc not in (0, -5):
+            check(rc)
+        out = sm.as_dict()
+        out["ok"] = rc == 0
+        return out
+
+    def download(self):
+        poses, intr, pts = (np.zeros_like(a) for a in self._keep)
+        check(lib().omvg_ba_download(self._h, poses.ctypes.data_as(_dp), intr.ctypes.data_as(_dp), pts.ctypes.data_as(_dp)))
+        return poses, intr, pts
+
+    def debug_eval(self, **opts):
+        o = default_options(**opts)
+        n = len(self._s["obs_view"])
+        r = np.zeros((n, 2)); Ji = np.zeros((n, 2, 8)); Jc = np.zeros((n, 2, 6)); Jp = np.zeros((n, 2, 3))
+        cost = ctypes.c_double()
+        d = lambda a: a.ctypes.data_as(_dp)   # noqa: E731
+        check(lib().omvg_ba_debug_eval(self._h, ctypes.byref(o), ctypes.byref(cost), d(r), d(Ji), d(Jc), d(Jp)))
+        return cost.value, r, Ji, Jc, Jp
+
+
+class Bundle_Adjustment_B200:
+    """Drop-in for Bundle_Adjustment_Ceres on the flat scene: Adjust(scene, options) -> bool, scene
+    updated in place iff the solution is usable (sfm_data_BA.hpp:91-105, sfm_data_BA_ceres.cpp:503-507)."""
+
+    def __init__(self, **ceres_options):
+        self.options = ceres_options
+        self.summary = None
+
+    def Adjust(self, scene: dict, intrinsics_opt=14, extrinsics_opt=6, structure_opt=1) -> bool:
+        r = solve(scene, intrinsics_opt=intrinsics_opt, extrinsics_opt=extrinsics_opt, structure_opt=structure_opt,
+                  **self.options)
+        self.summary = r
+        if r["ok"]:
+            scene["poses"][...] = r["poses"]; scene["intrinsics"][...] = r["intrinsics"]; scene["points"][...] = r["points"]
+        return bool(r["ok"])

@@ -1,0 +1,496 @@
+// ba.cu — host side of the bundle-adjustment hot path: problem packing, device structures and the
+// Levenberg-Marquardt controller that mirrors Ceres 1.13's TrustRegionMinimizer +
+// LevenbergMarquardtStrategy (reference: src/third_party/ceres-solver/internal/ceres/
+// trust_region_minimizer.cc:66-119,226-279,355-424,667-786; levenberg_marquardt_strategy.cc:65-160;
+// trust_region_step_evaluator.cc:51-59) as configured by openMVG
+// (src/openMVG/sfm/sfm_data_BA_ceres.cpp:242-253,275-305,321-344,394-395,477-493).
+// All arithmetic runs in the kernels of ba_kernels.cuh; the host only takes the accept/reject and
+// termination decisions from a handful of scalars read back once per LM iteration.
+#include "ba_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+using namespace omvg;
+using namespace omvg::ba;
+
+namespace {
+
+enum Slot { S_COST = 0, S_MODEL, S_STEP2_PT, S_STEP2_POSE, S_STEP2_INTR, S_X2_PT, S_X2_POSE, S_X2_INTR,
+            S_GMAX_PT, S_GMAX_CAM, S_GMAX_INTR, S_PCG_IT, S_PCG_RES, S_PCG_B, S_CAND_COST, S_COUNT = 16 };
+
+int model_nparams(int m) {
+  switch (m) { case 1: return 3; case 2: return 4; case 3: return 6; case 4: return 8; case 5: return 7; default: return -1; }
+}
+
+template <typename T> struct DevBuf {
+  T *p = nullptr; size_t n = 0;
+  int alloc(size_t count) { release(); n = count; if (!count) return OMVG_OK; OMVG_CUDA(cudaMalloc(&p, count * sizeof(T))); return OMVG_OK; }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct omvg_ba_ctx {
+  int device = 0, n_sms = 0;
+  cudaStream_t stream = nullptr;
+  int nc = 0, ni = 0, np = 0, nv = 0; long long no = 0;
+  int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0;
+  std::vector<int> perm;                    // sorted position -> caller's observation index
+  std::vector<int> h_intr_model;
+  // parameters: [0] current, [1] candidate, init = copy at create
+  DevBuf<double> pose[2], intr[2], pt[2], pose0, intr0, pt0;
+  DevBuf<int> intr_model, obs_pose, obs_intr, obs_pt, pt_start, cam_start, cam_obs;
+  DevBuf<double> obs_xy;
+  DevBuf<double> r, Jp, Jc, Ji, camR[2], camdR;
+  DevBuf<double> sc_pt, sc_cam, sc_intr, diag_pt, diag_cam, diag_intr, lmD_pt, lmD_cam, lmD_intr, g_cam, g_intr;
+  DevBuf<double> EtE, Etb, Einv, step_pt, step_red;
+  DevBuf<unsigned> bitmap, intr_mask; DevBuf<int> wprefix, rowptr, cols;
+  DevBuf<double> Scc, Sci, Sii, rhs, Minv_c, Minv_i, work_i;
+  DevBuf<double> z, res, pvec, w, zeta, pcg_part;
+  DevBuf<double> part, part2, part3, icol_part, scal;
+  DevBuf<int> fail;
+  double *h_scal = nullptr;                 // pinned
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evj0 = nullptr, evj1 = nullptr;
+  long long launches = 0;
+};
+
+namespace {
+
+#define LAUNCH_CHECK() OMVG_CUDA(cudaGetLastError())
+
+int validate(const omvg_ba_problem *P) {
+  if (!P) return fail(OMVG_E_ARG, "null problem");
+  if (P->n_poses < 1 || P->n_intrinsics < 1 || P->n_points < 1 || P->n_views < 1 || P->n_obs < 1) return fail(OMVG_E_ARG, "bad sizes (need >=1 pose, intrinsic, point, view, observation)");
+  if (!P->poses || !P->intrinsics || !P->intr_model || (!P->points && P->n_points) || !P->view_pose || !P->view_intr) return fail(OMVG_E_ARG, "null array");
+  if (P->n_obs && (!P->obs_view || !P->obs_point || !P->obs_xy)) return fail(OMVG_E_ARG, "null observation array");
+  if (P->n_obs >= (1ll << 31)) return fail(OMVG_E_UNSUPPORTED, "more than 2^31 observations");
+  for (int q = 0; q < P->n_intrinsics; ++q) if (model_nparams(P->intr_model[q]) < 0)
+    return fail(OMVG_E_UNSUPPORTED, "camera model %d is not implemented on the GPU path", P->intr_model[q]);
+  for (int v = 0; v < P->n_views; ++v)
+    if (P->view_pose[v] < 0 || P->view_pose[v] >= P->n_poses || P->view_intr[v] < 0 || P->view_intr[v] >= P->n_intrinsics) return fail(OMVG_E_ARG, "view %d out of range", v);
+  for (long long o = 0; o < P->n_obs; ++o)
+    if (P->obs_view[o] < 0 || P->obs_view[o] >= P->n_views || P->obs_point[o] < 0 || P->obs_point[o] >= P->n_points) return fail(OMVG_E_ARG, "observation %lld out of range", o);
+  if (P->n_poses > 32768) return fail(OMVG_E_UNSUPPORTED, "more than 32768 poses (camera-pair bitmap)");
+  if (P->n_intrinsics > 32) return fail(OMVG_E_UNSUPPORTED, "more than 32 intrinsic groups (dense border)");
+  return OMVG_OK;
+}
+
+template <typename T> int upload(DevBuf<T> &b, const T *h, size_t n, cudaStream_t s) {
+  int rc = b.alloc(n); if (rc) return rc;
+  if (n) OMVG_CUDA(cudaMemcpyAsync(b.p, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  return OMVG_OK;
+}
+
+int reduce_to(omvg_ba_ctx *c, const double *part, int n, int slot) {
+  reduce_partials_kernel<<<1, 1024, 0, c->stream>>>(part, n, c->scal.p + slot); LAUNCH_CHECK(); c->launches++; return OMVG_OK;
+}
+
+struct Masks { unsigned pose_mask; std::vector<unsigned> intr_mask; int pts_free; };
+
+// sfm_data_BA_ceres.cpp:275-305 (poses), 321-344 + Camera_Pinhole*.hpp subsetParameterization, 394-395
+Masks make_masks(const omvg_ba_ctx *c, const omvg_ba_options *o) {
+  Masks m; m.pts_free = o->structure_opt != 0;
+  if (o->extrinsics_opt == 1) m.pose_mask = 0;
+  else if (o->extrinsics_opt == 4) m.pose_mask = 0x38;      // ADJUST_TRANSLATION: rotation constant
+  else if (o->extrinsics_opt == 2) m.pose_mask = 0x07;      // ADJUST_ROTATION: translation constant
+  else m.pose_mask = 0x3f;
+  m.intr_mask.assign(c->ni, 0);
+  for (int q = 0; q < c->ni; ++q) {
+    if (o->intrinsics_opt & 1) continue;                    // NONE
+    const int k = model_nparams(c->h_intr_model[q]);
+    unsigned mm = 0;
+    for (int i = 0; i < k; ++i) {
+      bool constant = (i == 0) ? !(o->intrinsics_opt & 2) : (i <= 2 ? !(o->intrinsics_opt & 4) : !(o->intrinsics_opt & 8));
+      if (!constant) mm |= 1u << i;
+    }
+    m.intr_mask[q] = mm;
+  }
+  return m;
+}
+
+int eval_cost(omvg_ba_ctx *c, const omvg_ba_options *o, int which, int slot) {
+  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[which].p, c->nc, c->camR[which].p, c->camdR.p); LAUNCH_CHECK();
+  // NB: cam_prep overwrites camdR; the cost-only pass is always followed by a full evaluation before
+  // camdR is read again (accepted step) or the current pose's camdR is not needed (J is materialised).
+  EvalArgs A{}; A.poses = c->pose[which].p; A.intr = c->intr[which].p; A.pts = c->pt[which].p; A.camR = c->camR[which].p; A.camdR = c->camdR.p;
+  A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
+  A.n_obs = c->no; A.use_loss = o->use_loss; A.huber_a = o->huber_a; A.cost_partial = c->part.p;
+  eval_kernel<false><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  c->launches += 2;
+  return reduce_to(c, c->part.p, c->eval_blocks, slot);
+}
+
+int colsums(omvg_ba_ctx *c) {
+  point_accum_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->r.p, c->pt_start.p, c->np, c->no, c->EtE.p, c->Etb.p); LAUNCH_CHECK();
+  point_diag_from_EtE_kernel<<<(c->np + 255) / 256, 256, 0, c->stream>>>(c->EtE.p, c->np, c->diag_pt.p); LAUNCH_CHECK();
+  cam_colsum_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Jc.p, c->r.p, c->cam_start.p, c->cam_obs.p, c->nc, c->no, c->diag_cam.p, c->g_cam.p); LAUNCH_CHECK();
+  const int chunks = 64;
+  intr_colsum_kernel<<<dim3(chunks, c->ni), ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->icol_part.p); LAUNCH_CHECK();
+  intr_colsum_final_kernel<<<(c->ni8 + 63) / 64, 64, 0, c->stream>>>(c->icol_part.p, chunks, c->ni, c->diag_intr.p, c->g_intr.p); LAUNCH_CHECK();
+  c->launches += 5; return OMVG_OK;
+}
+
+// full evaluation at parameter set `which`: cost, corrected r and J (scaled), column sums, gradient max
+int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which, bool &have_scale, bool time_it) {
+  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[which].p, c->nc, c->camR[which].p, c->camdR.p); LAUNCH_CHECK();
+  EvalArgs A{}; A.poses = c->pose[which].p; A.intr = c->intr[which].p; A.pts = c->pt[which].p; A.camR = c->camR[which].p; A.camdR = c->camdR.p;
+  A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
+  A.n_obs = c->no; A.use_loss = o->use_loss; A.huber_a = o->huber_a; A.r = c->r.p; A.Jp = c->Jp.p; A.Jc = c->Jc.p; A.Ji = c->Ji.p;
+  A.cost_partial = c->part.p; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
+  if (have_scale) { A.sc_pt = c->sc_pt.p; A.sc_cam = c->sc_cam.p; A.sc_intr = c->sc_intr.p; }
+  if (time_it) OMVG_CUDA(cudaEventRecord(c->evj0, c->stream));
+  eval_kernel<true><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  if (time_it) OMVG_CUDA(cudaEventRecord(c->evj1, c->stream));
+  c->launches += 2;
+  int rc = reduce_to(c, c->part.p, c->eval_blocks, S_COST); if (rc) return rc;
+  if (!have_scale) {        // iteration 0: Jacobi scaling from the unscaled J (trust_region_minimizer.cc:239-253)
+    if ((rc = colsums(c))) return rc;
+    make_scale_kernel<<<(3 * c->np + 255) / 256, 256, 0, c->stream>>>(c->diag_pt.p, 3 * c->np, c->sc_pt.p); LAUNCH_CHECK();
+    make_scale_kernel<<<(6 * c->nc + 255) / 256, 256, 0, c->stream>>>(c->diag_cam.p, 6 * c->nc, c->sc_cam.p); LAUNCH_CHECK();
+    make_scale_kernel<<<(c->ni8 + 255) / 256, 256, 0, c->stream>>>(c->diag_intr.p, c->ni8, c->sc_intr.p); LAUNCH_CHECK();
+    scale_J_kernel<<<(unsigned)((c->no + 255) / 256), 256, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no,
+                                                                          c->sc_pt.p, c->sc_cam.p, c->sc_intr.p); LAUNCH_CHECK();
+    c->launches += 4; have_scale = true;
+  }
+  if ((rc = colsums(c))) return rc;
+  // gradient max norm (unscaled): g = J_scaled' r / scale
+  const int gb = 64;
+  grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->Etb.p, c->sc_pt.p, m.pts_free ? 3 * c->np : 0, c->part2.p); LAUNCH_CHECK();
+  grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->g_cam.p, c->sc_cam.p, 6 * c->nc, c->part2.p + gb); LAUNCH_CHECK();
+  grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->g_intr.p, c->sc_intr.p, c->ni8, c->part2.p + 2 * gb); LAUNCH_CHECK();
+  c->launches += 3;
+  return OMVG_OK;
+}
+
+int read_scalars(omvg_ba_ctx *c) {
+  OMVG_CUDA(cudaMemcpyAsync(c->h_scal, c->scal.p, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(c->h_scal + S_COUNT, c->part2.p, 3 * 64 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(c->h_scal + S_COUNT + 192, c->fail.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  return OMVG_OK;
+}
+double host_gmax(const omvg_ba_ctx *c) { double m = 0; for (int i = 0; i < 192; ++i) m = std::max(m, c->h_scal[S_COUNT + i]); return m; }
+
+int build_structure(omvg_ba_ctx *c) {
+  c->words = (c->nc + 31) / 32;
+  int rc;
+  if ((rc = c->bitmap.alloc((size_t)c->nc * c->words))) return rc;
+  if ((rc = c->wprefix.alloc((size_t)c->nc * c->words))) return rc;
+  if ((rc = c->rowptr.alloc(c->nc + 1))) return rc;
+  OMVG_CUDA(cudaMemsetAsync(c->bitmap.p, 0, (size_t)c->nc * c->words * 4, c->stream));
+  // every pose owns its diagonal block even without observations
+  std::vector<unsigned> diagbits((size_t)c->nc * c->words, 0u);
+  for (int a = 0; a < c->nc; ++a) diagbits[(size_t)a * c->words + (a >> 5)] |= 1u << (a & 31);
+  OMVG_CUDA(cudaMemcpyAsync(c->bitmap.p, diagbits.data(), diagbits.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  if (c->no) { bitmap_mark_kernel<<<(unsigned)((c->no + 255) / 256), 256, 0, c->stream>>>(c->obs_pose.p, c->obs_pt.p, c->pt_start.p, c->no, c->bitmap.p, c->words); LAUNCH_CHECK(); }
+  DevBuf<int> rowcount; if ((rc = rowcount.alloc(c->nc))) return rc;
+  bitmap_rowcount_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->bitmap.p, c->nc, c->words, c->wprefix.p, rowcount.p); LAUNCH_CHECK();
+  std::vector<int> hc(c->nc), hp(c->nc + 1, 0);
+  OMVG_CUDA(cudaMemcpyAsync(hc.data(), rowcount.p, c->nc * 4, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  for (int a = 0; a < c->nc; ++a) hp[a + 1] = hp[a] + hc[a];
+  c->nnzb = hp[c->nc];
+  OMVG_CUDA(cudaMemcpyAsync(c->rowptr.p, hp.data(), (c->nc + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = c->cols.alloc(c->nnzb))) return rc;
+  bitmap_cols_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->bitmap.p, c->rowptr.p, c->nc, c->words, c->cols.p); LAUNCH_CHECK();
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  c->launches += 3;
+  return c->Scc.alloc((size_t)c->nnzb * 36);
+}
+
+}  // namespace
+
+extern "C" {
+
+void omvg_ba_default_options(omvg_ba_options *o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof *o);
+  o->intrinsics_opt = 14; o->extrinsics_opt = 6; o->structure_opt = 1; o->use_loss = 1; o->huber_a = 16.0;
+  o->max_num_iterations = 50; o->max_consecutive_invalid_steps = 5;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->initial_radius = 1e4; o->max_radius = 1e16; o->min_radius = 1e-32; o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->pcg_tolerance = 1e-10; o->pcg_max_iterations = 2000; o->verbose = 0;
+}
+
+int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
+  if (!out) return fail(OMVG_E_ARG, "null ctx");
+  int rc = validate(P); if (rc) return rc;
+  int n = 0; OMVG_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail(OMVG_E_CUDA, "no CUDA device %d (found %d)", device, n);
+  cudaDeviceProp prop; OMVG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(OMVG_E_CUDA, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  OMVG_CUDA(cudaSetDevice(device));
+  omvg_ba_ctx *c = new omvg_ba_ctx; c->device = device; c->n_sms = prop.multiProcessorCount;
+  std::unique_ptr<omvg_ba_ctx, void (*)(omvg_ba_ctx *)> guard(c, [](omvg_ba_ctx *x) { omvg_ba_destroy(x); });
+  OMVG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  OMVG_CUDA(cudaEventCreate(&c->ev0)); OMVG_CUDA(cudaEventCreate(&c->ev1)); OMVG_CUDA(cudaEventCreate(&c->evj0)); OMVG_CUDA(cudaEventCreate(&c->evj1));
+  OMVG_CUDA(cudaMallocHost(&c->h_scal, (S_COUNT + 192 + 2) * sizeof(double)));
+  c->nc = P->n_poses; c->ni = P->n_intrinsics; c->np = P->n_points; c->nv = P->n_views; c->no = P->n_obs;
+  c->ni8 = KI * c->ni; c->nred = 6 * c->nc + c->ni8; c->eval_blocks = (int)std::max<long long>(1, (c->no + EVAL_THREADS - 1) / EVAL_THREADS);
+  c->h_intr_model.assign(P->intr_model, P->intr_model + c->ni);
+  // ---- sort observations by point (counting sort); build per-pose lists
+  const long long no = c->no;
+  std::vector<int> pt_start(c->np + 1, 0);
+  for (long long o = 0; o < no; ++o) pt_start[P->obs_point[o] + 1]++;
+  for (int j = 0; j < c->np; ++j) pt_start[j + 1] += pt_start[j];
+  c->perm.resize(no);
+  { std::vector<int> cur(pt_start.begin(), pt_start.end() - 1); for (long long o = 0; o < no; ++o) c->perm[cur[P->obs_point[o]]++] = (int)o; }
+  std::vector<int> s_pose(no), s_intr(no), s_pt(no); std::vector<double> s_xy(2 * no);
+  for (long long t = 0; t < no; ++t) { const int o = c->perm[t], v = P->obs_view[o];
+    s_pose[t] = P->view_pose[v]; s_intr[t] = P->view_intr[v]; s_pt[t] = P->obs_point[o]; s_xy[2 * t] = P->obs_xy[2 * o]; s_xy[2 * t + 1] = P->obs_xy[2 * o + 1]; }
+  std::vector<int> cam_start(c->nc + 1, 0), cam_obs(no);
+  for (long long t = 0; t < no; ++t) cam_start[s_pose[t] + 1]++;
+  for (int p = 0; p < c->nc; ++p) cam_start[p + 1] += cam_start[p];
+  { std::vector<int> cur(cam_start.begin(), cam_start.end() - 1); for (long long t = 0; t < no; ++t) cam_obs[cur[s_pose[t]]++] = (int)t; }
+  // intrinsics with the unused tail zeroed (so block norms only see real parameters)
+  std::vector<double> h_intr((size_t)c->ni8, 0.0);
+  for (int q = 0; q < c->ni; ++q) for (int k = 0; k < model_nparams(P->intr_model[q]); ++k) h_intr[KI * q + k] = P->intrinsics[KI * q + k];
+  cudaStream_t s = c->stream;
+#define UP(buf, ptr, cnt) if ((rc = upload(buf, ptr, (size_t)(cnt), s))) return rc
+  UP(c->pose0, P->poses, 6 * c->nc); UP(c->intr0, h_intr.data(), c->ni8); UP(c->pt0, P->points, 3 * (size_t)c->np);
+  UP(c->intr_model, P->intr_model, c->ni); UP(c->obs_pose, s_pose.data(), no); UP(c->obs_intr, s_intr.data(), no); UP(c->obs_pt, s_pt.data(), no);
+  UP(c->pt_start, pt_start.data(), c->np + 1); UP(c->cam_start, cam_start.data(), c->nc + 1); UP(c->cam_obs, cam_obs.data(), no); UP(c->obs_xy, s_xy.data(), 2 * no);
+#undef UP
+#define AL(buf, cnt) if ((rc = buf.alloc((size_t)(cnt)))) return rc
+  for (int w = 0; w < 2; ++w) { AL(c->pose[w], 6 * c->nc); AL(c->intr[w], c->ni8); AL(c->pt[w], 3 * (size_t)c->np); AL(c->camR[w], 9 * c->nc); }
+  AL(c->camdR, 27 * c->nc);
+  AL(c->r, 2 * no); AL(c->Jp, 6 * no); AL(c->Jc, 12 * no); AL(c->Ji, 2 * KI * no);
+  AL(c->sc_pt, 3 * (size_t)c->np); AL(c->sc_cam, 6 * c->nc); AL(c->sc_intr, c->ni8);
+  AL(c->diag_pt, 3 * (size_t)c->np); AL(c->diag_cam, 6 * c->nc); AL(c->diag_intr, c->ni8);
+  AL(c->lmD_pt, 3 * (size_t)c->np); AL(c->lmD_cam, 6 * c->nc); AL(c->lmD_intr, c->ni8); AL(c->g_cam, 6 * c->nc); AL(c->g_intr, c->ni8);
+  AL(c->EtE, 6 * (size_t)c->np); AL(c->Etb, 3 * (size_t)c->np); AL(c->Einv, 9 * (size_t)c->np); AL(c->step_pt, 3 * (size_t)c->np); AL(c->step_red, c->nred);
+  AL(c->intr_mask, c->ni);
+  AL(c->Sci, (size_t)c->ni8 * 6 * c->nc); AL(c->Sii, (size_t)c->ni8 * c->ni8); AL(c->rhs, c->nred); AL(c->Minv_c, 36 * (size_t)c->nc); AL(c->Minv_i, (size_t)c->ni8 * c->ni8);
+  AL(c->work_i, (size_t)c->ni8 * c->ni8 + c->ni8);
+  AL(c->z, c->nred); AL(c->res, c->nred); AL(c->pvec, c->nred); AL(c->w, c->nred); AL(c->zeta, c->nred); AL(c->pcg_part, 3 * (size_t)c->n_sms * 2);
+  AL(c->part, std::max(c->eval_blocks, 1024)); AL(c->part2, 1024); AL(c->part3, 1024); AL(c->icol_part, (size_t)c->ni * 64 * 16); AL(c->scal, S_COUNT); AL(c->fail, 1);
+#undef AL
+  OMVG_CUDA(cudaMemsetAsync(c->scal.p, 0, S_COUNT * sizeof(double), s));
+  if ((rc = build_structure(c))) return rc;
+  if ((rc = omvg_ba_reset(c))) return rc;
+  OMVG_CUDA(cudaStreamSynchronize(s));
+  guard.release();
+  *out = c; return OMVG_OK;
+}
+
+int omvg_ba_reset(omvg_ba_ctx *c) {
+  if (!c) return fail(OMVG_E_ARG, "null ctx");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  OMVG_CUDA(cudaMemcpyAsync(c->pose[0].p, c->pose0.p, 6 * c->nc * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(c->intr[0].p, c->intr0.p, c->ni8 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (c->np) OMVG_CUDA(cudaMemcpyAsync(c->pt[0].p, c->pt0.p, 3 * (size_t)c->np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return OMVG_OK;
+}
+
+int omvg_ba_destroy(omvg_ba_ctx *c) {
+  if (!c) return OMVG_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  for (cudaEvent_t e : {c->ev0, c->ev1, c->evj0, c->evj1}) if (e) cudaEventDestroy(e);
+  cudaStream_t s = c->stream;
+  delete c;                                   // DevBuf destructors free device memory
+  if (s) cudaStreamDestroy(s);
+  return OMVG_OK;
+}
+
+int omvg_ba_download(omvg_ba_ctx *c, double *poses, double *intrinsics, double *points) {
+  if (!c) return fail(OMVG_E_ARG, "null ctx");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  if (poses) OMVG_CUDA(cudaMemcpyAsync(poses, c->pose[0].p, 6 * c->nc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<double> hi(c->ni8);
+  if (intrinsics) OMVG_CUDA(cudaMemcpyAsync(hi.data(), c->intr[0].p, c->ni8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (points && c->np) OMVG_CUDA(cudaMemcpyAsync(points, c->pt[0].p, 3 * (size_t)c->np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  if (intrinsics) for (int q = 0; q < c->ni; ++q) for (int k = 0; k < model_nparams(c->h_intr_model[q]); ++k) intrinsics[KI * q + k] = hi[KI * q + k];
+  return OMVG_OK;
+}
+
+int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) {
+  if (!c || !O || !sum) return fail(OMVG_E_ARG, "null argument");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  std::memset(sum, 0, sizeof *sum);
+  const Masks m = make_masks(c, O);
+  OMVG_CUDA(cudaMemcpyAsync(c->intr_mask.p, m.intr_mask.data(), c->ni * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+  OMVG_CUDA(cudaMemsetAsync(c->fail.p, 0, sizeof(int), c->stream));
+  const long long launches0 = c->launches;
+  OMVG_CUDA(cudaEventRecord(c->ev0, c->stream));
+  int rc; bool have_scale = false;
+  double jac_ms = 0; long long jac_launches = 0;
+  auto account_jac = [&]() { float ms = 0; cudaEventSynchronize(c->evj1); cudaEventElapsedTime(&ms, c->evj0, c->evj1); jac_ms += ms; ++jac_launches; };
+
+  if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
+  if ((rc = read_scalars(c))) return rc;
+  account_jac();
+  double x_cost = c->h_scal[S_COST];
+  double gmax = host_gmax(c);
+  sum->initial_cost = x_cost;
+  double radius = O->initial_radius, decrease_factor = 2.0;
+  int iteration = 0, n_success = 0, n_fail = 0, n_invalid = 0, termination = 3;
+  double x_norm = -1.0;                                   // trust_region_minimizer.cc Init(): "x_norm_ = -1"
+  bool step_is_successful = true, failure = false;
+  double reference_cost = x_cost, accumulated_reference = 0.0, current_cost = x_cost;
+  long long pcg_total = 0;
+  const int pcg_grid = c->n_sms;
+
+  for (;;) {
+    if (step_is_successful) ++n_success; else ++n_fail;
+    if (iteration >= O->max_num_iterations) { termination = 3; break; }
+    if (step_is_successful && gmax <= O->gradient_tolerance) { termination = 2; break; }
+    if (radius <= O->min_radius) { termination = 4; break; }
+    ++iteration;
+    // ---- LM diagonal (levenberg_marquardt_strategy.cc:75-87); diag_* always belong to the current J
+    lm_diag_kernel<<<(3 * c->np + 255) / 256, 256, 0, c->stream>>>(c->diag_pt.p, 3 * c->np, O->min_lm_diagonal, O->max_lm_diagonal, radius, c->lmD_pt.p); LAUNCH_CHECK();
+    lm_diag_kernel<<<(6 * c->nc + 255) / 256, 256, 0, c->stream>>>(c->diag_cam.p, 6 * c->nc, O->min_lm_diagonal, O->max_lm_diagonal, radius, c->lmD_cam.p); LAUNCH_CHECK();
+    lm_diag_kernel<<<(c->ni8 + 255) / 256, 256, 0, c->stream>>>(c->diag_intr.p, c->ni8, O->min_lm_diagonal, O->max_lm_diagonal, radius, c->lmD_intr.p); LAUNCH_CHECK();
+    // ---- reduced camera system
+    OMVG_CUDA(cudaMemsetAsync(c->Scc.p, 0, (size_t)c->nnzb * 36 * sizeof(double), c->stream));
+    OMVG_CUDA(cudaMemsetAsync(c->Sci.p, 0, c->Sci.n * sizeof(double), c->stream));
+    OMVG_CUDA(cudaMemsetAsync(c->Sii.p, 0, c->Sii.n * sizeof(double), c->stream));
+    OMVG_CUDA(cudaMemsetAsync(c->rhs.p, 0, c->nred * sizeof(double), c->stream));
+    SchurArgs SA{}; SA.r = c->r.p; SA.Jp = c->Jp.p; SA.Jc = c->Jc.p; SA.Ji = c->Ji.p; SA.EtE = c->EtE.p; SA.Etb = c->Etb.p; SA.lmD_pt = c->lmD_pt.p;
+    SA.obs_pose = c->obs_pose.p; SA.obs_intr = c->obs_intr.p; SA.obs_pt = c->obs_pt.p; SA.pt_start = c->pt_start.p; SA.n = c->no; SA.n_poses = c->nc; SA.n_intr = c->ni;
+    SA.pts_free = m.pts_free; SA.bsr = Bsr{c->bitmap.p, c->wprefix.p, c->rowptr.p, c->words}; SA.Scc = c->Scc.p; SA.Sci = c->Sci.p; SA.Sii = c->Sii.p; SA.rhs = c->rhs.p;
+    SA.Einv = c->Einv.p; SA.fail = c->fail.p;
+    if (c->no) { schur_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA); LAUNCH_CHECK(); }
+    finish_cam_kernel<<<(c->nc + 63) / 64, 64, 0, c->stream>>>(c->Scc.p, SA.bsr, c->lmD_cam.p, m.pose_mask, c->nc, c->Minv_c.p, c->fail.p); LAUNCH_CHECK();
+    finish_intr_kernel<<<1, 32, 0, c->stream>>>(c->Sii.p, c->lmD_intr.p, c->intr_mask.p, c->ni8, c->Minv_i.p, c->work_i.p, c->fail.p); LAUNCH_CHECK();
+    // ---- PCG on S z = rhs
+    PcgArgs PA{}; PA.Scc = c->Scc.p; PA.rowptr = c->rowptr.p; PA.cols = c->cols.p; PA.Sci = c->Sci.p; PA.Sii = c->Sii.p; PA.rhs = c->rhs.p; PA.Minv_c = c->Minv_c.p; PA.Minv_i = c->Minv_i.p;
+    PA.n_poses = c->nc; PA.ni8 = c->ni8; PA.z = c->z.p; PA.res = c->res.p; PA.p = c->pvec.p; PA.w = c->w.p; PA.zeta = c->zeta.p; PA.part = c->pcg_part.p;
+    PA.tol = O->pcg_tolerance; PA.max_iter = O->pcg_max_iterations; PA.out = c->scal.p + S_PCG_IT;
+    { void *args[] = {&PA}; OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(pcg_grid), dim3(256), args, 0, c->stream)); }
+    // ---- back substitution, step = -y
+    backsub_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->Etb.p, c->Einv.p, c->obs_pose.p, c->obs_intr.p, c->pt_start.p, c->np, c->nc, c->no,
+                                                             c->z.p, m.pts_free, c->step_pt.p); LAUNCH_CHECK();
+    negate_kernel<<<(c->nred + 255) / 256, 256, 0, c->stream>>>(c->z.p, c->nred, c->step_red.p); LAUNCH_CHECK();
+    // ---- model cost change
+    model_kernel<<<c->eval_blocks, MODEL_THREADS, 0, c->stream>>>(c->r.p, c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no, c->nc, c->step_pt.p, c->step_red.p, c->part.p); LAUNCH_CHECK();
+    c->launches += 10;
+    if ((rc = reduce_to(c, c->part.p, c->eval_blocks, S_MODEL))) return rc;
+    // ---- candidate = Plus(x, step * scale)
+    const int ub = 64;
+    update_kernel<<<ub, 256, 0, c->stream>>>(c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, nullptr, 0, c->pt[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
+    if ((rc = reduce_to(c, c->part2.p, ub, S_STEP2_PT))) return rc; if ((rc = reduce_to(c, c->part3.p, ub, S_X2_PT))) return rc;
+    update_kernel<<<ub, 256, 0, c->stream>>>(c->pose[0].p, c->step_red.p, c->sc_cam.p, 6 * c->nc, 6, m.pose_mask, nullptr, 0, c->pose[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
+    if ((rc = reduce_to(c, c->part2.p, ub, S_STEP2_POSE))) return rc; if ((rc = reduce_to(c, c->part3.p, ub, S_X2_POSE))) return rc;
+    update_kernel<<<ub, 256, 0, c->stream>>>(c->intr[0].p, c->step_red.p + 6 * c->nc, c->sc_intr.p, c->ni8, KI, 0u, c->intr_mask.p, 0, c->intr[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
+    if ((rc = reduce_to(c, c->part2.p, ub, S_STEP2_INTR))) return rc; if ((rc = reduce_to(c, c->part3.p, ub, S_X2_INTR))) return rc;
+    c->launches += 3;
+    if ((rc = eval_cost(c, O, 1, S_CAND_COST))) return rc;
+    if ((rc = read_scalars(c))) return rc;
+    const double *h = c->h_scal;
+    pcg_total += (long long)h[S_PCG_IT];
+    int failflag; std::memcpy(&failflag, c->h_scal + S_COUNT + 192, sizeof(int));
+    const double model_cost_change = h[S_MODEL];
+    bool finite_step = std::isfinite(h[S_STEP2_PT]) && std::isfinite(h[S_STEP2_POSE]) && std::isfinite(h[S_STEP2_INTR]) && std::isfinite(model_cost_change);
+    const bool solved = failflag == 0 && finite_step;
+    if (failflag) OMVG_CUDA(cudaMemsetAsync(c->fail.p, 0, sizeof(int), c->stream));
+    if (O->verbose) fprintf(stderr, "[omvg_ba] it %d cost %.12e cand %.12e model %.6e radius %.3e pcg %d res %.2e\n", iteration, x_cost, h[S_CAND_COST], model_cost_change, radius, (int)h[S_PCG_IT], h[S_PCG_RES]);
+    if (!solved || !(model_cost_change > 0.0)) {            // HandleInvalidStep (:429-462)
+      if (++n_invalid >= O->max_consecutive_invalid_steps) { failure = true; termination = -1; break; }
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+      step_is_successful = false; continue;
+    }
+    n_invalid = 0;
+    const double candidate_cost = h[S_CAND_COST];
+    const double step_norm = std::sqrt(h[S_STEP2_PT] + h[S_STEP2_POSE] + h[S_STEP2_INTR]);
+    if (step_norm <= O->parameter_tolerance * (x_norm + O->parameter_tolerance)) { termination = 1; break; }
+    const double cost_change = x_cost - candidate_cost;
+    if (std::fabs(cost_change) <= O->function_tolerance * x_cost) { termination = 0; break; }
+    const double rel = (current_cost - candidate_cost) / model_cost_change;
+    const double hist = (reference_cost - candidate_cost) / (accumulated_reference + model_cost_change);
+    const double rho = std::max(rel, hist);
+    if (rho > O->min_relative_decrease) {                    // HandleSuccessfulStep (:767-780)
+      std::swap(c->pose[0].p, c->pose[1].p); std::swap(c->intr[0].p, c->intr[1].p); std::swap(c->pt[0].p, c->pt[1].p); std::swap(c->camR[0].p, c->camR[1].p);
+      // |x| of the accepted iterate = sqrt(|x_old|^2 ...) is not reusable: recompute from the candidate norms
+      if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
+      // x_norm of the new x: update_kernel measures |x| of its input; run the three norm passes on the new x
+      update_kernel<<<ub, 256, 0, c->stream>>>(c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, nullptr, 0, c->pt[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
+      if ((rc = reduce_to(c, c->part3.p, ub, S_X2_PT))) return rc;
+      update_kernel<<<ub, 256, 0, c->stream>>>(c->pose[0].p, c->step_red.p, c->sc_cam.p, 6 * c->nc, 6, m.pose_mask, nullptr, 0, c->pose[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
+      if ((rc = reduce_to(c, c->part3.p, ub, S_X2_POSE))) return rc;
+      update_kernel<<<ub, 256, 0, c->stream>>>(c->intr[0].p, c->step_red.p + 6 * c->nc, c->sc_intr.p, c->ni8, KI, 0u, c->intr_mask.p, 0, c->intr[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
+      if ((rc = reduce_to(c, c->part3.p, ub, S_X2_INTR))) return rc;
+      c->launches += 3;
+      // gradient partials were written to part2 by eval_jac before the norm passes reused it: re-run them last
+      const int gb = 64;
+      grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->Etb.p, c->sc_pt.p, m.pts_free ? 3 * c->np : 0, c->part2.p); LAUNCH_CHECK();
+      grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->g_cam.p, c->sc_cam.p, 6 * c->nc, c->part2.p + gb); LAUNCH_CHECK();
+      grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->g_intr.p, c->sc_intr.p, c->ni8, c->part2.p + 2 * gb); LAUNCH_CHECK();
+      c->launches += 3;
+      if ((rc = read_scalars(c))) return rc;
+      account_jac();
+      x_cost = c->h_scal[S_COST]; gmax = host_gmax(c);
+      x_norm = std::sqrt(c->h_scal[S_X2_PT] + c->h_scal[S_X2_POSE] + c->h_scal[S_X2_INTR]);
+      step_is_successful = true;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)); radius = std::min(O->max_radius, radius);
+      decrease_factor = 2.0;
+      current_cost = candidate_cost; reference_cost = candidate_cost; accumulated_reference = 0.0;
+    } else {                                                  // HandleUnsuccessfulStep (:782-786)
+      step_is_successful = false;
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+    }
+  }
+  OMVG_CUDA(cudaEventRecord(c->ev1, c->stream));
+  OMVG_CUDA(cudaEventSynchronize(c->ev1));
+  float ms = 0; OMVG_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  sum->final_cost = x_cost; sum->iterations = n_success + n_fail; sum->successful_steps = n_success; sum->unsuccessful_steps = n_fail;
+  sum->lm_steps = iteration; sum->termination = termination; sum->usable = failure ? 0 : 1; sum->pcg_iterations = pcg_total;
+  sum->kernel_launches = c->launches - launches0; sum->device_ms = ms; sum->jacobian_ms = jac_ms; sum->jacobian_launches = jac_launches;
+  return failure ? fail(OMVG_E_NUMERIC, "bundle adjustment failed: %d consecutive invalid steps", n_invalid) : OMVG_OK;
+}
+
+int omvg_ba_solve(omvg_ba_problem *P, const omvg_ba_options *O, omvg_ba_summary *sum) {
+  omvg_ba_options def; if (!O) { omvg_ba_default_options(&def); O = &def; }
+  omvg_ba_summary local; if (!sum) sum = &local;
+  omvg_ba_ctx *c = nullptr;
+  int rc = omvg_ba_create(&c, 0, P); if (rc) return rc;
+  rc = omvg_ba_run(c, O, sum);
+  if (rc == OMVG_OK) rc = omvg_ba_download(c, P->poses, P->intrinsics, P->points);   // state is copied back only when usable
+  omvg_ba_destroy(c);
+  return rc;
+}
+
+int omvg_ba_debug_eval(omvg_ba_ctx *c, const omvg_ba_options *O, double *cost, double *r, double *J_intr, double *J_pose, double *J_point) {
+  if (!c || !O) return fail(OMVG_E_ARG, "null argument");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  Masks m = make_masks(c, O);
+  OMVG_CUDA(cudaMemcpyAsync(c->intr_mask.p, m.intr_mask.data(), c->ni * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+  // unscaled evaluation
+  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[0].p, c->nc, c->camR[0].p, c->camdR.p); LAUNCH_CHECK();
+  EvalArgs A{}; A.poses = c->pose[0].p; A.intr = c->intr[0].p; A.pts = c->pt[0].p; A.camR = c->camR[0].p; A.camdR = c->camdR.p;
+  A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
+  A.n_obs = c->no; A.use_loss = O->use_loss; A.huber_a = O->huber_a; A.r = c->r.p; A.Jp = c->Jp.p; A.Jc = c->Jc.p; A.Ji = c->Ji.p;
+  A.cost_partial = c->part.p; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
+  eval_kernel<true><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  int rc = reduce_to(c, c->part.p, c->eval_blocks, S_COST); if (rc) return rc;
+  c->launches += 2;
+  const long long n = c->no;
+  std::vector<double> hr(2 * n), hp(6 * n), hc(12 * n), hi(2 * KI * n); double hcost = 0;
+  OMVG_CUDA(cudaMemcpyAsync(hr.data(), c->r.p, hr.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(hp.data(), c->Jp.p, hp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(hc.data(), c->Jc.p, hc.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(hi.data(), c->Ji.p, hi.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(&hcost, c->scal.p + S_COST, 8, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  if (cost) *cost = hcost;
+  for (long long t = 0; t < n; ++t) {
+    const long long o = c->perm[t];
+    for (int row = 0; row < 2; ++row) {
+      if (r) r[2 * o + row] = hr[row * n + t];
+      if (J_point) for (int k = 0; k < 3; ++k) J_point[(o * 2 + row) * 3 + k] = hp[(row * 3 + k) * n + t];
+      if (J_pose) for (int k = 0; k < 6; ++k) J_pose[(o * 2 + row) * 6 + k] = hc[(row * 6 + k) * n + t];
+      if (J_intr) for (int k = 0; k < KI; ++k) J_intr[(o * 2 + row) * KI + k] = hi[(row * KI + k) * n + t];
+    }
+  }
+  return OMVG_OK;
+}
+
+}  // extern "C"

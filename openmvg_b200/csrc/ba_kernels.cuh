@@ -669,7 +669,7 @@ __global__ void backsub_kernel(const double *__restrict__ Jp, const double *__re
                                const int *__restrict__ obs_intr, const int *__restrict__ pt_start, int n_points, int n_poses, long long n,
                                const double *__restrict__ z, int pts_free, double *__restrict__ step_pt) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n_points) return;
-  if (!pts_free) { step_pt[3 * j] = step_pt[3 * j + 1] = step_pt[3 * j + 2] = 0.0; return; }
+  if (!pts_free || pt_start[j] == pt_start[j + 1]) { step_pt[3 * j] = step_pt[3 * j + 1] = step_pt[3 * j + 2] = 0.0; return; }
   double b0 = Etb[3 * (size_t)j], b1 = Etb[3 * (size_t)j + 1], b2 = Etb[3 * (size_t)j + 2];
   for (long long o = pt_start[j]; o < pt_start[j + 1]; ++o) {
     const double *zc = z + 6 * obs_pose[o]; const double *zi = z + 6 * n_poses + KI * obs_intr[o];

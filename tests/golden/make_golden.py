@@ -1,0 +1,67 @@
+"""Generate tests/golden/*.json|npz by running THE REFERENCE ITSELF (oracle/_ref, built by
+oracle/Makefile from /root/reference sources in place) on seeded inputs from openmvg_b200.synth.
+Run in the build container:  python tests/golden/make_golden.py
+The inputs are regenerated from their seeds at test time; only the reference's outputs are stored."""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import checkers as ck          # noqa: E402
+from openmvg_b200 import synth  # noqa: E402
+
+MATCH_CASES = [
+    dict(name="ragged5", counts=[300, 129, 2, 257, 1000], seed=11, ratio=0.8),
+    dict(name="tiles3", counts=[128, 256, 384], seed=11, ratio=0.8),
+    dict(name="ratio06", counts=[400, 500, 300], seed=4, ratio=0.6),
+    dict(name="pair5000", counts=[5000, 5000], seed=11, ratio=0.8),
+]
+BA_CASES = [
+    dict(name="c1", scene=dict(n_cams=10, n_points=500, obs_per_point=4), opts={}),
+    dict(name="c30", scene=dict(n_cams=30, n_points=1500, obs_per_point=8), opts={}),
+    dict(name="c100", scene=dict(n_cams=100, n_points=5000, obs_per_point=10), opts={}),
+    dict(name="outliers", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5, outlier_frac=0.02), opts={}),
+    dict(name="intr_none", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5, outlier_frac=0.02), opts=dict(intrinsics_opt=1)),
+    dict(name="translation_only", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5, outlier_frac=0.02), opts=dict(extrinsics_opt=4)),
+    dict(name="focal_rotation", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5, outlier_frac=0.02), opts=dict(intrinsics_opt=2, extrinsics_opt=2)),
+    dict(name="structure_fixed", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5, outlier_frac=0.02), opts=dict(structure_opt=0)),
+    dict(name="points_only", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5, outlier_frac=0.02), opts=dict(intrinsics_opt=1, extrinsics_opt=1)),
+    dict(name="no_loss", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5, outlier_frac=0.02), opts=dict(use_loss=0)),
+    dict(name="radial1", scene=dict(n_cams=14, n_points=700, obs_per_point=6, seed=8, model=2), opts={}),
+    dict(name="radial3", scene=dict(n_cams=14, n_points=700, obs_per_point=6, seed=8, model=3), opts={}),
+    dict(name="brown", scene=dict(n_cams=14, n_points=700, obs_per_point=6, seed=8, model=4), opts={}),
+    dict(name="fisheye", scene=dict(n_cams=14, n_points=700, obs_per_point=6, seed=8, model=5), opts={}),
+    dict(name="config2_1000_100k_1M", scene=dict(n_cams=1000, n_points=100000, obs_per_point=10), opts={}),
+]
+
+
+def main():
+    out = {"match": [], "ba": []}
+    arrays = {}
+    for c in MATCH_CASES:
+        descs = synth.descriptors(len(c["counts"]), c["counts"], seed=c["seed"])
+        pi, pj = synth.exhaustive_pairs(len(c["counts"]))
+        off, ij = ck.ref_match_collection(descs, pi, pj, c["ratio"])
+        fnv = int(ck.oracle().oracle_fnv1a_ij(ij.ctypes.data_as(ck.ctypes.c_void_p), ck.ctypes.c_int64(len(ij))))
+        out["match"].append(dict(name=c["name"], counts=c["counts"], seed=c["seed"], ratio=c["ratio"], n_matches=int(len(ij)), fnv1a=str(fnv),
+                                 offsets=[int(x) for x in off]))
+        if len(ij) < 4000:
+            arrays["match_" + c["name"]] = ij
+        print("match", c["name"], len(ij), fnv)
+    for c in BA_CASES:
+        s = synth.ba_scene(**c["scene"])
+        ref_opts = {k: v for k, v in c["opts"].items() if k in ("intrinsics_opt", "extrinsics_opt", "structure_opt", "use_loss")}
+        r = ck.ref_ba_adjust(s, threads=8, **ref_opts)
+        out["ba"].append(dict(name=c["name"], scene=c["scene"], opts=c["opts"], ok=r["ok"], initial_cost=r["initial_cost"], final_cost=r["final_cost"],
+                              iterations=r["iterations"], successful=r["successful"], unsuccessful=r["unsuccessful"], termination=r["termination"]))
+        print("ba", c["name"], r["initial_cost"], r["final_cost"], r["iterations"], r["termination"])
+    json.dump(out, open(os.path.join(HERE, "reference_outputs.json"), "w"), indent=1)
+    np.savez_compressed(os.path.join(HERE, "reference_matches.npz"), **arrays)
+
+
+if __name__ == "__main__":
+    main()
