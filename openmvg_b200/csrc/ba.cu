@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <vector>
 
@@ -447,13 +448,50 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   return failure ? fail(OMVG_E_NUMERIC, "bundle adjustment failed: %d consecutive invalid steps", n_invalid) : OMVG_OK;
 }
 
+// AngleAxisToRotationMatrix (ceres/include/ceres/rotation.h:377-420), row-major
+static void aa_to_R(const double *aa, double R[9]) {
+  const double theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  if (theta2 > std::numeric_limits<double>::epsilon()) {
+    const double theta = std::sqrt(theta2), wx = aa[0] / theta, wy = aa[1] / theta, wz = aa[2] / theta;
+    const double c = std::cos(theta), s = std::sin(theta), k = 1.0 - c;
+    R[0] = c + wx * wx * k;      R[1] = wx * wy * k - wz * s; R[2] = wy * s + wx * wz * k;
+    R[3] = wz * s + wx * wy * k; R[4] = c + wy * wy * k;      R[5] = -wx * s + wy * wz * k;
+    R[6] = -wy * s + wx * wz * k; R[7] = wx * s + wy * wz * k; R[8] = c + wz * wz * k;
+  } else {
+    R[0] = 1; R[1] = -aa[2]; R[2] = aa[1]; R[3] = aa[2]; R[4] = 1; R[5] = -aa[0]; R[6] = -aa[1]; R[7] = aa[0]; R[8] = 1;
+  }
+}
+
 int omvg_ba_solve(omvg_ba_problem *P, const omvg_ba_options *O, omvg_ba_summary *sum) {
   omvg_ba_options def; if (!O) { omvg_ba_default_options(&def); O = &def; }
   omvg_ba_summary local; if (!sum) sum = &local;
   omvg_ba_ctx *c = nullptr;
   int rc = omvg_ba_create(&c, 0, P); if (rc) return rc;
   rc = omvg_ba_run(c, O, sum);
-  if (rc == OMVG_OK) rc = omvg_ba_download(c, P->poses, P->intrinsics, P->points);   // state is copied back only when usable
+  if (rc == OMVG_OK) {                       // state is copied back only when usable (solver.cc:445-448)
+    // Adjust's write-back rules (sfm_data_BA_ceres.cpp:528-568): poses only if extrinsics were refined,
+    // intrinsics only if intrinsics were refined; ADJUST_ROTATION keeps the pose CENTRE (t = -R_new C_old).
+    std::vector<double> np_((size_t)6 * P->n_poses), ni_((size_t)KI * P->n_intrinsics);
+    std::memcpy(ni_.data(), P->intrinsics, ni_.size() * sizeof(double));
+    rc = omvg_ba_download(c, np_.data(), ni_.data(), P->points);
+    if (rc == OMVG_OK) {
+      if (O->extrinsics_opt != 1) {
+        for (int p = 0; p < P->n_poses; ++p) {
+          double *dst = P->poses + 6 * p; const double *src = np_.data() + 6 * p;
+          if (O->extrinsics_opt == 2) {
+            double Ro[9], Rn[9], C[3];
+            aa_to_R(dst, Ro); aa_to_R(src, Rn);
+            for (int i = 0; i < 3; ++i) C[i] = -(Ro[0 * 3 + i] * dst[3] + Ro[1 * 3 + i] * dst[4] + Ro[2 * 3 + i] * dst[5]);
+            for (int i = 0; i < 3; ++i) dst[i] = src[i];
+            for (int i = 0; i < 3; ++i) dst[3 + i] = -(Rn[i * 3] * C[0] + Rn[i * 3 + 1] * C[1] + Rn[i * 3 + 2] * C[2]);
+          } else {
+            for (int i = 0; i < 6; ++i) dst[i] = src[i];
+          }
+        }
+      }
+      if (!(O->intrinsics_opt & 1)) std::memcpy(P->intrinsics, ni_.data(), ni_.size() * sizeof(double));
+    }
+  }
   omvg_ba_destroy(c);
   return rc;
 }

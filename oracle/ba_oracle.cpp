@@ -288,6 +288,35 @@ Layout make_layout(const Problem &P, const Options &O) {
   return L;
 }
 
+// ceres/include/ceres/rotation.h:377-420 AngleAxisToRotationMatrix (row-major R here)
+void aa_to_R(const double *aa, double R[9]) {
+  const double theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  if (theta2 > std::numeric_limits<double>::epsilon()) {
+    const double theta = std::sqrt(theta2), wx = aa[0] / theta, wy = aa[1] / theta, wz = aa[2] / theta;
+    const double c = std::cos(theta), s = std::sin(theta);
+    R[0] = c + wx * wx * (1.0 - c); R[3] = wz * s + wx * wy * (1.0 - c); R[6] = -wy * s + wx * wz * (1.0 - c);
+    R[1] = wx * wy * (1.0 - c) - wz * s; R[4] = c + wy * wy * (1.0 - c); R[7] = wx * s + wy * wz * (1.0 - c);
+    R[2] = wy * s + wx * wz * (1.0 - c); R[5] = -wx * s + wy * wz * (1.0 - c); R[8] = c + wz * wz * (1.0 - c);
+  } else {
+    R[0] = 1; R[3] = aa[2]; R[6] = -aa[1]; R[1] = -aa[2]; R[4] = 1; R[7] = aa[0]; R[2] = aa[1]; R[5] = -aa[0]; R[8] = 1;
+  }
+}
+
+// Write-back rule of Adjust (sfm_data_BA_ceres.cpp:528-555): with ADJUST_ROTATION only the rotation
+// of the Pose3 is replaced, its CENTRE is kept, so the returned t is -R_new * C_old (not the t that
+// Ceres held constant).  ADJUST_TRANSLATION / ADJUST_ALL return (R_refined, t_refined) unchanged.
+void write_back_poses(int extrinsics_opt, int n_poses, const double *old_poses, const double *x_pose, double *out) {
+  for (int p = 0; p < n_poses; ++p) {
+    for (int k = 0; k < 6; ++k) out[6 * p + k] = x_pose[6 * p + k];
+    if (extrinsics_opt != 2) continue;
+    double Ro[9], Rn[9], C[3];
+    aa_to_R(old_poses + 6 * p, Ro); aa_to_R(x_pose + 6 * p, Rn);
+    const double *t = old_poses + 6 * p + 3;
+    for (int i = 0; i < 3; ++i) C[i] = -(Ro[0 * 3 + i] * t[0] + Ro[1 * 3 + i] * t[1] + Ro[2 * 3 + i] * t[2]);
+    for (int i = 0; i < 3; ++i) out[6 * p + 3 + i] = -(Rn[i * 3 + 0] * C[0] + Rn[i * 3 + 1] * C[1] + Rn[i * 3 + 2] * C[2]);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -580,7 +609,10 @@ int oracle_ba_solve(int n_poses, double *poses, int n_intr, double *intr, const 
   }
   const bool usable = !failure;
   if (usable) {      // solver.cc: user state is updated only when the solution is usable
-    std::memcpy(poses, x_pose.data(), sizeof(double) * 6 * n_poses);
+    if (O.extrinsics_opt != 1) {                 // sfm_data_BA_ceres.cpp:529: poses untouched when extrinsics are NONE
+      std::vector<double> old(poses, poses + 6 * n_poses);
+      write_back_poses(O.extrinsics_opt, n_poses, old.data(), x_pose.data(), poses);
+    }
     std::memcpy(intr, x_intr.data(), sizeof(double) * KI * n_intr);
     std::memcpy(points, x_pt.data(), sizeof(double) * 3 * n_points);
   }

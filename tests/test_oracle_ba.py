@@ -1,0 +1,67 @@
+"""CPU: the BA oracle against the committed golden outputs of the reference's own
+Bundle_Adjustment_Ceres::Adjust (tests/golden/reference_outputs.json) and, when oracle/_ref is
+present, the compiled reference itself."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import checkers as ck
+from openmvg_b200 import synth
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.json")))
+SMALL = [c for c in GOLD["ba"] if c["scene"]["n_cams"] <= 100]
+
+
+@pytest.mark.parametrize("case", SMALL, ids=lambda c: c["name"])
+def test_golden_final_cost(case):
+    s = synth.ba_scene(**case["scene"])
+    o = ck.oracle_ba_solve(s, **case["opts"])
+    assert o["usable"] == case["ok"]
+    assert abs(o["initial_cost"] - case["initial_cost"]) <= 1e-12 * case["initial_cost"]
+    # the golden cost is recomputed from the scene Adjust RETURNS (write-back rules included)
+    returned = ck.oracle_ba_cost(s, o["poses"], o["intrinsics"], o["points"], use_loss=case["opts"].get("use_loss", 1))
+    assert abs(returned - case["final_cost"]) <= 1e-9 * case["final_cost"]        # observed: ~1e-15
+    if case["opts"].get("extrinsics_opt", 6) != 2:
+        assert abs(o["final_cost"] - case["final_cost"]) <= 1e-9 * case["final_cost"]
+    assert o["iterations"] == case["iterations"] and o["successful"] == case["successful"] and o["unsuccessful"] == case["unsuccessful"]
+    assert ("Function tolerance" in case["termination"]) == (o["termination"] == 0)
+
+
+def test_cost_matches_reference_formula():
+    """1/2 sum rho(|r|^2), Huber a=16 (sfm_data_BA_ceres.cpp:249; loss_function.cc:47-61)."""
+    s = synth.ba_scene(6, 100, 4, seed=1, outlier_frac=0.3)
+    _, r, *_ = ck.oracle_ba_eval(s, use_loss=0)
+    sq = (r ** 2).sum(1)
+    want = 0.5 * np.where(sq <= 256.0, sq, 32.0 * np.sqrt(sq) - 256.0).sum()
+    assert abs(ck.oracle_ba_cost(s) - want) <= 1e-12 * want
+    assert (sq > 256).any() and (sq <= 256).any()
+
+
+def test_jacobian_against_finite_differences():
+    s = synth.ba_scene(4, 30, 4, seed=9, model=4)
+    s["intrinsics"][:, 3:] = s["gt_dist"][3:]
+    _, r0, Ji, Jc, Jp = ck.oracle_ba_eval(s, use_loss=0)
+    h = 1e-6
+    for name, J, arr, width in (("poses", Jc, "poses", 6), ("points", Jp, "points", 3), ("intrinsics", Ji, "intrinsics", 8)):
+        for k in range(width):
+            s2 = dict(s); a = s[arr].copy(); a[:, k] += h; s2[arr] = a
+            _, r1, *_ = ck.oracle_ba_eval(s2, use_loss=0)
+            fd = (r1 - r0) / h
+            assert np.abs(fd - J[:, :, k]).max() <= 2e-4 * max(1.0, np.abs(J[:, :, k]).max()), (name, k)
+
+
+@pytest.mark.skipif(not ck.have_ref_ba(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("kw", [dict(), dict(intrinsics_opt=1), dict(extrinsics_opt=4), dict(structure_opt=0)])
+def test_against_compiled_reference(kw):
+    s = synth.ba_scene(12, 400, 5, seed=13, outlier_frac=0.01)
+    r = ck.ref_ba_adjust(s, threads=2, **kw)
+    o = ck.oracle_ba_solve(s, **kw)
+    assert r["ok"] and o["usable"]
+    assert abs(o["final_cost"] - r["final_cost"]) <= 1e-9 * r["final_cost"]
+    assert o["iterations"] == r["iterations"]
+    assert np.abs(o["points"] - r["points"]).max() < 1e-7 and np.abs(o["poses"][:, 3:] - r["poses"][:, 3:]).max() < 1e-7
+    from scipy.spatial.transform import Rotation   # angle-axis is ambiguous at theta ~ pi: compare the rotations
+    Ro = Rotation.from_rotvec(o["poses"][:, :3]).as_matrix(); Rr = Rotation.from_rotvec(r["poses"][:, :3]).as_matrix()
+    assert np.abs(Ro - Rr).max() < 1e-7
