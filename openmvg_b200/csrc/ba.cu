@@ -49,10 +49,12 @@ struct omvg_ba_ctx {
   DevBuf<double> obs_xy;
   DevBuf<double> r, Jp, Jc, Ji, camR[2], camdR;
   DevBuf<double> sc_pt, sc_cam, sc_intr, diag_pt, diag_cam, diag_intr, lmD_pt, lmD_cam, lmD_intr, g_cam, g_intr;
-  DevBuf<double> EtE, Etb, Einv, step_pt, step_red;
+  DevBuf<double> EtE, Etb, EtFi, FtF, FiFi, Einv, step_pt, step_red;
+  DevBuf<unsigned char> pt_single;
   DevBuf<unsigned> bitmap, intr_mask; DevBuf<int> wprefix, rowptr, cols;
   DevBuf<double> Scc, Sci, Sii, rhs, Minv_c, Minv_i, work_i;
   DevBuf<double> z, res, pvec, w, zeta, pcg_part;
+  DevBuf<double> gW, gAW, bX, bR, bP, bW, bZ, pcg2_part;   // two-level block-PCG workspaces
   DevBuf<double> part, part2, part3, icol_part, scal;
   DevBuf<int> fail;
   double *h_scal = nullptr;                 // pinned
@@ -127,12 +129,12 @@ int eval_cost(omvg_ba_ctx *c, const omvg_ba_options *o, int which, int slot) {
 }
 
 int colsums(omvg_ba_ctx *c) {
-  point_accum_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->r.p, c->pt_start.p, c->np, c->no, c->EtE.p, c->Etb.p); LAUNCH_CHECK();
+  point_accum_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Ji.p, c->r.p, c->pt_start.p, c->pt_single.p, c->np, c->no, c->EtE.p, c->Etb.p, c->EtFi.p); LAUNCH_CHECK();
   point_diag_from_EtE_kernel<<<(c->np + 255) / 256, 256, 0, c->stream>>>(c->EtE.p, c->np, c->diag_pt.p); LAUNCH_CHECK();
-  cam_colsum_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Jc.p, c->r.p, c->cam_start.p, c->cam_obs.p, c->nc, c->no, c->diag_cam.p, c->g_cam.p); LAUNCH_CHECK();
+  cam_colsum_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Jc.p, c->r.p, c->cam_start.p, c->cam_obs.p, c->nc, c->no, c->diag_cam.p, c->g_cam.p, c->FtF.p); LAUNCH_CHECK();
   const int chunks = 64;
   intr_colsum_kernel<<<dim3(chunks, c->ni), ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->icol_part.p); LAUNCH_CHECK();
-  intr_colsum_final_kernel<<<(c->ni8 + 63) / 64, 64, 0, c->stream>>>(c->icol_part.p, chunks, c->ni, c->diag_intr.p, c->g_intr.p); LAUNCH_CHECK();
+  intr_colsum_final_kernel<<<(c->ni * 72 + 63) / 64, 64, 0, c->stream>>>(c->icol_part.p, chunks, c->ni, c->diag_intr.p, c->g_intr.p, c->FiFi.p); LAUNCH_CHECK();
   c->launches += 5; return OMVG_OK;
 }
 
@@ -166,6 +168,20 @@ int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which
   grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->g_intr.p, c->sc_intr.p, c->ni8, c->part2.p + 2 * gb); LAUNCH_CHECK();
   c->launches += 3;
   return OMVG_OK;
+}
+
+// gauge generators for the coarse space of the two-level preconditioner (needs camR/camdR of the CURRENT poses,
+// i.e. must run right after eval_jac and before any cost-only evaluation of a candidate)
+int make_gauge(omvg_ba_ctx *c, const Masks &m, int &nw) {
+  unsigned gen = 0;
+  if (m.pts_free) {
+    if ((m.pose_mask & 0x38u) == 0x38u) gen |= 0x0fu;       // translations + scale move t
+    if ((m.pose_mask & 0x07u) == 0x07u) gen |= 0x70u;       // rotations move the angle-axis
+  }
+  nw = __builtin_popcount(gen);
+  if (nw == 0) return OMVG_OK;
+  gauge_kernel<<<(c->nc + 63) / 64, 64, 0, c->stream>>>(c->pose[0].p, c->camR[0].p, c->camdR.p, c->sc_cam.p, m.pose_mask, c->nc, gen, nw, c->gW.p); LAUNCH_CHECK();
+  c->launches++; return OMVG_OK;
 }
 
 int read_scalars(omvg_ba_ctx *c) {
@@ -245,6 +261,8 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   std::vector<int> s_pose(no), s_intr(no), s_pt(no); std::vector<double> s_xy(2 * no);
   for (long long t = 0; t < no; ++t) { const int o = c->perm[t], v = P->obs_view[o];
     s_pose[t] = P->view_pose[v]; s_intr[t] = P->view_intr[v]; s_pt[t] = P->obs_point[o]; s_xy[2 * t] = P->obs_xy[2 * o]; s_xy[2 * t + 1] = P->obs_xy[2 * o + 1]; }
+  std::vector<unsigned char> pt_single(c->np, 1);
+  for (int j = 0; j < c->np; ++j) for (int t = pt_start[j] + 1; t < pt_start[j + 1]; ++t) if (s_intr[t] != s_intr[pt_start[j]]) { pt_single[j] = 0; break; }
   std::vector<int> cam_start(c->nc + 1, 0), cam_obs(no);
   for (long long t = 0; t < no; ++t) cam_start[s_pose[t] + 1]++;
   for (int p = 0; p < c->nc; ++p) cam_start[p + 1] += cam_start[p];
@@ -256,7 +274,7 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
 #define UP(buf, ptr, cnt) if ((rc = upload(buf, ptr, (size_t)(cnt), s))) return rc
   UP(c->pose0, P->poses, 6 * c->nc); UP(c->intr0, h_intr.data(), c->ni8); UP(c->pt0, P->points, 3 * (size_t)c->np);
   UP(c->intr_model, P->intr_model, c->ni); UP(c->obs_pose, s_pose.data(), no); UP(c->obs_intr, s_intr.data(), no); UP(c->obs_pt, s_pt.data(), no);
-  UP(c->pt_start, pt_start.data(), c->np + 1); UP(c->cam_start, cam_start.data(), c->nc + 1); UP(c->cam_obs, cam_obs.data(), no); UP(c->obs_xy, s_xy.data(), 2 * no);
+  UP(c->pt_single, pt_single.data(), c->np); UP(c->pt_start, pt_start.data(), c->np + 1); UP(c->cam_start, cam_start.data(), c->nc + 1); UP(c->cam_obs, cam_obs.data(), no); UP(c->obs_xy, s_xy.data(), 2 * no);
 #undef UP
 #define AL(buf, cnt) if ((rc = buf.alloc((size_t)(cnt)))) return rc
   for (int w = 0; w < 2; ++w) { AL(c->pose[w], 6 * c->nc); AL(c->intr[w], c->ni8); AL(c->pt[w], 3 * (size_t)c->np); AL(c->camR[w], 9 * c->nc); }
@@ -265,12 +283,16 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   AL(c->sc_pt, 3 * (size_t)c->np); AL(c->sc_cam, 6 * c->nc); AL(c->sc_intr, c->ni8);
   AL(c->diag_pt, 3 * (size_t)c->np); AL(c->diag_cam, 6 * c->nc); AL(c->diag_intr, c->ni8);
   AL(c->lmD_pt, 3 * (size_t)c->np); AL(c->lmD_cam, 6 * c->nc); AL(c->lmD_intr, c->ni8); AL(c->g_cam, 6 * c->nc); AL(c->g_intr, c->ni8);
+  AL(c->EtFi, 3 * KI * (size_t)c->np); AL(c->FtF, 36 * (size_t)c->nc); AL(c->FiFi, 64 * (size_t)c->ni);
   AL(c->EtE, 6 * (size_t)c->np); AL(c->Etb, 3 * (size_t)c->np); AL(c->Einv, 9 * (size_t)c->np); AL(c->step_pt, 3 * (size_t)c->np); AL(c->step_red, c->nred);
   AL(c->intr_mask, c->ni);
   AL(c->Sci, (size_t)c->ni8 * 6 * c->nc); AL(c->Sii, (size_t)c->ni8 * c->ni8); AL(c->rhs, c->nred); AL(c->Minv_c, 36 * (size_t)c->nc); AL(c->Minv_i, (size_t)c->ni8 * c->ni8);
   AL(c->work_i, (size_t)c->ni8 * c->ni8 + c->ni8);
+  AL(c->gW, (size_t)MAXW * 6 * c->nc); AL(c->gAW, (size_t)MAXW * 6 * c->nc);
+  AL(c->bX, (size_t)MAXRHS * 6 * c->nc); AL(c->bR, (size_t)MAXRHS * 6 * c->nc); AL(c->bP, (size_t)MAXRHS * 6 * c->nc); AL(c->bW, (size_t)MAXRHS * 6 * c->nc); AL(c->bZ, (size_t)MAXRHS * 6 * c->nc);
+  AL(c->pcg2_part, (size_t)c->n_sms * PCG2_V);
   AL(c->z, c->nred); AL(c->res, c->nred); AL(c->pvec, c->nred); AL(c->w, c->nred); AL(c->zeta, c->nred); AL(c->pcg_part, 3 * (size_t)c->n_sms * 2);
-  AL(c->part, std::max(c->eval_blocks, 1024)); AL(c->part2, 1024); AL(c->part3, 1024); AL(c->icol_part, (size_t)c->ni * 64 * 16); AL(c->scal, S_COUNT); AL(c->fail, 1);
+  AL(c->part, std::max(c->eval_blocks, 1024)); AL(c->part2, 1024); AL(c->part3, 1024); AL(c->icol_part, (size_t)c->ni * 64 * ICS_W); AL(c->scal, S_COUNT); AL(c->fail, 1);
 #undef AL
   OMVG_CUDA(cudaMemsetAsync(c->scal.p, 0, S_COUNT * sizeof(double), s));
   if ((rc = build_structure(c))) return rc;
@@ -327,6 +349,11 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   auto account_jac = [&]() { float ms = 0; cudaEventSynchronize(c->evj1); cudaEventElapsedTime(&ms, c->evj0, c->evj1); jac_ms += ms; ++jac_launches; };
 
   if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
+  int nw = 0;
+  if ((rc = make_gauge(c, m, nw))) return rc;
+  int n_free_intr = 0; for (unsigned mm : m.intr_mask) n_free_intr += __builtin_popcount(mm);
+  const bool use_pcg2 = n_free_intr <= MAXRHS - 1 && !getenv("OMVG_BA_PCG1");
+  OMVG_CUDA(cudaFuncSetAttribute(pcg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
   if ((rc = read_scalars(c))) return rc;
   account_jac();
   double x_cost = c->h_scal[S_COST];
@@ -355,18 +382,29 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     OMVG_CUDA(cudaMemsetAsync(c->Sci.p, 0, c->Sci.n * sizeof(double), c->stream));
     OMVG_CUDA(cudaMemsetAsync(c->Sii.p, 0, c->Sii.n * sizeof(double), c->stream));
     OMVG_CUDA(cudaMemsetAsync(c->rhs.p, 0, c->nred * sizeof(double), c->stream));
-    SchurArgs SA{}; SA.r = c->r.p; SA.Jp = c->Jp.p; SA.Jc = c->Jc.p; SA.Ji = c->Ji.p; SA.EtE = c->EtE.p; SA.Etb = c->Etb.p; SA.lmD_pt = c->lmD_pt.p;
+    SchurArgs SA{}; SA.r = c->r.p; SA.Jp = c->Jp.p; SA.Jc = c->Jc.p; SA.Ji = c->Ji.p; SA.EtE = c->EtE.p; SA.Etb = c->Etb.p; SA.EtFi = c->EtFi.p; SA.lmD_pt = c->lmD_pt.p; SA.pt_single = c->pt_single.p; SA.FtF = c->FtF.p; SA.FiFi = c->FiFi.p; SA.g_cam = c->g_cam.p; SA.g_intr = c->g_intr.p;
     SA.obs_pose = c->obs_pose.p; SA.obs_intr = c->obs_intr.p; SA.obs_pt = c->obs_pt.p; SA.pt_start = c->pt_start.p; SA.n = c->no; SA.n_poses = c->nc; SA.n_intr = c->ni;
     SA.pts_free = m.pts_free; SA.bsr = Bsr{c->bitmap.p, c->wprefix.p, c->rowptr.p, c->words}; SA.Scc = c->Scc.p; SA.Sci = c->Sci.p; SA.Sii = c->Sii.p; SA.rhs = c->rhs.p;
     SA.Einv = c->Einv.p; SA.fail = c->fail.p;
-    if (c->no) { schur_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA); LAUNCH_CHECK(); }
+    { const int ninit = std::max(std::max(36 * c->nc, 64 * c->ni), c->nred); s_init_kernel<<<(ninit + 255) / 256, 256, 0, c->stream>>>(SA); LAUNCH_CHECK(); }
+    schur_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA); LAUNCH_CHECK();
+    mirror_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Scc.p, SA.bsr, c->cols.p, c->nc); LAUNCH_CHECK();
+    c->launches += 2;
     finish_cam_kernel<<<(c->nc + 63) / 64, 64, 0, c->stream>>>(c->Scc.p, SA.bsr, c->lmD_cam.p, m.pose_mask, c->nc, c->Minv_c.p, c->fail.p); LAUNCH_CHECK();
     finish_intr_kernel<<<1, 32, 0, c->stream>>>(c->Sii.p, c->lmD_intr.p, c->intr_mask.p, c->ni8, c->Minv_i.p, c->work_i.p, c->fail.p); LAUNCH_CHECK();
     // ---- PCG on S z = rhs
     PcgArgs PA{}; PA.Scc = c->Scc.p; PA.rowptr = c->rowptr.p; PA.cols = c->cols.p; PA.Sci = c->Sci.p; PA.Sii = c->Sii.p; PA.rhs = c->rhs.p; PA.Minv_c = c->Minv_c.p; PA.Minv_i = c->Minv_i.p;
     PA.n_poses = c->nc; PA.ni8 = c->ni8; PA.z = c->z.p; PA.res = c->res.p; PA.p = c->pvec.p; PA.w = c->w.p; PA.zeta = c->zeta.p; PA.part = c->pcg_part.p;
     PA.tol = O->pcg_tolerance; PA.max_iter = O->pcg_max_iterations; PA.out = c->scal.p + S_PCG_IT;
-    { void *args[] = {&PA}; OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(pcg_grid), dim3(256), args, 0, c->stream)); }
+    if (use_pcg2) {
+      Pcg2Args P2{}; P2.Scc = c->Scc.p; P2.rowptr = c->rowptr.p; P2.cols = c->cols.p; P2.Sci = c->Sci.p; P2.Sii = c->Sii.p; P2.rhs = c->rhs.p; P2.Minv_c = c->Minv_c.p;
+      P2.W = c->gW.p; P2.intr_mask = c->intr_mask.p; P2.n_poses = c->nc; P2.ni8 = c->ni8; P2.nw = nw; P2.X = c->bX.p; P2.Rv = c->bR.p; P2.Pv = c->bP.p; P2.Wv = c->bW.p; P2.Zv = c->bZ.p;
+      P2.AW = c->gAW.p; P2.part = c->pcg2_part.p; P2.z = c->z.p; P2.tol = O->pcg_tolerance; P2.max_iter = O->pcg_max_iterations; P2.out = c->scal.p + S_PCG_IT;
+      void *args[] = {&P2};
+      OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg2_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem), c->stream));
+    } else {
+      void *args[] = {&PA}; OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(pcg_grid), dim3(256), args, 0, c->stream));
+    }
     // ---- back substitution, step = -y
     backsub_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->Etb.p, c->Einv.p, c->obs_pose.p, c->obs_intr.p, c->pt_start.p, c->np, c->nc, c->no,
                                                              c->z.p, m.pts_free, c->step_pt.p); LAUNCH_CHECK();
@@ -412,6 +450,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       std::swap(c->pose[0].p, c->pose[1].p); std::swap(c->intr[0].p, c->intr[1].p); std::swap(c->pt[0].p, c->pt[1].p); std::swap(c->camR[0].p, c->camR[1].p);
       // |x| of the accepted iterate = sqrt(|x_old|^2 ...) is not reusable: recompute from the candidate norms
       if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
+      if ((rc = make_gauge(c, m, nw))) return rc;
       // x_norm of the new x: update_kernel measures |x| of its input; run the three norm passes on the new x
       update_kernel<<<ub, 256, 0, c->stream>>>(c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, nullptr, 0, c->pt[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
       if ((rc = reduce_to(c, c->part3.p, ub, S_X2_PT))) return rc;

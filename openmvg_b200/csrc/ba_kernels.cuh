@@ -248,72 +248,112 @@ __global__ void reduce_partials_kernel(const double *__restrict__ part, int n, d
 }
 
 // ------------------------------------------------------------------------------ column sums
-// per point: EtE (6 unique: 00,10,11,20,21,22), Etb (3) from the (scaled) point blocks.
-__global__ void point_accum_kernel(const double *__restrict__ Jp, const double *__restrict__ r, const int *__restrict__ pt_start,
-                                   int n_points, long long n, double *__restrict__ EtE, double *__restrict__ Etb) {
+// per point: EtE (6 unique: 00,10,11,20,21,22), Etb (3) and, for points whose observations all use one
+// intrinsic group (pt_single), EtFi = sum_obs Jp' Ji (3 x KI) from the (scaled) blocks.
+__global__ void point_accum_kernel(const double *__restrict__ Jp, const double *__restrict__ Ji, const double *__restrict__ r, const int *__restrict__ pt_start,
+                                   const unsigned char *__restrict__ pt_single, int n_points, long long n, double *__restrict__ EtE, double *__restrict__ Etb,
+                                   double *__restrict__ EtFi) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_points) return;
   double e00 = 0, e10 = 0, e11 = 0, e20 = 0, e21 = 0, e22 = 0, b0 = 0, b1 = 0, b2 = 0;
+  double fi[3 * KI];
+  #pragma unroll
+  for (int k = 0; k < 3 * KI; ++k) fi[k] = 0.0;
+  const bool single = pt_single[j] != 0;
   for (long long o = pt_start[j]; o < pt_start[j + 1]; ++o) {
     #pragma unroll
     for (int row = 0; row < 2; ++row) {
       const double a = Jp[(row * 3 + 0) * n + o], b = Jp[(row * 3 + 1) * n + o], c = Jp[(row * 3 + 2) * n + o], rr = r[row * n + o];
       e00 += a * a; e10 += b * a; e11 += b * b; e20 += c * a; e21 += c * b; e22 += c * c;
       b0 += a * rr; b1 += b * rr; b2 += c * rr;
+      if (single) {
+        #pragma unroll
+        for (int k = 0; k < KI; ++k) { const double v = Ji[(row * KI + k) * n + o]; fi[k] += a * v; fi[KI + k] += b * v; fi[2 * KI + k] += c * v; }
+      }
     }
   }
   double *E = EtE + 6 * (size_t)j; E[0] = e00; E[1] = e10; E[2] = e11; E[3] = e20; E[4] = e21; E[5] = e22;
   Etb[3 * (size_t)j] = b0; Etb[3 * (size_t)j + 1] = b1; Etb[3 * (size_t)j + 2] = b2;
+  #pragma unroll
+  for (int k = 0; k < 3 * KI; ++k) EtFi[(size_t)j * 3 * KI + k] = fi[k];
 }
 
-// per pose (one warp): squared column norms and gradient over the pose's observation list.
+// per pose (one warp): Fc'Fc (6x6, full), squared column norms (its diagonal) and gradient Fc'r over the
+// pose's observation list — fixed order, no atomics.
 __global__ void cam_colsum_kernel(const double *__restrict__ Jc, const double *__restrict__ r, const int *__restrict__ cam_start,
                                   const int *__restrict__ cam_obs, int n_poses, long long n, double *__restrict__ diag_cam,
-                                  double *__restrict__ g_cam) {
+                                  double *__restrict__ g_cam, double *__restrict__ FtF) {
   const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (p >= n_poses) return;
-  double d[6] = {0, 0, 0, 0, 0, 0}, g[6] = {0, 0, 0, 0, 0, 0};
+  double m[21], g[6] = {0, 0, 0, 0, 0, 0};
+  #pragma unroll
+  for (int k = 0; k < 21; ++k) m[k] = 0.0;
   for (int t = cam_start[p] + lane; t < cam_start[p + 1]; t += 32) {
     const long long o = cam_obs[t];
     const double r0 = r[o], r1 = r[n + o];
+    double a[6], b[6];
     #pragma unroll
-    for (int k = 0; k < 6; ++k) { const double a = Jc[k * n + o], b = Jc[(6 + k) * n + o]; d[k] += a * a + b * b; g[k] += a * r0 + b * r1; }
+    for (int k = 0; k < 6; ++k) { a[k] = Jc[k * n + o]; b[k] = Jc[(6 + k) * n + o]; g[k] += a[k] * r0 + b[k] * r1; }
+    int q = 0;
+    #pragma unroll
+    for (int i = 0; i < 6; ++i)
+      #pragma unroll
+      for (int k = 0; k <= i; ++k) m[q++] += a[i] * a[k] + b[i] * b[k];
   }
   #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { d[k] += __shfl_down_sync(0xffffffffu, d[k], o); g[k] += __shfl_down_sync(0xffffffffu, g[k], o); }
-    if (lane == 0) { diag_cam[6 * p + k] = d[k]; g_cam[6 * p + k] = g[k]; }
+  for (int k = 0; k < 21; ++k) { for (int o = 16; o > 0; o >>= 1) m[k] += __shfl_down_sync(0xffffffffu, m[k], o); }
+  #pragma unroll
+  for (int k = 0; k < 6; ++k) { for (int o = 16; o > 0; o >>= 1) g[k] += __shfl_down_sync(0xffffffffu, g[k], o); }
+  if (lane == 0) {
+    int q = 0;
+    for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) { FtF[36 * (size_t)p + i * 6 + k] = m[q]; FtF[36 * (size_t)p + k * 6 + i] = m[q]; ++q; }
+    for (int k = 0; k < 6; ++k) { diag_cam[6 * p + k] = FtF[36 * (size_t)p + k * 6 + k]; g_cam[6 * p + k] = g[k]; }
   }
 }
 
-// per intrinsic (one block): squared column norms and gradient over all observations using it.
+// per intrinsic group: Fi'Fi (KI x KI, full), its diagonal and the gradient Fi'r, reduced in fixed order
+// (chunks x blocks, then a final pass): part[q][chunk][80] = {64 FiFi, 8 g, 8 unused}
 constexpr int ICS_THREADS = 256;
+constexpr int ICS_W = 80;
 __global__ void __launch_bounds__(ICS_THREADS) intr_colsum_kernel(const double *__restrict__ Ji, const double *__restrict__ r, const int *__restrict__ obs_intr,
-                                   long long n, int chunks, double *__restrict__ part /* [n_intr][chunks][16] */) {
+                                   long long n, int chunks, double *__restrict__ part) {
   __shared__ double sh[ICS_THREADS / 32];
   const int q = blockIdx.y, chunk = blockIdx.x;
-  double d[KI], g[KI];
-  for (int k = 0; k < KI; ++k) { d[k] = 0; g[k] = 0; }
+  double m[36], g[KI];
+  #pragma unroll
+  for (int k = 0; k < 36; ++k) m[k] = 0;
+  #pragma unroll
+  for (int k = 0; k < KI; ++k) g[k] = 0;
   const long long per = (n + chunks - 1) / chunks, lo = per * chunk, hi = lo + per < n ? lo + per : n;
   for (long long o = lo + threadIdx.x; o < hi; o += ICS_THREADS) {
     if (obs_intr[o] != q) continue;
     const double r0 = r[o], r1 = r[n + o];
+    double a[KI], b[KI];
     #pragma unroll
-    for (int k = 0; k < KI; ++k) { const double a = Ji[k * n + o], b = Ji[(KI + k) * n + o]; d[k] += a * a + b * b; g[k] += a * r0 + b * r1; }
+    for (int k = 0; k < KI; ++k) { a[k] = Ji[k * n + o]; b[k] = Ji[(KI + k) * n + o]; g[k] += a[k] * r0 + b[k] * r1; }
+    int t = 0;
+    #pragma unroll
+    for (int i = 0; i < KI; ++i)
+      #pragma unroll
+      for (int k = 0; k <= i; ++k) m[t++] += a[i] * a[k] + b[i] * b[k];
   }
-  for (int k = 0; k < KI; ++k) {
-    const double td = block_sum<ICS_THREADS>(d[k], sh); const double tg = block_sum<ICS_THREADS>(g[k], sh);
-    if (threadIdx.x == 0) { part[((size_t)q * chunks + chunk) * 16 + k] = td; part[((size_t)q * chunks + chunk) * 16 + 8 + k] = tg; }
+  double *dst = part + ((size_t)q * chunks + chunk) * ICS_W;
+  int t = 0;
+  for (int i = 0; i < KI; ++i) for (int k = 0; k <= i; ++k) {
+    const double v = block_sum<ICS_THREADS>(m[t++], sh);
+    if (threadIdx.x == 0) { dst[i * KI + k] = v; dst[k * KI + i] = v; }
   }
+  for (int k = 0; k < KI; ++k) { const double v = block_sum<ICS_THREADS>(g[k], sh); if (threadIdx.x == 0) dst[64 + k] = v; }
 }
-__global__ void intr_colsum_final_kernel(const double *__restrict__ part, int chunks, int n_intr, double *__restrict__ diag_intr, double *__restrict__ g_intr) {
+__global__ void intr_colsum_final_kernel(const double *__restrict__ part, int chunks, int n_intr, double *__restrict__ diag_intr, double *__restrict__ g_intr,
+                                         double *__restrict__ FiFi) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_intr * KI) return;
-  const int q = t / KI, k = t % KI;
-  double d = 0, g = 0;
-  for (int c = 0; c < chunks; ++c) { d += part[((size_t)q * chunks + c) * 16 + k]; g += part[((size_t)q * chunks + c) * 16 + 8 + k]; }
-  diag_intr[t] = d; g_intr[t] = g;
+  if (t >= n_intr * 72) return;
+  const int q = t / 72, e = t % 72;
+  double v = 0;
+  for (int c = 0; c < chunks; ++c) v += part[((size_t)q * chunks + c) * ICS_W + e];
+  if (e < 64) { FiFi[(size_t)q * 64 + e] = v; if (e / KI == e % KI) diag_intr[q * KI + e / KI] = v; }
+  else g_intr[q * KI + (e - 64)] = v;
 }
 
 // scale[i] = 1 / (1 + sqrt(colnorm2[i]))    (trust_region_minimizer.cc:239-250)
@@ -378,8 +418,9 @@ __global__ void bitmap_cols_kernel(const unsigned *__restrict__ bitmap, const in
 }
 
 struct SchurArgs {
-  const double *r, *Jp, *Jc, *Ji, *EtE, *Etb, *lmD_pt;
-  const int *obs_pose, *obs_intr, *obs_pt, *pt_start;
+  const double *r, *Jp, *Jc, *Ji, *EtE, *Etb, *EtFi, *lmD_pt;
+  const int *obs_pose, *obs_intr, *obs_pt, *pt_start; const unsigned char *pt_single;
+  const double *FtF, *FiFi, *g_cam, *g_intr;
   long long n; int n_poses, n_intr, pts_free;
   Bsr bsr;
   double *Scc;      // [nnzb][36]
@@ -390,122 +431,166 @@ struct SchurArgs {
   int *fail;
 };
 
-// One thread per observation t; loops over all observations u of the same point.
+// Radius-independent part of the reduced system, computed once per Jacobian evaluation without atomics
+// (cam_colsum / intr_colsum): Scc(p,p) = Fc'Fc, Sii(q,q) = Fi'Fi, rhs = [Fc'r ; Fi'r].  S must be zeroed first.
+__global__ void s_init_kernel(SchurArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nc36 = 36 * A.n_poses, ni64 = 64 * A.n_intr, nred = 6 * A.n_poses + KI * A.n_intr;
+  if (i < nc36) { const int p = i / 36; A.Scc[36 * (size_t)bsr_find(A.bsr, p, p) + i % 36] = A.FtF[i]; }
+  if (i < ni64) { const int q = i / 64, e = i % 64; A.Sii[(size_t)(KI * q + e / KI) * (KI * A.n_intr) + KI * q + e % KI] = A.FiFi[i]; }
+  if (i < nred) A.rhs[i] = i < 6 * A.n_poses ? A.g_cam[i] : A.g_intr[i - 6 * A.n_poses];
+}
+
+// One thread per observation t.  Adds the point-elimination terms  -(E'F)' (E'E + D^2)^-1 (E'F)  and the
+// same-observation border term Fi'Fc.  Camera-pair blocks are accumulated for cam(u) >= cam(t) only
+// (mirror_kernel fills the lower triangle); everything hot (the intrinsics corner, its right-hand side) is
+// reduced per point first so that no address sees more than ~one atomic per point.
 constexpr int SCHUR_THREADS = 128;
 __global__ void __launch_bounds__(SCHUR_THREADS) schur_kernel(SchurArgs A) {
+  __shared__ double s_ii[KI * KI + KI];
+  __shared__ int s_q0;
   const long long t = (long long)blockIdx.x * SCHUR_THREADS + threadIdx.x;
-  if (t >= A.n) return;
   const long long n = A.n;
-  const int j = A.obs_pt[t], ct = A.obs_pose[t], qt = A.obs_intr[t];
-  const int nred_c = 6 * A.n_poses;
-  double jc[12], ji[2 * KI], jp[6];
-  #pragma unroll
-  for (int k = 0; k < 12; ++k) jc[k] = A.Jc[k * n + t];
-  #pragma unroll
-  for (int k = 0; k < 2 * KI; ++k) ji[k] = A.Ji[k * n + t];
-  #pragma unroll
-  for (int k = 0; k < 6; ++k) jp[k] = A.Jp[k * n + t];
-  const double r0 = A.r[t], r1 = A.r[n + t];
-  double inv[9], ie[3] = {0, 0, 0};
-  bool have_e = A.pts_free != 0;
-  if (have_e) {
-    double m[6];
-    const double *E = A.EtE + 6 * (size_t)j;
-    const double d0 = A.lmD_pt[3 * j], d1 = A.lmD_pt[3 * j + 1], d2 = A.lmD_pt[3 * j + 2];
-    m[0] = E[0] + d0 * d0; m[1] = E[1]; m[2] = E[2] + d1 * d1; m[3] = E[3]; m[4] = E[4]; m[5] = E[5] + d2 * d2;
-    if (!inv3_spd(m, inv)) { atomicExch(A.fail, 1); return; }
-    const double *b = A.Etb + 3 * (size_t)j;
+  if (threadIdx.x < KI * KI + KI) s_ii[threadIdx.x] = 0.0;
+  if (threadIdx.x == 0) s_q0 = A.obs_intr[(long long)blockIdx.x * SCHUR_THREADS];
+  __syncthreads();
+  const int q0 = s_q0;
+  const int nred_c = 6 * A.n_poses, ni8 = KI * A.n_intr;
+  if (t < n) {
+    const int j = A.obs_pt[t], ct = A.obs_pose[t], qt = A.obs_intr[t];
+    double jc[12], ji[2 * KI], jp[6];
     #pragma unroll
-    for (int a = 0; a < 3; ++a) ie[a] = inv[a * 3] * b[0] + inv[a * 3 + 1] * b[1] + inv[a * 3 + 2] * b[2];
-    if (t == A.pt_start[j]) { for (int a = 0; a < 9; ++a) A.Einv[9 * (size_t)j + a] = inv[a]; }
-  }
-  // EtFc_t (3x6), EtFi_t (3xKI)
-  double efc[18], efi[3 * KI];
-  #pragma unroll
-  for (int a = 0; a < 3; ++a) {
+    for (int k = 0; k < 12; ++k) jc[k] = A.Jc[k * n + t];
     #pragma unroll
-    for (int c = 0; c < 6; ++c) efc[a * 6 + c] = jp[a] * jc[c] + jp[3 + a] * jc[6 + c];
+    for (int k = 0; k < 2 * KI; ++k) ji[k] = A.Ji[k * n + t];
     #pragma unroll
-    for (int c = 0; c < KI; ++c) efi[a * KI + c] = jp[a] * ji[c] + jp[3 + a] * ji[KI + c];
-  }
-  // rhs_c += Fc'r - EtFc' (Einv Etb) ; rhs_i likewise
-  #pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    double v = jc[c] * r0 + jc[6 + c] * r1;
-    if (have_e) v -= efc[c] * ie[0] + efc[6 + c] * ie[1] + efc[12 + c] * ie[2];
-    atomicAdd(&A.rhs[6 * ct + c], v);
-  }
-  #pragma unroll
-  for (int c = 0; c < KI; ++c) {
-    double v = ji[c] * r0 + ji[KI + c] * r1;
-    if (have_e) v -= efi[c] * ie[0] + efi[KI + c] * ie[1] + efi[2 * KI + c] * ie[2];
-    if (v != 0.0) atomicAdd(&A.rhs[nred_c + KI * qt + c], v);
-  }
-  // same-observation terms: Fc'Fc, Fi'Fc, Fi'Fi
-  {
-    double *blk = A.Scc + 36 * (size_t)bsr_find(A.bsr, ct, ct);
-    #pragma unroll
-    for (int a = 0; a < 6; ++a)
+    for (int k = 0; k < 6; ++k) jp[k] = A.Jp[k * n + t];
+    double *sci_row0 = A.Sci + (size_t)(KI * qt) * nred_c + 6 * ct;
+    if (!A.pts_free) {
       #pragma unroll
-      for (int b = 0; b < 6; ++b) atomicAdd(&blk[a * 6 + b], jc[a] * jc[b] + jc[6 + a] * jc[6 + b]);
-    #pragma unroll
-    for (int a = 0; a < KI; ++a) {
-      if (ji[a] == 0.0 && ji[KI + a] == 0.0) continue;
+      for (int a = 0; a < KI; ++a) {
+        if (ji[a] == 0.0 && ji[KI + a] == 0.0) continue;
+        #pragma unroll
+        for (int b = 0; b < 6; ++b) atomicAdd(&sci_row0[(size_t)a * nred_c + b], ji[a] * jc[b] + ji[KI + a] * jc[6 + b]);
+      }
+    } else {
+      double inv[9], ie[3], m[6];
+      const double *E = A.EtE + 6 * (size_t)j;
+      const double d0 = A.lmD_pt[3 * j], d1 = A.lmD_pt[3 * j + 1], d2 = A.lmD_pt[3 * j + 2];
+      m[0] = E[0] + d0 * d0; m[1] = E[1]; m[2] = E[2] + d1 * d1; m[3] = E[3]; m[4] = E[4]; m[5] = E[5] + d2 * d2;
+      const bool ok = inv3_spd(m, inv);
+      if (!ok) atomicExch(A.fail, 1);
+      const double *eb = A.Etb + 3 * (size_t)j;
       #pragma unroll
-      for (int b = 0; b < 6; ++b) atomicAdd(&A.Sci[(size_t)(KI * qt + a) * nred_c + 6 * ct + b], ji[a] * jc[b] + ji[KI + a] * jc[6 + b]);
+      for (int a = 0; a < 3; ++a) ie[a] = inv[a * 3] * eb[0] + inv[a * 3 + 1] * eb[1] + inv[a * 3 + 2] * eb[2];
+      const bool first = t == A.pt_start[j];
+      if (first) { for (int a = 0; a < 9; ++a) A.Einv[9 * (size_t)j + a] = inv[a]; }
+      double efc[18];                                          // E'Fc of this observation (3x6)
       #pragma unroll
-      for (int b = 0; b < KI; ++b) { const double v = ji[a] * ji[b] + ji[KI + a] * ji[KI + b]; if (v != 0.0) atomicAdd(&A.Sii[(size_t)(KI * qt + a) * (KI * A.n_intr) + KI * qt + b], v); }
-    }
-  }
-  if (!have_e) return;
-  // cross terms with every observation u of the point:  -(EtF_t)' Einv (EtF_u)
-  double gt_c[18], gt_i[3 * KI];                              // Einv * EtF_t  (3x6, 3xKI)
-  #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    #pragma unroll
-    for (int c = 0; c < 6; ++c) gt_c[a * 6 + c] = inv[a * 3] * efc[c] + inv[a * 3 + 1] * efc[6 + c] + inv[a * 3 + 2] * efc[12 + c];
-    #pragma unroll
-    for (int c = 0; c < KI; ++c) gt_i[a * KI + c] = inv[a * 3] * efi[c] + inv[a * 3 + 1] * efi[KI + c] + inv[a * 3 + 2] * efi[2 * KI + c];
-  }
-  for (long long u = A.pt_start[j]; u < A.pt_start[j + 1]; ++u) {
-    const int cu = A.obs_pose[u], qu = A.obs_intr[u];
-    double up[6], uc[12];
-    #pragma unroll
-    for (int k = 0; k < 6; ++k) up[k] = A.Jp[k * n + u];
-    #pragma unroll
-    for (int k = 0; k < 12; ++k) uc[k] = A.Jc[k * n + u];
-    double efu[18];
-    #pragma unroll
-    for (int a = 0; a < 3; ++a)
+      for (int a = 0; a < 3; ++a)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) efc[a * 6 + c] = jp[a] * jc[c] + jp[3 + a] * jc[6 + c];
+      // rhs_c -= (E'Fc)' (Einv E'b)
       #pragma unroll
-      for (int c = 0; c < 6; ++c) efu[a * 6 + c] = up[a] * uc[c] + up[3 + a] * uc[6 + c];
-    // Scc(ct, cu) -= gt_c' efu          (6x6)
-    double *blk = A.Scc + 36 * (size_t)bsr_find(A.bsr, ct, cu);
-    #pragma unroll
-    for (int a = 0; a < 6; ++a)
+      for (int c = 0; c < 6; ++c) atomicAdd(&A.rhs[6 * ct + c], -(efc[c] * ie[0] + efc[6 + c] * ie[1] + efc[12 + c] * ie[2]));
+      const bool single = A.pt_single[j] != 0;
+      if (single) {
+        // border with the point-summed E'Fi:  Sci(qt; ct) += Fi'Fc - (Einv E'Fi_pt)' E'Fc
+        const double *fi = A.EtFi + (size_t)j * 3 * KI;
+        #pragma unroll
+        for (int a = 0; a < KI; ++a) {
+          const double f0 = fi[a], f1 = fi[KI + a], f2 = fi[2 * KI + a];
+          if (f0 == 0.0 && f1 == 0.0 && f2 == 0.0 && ji[a] == 0.0 && ji[KI + a] == 0.0) continue;   // constant parameter
+          const double g0 = inv[0] * f0 + inv[1] * f1 + inv[2] * f2, g1 = inv[3] * f0 + inv[4] * f1 + inv[5] * f2, g2 = inv[6] * f0 + inv[7] * f1 + inv[8] * f2;
+          #pragma unroll
+          for (int b = 0; b < 6; ++b)
+            atomicAdd(&sci_row0[(size_t)a * nred_c + b], ji[a] * jc[b] + ji[KI + a] * jc[6 + b] - (g0 * efc[b] + g1 * efc[6 + b] + g2 * efc[12 + b]));
+          if (first) {                                          // once per point: corner and its right-hand side
+            const double rv = -(f0 * ie[0] + f1 * ie[1] + f2 * ie[2]);
+            if (qt == q0) atomicAdd(&s_ii[KI * KI + a], rv); else atomicAdd(&A.rhs[nred_c + KI * qt + a], rv);
+            #pragma unroll
+            for (int b = 0; b < KI; ++b) {
+              const double v = -(g0 * fi[b] + g1 * fi[KI + b] + g2 * fi[2 * KI + b]);
+              if (v == 0.0) continue;
+              if (qt == q0) atomicAdd(&s_ii[a * KI + b], v); else atomicAdd(&A.Sii[(size_t)(KI * qt + a) * ni8 + KI * qt + b], v);
+            }
+          }
+        }
+      }
+      double gt_c[18];                                         // Einv * E'Fc_t
       #pragma unroll
-      for (int b = 0; b < 6; ++b) atomicAdd(&blk[a * 6 + b], -(gt_c[a] * efu[b] + gt_c[6 + a] * efu[6 + b] + gt_c[12 + a] * efu[12 + b]));
-    // Sci(qt ; cu) -= gt_i' efu         (KI x 6)
-    #pragma unroll
-    for (int a = 0; a < KI; ++a) {
-      if (gt_i[a] == 0.0 && gt_i[KI + a] == 0.0 && gt_i[2 * KI + a] == 0.0) continue;
-      #pragma unroll
-      for (int b = 0; b < 6; ++b) atomicAdd(&A.Sci[(size_t)(KI * qt + a) * nred_c + 6 * cu + b], -(gt_i[a] * efu[b] + gt_i[KI + a] * efu[6 + b] + gt_i[2 * KI + a] * efu[12 + b]));
-    }
-    // Sii(qt, qu) -= gt_i' EtFi_u       (KI x KI)
-    double ui[2 * KI];
-    #pragma unroll
-    for (int k = 0; k < 2 * KI; ++k) ui[k] = A.Ji[k * n + u];
-    #pragma unroll
-    for (int a = 0; a < KI; ++a) {
-      if (gt_i[a] == 0.0 && gt_i[KI + a] == 0.0 && gt_i[2 * KI + a] == 0.0) continue;
-      #pragma unroll
-      for (int b = 0; b < KI; ++b) {
-        const double e0 = up[0] * ui[b] + up[3] * ui[KI + b], e1 = up[1] * ui[b] + up[4] * ui[KI + b], e2 = up[2] * ui[b] + up[5] * ui[KI + b];
-        const double v = gt_i[a] * e0 + gt_i[KI + a] * e1 + gt_i[2 * KI + a] * e2;
-        if (v != 0.0) atomicAdd(&A.Sii[(size_t)(KI * qt + a) * (KI * A.n_intr) + KI * qu + b], -v);
+      for (int a = 0; a < 3; ++a)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) gt_c[a * 6 + c] = inv[a * 3] * efc[c] + inv[a * 3 + 1] * efc[6 + c] + inv[a * 3 + 2] * efc[12 + c];
+      double gt_i[3 * KI];
+      if (!single) {                                           // general (rare) path: per-observation-pair border terms
+        #pragma unroll
+        for (int a = 0; a < KI; ++a) {
+          const double e0 = jp[0] * ji[a] + jp[3] * ji[KI + a], e1 = jp[1] * ji[a] + jp[4] * ji[KI + a], e2 = jp[2] * ji[a] + jp[5] * ji[KI + a];
+          gt_i[a] = inv[0] * e0 + inv[1] * e1 + inv[2] * e2; gt_i[KI + a] = inv[3] * e0 + inv[4] * e1 + inv[5] * e2; gt_i[2 * KI + a] = inv[6] * e0 + inv[7] * e1 + inv[8] * e2;
+          const double rv = -(e0 * ie[0] + e1 * ie[1] + e2 * ie[2]);
+          if (rv != 0.0) atomicAdd(&A.rhs[nred_c + KI * qt + a], rv);
+          if (ji[a] == 0.0 && ji[KI + a] == 0.0) continue;
+          #pragma unroll
+          for (int b = 0; b < 6; ++b) atomicAdd(&sci_row0[(size_t)a * nred_c + b], ji[a] * jc[b] + ji[KI + a] * jc[6 + b]);
+        }
+      }
+      for (long long u = A.pt_start[j]; u < A.pt_start[j + 1]; ++u) {
+        const int cu = A.obs_pose[u];
+        if (cu < ct && single) continue;
+        double up[6], uc[12], efu[18];
+        #pragma unroll
+        for (int k = 0; k < 6; ++k) up[k] = A.Jp[k * n + u];
+        #pragma unroll
+        for (int k = 0; k < 12; ++k) uc[k] = A.Jc[k * n + u];
+        #pragma unroll
+        for (int a = 0; a < 3; ++a)
+          #pragma unroll
+          for (int c = 0; c < 6; ++c) efu[a * 6 + c] = up[a] * uc[c] + up[3 + a] * uc[6 + c];
+        if (cu >= ct) {                                        // Scc(ct, cu) -= (Einv E'Fc_t)' E'Fc_u
+          double *blk = A.Scc + 36 * (size_t)bsr_find(A.bsr, ct, cu);
+          #pragma unroll
+          for (int a = 0; a < 6; ++a)
+            #pragma unroll
+            for (int b = 0; b < 6; ++b) atomicAdd(&blk[a * 6 + b], -(gt_c[a] * efu[b] + gt_c[6 + a] * efu[6 + b] + gt_c[12 + a] * efu[12 + b]));
+        }
+        if (!single) {
+          const int qu = A.obs_intr[u];
+          #pragma unroll
+          for (int a = 0; a < KI; ++a) {
+            if (gt_i[a] == 0.0 && gt_i[KI + a] == 0.0 && gt_i[2 * KI + a] == 0.0) continue;
+            #pragma unroll
+            for (int b = 0; b < 6; ++b) atomicAdd(&A.Sci[(size_t)(KI * qt + a) * nred_c + 6 * cu + b], -(gt_i[a] * efu[b] + gt_i[KI + a] * efu[6 + b] + gt_i[2 * KI + a] * efu[12 + b]));
+            #pragma unroll
+            for (int b = 0; b < KI; ++b) {
+              const double ui0 = A.Ji[b * n + u], ui1 = A.Ji[(KI + b) * n + u];
+              const double e0 = up[0] * ui0 + up[3] * ui1, e1 = up[1] * ui0 + up[4] * ui1, e2 = up[2] * ui0 + up[5] * ui1;
+              const double v = gt_i[a] * e0 + gt_i[KI + a] * e1 + gt_i[2 * KI + a] * e2;
+              if (v != 0.0) atomicAdd(&A.Sii[(size_t)(KI * qt + a) * ni8 + KI * qu + b], -v);
+            }
+          }
+        }
       }
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < KI * KI + KI) {
+    const double v = s_ii[threadIdx.x];
+    if (v != 0.0) {
+      if (threadIdx.x < KI * KI) atomicAdd(&A.Sii[(size_t)(KI * q0 + threadIdx.x / KI) * ni8 + KI * q0 + threadIdx.x % KI], v);
+      else atomicAdd(&A.rhs[nred_c + KI * q0 + (threadIdx.x - KI * KI)], v);
+    }
+  }
+}
+
+// lower triangle of Scc from the upper one: block (a,b), a > b, = block (b,a)'
+__global__ void mirror_kernel(double *__restrict__ Scc, Bsr B, const int *__restrict__ cols, int n_poses) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (a >= n_poses) return;
+  for (int e = B.rowptr[a]; e < B.rowptr[a + 1]; ++e) {
+    const int b = cols[e]; if (b >= a) break;
+    const double *src = Scc + 36 * (size_t)bsr_find(B, b, a); double *dst = Scc + 36 * (size_t)e;
+    for (int k = lane; k < 36; k += 32) dst[k] = src[(k % 6) * 6 + k / 6];
   }
 }
 
@@ -660,6 +745,303 @@ __global__ void __launch_bounds__(256) pcg_kernel(PcgArgs A) {
     }
   }
   if (tid == 0) { A.out[0] = (double)(it > A.max_iter ? A.max_iter : it); A.out[1] = bnorm2 > 0 ? sqrt(rr / bnorm2) : 0.0; A.out[2] = sqrt(bnorm2); }
+}
+
+// ------------------------------------------------------------------------------ PCG v2
+// Two-level preconditioned block-PCG on the camera-camera part of the reduced system, with the
+// (small, dense) intrinsics border removed by block elimination:
+//     [Scc Sci'] [zc]   [bc]        Scc Y = [bc | Sci'] (1 + ni8 right-hand sides, solved together)
+//     [Sci Sii ] [zi] = [bi]   =>   (Sii - Sci Y2) zi = bi - Sci y1 ;  zc = y1 - Y2 zi
+// Preconditioner: M^-1 = blockdiag(Scc_pp)^-1 + W (W' Scc W)^-1 W', where the columns of W are the
+// (<= 7) gauge generators of the scene (3 translations, scale, 3 rotations) expressed in the scaled
+// camera coordinates.  Those are exactly the eigenvectors LM damping leaves at ~1/radius; with them
+// in the coarse space the preconditioned spectrum is radius-independent (cond ~ 3-4), so ~20-30
+// iterations reach 1e-10 where block-Jacobi alone needs > 1000.
+constexpr int MAXW = 7;
+constexpr int MAXRHS = 1 + 32;     // bc + up to 32 free intrinsic columns handled by block elimination
+
+// gauge generators, camera part, scaled:  W[m][6p+k] = g_m[6p+k] / scale[6p+k] (0 on constant coordinates)
+__global__ void gauge_kernel(const double *__restrict__ poses, const double *__restrict__ camR, const double *__restrict__ camdR,
+                             const double *__restrict__ sc_cam, unsigned pose_mask, int n_poses, unsigned gen_mask, int nw, double *__restrict__ W) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x; if (p >= n_poses) return;
+  const double *R = camR + 9 * p, *dR = camdR + 27 * p, *t = poses + 6 * p + 3;
+  double g[7][6];
+  for (int m = 0; m < 7; ++m) for (int k = 0; k < 6; ++k) g[m][k] = 0.0;
+  for (int a = 0; a < 3; ++a) for (int i = 0; i < 3; ++i) g[a][3 + i] = -R[i * 3 + a];        // X += e_a : dt = -R e_a
+  for (int i = 0; i < 3; ++i) g[3][3 + i] = t[i];                                             // X *= (1+s): dt = t
+  // X -> (I + [e_a]x) X : R' = R (I - [e_a]x), t' = t.  Solve sum_k dR_k dw_k = -R [e_a]x (least squares, exact)
+  double AtA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) { double v = 0; for (int i = 0; i < 9; ++i) v += dR[9 * k + i] * dR[9 * l + i]; AtA[k * 3 + l] = v; }
+  const double m6[6] = {AtA[0], AtA[3], AtA[4], AtA[6], AtA[7], AtA[8]};
+  double inv[9];
+  if (inv3_spd(m6, inv)) {
+    for (int a = 0; a < 3; ++a) {
+      double B[9];                                      // -R [e_a]x ; ([e]x)_{lj}: column j = e x e_j
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        // [e_a]x = [[0,-e2,e1],[e2,0,-e0],[-e1,e0,0]]
+        double v = 0;
+        for (int l = 0; l < 3; ++l) {
+          double ex = 0;
+          if (l == 0 && j == 1) ex = -(a == 2); if (l == 0 && j == 2) ex = (a == 1);
+          if (l == 1 && j == 0) ex = (a == 2);  if (l == 1 && j == 2) ex = -(a == 0);
+          if (l == 2 && j == 0) ex = -(a == 1); if (l == 2 && j == 1) ex = (a == 0);
+          v += R[i * 3 + l] * ex;
+        }
+        B[i * 3 + j] = -v;
+      }
+      double Atb[3];
+      for (int k = 0; k < 3; ++k) { double v = 0; for (int i = 0; i < 9; ++i) v += dR[9 * k + i] * B[i]; Atb[k] = v; }
+      for (int k = 0; k < 3; ++k) g[4 + a][k] = inv[k * 3] * Atb[0] + inv[k * 3 + 1] * Atb[1] + inv[k * 3 + 2] * Atb[2];
+    }
+  }
+  int row = 0;
+  for (int m = 0; m < 7; ++m) {
+    if (!((gen_mask >> m) & 1)) continue;
+    for (int k = 0; k < 6; ++k) W[(size_t)row * 6 * n_poses + 6 * p + k] = ((pose_mask >> k) & 1) ? g[m][k] / sc_cam[6 * p + k] : 0.0;
+    ++row;
+  }
+  (void)nw;
+}
+
+struct Pcg2Args {
+  const double *Scc; const int *rowptr, *cols; const double *Sci, *Sii, *rhs, *Minv_c;
+  const double *W;            // [nw][nc6]
+  const unsigned *intr_mask;  // free intrinsic parameters (block elimination columns)
+  int n_poses, ni8, nw;
+  double *X, *Rv, *Pv, *Wv, *Zv;   // [nrhs][nc6] each
+  double *AW;                 // [nw][nc6]
+  double *part;               // [gridDim.x][PCG2_V] partial reductions
+  double *z;                  // out: reduced step [nc6 + ni8]
+  double tol; int max_iter;
+  double *out;                // [0]=iterations, [1]=max relative residual, [2]=|bc|
+};
+constexpr int PCG2_V = 320;   // max reduction width: nrhs*(1+nw) <= 33*8 = 264, border 32*33 handled in chunks
+constexpr int PCG2_THREADS = 256;
+
+struct Pcg2Smem {
+  double wpart[PCG2_THREADS / 32][PCG2_V];   // per-warp partials
+  double bv[PCG2_V], tot[PCG2_V];
+  double Einv[MAXW * MAXW];
+  double alpha[MAXRHS], beta[MAXRHS], rz[MAXRHS], bb[MAXRHS], zi[MAXRHS];
+  double T[32][33];
+  int rhs_col[MAXRHS];
+  unsigned char done[MAXRHS];
+  int nrhs, all_done; double worst;
+};
+
+// warp-reduce v; lane 0 ADDS it into this warp's slot idx (slots are zeroed by vsum_begin)
+__device__ __forceinline__ void warp_acc(Pcg2Smem &S, double v, int idx) {
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) S.wpart[threadIdx.x >> 5][idx] += v;
+}
+__device__ __forceinline__ void vsum_begin(Pcg2Smem &S, int V) {
+  for (int i = threadIdx.x; i < V * (PCG2_THREADS / 32); i += PCG2_THREADS) S.wpart[i / V][i % V] = 0.0;
+  __syncthreads();
+}
+// block partials -> global -> grid.sync -> fixed-order totals in S.tot[0..V) (identical in every block)
+__device__ __forceinline__ void vsum_end(cg::grid_group &grid, Pcg2Smem &S, int V, double *part) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < V; i += PCG2_THREADS) { double t = 0; for (int w = 0; w < PCG2_THREADS / 32; ++w) t += S.wpart[w][i]; part[(size_t)blockIdx.x * PCG2_V + i] = t; }
+  grid.sync();
+  for (int i = threadIdx.x; i < V; i += PCG2_THREADS) { double t = 0; for (int b = 0; b < (int)gridDim.x; ++b) t += part[(size_t)b * PCG2_V + i]; S.tot[i] = t; }
+  __syncthreads();
+}
+
+// Y[j] = Scc X[j] for j < nv (every S block is read once per group of 3 vectors).  If dot_base >= 0,
+// lane 0 also accumulates X[j].Y[j] over its rows into this warp's slot dot_base + j.
+__device__ __forceinline__ void spmv_multi(const Pcg2Args &A, Pcg2Smem &S, const double *__restrict__ X, double *__restrict__ Y, int nv,
+                                           const unsigned char *skip, int dot_base) {
+  const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const size_t nc6 = 6 * (size_t)A.n_poses;
+  for (int a = warp; a < A.n_poses; a += nwarps) {
+    for (int j0 = 0; j0 < nv; j0 += 3) {
+      double acc[3][6];
+      #pragma unroll
+      for (int j = 0; j < 3; ++j)
+        #pragma unroll
+        for (int i = 0; i < 6; ++i) acc[j][i] = 0.0;
+      for (int e = A.rowptr[a] + lane; e < A.rowptr[a + 1]; e += 32) {
+        const double *blk = A.Scc + 36 * (size_t)e; const int cb = 6 * A.cols[e];
+        double b[36];
+        #pragma unroll
+        for (int i = 0; i < 36; ++i) b[i] = blk[i];
+        #pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (j0 + j < nv && !(skip && skip[j0 + j])) {
+            const double *xb = X + (size_t)(j0 + j) * nc6 + cb;
+            double xv[6];
+            #pragma unroll
+            for (int k = 0; k < 6; ++k) xv[k] = xb[k];
+            #pragma unroll
+            for (int i = 0; i < 6; ++i)
+              #pragma unroll
+              for (int k = 0; k < 6; ++k) acc[j][i] += b[i * 6 + k] * xv[k];
+          }
+        }
+      }
+      #pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (j0 + j < nv && !(skip && skip[j0 + j])) {
+          double d = 0;
+          #pragma unroll
+          for (int i = 0; i < 6; ++i) { double v = acc[j][i]; for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o); acc[j][i] = v; }
+          if (lane == 0) {
+            for (int i = 0; i < 6; ++i) { Y[(size_t)(j0 + j) * nc6 + 6 * a + i] = acc[j][i]; d += acc[j][i] * X[(size_t)(j0 + j) * nc6 + 6 * a + i]; }
+            if (dot_base >= 0) S.wpart[threadIdx.x >> 5][dot_base + j0 + j] += d;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PCG2_THREADS) pcg2_kernel(Pcg2Args A) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ unsigned char pcg2_smem_raw[];
+  Pcg2Smem &S = *reinterpret_cast<Pcg2Smem *>(pcg2_smem_raw);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const size_t nc6 = 6 * (size_t)A.n_poses;
+  const int nw = A.nw;
+  if (threadIdx.x == 0) {
+    int n = 1; S.rhs_col[0] = -1;
+    for (int q = 0; q < A.ni8; ++q) if ((A.intr_mask[q / KI] >> (q % KI)) & 1) { if (n < MAXRHS) S.rhs_col[n++] = q; }
+    S.nrhs = n;
+  }
+  __syncthreads();
+  const int nrhs = S.nrhs;
+  // ---- coarse operator E = W' Scc W, explicit inverse (nw <= 7)
+  if (nw > 0) {
+    spmv_multi(A, S, A.W, A.AW, nw, nullptr, -1);
+    grid.sync();
+    vsum_begin(S, nw * nw);
+    for (int a = 0; a < nw; ++a) for (int b = 0; b < nw; ++b) {
+      double v = 0; for (size_t i = tid; i < nc6; i += nt) v += A.W[a * nc6 + i] * A.AW[b * nc6 + i];
+      warp_acc(S, v, a * nw + b);
+    }
+    vsum_end(grid, S, nw * nw, A.part);
+    if (threadIdx.x == 0) {                 // Gauss-Jordan inverse (symmetrised input), scratch in S.T
+      double (*M)[33] = S.T;
+      for (int a = 0; a < nw; ++a) for (int b = 0; b < nw; ++b) { M[a][b] = 0.5 * (S.tot[a * nw + b] + S.tot[b * nw + a]); M[a][nw + b] = a == b ? 1.0 : 0.0; }
+      for (int c = 0; c < nw; ++c) {
+        int piv = c; for (int r2 = c + 1; r2 < nw; ++r2) if (fabs(M[r2][c]) > fabs(M[piv][c])) piv = r2;
+        if (piv != c) for (int q = 0; q < 2 * nw; ++q) { const double t2 = M[c][q]; M[c][q] = M[piv][q]; M[piv][q] = t2; }
+        const double d = M[c][c];
+        for (int q = 0; q < 2 * nw; ++q) M[c][q] /= d;
+        for (int r2 = 0; r2 < nw; ++r2) if (r2 != c) { const double f = M[r2][c]; if (f != 0.0) for (int q = 0; q < 2 * nw; ++q) M[r2][q] -= f * M[c][q]; }
+      }
+      for (int a = 0; a < nw; ++a) for (int b = 0; b < nw; ++b) S.Einv[a * nw + b] = M[a][nw + b];
+    }
+    __syncthreads();
+  }
+  // ---- init: X = 0, R = B, |b|^2
+  vsum_begin(S, nrhs);
+  for (int j = 0; j < nrhs; ++j) {
+    const double *src = j == 0 ? A.rhs : A.Sci + (size_t)S.rhs_col[j] * nc6;
+    double v = 0;
+    for (size_t i = tid; i < nc6; i += nt) { const double b = src[i]; A.X[j * nc6 + i] = 0.0; A.Rv[j * nc6 + i] = b; v += b * b; }
+    warp_acc(S, v, j);
+  }
+  vsum_end(grid, S, nrhs, A.part);
+  if (threadIdx.x < nrhs) { const int j = threadIdx.x; S.bb[j] = S.tot[j]; S.done[j] = !(S.tot[j] > 0.0); S.alpha[j] = 0; S.beta[j] = 0; S.rz[j] = 0; }
+  if (threadIdx.x == 0) { S.worst = 0; S.all_done = 0; }
+  __syncthreads();
+  int it = 0;
+  for (;;) {
+    // (a) coarse components c_j = W' r_j
+    if (nw > 0) {
+      vsum_begin(S, nrhs * nw);
+      for (int j = 0; j < nrhs; ++j) {
+        if (S.done[j]) continue;
+        for (int a = 0; a < nw; ++a) { double v = 0; for (size_t i = tid; i < nc6; i += nt) v += A.W[a * nc6 + i] * A.Rv[j * nc6 + i]; warp_acc(S, v, j * nw + a); }
+      }
+      vsum_end(grid, S, nrhs * nw, A.part);
+    }
+    // (b) z = Minv r + W Einv c ;  r'z
+    vsum_begin(S, nrhs);
+    for (int j = 0; j < nrhs; ++j) {
+      if (S.done[j]) continue;
+      double coef[MAXW];
+      #pragma unroll
+      for (int a = 0; a < MAXW; ++a) { double c = 0; if (a < nw) for (int b = 0; b < nw; ++b) c += S.Einv[a * nw + b] * S.tot[j * nw + b]; coef[a] = c; }
+      double v = 0;
+      for (size_t i = tid; i < nc6; i += nt) {
+        const size_t a6 = i / 6; const int k = (int)(i % 6); const double *M = A.Minv_c + 36 * a6 + 6 * k; const double *rb = A.Rv + j * nc6 + 6 * a6;
+        double zz = M[0] * rb[0] + M[1] * rb[1] + M[2] * rb[2] + M[3] * rb[3] + M[4] * rb[4] + M[5] * rb[5];
+        #pragma unroll
+        for (int a = 0; a < MAXW; ++a) if (a < nw) zz += A.W[a * nc6 + i] * coef[a];
+        A.Zv[j * nc6 + i] = zz; v += zz * A.Rv[j * nc6 + i];
+      }
+      warp_acc(S, v, j);
+    }
+    vsum_end(grid, S, nrhs, A.part);
+    if (threadIdx.x < nrhs) { const int j = threadIdx.x; if (!S.done[j]) { const double rzn = S.tot[j]; S.beta[j] = it == 0 ? 0.0 : rzn / S.rz[j]; S.rz[j] = rzn; } }
+    __syncthreads();
+    // (c) p = z + beta p
+    for (int j = 0; j < nrhs; ++j) {
+      if (S.done[j]) continue;
+      if (it == 0) { for (size_t i = tid; i < nc6; i += nt) A.Pv[j * nc6 + i] = A.Zv[j * nc6 + i]; }
+      else { const double bt = S.beta[j]; for (size_t i = tid; i < nc6; i += nt) A.Pv[j * nc6 + i] = A.Zv[j * nc6 + i] + bt * A.Pv[j * nc6 + i]; }
+    }
+    grid.sync();
+    if (it >= A.max_iter) break;
+    // (d) w = Scc p ; p'w (accumulated inside the SpMV)
+    vsum_begin(S, nrhs);
+    spmv_multi(A, S, A.Pv, A.Wv, nrhs, S.done, 0);
+    vsum_end(grid, S, nrhs, A.part);            // its grid.sync also publishes Wv
+    if (threadIdx.x < nrhs) { const int j = threadIdx.x; S.alpha[j] = S.done[j] ? 0.0 : S.rz[j] / S.tot[j]; }
+    __syncthreads();
+    // (e) x += alpha p ; r -= alpha w ; |r|^2
+    vsum_begin(S, nrhs);
+    for (int j = 0; j < nrhs; ++j) {
+      if (S.done[j]) continue;
+      const double al = S.alpha[j]; double v = 0;
+      for (size_t i = tid; i < nc6; i += nt) { A.X[j * nc6 + i] += al * A.Pv[j * nc6 + i]; const double rn = A.Rv[j * nc6 + i] - al * A.Wv[j * nc6 + i]; A.Rv[j * nc6 + i] = rn; v += rn * rn; }
+      warp_acc(S, v, j);
+    }
+    vsum_end(grid, S, nrhs, A.part);
+    ++it;
+    if (threadIdx.x == 0) {
+      int ad = 1; double wmax = 0;
+      for (int j = 0; j < nrhs; ++j) if (!S.done[j]) { const double rel2 = S.tot[j] / S.bb[j]; wmax = fmax(wmax, rel2); if (!(rel2 > A.tol * A.tol)) S.done[j] = 1; else ad = 0; }
+      S.all_done = ad; S.worst = fmax(wmax, 0.0);
+    }
+    __syncthreads();
+    if (S.all_done) break;
+  }
+  // ---- border: (Sii - Sci Y2) zi = bi - Sci y1 ; zc = y1 - Y2 zi
+  const int k = nrhs - 1;
+  if (k > 0) {
+    for (int a = 0; a < k; ++a) {                     // one reduction round per row: k+1 <= 33 values
+      vsum_begin(S, k + 1);
+      const double *row = A.Sci + (size_t)S.rhs_col[1 + a] * nc6;
+      for (int b = 0; b <= k; ++b) {                  // b == k -> X[0]
+        const double *x = A.X + (size_t)(b == k ? 0 : 1 + b) * nc6;
+        double v = 0; for (size_t i = tid; i < nc6; i += nt) v += row[i] * x[i];
+        warp_acc(S, v, b);
+      }
+      vsum_end(grid, S, k + 1, A.part);
+      if (threadIdx.x <= k) {
+        const int b = threadIdx.x;
+        if (b < k) S.T[a][b] = A.Sii[(size_t)S.rhs_col[1 + a] * A.ni8 + S.rhs_col[1 + b]] - S.tot[b];
+        else S.T[a][k] = A.rhs[nc6 + S.rhs_col[1 + a]] - S.tot[k];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {        // Gaussian elimination with partial pivoting (k <= 32), on the symmetrised T
+      for (int a = 0; a < k; ++a) for (int b = a + 1; b < k; ++b) { const double m = 0.5 * (S.T[a][b] + S.T[b][a]); S.T[a][b] = m; S.T[b][a] = m; }
+      for (int c = 0; c < k; ++c) {
+        int piv = c; for (int r2 = c + 1; r2 < k; ++r2) if (fabs(S.T[r2][c]) > fabs(S.T[piv][c])) piv = r2;
+        if (piv != c) for (int q = 0; q <= k; ++q) { const double t2 = S.T[c][q]; S.T[c][q] = S.T[piv][q]; S.T[piv][q] = t2; }
+        for (int r2 = c + 1; r2 < k; ++r2) { const double f = S.T[r2][c] / S.T[c][c]; for (int q = c; q <= k; ++q) S.T[r2][q] -= f * S.T[c][q]; }
+      }
+      for (int c = k - 1; c >= 0; --c) { double sacc = S.T[c][k]; for (int q = c + 1; q < k; ++q) sacc -= S.T[c][q] * S.zi[q]; S.zi[c] = sacc / S.T[c][c]; }
+    }
+    __syncthreads();
+  }
+  for (size_t i = tid; i < nc6; i += nt) { double v = A.X[i]; for (int a = 0; a < k; ++a) v -= A.X[(size_t)(1 + a) * nc6 + i] * S.zi[a]; A.z[i] = v; }
+  for (int q = tid; q < A.ni8; q += nt) { double v = 0; for (int a = 0; a < k; ++a) if (S.rhs_col[1 + a] == q) v = S.zi[a]; A.z[nc6 + q] = v; }
+  if (tid == 0) { A.out[0] = (double)it; A.out[1] = sqrt(S.worst); A.out[2] = sqrt(S.bb[0]); }
 }
 
 // ------------------------------------------------------------------------------ back substitution

@@ -72,6 +72,27 @@ def test_distortion_models_solve(ba, model):
     assert abs(g["final_cost"] - o["final_cost"]) <= 1e-6 * o["final_cost"], (g["final_cost"], o["final_cost"])
 
 
+@pytest.mark.parametrize("n_intr,model", [(3, 1), (2, 2)])
+def test_multiple_intrinsic_groups(ba, n_intr, model):
+    """Points seen through several intrinsic groups: the general (per-observation-pair) border path."""
+    s = synth.ba_scene(18, 900, 6, seed=6, model=model, n_intrinsics=n_intr)
+    g = ba.solve(s)
+    o = ck.oracle_ba_solve(s)
+    assert g["ok"] and o["usable"]
+    assert abs(g["final_cost"] - o["final_cost"]) <= 1e-6 * o["final_cost"], (g["final_cost"], o["final_cost"])
+    assert g["iterations"] == o["iterations"]
+
+
+def test_pcg_variants_agree(ba, monkeypatch):
+    """Two-level block-PCG (default) and plain block-Jacobi PCG with the border inside the iteration."""
+    s = synth.ba_scene(40, 2000, 8, seed=12)
+    a = ba.solve(s)
+    monkeypatch.setenv("OMVG_BA_PCG1", "1")
+    b = ba.solve(s)
+    assert abs(a["final_cost"] - b["final_cost"]) <= 1e-8 * a["final_cost"]
+    assert a["iterations"] == b["iterations"] and a["pcg_iterations"] < b["pcg_iterations"]
+
+
 def test_context_reset_is_reproducible(ba):
     s = synth.ba_scene(20, 1000, 6, seed=2)
     ctx = ba.BAContext(s)
