@@ -40,14 +40,14 @@ struct omvg_ba_ctx {
   int device = 0, n_sms = 0;
   cudaStream_t stream = nullptr;
   int nc = 0, ni = 0, np = 0, nv = 0; long long no = 0;
-  int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0;
+  int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0, kiu = KI;
   std::vector<int> perm;                    // sorted position -> caller's observation index
   std::vector<int> h_intr_model;
   // parameters: [0] current, [1] candidate, init = copy at create
   DevBuf<double> pose[2], intr[2], pt[2], pose0, intr0, pt0;
   DevBuf<int> intr_model, obs_pose, obs_intr, obs_pt, pt_start, cam_start, cam_obs;
   DevBuf<double> obs_xy;
-  DevBuf<double> r, Jp, Jc, Ji, camR[2], camdR;
+  DevBuf<double> r, Jp, Jc, Ji, camR[2], camdR, camrec[2];
   DevBuf<double> sc_pt, sc_cam, sc_intr, diag_pt, diag_cam, diag_intr, lmD_pt, lmD_cam, lmD_intr, g_cam, g_intr;
   DevBuf<double> EtE, Etb, EtFi, FtF, FiFi, Einv, step_pt, step_red;
   DevBuf<unsigned char> pt_single;
@@ -55,6 +55,7 @@ struct omvg_ba_ctx {
   DevBuf<double> Scc, Sci, Sii, rhs, Minv_c, Minv_i, work_i;
   DevBuf<double> z, res, pvec, w, zeta, pcg_part;
   DevBuf<double> gW, gAW, bX, bR, bP, bW, bZ, pcg2_part;   // two-level block-PCG workspaces
+  DevBuf<int> agg_of, agg_start, agg_cams, brow; DevBuf<double> cE, cEinv, cT, cCv, cYv, bP2; int ng = 0;
   DevBuf<double> part, part2, part3, icol_part, scal;
   DevBuf<int> fail;
   double *h_scal = nullptr;                 // pinned
@@ -117,37 +118,41 @@ Masks make_masks(const omvg_ba_ctx *c, const omvg_ba_options *o) {
 }
 
 int eval_cost(omvg_ba_ctx *c, const omvg_ba_options *o, int which, int slot) {
-  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[which].p, c->nc, c->camR[which].p, c->camdR.p); LAUNCH_CHECK();
+  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[which].p, c->nc, c->camR[which].p, c->camdR.p, c->camrec[which].p); LAUNCH_CHECK();
   // NB: cam_prep overwrites camdR; the cost-only pass is always followed by a full evaluation before
   // camdR is read again (accepted step) or the current pose's camdR is not needed (J is materialised).
-  EvalArgs A{}; A.poses = c->pose[which].p; A.intr = c->intr[which].p; A.pts = c->pt[which].p; A.camR = c->camR[which].p; A.camdR = c->camdR.p;
+  EvalArgs A{}; A.poses = c->pose[which].p; A.intr = c->intr[which].p; A.pts = c->pt[which].p; A.camR = c->camR[which].p; A.camdR = c->camdR.p; A.camrec = c->camrec[which].p;
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = o->use_loss; A.huber_a = o->huber_a; A.cost_partial = c->part.p;
-  eval_kernel<false><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  eval_kernel<false, 8><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
   c->launches += 2;
   return reduce_to(c, c->part.p, c->eval_blocks, slot);
 }
 
 int colsums(omvg_ba_ctx *c) {
-  point_accum_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Ji.p, c->r.p, c->pt_start.p, c->pt_single.p, c->np, c->no, c->EtE.p, c->Etb.p, c->EtFi.p); LAUNCH_CHECK();
+  point_accum_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Ji.p, c->r.p, c->pt_start.p, c->pt_single.p, c->np, c->no, c->kiu, c->EtE.p, c->Etb.p, c->EtFi.p); LAUNCH_CHECK();
   point_diag_from_EtE_kernel<<<(c->np + 255) / 256, 256, 0, c->stream>>>(c->EtE.p, c->np, c->diag_pt.p); LAUNCH_CHECK();
   cam_colsum_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Jc.p, c->r.p, c->cam_start.p, c->cam_obs.p, c->nc, c->no, c->diag_cam.p, c->g_cam.p, c->FtF.p); LAUNCH_CHECK();
   const int chunks = 64;
-  intr_colsum_kernel<<<dim3(chunks, c->ni), ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->icol_part.p); LAUNCH_CHECK();
+  intr_colsum_kernel<<<dim3(chunks, c->ni), ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->kiu, c->icol_part.p); LAUNCH_CHECK();
   intr_colsum_final_kernel<<<(c->ni * 72 + 63) / 64, 64, 0, c->stream>>>(c->icol_part.p, chunks, c->ni, c->diag_intr.p, c->g_intr.p, c->FiFi.p); LAUNCH_CHECK();
   c->launches += 5; return OMVG_OK;
 }
 
 // full evaluation at parameter set `which`: cost, corrected r and J (scaled), column sums, gradient max
 int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which, bool &have_scale, bool time_it) {
-  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[which].p, c->nc, c->camR[which].p, c->camdR.p); LAUNCH_CHECK();
-  EvalArgs A{}; A.poses = c->pose[which].p; A.intr = c->intr[which].p; A.pts = c->pt[which].p; A.camR = c->camR[which].p; A.camdR = c->camdR.p;
+  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[which].p, c->nc, c->camR[which].p, c->camdR.p, c->camrec[which].p); LAUNCH_CHECK();
+  EvalArgs A{}; A.poses = c->pose[which].p; A.intr = c->intr[which].p; A.pts = c->pt[which].p; A.camR = c->camR[which].p; A.camdR = c->camdR.p; A.camrec = c->camrec[which].p;
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = o->use_loss; A.huber_a = o->huber_a; A.r = c->r.p; A.Jp = c->Jp.p; A.Jc = c->Jc.p; A.Ji = c->Ji.p;
-  A.cost_partial = c->part.p; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
+  A.cost_partial = c->part.p; A.kiu = c->kiu; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
   if (have_scale) { A.sc_pt = c->sc_pt.p; A.sc_cam = c->sc_cam.p; A.sc_intr = c->sc_intr.p; }
   if (time_it) OMVG_CUDA(cudaEventRecord(c->evj0, c->stream));
-  eval_kernel<true><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  static const int minb = getenv("OMVG_BA_EVAL_MINB") ? atoi(getenv("OMVG_BA_EVAL_MINB")) : 4;
+  if (minb >= 8) eval_kernel<true, 8><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A);
+  else if (minb >= 6) eval_kernel<true, 6><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A);
+  else eval_kernel<true, 4><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A);
+  LAUNCH_CHECK();
   if (time_it) OMVG_CUDA(cudaEventRecord(c->evj1, c->stream));
   c->launches += 2;
   int rc = reduce_to(c, c->part.p, c->eval_blocks, S_COST); if (rc) return rc;
@@ -156,7 +161,7 @@ int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which
     make_scale_kernel<<<(3 * c->np + 255) / 256, 256, 0, c->stream>>>(c->diag_pt.p, 3 * c->np, c->sc_pt.p); LAUNCH_CHECK();
     make_scale_kernel<<<(6 * c->nc + 255) / 256, 256, 0, c->stream>>>(c->diag_cam.p, 6 * c->nc, c->sc_cam.p); LAUNCH_CHECK();
     make_scale_kernel<<<(c->ni8 + 255) / 256, 256, 0, c->stream>>>(c->diag_intr.p, c->ni8, c->sc_intr.p); LAUNCH_CHECK();
-    scale_J_kernel<<<(unsigned)((c->no + 255) / 256), 256, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no,
+    scale_J_kernel<<<(unsigned)((c->no + 255) / 256), 256, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no, c->kiu,
                                                                           c->sc_pt.p, c->sc_cam.p, c->sc_intr.p); LAUNCH_CHECK();
     c->launches += 4; have_scale = true;
   }
@@ -217,6 +222,48 @@ int build_structure(omvg_ba_ctx *c) {
   bitmap_cols_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->bitmap.p, c->rowptr.p, c->nc, c->words, c->cols.p); LAUNCH_CHECK();
   OMVG_CUDA(cudaStreamSynchronize(c->stream));
   c->launches += 3;
+  // ---- aggregates for the coarse space of the PCG preconditioner: greedy over the camera graph
+  std::vector<int> hcols(c->nnzb), brow(c->nnzb);
+  OMVG_CUDA(cudaMemcpy(hcols.data(), c->cols.p, (size_t)c->nnzb * 4, cudaMemcpyDeviceToHost));
+  for (int a = 0; a < c->nc; ++a) for (int e = hp[a]; e < hp[a + 1]; ++e) brow[e] = a;
+  int agg_max = std::max(8, (7 * c->nc + 1023) / 1024);     // coarse dimension 7*nc/agg_max <= ~1024
+  if (const char *e = getenv("OMVG_BA_AGG")) agg_max = std::max(agg_max > 8 ? agg_max : 2, atoi(e));
+  std::vector<int> agg_of(c->nc, -1), agg_size;
+  for (int a = 0; a < c->nc; ++a) {
+    if (agg_of[a] >= 0) continue;
+    const int g = (int)agg_size.size(); agg_of[a] = g; int cnt = 1;
+    std::vector<std::pair<int, int>> nb;                      // unaggregated neighbours, closest index first
+    for (int e = hp[a]; e < hp[a + 1]; ++e) { const int b = hcols[e]; if (b != a && agg_of[b] < 0) nb.emplace_back(std::abs(b - a), b); }
+    std::sort(nb.begin(), nb.end());
+    for (auto &pr : nb) { if (cnt >= agg_max) break; agg_of[pr.second] = g; ++cnt; }
+    agg_size.push_back(cnt);
+  }
+  // singletons cannot carry 7 independent generators: merge them into a neighbouring aggregate
+  for (int a = 0; a < c->nc; ++a) if (agg_size[agg_of[a]] == 1 && agg_size.size() > 1) {
+    int tgt = -1;
+    for (int e = hp[a]; e < hp[a + 1] && tgt < 0; ++e) { const int b = hcols[e]; if (b != a) tgt = agg_of[b]; }
+    if (tgt < 0) tgt = agg_of[a == 0 ? 1 : a - 1];
+    agg_size[agg_of[a]] = 0; agg_of[a] = tgt; agg_size[tgt]++;
+  }
+  std::vector<int> remap(agg_size.size(), -1); int ng = 0;
+  for (size_t g = 0; g < agg_size.size(); ++g) if (agg_size[g] > 0) remap[g] = ng++;
+  std::vector<int> agg_start(ng + 1, 0), agg_cams(c->nc);
+  for (int a = 0; a < c->nc; ++a) { agg_of[a] = remap[agg_of[a]]; agg_start[agg_of[a] + 1]++; }
+  for (int g = 0; g < ng; ++g) agg_start[g + 1] += agg_start[g];
+  { std::vector<int> cur(agg_start.begin(), agg_start.end() - 1); for (int a = 0; a < c->nc; ++a) agg_cams[cur[agg_of[a]]++] = a; }
+  c->ng = ng;
+  if ((rc = upload(c->agg_of, agg_of.data(), c->nc, c->stream))) return rc;
+  if ((rc = upload(c->agg_start, agg_start.data(), ng + 1, c->stream))) return rc;
+  if ((rc = upload(c->agg_cams, agg_cams.data(), c->nc, c->stream))) return rc;
+  if ((rc = upload(c->brow, brow.data(), c->nnzb, c->stream))) return rc;
+  const size_t nco_max = (size_t)ng * MAXW;
+  if ((rc = c->cE.alloc(nco_max * nco_max))) return rc;
+  if ((rc = c->cEinv.alloc(nco_max * nco_max))) return rc;
+  if ((rc = c->cT.alloc(nco_max * nco_max))) return rc;
+  if ((rc = c->cCv.alloc((size_t)MAXRHS * nco_max))) return rc;
+  if ((rc = c->cYv.alloc((size_t)MAXRHS * nco_max))) return rc;
+  if ((rc = c->bP2.alloc((size_t)MAXRHS * 6 * c->nc))) return rc;
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
   return c->Scc.alloc((size_t)c->nnzb * 36);
 }
 
@@ -251,6 +298,7 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   c->nc = P->n_poses; c->ni = P->n_intrinsics; c->np = P->n_points; c->nv = P->n_views; c->no = P->n_obs;
   c->ni8 = KI * c->ni; c->nred = 6 * c->nc + c->ni8; c->eval_blocks = (int)std::max<long long>(1, (c->no + EVAL_THREADS - 1) / EVAL_THREADS);
   c->h_intr_model.assign(P->intr_model, P->intr_model + c->ni);
+  c->kiu = 0; for (int q = 0; q < c->ni; ++q) c->kiu = std::max(c->kiu, model_nparams(P->intr_model[q]));
   // ---- sort observations by point (counting sort); build per-pose lists
   const long long no = c->no;
   std::vector<int> pt_start(c->np + 1, 0);
@@ -277,7 +325,7 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   UP(c->pt_single, pt_single.data(), c->np); UP(c->pt_start, pt_start.data(), c->np + 1); UP(c->cam_start, cam_start.data(), c->nc + 1); UP(c->cam_obs, cam_obs.data(), no); UP(c->obs_xy, s_xy.data(), 2 * no);
 #undef UP
 #define AL(buf, cnt) if ((rc = buf.alloc((size_t)(cnt)))) return rc
-  for (int w = 0; w < 2; ++w) { AL(c->pose[w], 6 * c->nc); AL(c->intr[w], c->ni8); AL(c->pt[w], 3 * (size_t)c->np); AL(c->camR[w], 9 * c->nc); }
+  for (int w = 0; w < 2; ++w) { AL(c->pose[w], 6 * c->nc); AL(c->intr[w], c->ni8); AL(c->pt[w], 3 * (size_t)c->np); AL(c->camR[w], 9 * c->nc); AL(c->camrec[w], (size_t)CAMREC * c->nc); }
   AL(c->camdR, 27 * c->nc);
   AL(c->r, 2 * no); AL(c->Jp, 6 * no); AL(c->Jc, 12 * no); AL(c->Ji, 2 * KI * no);
   AL(c->sc_pt, 3 * (size_t)c->np); AL(c->sc_cam, 6 * c->nc); AL(c->sc_intr, c->ni8);
@@ -353,7 +401,9 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   if ((rc = make_gauge(c, m, nw))) return rc;
   int n_free_intr = 0; for (unsigned mm : m.intr_mask) n_free_intr += __builtin_popcount(mm);
   const bool use_pcg2 = n_free_intr <= MAXRHS - 1 && !getenv("OMVG_BA_PCG1");
+  const bool use_pcg3 = use_pcg2 && !getenv("OMVG_BA_PCG2") && c->nc >= 2;
   OMVG_CUDA(cudaFuncSetAttribute(pcg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
+  OMVG_CUDA(cudaFuncSetAttribute(pcg3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
   if ((rc = read_scalars(c))) return rc;
   account_jac();
   double x_cost = c->h_scal[S_COST];
@@ -384,7 +434,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     OMVG_CUDA(cudaMemsetAsync(c->rhs.p, 0, c->nred * sizeof(double), c->stream));
     SchurArgs SA{}; SA.r = c->r.p; SA.Jp = c->Jp.p; SA.Jc = c->Jc.p; SA.Ji = c->Ji.p; SA.EtE = c->EtE.p; SA.Etb = c->Etb.p; SA.EtFi = c->EtFi.p; SA.lmD_pt = c->lmD_pt.p; SA.pt_single = c->pt_single.p; SA.FtF = c->FtF.p; SA.FiFi = c->FiFi.p; SA.g_cam = c->g_cam.p; SA.g_intr = c->g_intr.p;
     SA.obs_pose = c->obs_pose.p; SA.obs_intr = c->obs_intr.p; SA.obs_pt = c->obs_pt.p; SA.pt_start = c->pt_start.p; SA.n = c->no; SA.n_poses = c->nc; SA.n_intr = c->ni;
-    SA.pts_free = m.pts_free; SA.bsr = Bsr{c->bitmap.p, c->wprefix.p, c->rowptr.p, c->words}; SA.Scc = c->Scc.p; SA.Sci = c->Sci.p; SA.Sii = c->Sii.p; SA.rhs = c->rhs.p;
+    SA.pts_free = m.pts_free; SA.kiu = c->kiu; SA.bsr = Bsr{c->bitmap.p, c->wprefix.p, c->rowptr.p, c->words}; SA.Scc = c->Scc.p; SA.Sci = c->Sci.p; SA.Sii = c->Sii.p; SA.rhs = c->rhs.p;
     SA.Einv = c->Einv.p; SA.fail = c->fail.p;
     { const int ninit = std::max(std::max(36 * c->nc, 64 * c->ni), c->nred); s_init_kernel<<<(ninit + 255) / 256, 256, 0, c->stream>>>(SA); LAUNCH_CHECK(); }
     schur_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA); LAUNCH_CHECK();
@@ -400,17 +450,34 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       Pcg2Args P2{}; P2.Scc = c->Scc.p; P2.rowptr = c->rowptr.p; P2.cols = c->cols.p; P2.Sci = c->Sci.p; P2.Sii = c->Sii.p; P2.rhs = c->rhs.p; P2.Minv_c = c->Minv_c.p;
       P2.W = c->gW.p; P2.intr_mask = c->intr_mask.p; P2.n_poses = c->nc; P2.ni8 = c->ni8; P2.nw = nw; P2.X = c->bX.p; P2.Rv = c->bR.p; P2.Pv = c->bP.p; P2.Wv = c->bW.p; P2.Zv = c->bZ.p;
       P2.AW = c->gAW.p; P2.part = c->pcg2_part.p; P2.z = c->z.p; P2.tol = O->pcg_tolerance; P2.max_iter = O->pcg_max_iterations; P2.out = c->scal.p + S_PCG_IT;
-      void *args[] = {&P2};
-      OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg2_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem), c->stream));
+      if (use_pcg3) {
+        Pcg3Args P3{}; P3.base = P2; P3.C = Coarse{c->agg_of.p, c->agg_start.p, c->agg_cams.p, c->ng, nw, c->ng * nw}; P3.Einv = c->cEinv.p; P3.Cv = c->cCv.p; P3.Yv = c->cYv.p; P3.Pv2 = c->bP2.p;
+        const int nco = P3.C.nco;
+        if (nco > 0) {
+          OMVG_CUDA(cudaMemsetAsync(c->cE.p, 0, (size_t)nco * nco * sizeof(double), c->stream));
+          coarse_assemble_kernel<<<(c->nnzb + 127) / 128, 128, 0, c->stream>>>(c->Scc.p, c->brow.p, c->cols.p, c->nnzb, c->gW.p, c->nc, P3.C, c->cE.p); LAUNCH_CHECK();
+          { const size_t sm = sizeof(double) * std::max<size_t>((size_t)CNB * CNB, (size_t)8 * nco);
+            OMVG_CUDA(cudaFuncSetAttribute(coarse_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            double *Ep = c->cE.p, *Tp = c->cT.p, *Ip = c->cEinv.p; int nn = nco; int *fp = c->fail.p;
+            void *cargs[] = {&Ep, &nn, &Tp, &Ip, &fp};
+            OMVG_CUDA(cudaLaunchCooperativeKernel((void *)coarse_setup_kernel, dim3(pcg_grid), dim3(256), cargs, sm, c->stream)); }
+          c->launches += 2;
+        }
+        void *args[] = {&P3};
+        OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg3_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem), c->stream));
+      } else {
+        void *args[] = {&P2};
+        OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg2_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem), c->stream));
+      }
     } else {
       void *args[] = {&PA}; OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(pcg_grid), dim3(256), args, 0, c->stream));
     }
     // ---- back substitution, step = -y
-    backsub_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->Etb.p, c->Einv.p, c->obs_pose.p, c->obs_intr.p, c->pt_start.p, c->np, c->nc, c->no,
+    backsub_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->Etb.p, c->Einv.p, c->obs_pose.p, c->obs_intr.p, c->pt_start.p, c->np, c->nc, c->no, c->kiu,
                                                              c->z.p, m.pts_free, c->step_pt.p); LAUNCH_CHECK();
     negate_kernel<<<(c->nred + 255) / 256, 256, 0, c->stream>>>(c->z.p, c->nred, c->step_red.p); LAUNCH_CHECK();
     // ---- model cost change
-    model_kernel<<<c->eval_blocks, MODEL_THREADS, 0, c->stream>>>(c->r.p, c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no, c->nc, c->step_pt.p, c->step_red.p, c->part.p); LAUNCH_CHECK();
+    model_kernel<<<c->eval_blocks, MODEL_THREADS, 0, c->stream>>>(c->r.p, c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no, c->nc, c->kiu, c->step_pt.p, c->step_red.p, c->part.p); LAUNCH_CHECK();
     c->launches += 10;
     if ((rc = reduce_to(c, c->part.p, c->eval_blocks, S_MODEL))) return rc;
     // ---- candidate = Plus(x, step * scale)
@@ -447,7 +514,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     const double hist = (reference_cost - candidate_cost) / (accumulated_reference + model_cost_change);
     const double rho = std::max(rel, hist);
     if (rho > O->min_relative_decrease) {                    // HandleSuccessfulStep (:767-780)
-      std::swap(c->pose[0].p, c->pose[1].p); std::swap(c->intr[0].p, c->intr[1].p); std::swap(c->pt[0].p, c->pt[1].p); std::swap(c->camR[0].p, c->camR[1].p);
+      std::swap(c->pose[0].p, c->pose[1].p); std::swap(c->intr[0].p, c->intr[1].p); std::swap(c->pt[0].p, c->pt[1].p); std::swap(c->camR[0].p, c->camR[1].p); std::swap(c->camrec[0].p, c->camrec[1].p);
       // |x| of the accepted iterate = sqrt(|x_old|^2 ...) is not reusable: recompute from the candidate norms
       if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
       if ((rc = make_gauge(c, m, nw))) return rc;
@@ -540,13 +607,14 @@ int omvg_ba_debug_eval(omvg_ba_ctx *c, const omvg_ba_options *O, double *cost, d
   OMVG_CUDA(cudaSetDevice(c->device));
   Masks m = make_masks(c, O);
   OMVG_CUDA(cudaMemcpyAsync(c->intr_mask.p, m.intr_mask.data(), c->ni * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
-  // unscaled evaluation
-  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[0].p, c->nc, c->camR[0].p, c->camdR.p); LAUNCH_CHECK();
-  EvalArgs A{}; A.poses = c->pose[0].p; A.intr = c->intr[0].p; A.pts = c->pt[0].p; A.camR = c->camR[0].p; A.camdR = c->camdR.p;
+  // unscaled evaluation (intrinsic columns >= kiu are never written: present them as zeros)
+  OMVG_CUDA(cudaMemsetAsync(c->Ji.p, 0, c->Ji.n * sizeof(double), c->stream));
+  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[0].p, c->nc, c->camR[0].p, c->camdR.p, c->camrec[0].p); LAUNCH_CHECK();
+  EvalArgs A{}; A.poses = c->pose[0].p; A.intr = c->intr[0].p; A.pts = c->pt[0].p; A.camR = c->camR[0].p; A.camdR = c->camdR.p; A.camrec = c->camrec[0].p;
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = O->use_loss; A.huber_a = O->huber_a; A.r = c->r.p; A.Jp = c->Jp.p; A.Jc = c->Jc.p; A.Ji = c->Ji.p;
-  A.cost_partial = c->part.p; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
-  eval_kernel<true><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  A.cost_partial = c->part.p; A.kiu = c->kiu; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
+  eval_kernel<true, 4><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
   int rc = reduce_to(c, c->part.p, c->eval_blocks, S_COST); if (rc) return rc;
   c->launches += 2;
   const long long n = c->no;

@@ -70,7 +70,10 @@ __device__ __forceinline__ bool inv3_spd(const double m[6], double inv[9]) {
 // ------------------------------------------------------------------------------ per-pose rotation
 // camR[p][9] row-major R(w); camdR[p][k][9] = dR/dw_k.  Same expression as AngleAxisRotatePoint:
 // R = cos I + sin [w]x + (1-cos) w w^T with w = aa/theta;  theta^2 <= eps: R = I + [aa]x.
-__global__ void cam_prep_kernel(const double *__restrict__ poses, int n_poses, double *__restrict__ camR, double *__restrict__ camdR) {
+// camrec[p][22] = {R (9), Jr (9, row-major; column k = vee(R' dR_k), so dR_k X = R (Jr e_k x X)), t (3), pad}:
+// the compact per-pose record the per-observation kernel gathers with 11 x 16-byte loads.
+constexpr int CAMREC = 22;
+__global__ void cam_prep_kernel(const double *__restrict__ poses, int n_poses, double *__restrict__ camR, double *__restrict__ camdR, double *__restrict__ camrec) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_poses) return;
   typedef Dual<3> D;
@@ -96,11 +99,19 @@ __global__ void cam_prep_kernel(const double *__restrict__ poses, int n_poses, d
     }
   }
   for (int i = 0; i < 9; ++i) { camR[9 * p + i] = R[i].a; for (int k = 0; k < 3; ++k) camdR[27 * p + 9 * k + i] = R[i].v[k]; }
+  double *rec = camrec + (size_t)CAMREC * p;
+  for (int i = 0; i < 9; ++i) rec[i] = R[i].a;
+  for (int k = 0; k < 3; ++k) {
+    double M[9];                                             // R' dR_k  (skew up to rounding)
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double v = 0; for (int l = 0; l < 3; ++l) v += R[l * 3 + i].a * R[l * 3 + j].v[k]; M[i * 3 + j] = v; }
+    rec[9 + 0 * 3 + k] = 0.5 * (M[7] - M[5]); rec[9 + 1 * 3 + k] = 0.5 * (M[2] - M[6]); rec[9 + 2 * 3 + k] = 0.5 * (M[3] - M[1]);
+  }
+  rec[18] = poses[6 * p + 3]; rec[19] = poses[6 * p + 4]; rec[20] = poses[6 * p + 5]; rec[21] = 0.0;
 }
 
 // ------------------------------------------------------------------------------ residual / Jacobian
 struct EvalArgs {
-  const double *poses, *intr, *pts, *camR, *camdR, *obs_xy;
+  const double *poses, *intr, *pts, *camR, *camdR, *camrec, *obs_xy;
   const int *intr_model, *obs_pose, *obs_intr, *obs_pt;
   long long n_obs;
   int use_loss; double huber_a;
@@ -109,6 +120,7 @@ struct EvalArgs {
   double *cost_partial;
   // scaling & masks
   const double *sc_pt, *sc_cam, *sc_intr;   // null => unscaled
+  int kiu;                                  // intrinsic columns in use (max nparams over the groups)
   unsigned pose_mask;                       // bit k set => pose coordinate k is free
   const unsigned *intr_mask;                // per intrinsic: bit k set => parameter k is free
   int pts_free;
@@ -166,16 +178,19 @@ __device__ __forceinline__ void distort(int model, const double *K, double x, do
 }
 
 constexpr int EVAL_THREADS = 128;
-template <bool WANT_J>
-__global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs A) {
+template <bool WANT_J, int MINB>
+__global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
   __shared__ double sh[EVAL_THREADS / 32];
   const long long o = (long long)blockIdx.x * EVAL_THREADS + threadIdx.x;
   double cost = 0.0;
   if (o < A.n_obs) {
     const int ip = A.obs_pose[o], iq = A.obs_intr[o], j = A.obs_pt[o];
-    const double *R = A.camR + 9 * ip;
+    double R[CAMREC];
+    { const double2 *rp = reinterpret_cast<const double2 *>(A.camrec + (size_t)CAMREC * ip);
+      #pragma unroll
+      for (int q = 0; q < CAMREC / 2; ++q) { const double2 v = __ldg(rp + q); R[2 * q] = v.x; R[2 * q + 1] = v.y; } }
     const double X0 = A.pts[3 * j], X1 = A.pts[3 * j + 1], X2 = A.pts[3 * j + 2];
-    const double *T = A.poses + 6 * ip + 3;
+    const double *T = R + 18;
     const double p0 = R[0] * X0 + R[1] * X1 + R[2] * X2 + T[0];
     const double p1 = R[3] * X0 + R[4] * X1 + R[5] * X2 + T[1];
     const double p2 = R[6] * X0 + R[7] * X1 + R[8] * X2 + T[2];
@@ -208,12 +223,14 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs A) {
         A.Jp[(1 * 3 + c) * n + o] = sc * (g[3] * R[c] + g[4] * R[3 + c] + g[5] * R[6 + c]);
       }
       // pose block: rotation columns g * (dR_k X), translation columns g
-      const double *dR = A.camdR + 27 * ip;
       #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const double q0 = dR[9 * k + 0] * X0 + dR[9 * k + 1] * X1 + dR[9 * k + 2] * X2;
-        const double q1 = dR[9 * k + 3] * X0 + dR[9 * k + 4] * X1 + dR[9 * k + 5] * X2;
-        const double q2 = dR[9 * k + 6] * X0 + dR[9 * k + 7] * X1 + dR[9 * k + 8] * X2;
+        // dR_k X = R (j_k x X), j_k = column k of Jr
+        const double j0 = R[9 + k], j1 = R[12 + k], j2 = R[15 + k];
+        const double v0 = j1 * X2 - j2 * X1, v1 = j2 * X0 - j0 * X2, v2 = j0 * X1 - j1 * X0;
+        const double q0 = R[0] * v0 + R[1] * v1 + R[2] * v2;
+        const double q1 = R[3] * v0 + R[4] * v1 + R[5] * v2;
+        const double q2 = R[6] * v0 + R[7] * v1 + R[8] * v2;
         const double sc = ((A.pose_mask >> k) & 1) ? (A.sc_cam ? A.sc_cam[6 * ip + k] : 1.0) : 0.0;
         A.Jc[(0 * 6 + k) * n + o] = sc * (g[0] * q0 + g[1] * q1 + g[2] * q2);
         A.Jc[(1 * 6 + k) * n + o] = sc * (g[3] * q0 + g[4] * q1 + g[5] * q2);
@@ -230,8 +247,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs A) {
       #pragma unroll
       for (int k = 0; k < KI; ++k) {
         const double sc = ((im >> k) & 1) ? (A.sc_intr ? A.sc_intr[KI * iq + k] : 1.0) : 0.0;
-        A.Ji[(0 * KI + k) * n + o] = sc * ji0[k];
-        A.Ji[(1 * KI + k) * n + o] = sc * ji1[k];
+        if (k < A.kiu) { A.Ji[(0 * KI + k) * n + o] = sc * ji0[k]; A.Ji[(1 * KI + k) * n + o] = sc * ji1[k]; }
       }
     }
   }
@@ -251,7 +267,7 @@ __global__ void reduce_partials_kernel(const double *__restrict__ part, int n, d
 // per point: EtE (6 unique: 00,10,11,20,21,22), Etb (3) and, for points whose observations all use one
 // intrinsic group (pt_single), EtFi = sum_obs Jp' Ji (3 x KI) from the (scaled) blocks.
 __global__ void point_accum_kernel(const double *__restrict__ Jp, const double *__restrict__ Ji, const double *__restrict__ r, const int *__restrict__ pt_start,
-                                   const unsigned char *__restrict__ pt_single, int n_points, long long n, double *__restrict__ EtE, double *__restrict__ Etb,
+                                   const unsigned char *__restrict__ pt_single, int n_points, long long n, int kiu, double *__restrict__ EtE, double *__restrict__ Etb,
                                    double *__restrict__ EtFi) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_points) return;
@@ -268,7 +284,7 @@ __global__ void point_accum_kernel(const double *__restrict__ Jp, const double *
       b0 += a * rr; b1 += b * rr; b2 += c * rr;
       if (single) {
         #pragma unroll
-        for (int k = 0; k < KI; ++k) { const double v = Ji[(row * KI + k) * n + o]; fi[k] += a * v; fi[KI + k] += b * v; fi[2 * KI + k] += c * v; }
+        for (int k = 0; k < KI; ++k) { const double v = k < kiu ? Ji[(row * KI + k) * n + o] : 0.0; fi[k] += a * v; fi[KI + k] += b * v; fi[2 * KI + k] += c * v; }
       }
     }
   }
@@ -316,7 +332,7 @@ __global__ void cam_colsum_kernel(const double *__restrict__ Jc, const double *_
 constexpr int ICS_THREADS = 256;
 constexpr int ICS_W = 80;
 __global__ void __launch_bounds__(ICS_THREADS) intr_colsum_kernel(const double *__restrict__ Ji, const double *__restrict__ r, const int *__restrict__ obs_intr,
-                                   long long n, int chunks, double *__restrict__ part) {
+                                   long long n, int chunks, int kiu, double *__restrict__ part) {
   __shared__ double sh[ICS_THREADS / 32];
   const int q = blockIdx.y, chunk = blockIdx.x;
   double m[36], g[KI];
@@ -330,7 +346,7 @@ __global__ void __launch_bounds__(ICS_THREADS) intr_colsum_kernel(const double *
     const double r0 = r[o], r1 = r[n + o];
     double a[KI], b[KI];
     #pragma unroll
-    for (int k = 0; k < KI; ++k) { a[k] = Ji[k * n + o]; b[k] = Ji[(KI + k) * n + o]; g[k] += a[k] * r0 + b[k] * r1; }
+    for (int k = 0; k < KI; ++k) { a[k] = k < kiu ? Ji[k * n + o] : 0.0; b[k] = k < kiu ? Ji[(KI + k) * n + o] : 0.0; g[k] += a[k] * r0 + b[k] * r1; }
     int t = 0;
     #pragma unroll
     for (int i = 0; i < KI; ++i)
@@ -366,14 +382,14 @@ __global__ void point_diag_from_EtE_kernel(const double *__restrict__ EtE, int n
 }
 // apply the just-computed column scaling to the unscaled J of iteration 0 (ScaleColumns, :253)
 __global__ void scale_J_kernel(double *__restrict__ Jp, double *__restrict__ Jc, double *__restrict__ Ji, const int *__restrict__ obs_pose,
-                               const int *__restrict__ obs_intr, const int *__restrict__ obs_pt, long long n,
+                               const int *__restrict__ obs_intr, const int *__restrict__ obs_pt, long long n, int kiu,
                                const double *__restrict__ sc_pt, const double *__restrict__ sc_cam, const double *__restrict__ sc_intr) {
   const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n) return;
   const int ip = obs_pose[o], iq = obs_intr[o], j = obs_pt[o];
   for (int row = 0; row < 2; ++row) {
     for (int c = 0; c < 3; ++c) Jp[(row * 3 + c) * n + o] *= sc_pt[3 * j + c];
     for (int c = 0; c < 6; ++c) Jc[(row * 6 + c) * n + o] *= sc_cam[6 * ip + c];
-    for (int c = 0; c < KI; ++c) Ji[(row * KI + c) * n + o] *= sc_intr[KI * iq + c];
+    for (int c = 0; c < kiu; ++c) Ji[(row * KI + c) * n + o] *= sc_intr[KI * iq + c];
   }
 }
 // g_unscaled = g_scaled / scale ; then max |g| over free columns (gradient_max_norm)
@@ -421,7 +437,7 @@ struct SchurArgs {
   const double *r, *Jp, *Jc, *Ji, *EtE, *Etb, *EtFi, *lmD_pt;
   const int *obs_pose, *obs_intr, *obs_pt, *pt_start; const unsigned char *pt_single;
   const double *FtF, *FiFi, *g_cam, *g_intr;
-  long long n; int n_poses, n_intr, pts_free;
+  long long n; int n_poses, n_intr, pts_free, kiu;
   Bsr bsr;
   double *Scc;      // [nnzb][36]
   double *Sci;      // [KI*n_intr][6*n_poses]
@@ -462,7 +478,7 @@ __global__ void __launch_bounds__(SCHUR_THREADS) schur_kernel(SchurArgs A) {
     #pragma unroll
     for (int k = 0; k < 12; ++k) jc[k] = A.Jc[k * n + t];
     #pragma unroll
-    for (int k = 0; k < 2 * KI; ++k) ji[k] = A.Ji[k * n + t];
+    for (int k = 0; k < 2 * KI; ++k) ji[k] = (k % KI) < A.kiu ? A.Ji[k * n + t] : 0.0;
     #pragma unroll
     for (int k = 0; k < 6; ++k) jp[k] = A.Jp[k * n + t];
     double *sci_row0 = A.Sci + (size_t)(KI * qt) * nred_c + 6 * ct;
@@ -563,7 +579,7 @@ __global__ void __launch_bounds__(SCHUR_THREADS) schur_kernel(SchurArgs A) {
             for (int b = 0; b < 6; ++b) atomicAdd(&A.Sci[(size_t)(KI * qt + a) * nred_c + 6 * cu + b], -(gt_i[a] * efu[b] + gt_i[KI + a] * efu[6 + b] + gt_i[2 * KI + a] * efu[12 + b]));
             #pragma unroll
             for (int b = 0; b < KI; ++b) {
-              const double ui0 = A.Ji[b * n + u], ui1 = A.Ji[(KI + b) * n + u];
+              const double ui0 = b < A.kiu ? A.Ji[b * n + u] : 0.0, ui1 = b < A.kiu ? A.Ji[(KI + b) * n + u] : 0.0;
               const double e0 = up[0] * ui0 + up[3] * ui1, e1 = up[1] * ui0 + up[4] * ui1, e2 = up[2] * ui0 + up[5] * ui1;
               const double v = gt_i[a] * e0 + gt_i[KI + a] * e1 + gt_i[2 * KI + a] * e2;
               if (v != 0.0) atomicAdd(&A.Sii[(size_t)(KI * qt + a) * ni8 + KI * qu + b], -v);
@@ -839,12 +855,21 @@ __device__ __forceinline__ void vsum_begin(Pcg2Smem &S, int V) {
   for (int i = threadIdx.x; i < V * (PCG2_THREADS / 32); i += PCG2_THREADS) S.wpart[i / V][i % V] = 0.0;
   __syncthreads();
 }
-// block partials -> global -> grid.sync -> fixed-order totals in S.tot[0..V) (identical in every block)
+// block partials -> global -> grid.sync -> fixed-order totals in S.tot[0..V) (identical in every block).
+// Cross-block sum: one warp per value, lanes stride over the blocks (5 loads each at 148 blocks), then a
+// fixed butterfly — the same order in every block, hence bitwise identical totals everywhere.
 __device__ __forceinline__ void vsum_end(cg::grid_group &grid, Pcg2Smem &S, int V, double *part) {
   __syncthreads();
   for (int i = threadIdx.x; i < V; i += PCG2_THREADS) { double t = 0; for (int w = 0; w < PCG2_THREADS / 32; ++w) t += S.wpart[w][i]; part[(size_t)blockIdx.x * PCG2_V + i] = t; }
   grid.sync();
-  for (int i = threadIdx.x; i < V; i += PCG2_THREADS) { double t = 0; for (int b = 0; b < (int)gridDim.x; ++b) t += part[(size_t)b * PCG2_V + i]; S.tot[i] = t; }
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nb = (int)gridDim.x;
+  for (int i = wib; i < V; i += PCG2_THREADS / 32) {
+    double t = 0;
+    for (int b = lane; b < nb; b += 32) t += part[(size_t)b * PCG2_V + i];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) S.tot[i] = t;
+  }
   __syncthreads();
 }
 
@@ -1044,11 +1069,367 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg2_kernel(Pcg2Args A) {
   if (tid == 0) { A.out[0] = (double)it; A.out[1] = sqrt(S.worst); A.out[2] = sqrt(S.bb[0]); }
 }
 
+// ------------------------------------------------------------------------------ PCG v3 (aggregated coarse space)
+// Same block elimination of the intrinsics border as v2, but the coarse space of the two-level
+// preconditioner is piecewise: the cameras are partitioned into aggregates (<= ~16 graph neighbours,
+// built on the host from the camera-pair structure) and every aggregate carries its own copy of the
+// <= 7 gauge generators.  Long camera chains drift by slowly varying similarity transforms — exactly
+// what piecewise-rigid coarse functions capture — so the iteration count stays ~30-70 from 10 to
+// 1000+ cameras where the single global gauge space needs 500-900 (measured, tools/ notes in DESIGN.md).
+//   M^-1 = blockdiag(Scc_pp)^-1 + Wa (Wa' Scc Wa)^-1 Wa',   Wa[(g,m)] = W[m] restricted to aggregate g.
+struct Coarse { const int *agg_of, *agg_start, *agg_cams; int ng, nw, nco; };
+
+// E += Wa' Scc Wa, one thread per S block (a,b): the nw x nw coupling of aggregates g(a), g(b)
+__global__ void coarse_assemble_kernel(const double *__restrict__ Scc, const int *__restrict__ brow, const int *__restrict__ cols, int nnzb,
+                                       const double *__restrict__ W, int n_poses, Coarse C, double *__restrict__ E) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x; if (e >= nnzb) return;
+  const int a = brow[e], b = cols[e];
+  const size_t nc6 = 6 * (size_t)n_poses;
+  double blk[36];
+  #pragma unroll
+  for (int i = 0; i < 36; ++i) blk[i] = Scc[36 * (size_t)e + i];
+  const int ga = C.agg_of[a], gb = C.agg_of[b];
+  for (int m2 = 0; m2 < C.nw; ++m2) {
+    double wb[6], sw[6];
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) wb[k] = W[m2 * nc6 + 6 * b + k];
+    #pragma unroll
+    for (int i = 0; i < 6; ++i) { double v = 0;
+      #pragma unroll
+      for (int k = 0; k < 6; ++k) v += blk[i * 6 + k] * wb[k];
+      sw[i] = v; }
+    for (int m1 = 0; m1 < C.nw; ++m1) {
+      double v = 0;
+      #pragma unroll
+      for (int i = 0; i < 6; ++i) v += W[m1 * nc6 + 6 * a + i] * sw[i];
+      if (v != 0.0) atomicAdd(&E[(size_t)(ga * C.nw + m1) * C.nco + gb * C.nw + m2], v);
+    }
+  }
+}
+
+// Coarse operator setup in ONE cooperative kernel: blocked right-looking Cholesky of the symmetrised
+// E (+ tiny ridge), T = (L^-1)' by one warp per column, Einv = T T' (i.e. L^-T L^-1).  E is <= ~1000^2.
+constexpr int CNB = 32;
+__global__ void __launch_bounds__(256) coarse_setup_kernel(double *__restrict__ E, int n, double *__restrict__ T, double *__restrict__ Einv, int *__restrict__ fail) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double csm[];            // max(CNB*CNB, 8*n) doubles
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gwarp = tid >> 5, nwarps = nt >> 5;
+  __shared__ double s_ridge;
+  // symmetrise (lower <- average) ; ridge
+  for (long long idx = tid; idx < (long long)n * n; idx += nt) { const int i = (int)(idx / n), j = (int)(idx % n); if (j < i) E[(size_t)i * n + j] = 0.5 * (E[(size_t)i * n + j] + E[(size_t)j * n + i]); }
+  if (threadIdx.x == 0) { double mx = 0; for (int i = 0; i < n; ++i) mx = fmax(mx, E[(size_t)i * n + i]); s_ridge = 1e-15 * mx; }
+  grid.sync();
+  const double ridge = s_ridge;
+  for (int kb = 0; kb < n; kb += CNB) {
+    const int nb = min(CNB, n - kb);
+    // (1) every block factors the nb x nb diagonal block redundantly in shared memory (cheap, avoids a broadcast)
+    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) { const int i = idx / nb, j = idx % nb; csm[i * CNB + j] = j <= i ? E[(size_t)(kb + i) * n + kb + j] + (i == j ? ridge : 0.0) : 0.0; }
+    __syncthreads();
+    if (wib == 0) {
+      for (int k = 0; k < nb; ++k) {
+        double d = csm[k * CNB + k];
+        if (!(d > 0.0) || !isfinite(d)) { if (lane == 0 && blockIdx.x == 0) atomicExch(fail, 4); d = 1.0; }
+        d = sqrt(d);
+        __syncwarp();
+        if (lane == 0) csm[k * CNB + k] = d;
+        for (int i = k + 1 + lane; i < nb; i += 32) csm[i * CNB + k] /= d;
+        __syncwarp();
+        for (int i = k + 1 + lane; i < nb; i += 32) { const double lik = csm[i * CNB + k]; for (int j = k + 1; j <= i; ++j) csm[i * CNB + j] -= lik * csm[j * CNB + k]; }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) { const int i = idx / nb, j = idx % nb; if (j <= i) E[(size_t)(kb + i) * n + kb + j] = csm[i * CNB + j]; }
+    // (2) panel: row i below the block solves  L[i, kb:kb+nb] D' = A[i, kb:kb+nb]   (thread per row)
+    for (int i = kb + nb + tid; i < n; i += nt) {
+      double x[CNB];
+      #pragma unroll
+      for (int j = 0; j < CNB; ++j) x[j] = j < nb ? E[(size_t)i * n + kb + j] : 0.0;
+      #pragma unroll
+      for (int j = 0; j < CNB; ++j) if (j < nb) {
+        double v = x[j];
+        #pragma unroll
+        for (int q = 0; q < CNB; ++q) if (q < j) v -= x[q] * csm[j * CNB + q];
+        x[j] = v / csm[j * CNB + j];
+      }
+      #pragma unroll
+      for (int j = 0; j < CNB; ++j) if (j < nb) E[(size_t)i * n + kb + j] = x[j];
+    }
+    grid.sync();
+    // (3) trailing update of the lower triangle: A[i][j] -= L[i,kb:]. L[j,kb:]
+    const int r0 = kb + nb, m = n - r0;
+    for (long long idx = tid; idx < (long long)m * m; idx += nt) {
+      const int i = r0 + (int)(idx / m), j = r0 + (int)(idx % m);
+      if (j > i) continue;
+      const double *li = E + (size_t)i * n + kb, *lj = E + (size_t)j * n + kb;
+      double v = 0;
+      for (int q = 0; q < nb; ++q) v += li[q] * lj[q];
+      E[(size_t)i * n + j] -= v;
+    }
+    grid.sync();
+  }
+  // T[c][i] = (L^-1)[i][c] : forward substitution, one warp per column, x in shared memory
+  for (int c = gwarp; c < n; c += nwarps) {
+    double *x = csm + (size_t)wib * n;
+    for (int i = lane; i < n; i += 32) x[i] = 0.0;
+    __syncwarp();
+    for (int i = c; i < n; ++i) {
+      double v = 0; for (int k = c + lane; k < i; k += 32) v += E[(size_t)i * n + k] * x[k];
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) x[i] = ((i == c ? 1.0 : 0.0) - v) / E[(size_t)i * n + i];
+      __syncwarp();
+    }
+    for (int i = lane; i < n; i += 32) T[(size_t)c * n + i] = x[i];
+    __syncwarp();
+  }
+  grid.sync();
+  // Einv[i][j] = sum_k (L^-1)[k][i] (L^-1)[k][j] = T[i,:].T[j,:]   (entries with k < max(i,j) are zero)
+  for (long long p = gwarp; p < (long long)n * n; p += nwarps) {
+    const int i = (int)(p / n), j = (int)(p % n);
+    if (j > i) continue;
+    const double *ti = T + (size_t)i * n, *tj = T + (size_t)j * n;
+    double v = 0; for (int k = i + lane; k < n; k += 32) v += ti[k] * tj[k];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) { Einv[(size_t)i * n + j] = v; Einv[(size_t)j * n + i] = v; }
+  }
+}
+
+struct Pcg3Args {
+  Pcg2Args base;          // Scc, Sci, Sii, rhs, Minv_c, W, intr_mask, X/Rv/Pv/Wv/Zv, part, z, tol, max_iter, out
+  Coarse C;
+  const double *Einv;     // [nco][nco]
+  double *Cv;             // [MAXRHS][nco] coarse residuals  W_a' r
+  double *Yv;             // [MAXRHS][nco] coarse corrections Einv c
+  double *Pv2;            // second direction buffer (ping-pong with base.Pv)
+};
+
+// w_j = Scc p_j with p_j = z_j + beta_j * pold_j formed ON THE FLY for the gathered columns (so the
+// direction update needs no grid sync of its own); the owner warp of row a stores p_j(a) into pnew and
+// accumulates p_j.w_j over its rows into this warp's reduction slot j.
+__device__ __forceinline__ void spmv_pcg(const Pcg2Args &A, Pcg2Smem &S, const double *__restrict__ Z, const double *__restrict__ Pold,
+                                         double *__restrict__ Pnew, double *__restrict__ Wv, int nv) {
+  const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const size_t nc6 = 6 * (size_t)A.n_poses;
+  for (int a = warp; a < A.n_poses; a += nwarps) {
+    for (int j0 = 0; j0 < nv; j0 += 4) {
+      double acc[4][6];
+      #pragma unroll
+      for (int j = 0; j < 4; ++j)
+        #pragma unroll
+        for (int i = 0; i < 6; ++i) acc[j][i] = 0.0;
+      for (int e = A.rowptr[a] + lane; e < A.rowptr[a + 1]; e += 32) {
+        const double *blk = A.Scc + 36 * (size_t)e; const int cb = 6 * A.cols[e];
+        double b[36];
+        #pragma unroll
+        for (int i = 0; i < 36; ++i) b[i] = blk[i];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j0 + j < nv && !S.done[j0 + j]) {
+            const size_t off = (size_t)(j0 + j) * nc6 + cb; const double bt = S.beta[j0 + j];
+            double xv[6];
+            #pragma unroll
+            for (int k = 0; k < 6; ++k) xv[k] = Z[off + k] + bt * Pold[off + k];
+            #pragma unroll
+            for (int i = 0; i < 6; ++i)
+              #pragma unroll
+              for (int k = 0; k < 6; ++k) acc[j][i] += b[i * 6 + k] * xv[k];
+          }
+        }
+      }
+      #pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j0 + j < nv && !S.done[j0 + j]) {
+          #pragma unroll
+          for (int i = 0; i < 6; ++i) { double v = acc[j][i]; for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o); acc[j][i] = v; }
+          if (lane == 0) {
+            const size_t off = (size_t)(j0 + j) * nc6 + 6 * (size_t)a; const double bt = S.beta[j0 + j];
+            double d = 0;
+            for (int i = 0; i < 6; ++i) { const double pv = Z[off + i] + bt * Pold[off + i]; Pnew[off + i] = pv; Wv[off + i] = acc[j][i]; d += acc[j][i] * pv; }
+            S.wpart[threadIdx.x >> 5][j0 + j] += d;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ unsigned char pcg2_smem_raw[];
+  Pcg2Smem &S = *reinterpret_cast<Pcg2Smem *>(pcg2_smem_raw);
+  const Pcg2Args &A = P.base; const Coarse &C = P.C;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, gwarp = tid >> 5, nwarps = nt >> 5;
+  const size_t nc6 = 6 * (size_t)A.n_poses;
+  const int nw = C.nw, nco = C.nco;
+  if (threadIdx.x == 0) {
+    int n = 1; S.rhs_col[0] = -1;
+    for (int q = 0; q < A.ni8; ++q) if ((A.intr_mask[q / KI] >> (q % KI)) & 1) { if (n < MAXRHS) S.rhs_col[n++] = q; }
+    S.nrhs = n;
+  }
+  __syncthreads();
+  const int nrhs = S.nrhs;
+  double *Pcur = A.Pv, *Pnext = P.Pv2;
+  // ---- init (aggregate-owned elements): X = 0, P = 0, R = B, |b|^2, coarse residual
+  vsum_begin(S, nrhs);
+  for (int g = gwarp; g < C.ng; g += nwarps) {
+    const int c0 = C.agg_start[g], ne = 6 * (C.agg_start[g + 1] - c0);
+    for (int j = 0; j < nrhs; ++j) {
+      const double *src = j == 0 ? A.rhs : A.Sci + (size_t)S.rhs_col[j] * nc6;
+      double v = 0;
+      double cm[MAXW];
+      #pragma unroll
+      for (int m = 0; m < MAXW; ++m) cm[m] = 0.0;
+      for (int idx = lane; idx < ne; idx += 32) {
+        const size_t e = 6 * (size_t)C.agg_cams[c0 + idx / 6] + idx % 6; const double b = src[e];
+        A.X[j * nc6 + e] = 0.0; Pcur[j * nc6 + e] = 0.0; A.Rv[j * nc6 + e] = b; v += b * b;
+        #pragma unroll
+        for (int m = 0; m < MAXW; ++m) if (m < nw) cm[m] += A.W[m * nc6 + e] * b;
+      }
+      warp_acc(S, v, j);
+      #pragma unroll
+      for (int m = 0; m < MAXW; ++m) if (m < nw) {
+        double cv = cm[m]; for (int o = 16; o > 0; o >>= 1) cv += __shfl_xor_sync(0xffffffffu, cv, o);
+        if (lane == 0) P.Cv[(size_t)j * nco + g * nw + m] = cv;
+      }
+    }
+  }
+  vsum_end(grid, S, nrhs, A.part);
+  if (threadIdx.x < nrhs) { const int j = threadIdx.x; S.bb[j] = S.tot[j]; S.done[j] = !(S.tot[j] > 0.0); S.alpha[j] = 0; S.beta[j] = 0; S.rz[j] = 0; }
+  if (threadIdx.x == 0) { S.worst = 0; S.all_done = 0; }
+  __syncthreads();
+  int it = 0;
+  for (;;) {
+    // (y) coarse solve  Y_j = Einv C_j, rows distributed over all warps (Einv row read once for all j)
+    if (nco > 0) {
+      for (int row = gwarp; row < nco; row += nwarps) {
+        const double *er = P.Einv + (size_t)row * nco;
+        for (int j0 = 0; j0 < nrhs; j0 += 4) {
+          double acc[4] = {0, 0, 0, 0};
+          for (int k = lane; k < nco; k += 32) {
+            const double ev = er[k];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) if (j0 + j < nrhs) acc[j] += ev * P.Cv[(size_t)(j0 + j) * nco + k];
+          }
+          #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double v = acc[j]; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && j0 + j < nrhs) P.Yv[(size_t)(j0 + j) * nco + row] = v;
+          }
+        }
+      }
+      grid.sync();
+    }
+    // (b) z = Minv r + Wa y ;  r'z
+    vsum_begin(S, nrhs);
+    for (int g = gwarp; g < C.ng; g += nwarps) {
+      const int c0 = C.agg_start[g], ne = 6 * (C.agg_start[g + 1] - c0);
+      for (int j = 0; j < nrhs; ++j) {
+        if (S.done[j]) continue;
+        double y[MAXW];
+        #pragma unroll
+        for (int m = 0; m < MAXW; ++m) y[m] = m < nw ? P.Yv[(size_t)j * nco + g * nw + m] : 0.0;
+        double rzp = 0;
+        for (int idx = lane; idx < ne; idx += 32) {
+          const size_t cam = C.agg_cams[c0 + idx / 6]; const int k = idx % 6; const size_t e = 6 * cam + k;
+          const double *M = A.Minv_c + 36 * cam + 6 * k; const double *rb = A.Rv + j * nc6 + 6 * cam;
+          double zz = M[0] * rb[0] + M[1] * rb[1] + M[2] * rb[2] + M[3] * rb[3] + M[4] * rb[4] + M[5] * rb[5];
+          #pragma unroll
+          for (int m = 0; m < MAXW; ++m) if (m < nw) zz += A.W[m * nc6 + e] * y[m];
+          A.Zv[j * nc6 + e] = zz; rzp += zz * rb[k];
+        }
+        warp_acc(S, rzp, j);
+      }
+    }
+    vsum_end(grid, S, nrhs, A.part);
+    if (threadIdx.x < nrhs) { const int j = threadIdx.x; if (!S.done[j]) { const double rzn = S.tot[j]; S.beta[j] = it == 0 ? 0.0 : rzn / S.rz[j]; S.rz[j] = rzn; } }
+    __syncthreads();
+    if (it >= A.max_iter) break;
+    // (c+d) p = z + beta p (on the fly) ; w = Scc p ; p'w
+    vsum_begin(S, nrhs);
+    spmv_pcg(A, S, A.Zv, Pcur, Pnext, A.Wv, nrhs);
+    vsum_end(grid, S, nrhs, A.part);
+    { double *t2 = Pcur; Pcur = Pnext; Pnext = t2; }
+    if (threadIdx.x < nrhs) { const int j = threadIdx.x; S.alpha[j] = S.done[j] ? 0.0 : S.rz[j] / S.tot[j]; }
+    __syncthreads();
+    // (e) x += alpha p ; r -= alpha w ; |r|^2 ; coarse residual of the new r
+    vsum_begin(S, nrhs);
+    for (int g = gwarp; g < C.ng; g += nwarps) {
+      const int c0 = C.agg_start[g], ne = 6 * (C.agg_start[g + 1] - c0);
+      for (int j = 0; j < nrhs; ++j) {
+        if (S.done[j]) continue;
+        const double al = S.alpha[j]; double v = 0;
+        double cm[MAXW];
+        #pragma unroll
+        for (int m = 0; m < MAXW; ++m) cm[m] = 0.0;
+        for (int idx = lane; idx < ne; idx += 32) {
+          const size_t e = 6 * (size_t)C.agg_cams[c0 + idx / 6] + idx % 6;
+          A.X[j * nc6 + e] += al * Pcur[j * nc6 + e];
+          const double rn = A.Rv[j * nc6 + e] - al * A.Wv[j * nc6 + e]; A.Rv[j * nc6 + e] = rn; v += rn * rn;
+          #pragma unroll
+          for (int m = 0; m < MAXW; ++m) if (m < nw) cm[m] += A.W[m * nc6 + e] * rn;
+        }
+        warp_acc(S, v, j);
+        #pragma unroll
+        for (int m = 0; m < MAXW; ++m) if (m < nw) {
+          double cv = cm[m]; for (int o = 16; o > 0; o >>= 1) cv += __shfl_xor_sync(0xffffffffu, cv, o);
+          if (lane == 0) P.Cv[(size_t)j * nco + g * nw + m] = cv;
+        }
+      }
+    }
+    vsum_end(grid, S, nrhs, A.part);                // its grid.sync publishes Cv as well
+    ++it;
+    if (threadIdx.x == 0) {
+      int ad = 1; double wmax = 0;
+      for (int j = 0; j < nrhs; ++j) if (!S.done[j]) { const double rel2 = S.tot[j] / S.bb[j]; wmax = fmax(wmax, rel2); if (!(rel2 > A.tol * A.tol)) S.done[j] = 1; else ad = 0; }
+      S.all_done = ad; S.worst = wmax;
+    }
+    __syncthreads();
+    if (S.all_done) break;
+  }
+  // ---- border: (Sii - Sci Y2) zi = bi - Sci y1 ; zc = y1 - Y2 zi
+  const int k = nrhs - 1;
+  if (k > 0) {
+    for (int a = 0; a < k; ++a) {
+      vsum_begin(S, k + 1);
+      const double *row = A.Sci + (size_t)S.rhs_col[1 + a] * nc6;
+      for (int b = 0; b <= k; ++b) {
+        const double *x = A.X + (size_t)(b == k ? 0 : 1 + b) * nc6;
+        double v = 0; for (size_t i = tid; i < nc6; i += nt) v += row[i] * x[i];
+        warp_acc(S, v, b);
+      }
+      vsum_end(grid, S, k + 1, A.part);
+      if (threadIdx.x <= k) {
+        const int b = threadIdx.x;
+        if (b < k) S.T[a][b] = A.Sii[(size_t)S.rhs_col[1 + a] * A.ni8 + S.rhs_col[1 + b]] - S.tot[b];
+        else S.T[a][k] = A.rhs[nc6 + S.rhs_col[1 + a]] - S.tot[k];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      for (int a = 0; a < k; ++a) for (int b = a + 1; b < k; ++b) { const double m = 0.5 * (S.T[a][b] + S.T[b][a]); S.T[a][b] = m; S.T[b][a] = m; }
+      for (int c = 0; c < k; ++c) {
+        int piv = c; for (int r2 = c + 1; r2 < k; ++r2) if (fabs(S.T[r2][c]) > fabs(S.T[piv][c])) piv = r2;
+        if (piv != c) for (int q = 0; q <= k; ++q) { const double t2 = S.T[c][q]; S.T[c][q] = S.T[piv][q]; S.T[piv][q] = t2; }
+        for (int r2 = c + 1; r2 < k; ++r2) { const double f = S.T[r2][c] / S.T[c][c]; for (int q = c; q <= k; ++q) S.T[r2][q] -= f * S.T[c][q]; }
+      }
+      for (int c = k - 1; c >= 0; --c) { double sacc = S.T[c][k]; for (int q = c + 1; q < k; ++q) sacc -= S.T[c][q] * S.zi[q]; S.zi[c] = sacc / S.T[c][c]; }
+    }
+    __syncthreads();
+  }
+  for (size_t i = tid; i < nc6; i += nt) { double v = A.X[i]; for (int a = 0; a < k; ++a) v -= A.X[(size_t)(1 + a) * nc6 + i] * S.zi[a]; A.z[i] = v; }
+  for (int q = tid; q < A.ni8; q += nt) { double v = 0; for (int a = 0; a < k; ++a) if (S.rhs_col[1 + a] == q) v = S.zi[a]; A.z[nc6 + q] = v; }
+  if (tid == 0) { A.out[0] = (double)it; A.out[1] = sqrt(S.worst); A.out[2] = sqrt(S.bb[0]); }
+}
+
 // ------------------------------------------------------------------------------ back substitution
 // y_pt = Einv (Etb - sum_obs EtFc z_c + EtFi z_i) ; step = -y  (levenberg_marquardt_strategy.cc:120)
 __global__ void backsub_kernel(const double *__restrict__ Jp, const double *__restrict__ Jc, const double *__restrict__ Ji,
                                const double *__restrict__ Etb, const double *__restrict__ Einv, const int *__restrict__ obs_pose,
-                               const int *__restrict__ obs_intr, const int *__restrict__ pt_start, int n_points, int n_poses, long long n,
+                               const int *__restrict__ obs_intr, const int *__restrict__ pt_start, int n_points, int n_poses, long long n, int kiu,
                                const double *__restrict__ z, int pts_free, double *__restrict__ step_pt) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n_points) return;
   if (!pts_free || pt_start[j] == pt_start[j + 1]) { step_pt[3 * j] = step_pt[3 * j + 1] = step_pt[3 * j + 2] = 0.0; return; }
@@ -1059,7 +1440,7 @@ __global__ void backsub_kernel(const double *__restrict__ Jp, const double *__re
     #pragma unroll
     for (int k = 0; k < 6; ++k) { f0 += Jc[k * n + o] * zc[k]; f1 += Jc[(6 + k) * n + o] * zc[k]; }
     #pragma unroll
-    for (int k = 0; k < KI; ++k) { f0 += Ji[k * n + o] * zi[k]; f1 += Ji[(KI + k) * n + o] * zi[k]; }
+    for (int k = 0; k < KI; ++k) if (k < kiu) { f0 += Ji[k * n + o] * zi[k]; f1 += Ji[(KI + k) * n + o] * zi[k]; }
     b0 -= Jp[0 * n + o] * f0 + Jp[3 * n + o] * f1; b1 -= Jp[1 * n + o] * f0 + Jp[4 * n + o] * f1; b2 -= Jp[2 * n + o] * f0 + Jp[5 * n + o] * f1;
   }
   const double *I = Einv + 9 * (size_t)j;
@@ -1070,7 +1451,7 @@ __global__ void negate_kernel(const double *__restrict__ z, int n, double *__res
 // model_cost_change partials: - m . (r + m/2), m = J step    (trust_region_minimizer.cc:402-405)
 constexpr int MODEL_THREADS = 128;
 __global__ void __launch_bounds__(MODEL_THREADS) model_kernel(const double *__restrict__ r, const double *__restrict__ Jp, const double *__restrict__ Jc, const double *__restrict__ Ji,
-                             const int *__restrict__ obs_pose, const int *__restrict__ obs_intr, const int *__restrict__ obs_pt, long long n, int n_poses,
+                             const int *__restrict__ obs_pose, const int *__restrict__ obs_intr, const int *__restrict__ obs_pt, long long n, int n_poses, int kiu,
                              const double *__restrict__ step_pt, const double *__restrict__ step_red, double *__restrict__ part) {
   __shared__ double sh[MODEL_THREADS / 32];
   const long long o = (long long)blockIdx.x * MODEL_THREADS + threadIdx.x;
@@ -1085,7 +1466,7 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_kernel(const double *__re
       #pragma unroll
       for (int k = 0; k < 6; ++k) m += Jc[(row * 6 + k) * n + o] * sc[k];
       #pragma unroll
-      for (int k = 0; k < KI; ++k) m += Ji[(row * KI + k) * n + o] * si[k];
+      for (int k = 0; k < KI; ++k) if (k < kiu) m += Ji[(row * KI + k) * n + o] * si[k];
       v += -m * (r[row * n + o] + m / 2.0);
     }
   }

@@ -41,16 +41,19 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
   public:
   struct BA_B200_options            // the knobs of BA_Ceres_options that still mean something here
   {
-    bool bVerbose_ = false;
-    bool bUse_loss_function_ = true;
-    unsigned int max_num_iterations_ = 50;
-    double parameter_tolerance_ = 1e-8;
-    double gradient_tolerance_ = 1e-10;
-    int device_ = 0;
+    BA_B200_options()
+      : bVerbose_(false), bUse_loss_function_(true), max_num_iterations_(50),
+        parameter_tolerance_(1e-8), gradient_tolerance_(1e-10), device_(0) {}
+    bool bVerbose_;
+    bool bUse_loss_function_;
+    unsigned int max_num_iterations_;
+    double parameter_tolerance_;
+    double gradient_tolerance_;
+    int device_;
   };
 
-  explicit Bundle_Adjustment_B200(const BA_B200_options & options = BA_B200_options())
-    : options_(options) {}
+  Bundle_Adjustment_B200() {}
+  explicit Bundle_Adjustment_B200(const BA_B200_options & options) : options_(options) {}
 
   BA_B200_options & b200_options() { return options_; }
   const omvg_ba_summary & summary() const { return summary_; }

@@ -1,0 +1,152 @@
+// dropin_test.cpp — the drop-in boundary exercised through openMVG's OWN types.
+//
+// TEST INFRASTRUCTURE ONLY.  Links the reference's compiled code (oracle/_ref objects) and
+// libomvg_b200.so, then runs, on identical inputs,
+//   reference  Matcher_Regions(0.8f, BRUTE_FORCE_L2)::Match   vs   Matcher_Regions_B200::Match
+//   reference  Bundle_Adjustment_Ceres::Adjust                vs   Bundle_Adjustment_B200::Adjust
+// through the abstract interfaces Matcher (matching_image_collection/Matcher.hpp:34-48) and
+// Bundle_Adjustment (sfm/sfm_data_BA.hpp:91-105).  MATCH must be identical; BA final Huber cost
+// must agree to 1e-6 relative.  Needs a B200; run by tests/test_dropin_gpu.py on the GPU box.
+#include "openMVG/cameras/cameras.hpp"
+#include "openMVG/features/regions_factory.hpp"
+#include "openMVG/matching_image_collection/Matcher_Regions.hpp"
+#include "openMVG/numeric/numeric.h"
+#include "openMVG/sfm/sfm_data.hpp"
+#include "openMVG/sfm/sfm_data_BA_ceres.hpp"
+
+#include "../openmvg_b200/host/Bundle_Adjustment_B200.hpp"
+#include "../openmvg_b200/host/Matcher_Regions_B200.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <random>
+
+using namespace openMVG;
+using namespace openMVG::cameras;
+using namespace openMVG::geometry;
+using namespace openMVG::sfm;
+
+namespace {
+
+struct InMemory_Regions_Provider : public sfm::Regions_Provider
+{
+  void set(IndexT id, std::shared_ptr<features::Regions> r) { cache_[id] = std::move(r); }
+  void set_type(features::Regions * r) { region_type_.reset(r); }
+};
+
+std::shared_ptr<features::SIFT_Regions> random_regions(int n, unsigned seed, const features::SIFT_Regions * base)
+{
+  std::mt19937 g(seed);
+  std::uniform_int_distribution<int> u(0, 255), nz(-8, 8);
+  std::uniform_real_distribution<double> p(0, 1);
+  auto r = std::make_shared<features::SIFT_Regions>();
+  r->Features().resize(n); r->Descriptors().resize(n);
+  for (int i = 0; i < n; ++i) {
+    r->Features()[i] = features::SIOPointFeature(float(i), float(i), 1.f, 0.f);
+    if (base && i < int(base->RegionCount()) && p(g) < 0.3)
+      for (int k = 0; k < 128; ++k) { const int v = int(base->Descriptors()[i][k]) + nz(g); r->Descriptors()[i][k] = (unsigned char)std::min(255, std::max(0, v)); }
+    else
+      for (int k = 0; k < 128; ++k) r->Descriptors()[i][k] = (unsigned char)(u(g) * u(g) / 255);
+  }
+  return r;
+}
+
+double huber_cost(const SfM_Data & s)
+{
+  long double c = 0;
+  for (const auto & l : s.structure)
+    for (const auto & o : l.second.obs) {
+      const View * v = s.views.at(o.first).get();
+      const Vec2 r = s.intrinsics.at(v->id_intrinsic)->residual(s.poses.at(v->id_pose)(l.second.X), o.second.x);
+      const double sq = r.squaredNorm();
+      c += 0.5 * (sq <= 256.0 ? sq : 32.0 * std::sqrt(sq) - 256.0);
+    }
+  return double(c);
+}
+
+SfM_Data make_scene(int C, int P, int K)
+{
+  std::mt19937 g(42);
+  std::uniform_real_distribution<double> U(-0.6, 0.6);
+  std::normal_distribution<double> N(0, 1);
+  SfM_Data s;
+  const double f = 1000, cx = 500, cy = 500;
+  s.intrinsics[7] = std::make_shared<Pinhole_Intrinsic>(1000, 1000, f, cx, cy);     // non-dense ids on purpose
+  std::vector<Pose3> gt(C);
+  for (int i = 0; i < C; ++i) {
+    const double th = i * 2 * M_PI / C;
+    const Vec3 c(1.5 * std::sin(th), 0.2 * std::sin(3 * th), 1.5 * std::cos(th));
+    const Mat3 R = LookAt(Vec3(-c));
+    gt[i] = Pose3(R, c);
+    s.views[10 + i] = std::make_shared<View>("", 10 + i, 7, 100 + i, 1000, 1000);
+    const Vec3 aa(N(g) * 0.005, N(g) * 0.005, N(g) * 0.005);
+    const Mat3 dR = Eigen::AngleAxisd(aa.norm(), aa.normalized()).toRotationMatrix();
+    s.poses[100 + i] = Pose3(dR * R, c + Vec3(N(g), N(g), N(g)) * 0.005);
+  }
+  std::uniform_int_distribution<int> start(0, C - 1);
+  for (int j = 0; j < P; ++j) {
+    const Vec3 X(U(g), U(g), U(g));
+    Landmark L;
+    const int s0 = start(g);
+    for (int k = 0; k < K; ++k) {
+      const int i = (s0 + k) % C;
+      const Vec3 Xc = gt[i](X);
+      L.obs[10 + i] = Observation(Vec2(cx + f * Xc(0) / Xc(2) + 0.5 * N(g), cy + f * Xc(1) / Xc(2) + 0.5 * N(g)), j);
+    }
+    L.X = X + Vec3(N(g), N(g), N(g)) * 0.01;
+    s.structure[1000 + j] = L;
+  }
+  return s;
+}
+
+}  // namespace
+
+int main()
+{
+  int failures = 0;
+  // ------------------------------------------------------------------ MATCH
+  {
+    auto provider = std::make_shared<InMemory_Regions_Provider>();
+    provider->set_type(new features::SIFT_Regions);
+    const int counts[5] = {700, 650, 0, 300, 1};
+    std::shared_ptr<features::SIFT_Regions> prev;
+    for (int k = 0; k < 5; ++k) { auto r = random_regions(counts[k], 100 + k, prev.get()); provider->set(3 * k + 1, r); if (counts[k] > 1) prev = r; }
+    Pair_Set pairs;
+    for (int a = 0; a < 5; ++a) for (int b = a + 1; b < 5; ++b) pairs.insert({3 * a + 1, 3 * b + 1});
+    matching::PairWiseMatches ref, ours;
+    std::unique_ptr<matching_image_collection::Matcher> m_ref(new matching_image_collection::Matcher_Regions(0.8f, matching::BRUTE_FORCE_L2));
+    std::unique_ptr<matching_image_collection::Matcher> m_b200(new matching_image_collection::Matcher_Regions_B200(0.8f));
+    m_ref->Match(provider, pairs, ref, nullptr);
+    m_b200->Match(provider, pairs, ours, nullptr);
+    bool same = ref.size() == ours.size();
+    size_t total = 0;
+    for (const auto & kv : ref) {
+      const auto it = ours.find(kv.first);
+      if (it == ours.end() || it->second.size() != kv.second.size()) { same = false; break; }
+      for (size_t i = 0; i < kv.second.size(); ++i)
+        if (kv.second[i].i_ != it->second[i].i_ || kv.second[i].j_ != it->second[i].j_) { same = false; break; }
+      total += kv.second.size();
+    }
+    std::printf("MATCH drop-in: %zu pairs with matches, %zu matches, %s\n", ref.size(), total, same ? "IDENTICAL" : "DIFFERENT");
+    if (!same || total == 0) ++failures;
+  }
+  // ------------------------------------------------------------------ BA
+  {
+    SfM_Data a = make_scene(24, 1200, 6), b = a;
+    // deep-copy the shared intrinsic so the two runs do not alias
+    b.intrinsics[7] = std::shared_ptr<IntrinsicBase>(a.intrinsics.at(7)->clone());
+    const double c0 = huber_cost(a);
+    std::unique_ptr<Bundle_Adjustment> ba_ref(new Bundle_Adjustment_Ceres(Bundle_Adjustment_Ceres::BA_Ceres_options(false, true)));
+    std::unique_ptr<Bundle_Adjustment> ba_b200(new Bundle_Adjustment_B200());
+    const Optimize_Options opt(Intrinsic_Parameter_Type::ADJUST_ALL, Extrinsic_Parameter_Type::ADJUST_ALL, Structure_Parameter_Type::ADJUST_ALL);
+    const bool ok_ref = ba_ref->Adjust(a, opt);
+    const bool ok_b200 = ba_b200->Adjust(b, opt);
+    const double ca = huber_cost(a), cb = huber_cost(b);
+    const double rel = std::fabs(ca - cb) / ca;
+    std::printf("BA drop-in: initial %.6f  reference %.9f  B200 %.9f  rel %.3e  ok %d/%d\n", c0, ca, cb, rel, int(ok_ref), int(ok_b200));
+    if (!ok_ref || !ok_b200 || !(rel <= 1e-6) || !(ca < c0)) ++failures;
+  }
+  std::printf(failures ? "DROPIN FAILED\n" : "DROPIN OK\n");
+  return failures;
+}
