@@ -456,7 +456,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
         if (nco > 0) {
           OMVG_CUDA(cudaMemsetAsync(c->cE.p, 0, (size_t)nco * nco * sizeof(double), c->stream));
           coarse_assemble_kernel<<<(c->nnzb + 127) / 128, 128, 0, c->stream>>>(c->Scc.p, c->brow.p, c->cols.p, c->nnzb, c->gW.p, c->nc, P3.C, c->cE.p); LAUNCH_CHECK();
-          { const size_t sm = sizeof(double) * std::max<size_t>((size_t)CNB * CNB, (size_t)8 * nco);
+          { const size_t sm = sizeof(double) * ((size_t)CNB * CNB + 2 * CT * (CNB + 1) + 2 * CT * (CT + 1));
             OMVG_CUDA(cudaFuncSetAttribute(coarse_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             double *Ep = c->cE.p, *Tp = c->cT.p, *Ip = c->cEinv.p; int nn = nco; int *fp = c->fail.p;
             void *cargs[] = {&Ep, &nn, &Tp, &Ip, &fp};

@@ -184,12 +184,12 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
   const long long o = (long long)blockIdx.x * EVAL_THREADS + threadIdx.x;
   double cost = 0.0;
   if (o < A.n_obs) {
-    const int ip = A.obs_pose[o], iq = A.obs_intr[o], j = A.obs_pt[o];
+    const int ip = __ldcs(A.obs_pose + o), iq = __ldcs(A.obs_intr + o), j = __ldcs(A.obs_pt + o);
     double R[CAMREC];
     { const double2 *rp = reinterpret_cast<const double2 *>(A.camrec + (size_t)CAMREC * ip);
       #pragma unroll
       for (int q = 0; q < CAMREC / 2; ++q) { const double2 v = __ldg(rp + q); R[2 * q] = v.x; R[2 * q + 1] = v.y; } }
-    const double X0 = A.pts[3 * j], X1 = A.pts[3 * j + 1], X2 = A.pts[3 * j + 2];
+    const double X0 = __ldg(A.pts + 3 * j), X1 = __ldg(A.pts + 3 * j + 1), X2 = __ldg(A.pts + 3 * j + 2);
     const double *T = R + 18;
     const double p0 = R[0] * X0 + R[1] * X1 + R[2] * X2 + T[0];
     const double p1 = R[3] * X0 + R[4] * X1 + R[5] * X2 + T[1];
@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
     double dx, dy, dd[4], dk[10];
     distort(model, K, x, y, dx, dy, dd, dk, WANT_J);
     const double f = K[0];
-    double r0 = K[1] + dx * f - A.obs_xy[2 * o], r1 = K[2] + dy * f - A.obs_xy[2 * o + 1];
+    const double2 xy = __ldcs(reinterpret_cast<const double2 *>(A.obs_xy) + o);
+    double r0 = K[1] + dx * f - xy.x, r1 = K[2] + dy * f - xy.y;
     const double s = r0 * r0 + r1 * r1;
     double rho0 = s, rho1 = 1.0;
     const double b = A.huber_a * A.huber_a;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
     if (WANT_J) {
       const double w = sqrt(rho1);                              // Huber: rho'' <= 0 => r, J scaled by sqrt(rho')
       const long long n = A.n_obs;
-      A.r[o] = w * r0; A.r[n + o] = w * r1;
+      __stcs(A.r + o, w * r0); __stcs(A.r + n + o, w * r1);
       // d r / d u = f * dd ; d u / d p = [[iz,0,-x iz],[0,iz,-y iz]]
       const double a00 = w * f * dd[0], a01 = w * f * dd[1], a10 = w * f * dd[2], a11 = w * f * dd[3];
       double g[6];                                              // d r / d p (2x3)
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
       #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const double sc = A.pts_free ? (A.sc_pt ? A.sc_pt[3 * j + c] : 1.0) : 0.0;
-        A.Jp[(0 * 3 + c) * n + o] = sc * (g[0] * R[c] + g[1] * R[3 + c] + g[2] * R[6 + c]);
-        A.Jp[(1 * 3 + c) * n + o] = sc * (g[3] * R[c] + g[4] * R[3 + c] + g[5] * R[6 + c]);
+        __stcs(A.Jp + (0 * 3 + c) * n + o, sc * (g[0] * R[c] + g[1] * R[3 + c] + g[2] * R[6 + c]));
+        __stcs(A.Jp + (1 * 3 + c) * n + o, sc * (g[3] * R[c] + g[4] * R[3 + c] + g[5] * R[6 + c]));
       }
       // pose block: rotation columns g * (dR_k X), translation columns g
       #pragma unroll
@@ -232,11 +233,11 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
         const double q1 = R[3] * v0 + R[4] * v1 + R[5] * v2;
         const double q2 = R[6] * v0 + R[7] * v1 + R[8] * v2;
         const double sc = ((A.pose_mask >> k) & 1) ? (A.sc_cam ? A.sc_cam[6 * ip + k] : 1.0) : 0.0;
-        A.Jc[(0 * 6 + k) * n + o] = sc * (g[0] * q0 + g[1] * q1 + g[2] * q2);
-        A.Jc[(1 * 6 + k) * n + o] = sc * (g[3] * q0 + g[4] * q1 + g[5] * q2);
+        __stcs(A.Jc + (0 * 6 + k) * n + o, sc * (g[0] * q0 + g[1] * q1 + g[2] * q2));
+        __stcs(A.Jc + (1 * 6 + k) * n + o, sc * (g[3] * q0 + g[4] * q1 + g[5] * q2));
         const double st = ((A.pose_mask >> (3 + k)) & 1) ? (A.sc_cam ? A.sc_cam[6 * ip + 3 + k] : 1.0) : 0.0;
-        A.Jc[(0 * 6 + 3 + k) * n + o] = st * g[k];
-        A.Jc[(1 * 6 + 3 + k) * n + o] = st * g[3 + k];
+        __stcs(A.Jc + (0 * 6 + 3 + k) * n + o, st * g[k]);
+        __stcs(A.Jc + (1 * 6 + 3 + k) * n + o, st * g[3 + k]);
       }
       // intrinsic block: [f, ppx, ppy, K3..K7]
       const unsigned im = A.intr_mask[iq];
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
       #pragma unroll
       for (int k = 0; k < KI; ++k) {
         const double sc = ((im >> k) & 1) ? (A.sc_intr ? A.sc_intr[KI * iq + k] : 1.0) : 0.0;
-        if (k < A.kiu) { A.Ji[(0 * KI + k) * n + o] = sc * ji0[k]; A.Ji[(1 * KI + k) * n + o] = sc * ji1[k]; }
+        if (k < A.kiu) { __stcs(A.Ji + (0 * KI + k) * n + o, sc * ji0[k]); __stcs(A.Ji + (1 * KI + k) * n + o, sc * ji1[k]); }
       }
     }
   }
@@ -1108,22 +1109,69 @@ __global__ void coarse_assemble_kernel(const double *__restrict__ Scc, const int
 }
 
 // Coarse operator setup in ONE cooperative kernel: blocked right-looking Cholesky of the symmetrised
-// E (+ tiny ridge), T = (L^-1)' by one warp per column, Einv = T T' (i.e. L^-T L^-1).  E is <= ~1000^2.
-constexpr int CNB = 32;
+// E (+ tiny ridge) with a shared-memory tiled trailing update, T = (L^-1)' by one warp per column,
+// Einv = T T' (= L^-T L^-1) with the same tiled product.  E is <= ~1000^2, FP64 on the CUDA cores.
+constexpr int CNB = 32;          // panel width
+constexpr int CT = 64;           // output tile
+// C[i][j] (-)= sum_{k in [k0,k1)} A[i][k] B[j][k] for the CT x CT tile at (i0,j0); 256 threads, 4x4 outputs each
+// (rows i0 + ty + 16 q, cols j0 + tx + 16 q: conflict-free shared-memory reads).  sm: 2 * CT * (CNB+1) doubles.
+// MODE 0: C[i][j] -= acc (lower part), 1: C[i][j] = C[j][i] = acc (lower part, mirrored), 2: full tile to shared Cs[64][65]
+template <int MODE>
+__device__ __forceinline__ void tile_abt(double *__restrict__ C, const double *__restrict__ A, const double *__restrict__ B, int n,
+                                         int i0, int j0, int k0, int k1, double *sm) {
+  double (*As)[CNB + 1] = reinterpret_cast<double (*)[CNB + 1]>(sm);
+  double (*Bs)[CNB + 1] = reinterpret_cast<double (*)[CNB + 1]>(sm + CT * (CNB + 1));
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+  #pragma unroll
+  for (int p = 0; p < 4; ++p)
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+  for (int kp = k0; kp < k1; kp += CNB) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < CT * CNB; idx += 256) {
+      const int rr = idx / CNB, cc = idx % CNB, k = kp + cc;
+      As[rr][cc] = (i0 + rr < n && k < k1) ? A[(size_t)(i0 + rr) * n + k] : 0.0;
+      Bs[rr][cc] = (j0 + rr < n && k < k1) ? B[(size_t)(j0 + rr) * n + k] : 0.0;
+    }
+    __syncthreads();
+    #pragma unroll 8
+    for (int kk = 0; kk < CNB; ++kk) {
+      double av[4], bv[4];
+      #pragma unroll
+      for (int p = 0; p < 4; ++p) { av[p] = As[ty + 16 * p][kk]; bv[p] = Bs[tx + 16 * p][kk]; }
+      #pragma unroll
+      for (int p = 0; p < 4; ++p)
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] += av[p] * bv[q];
+    }
+  }
+  #pragma unroll
+  for (int p = 0; p < 4; ++p)
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + ty + 16 * p, j = j0 + tx + 16 * q;
+      if (MODE == 2) { C[(ty + 16 * p) * (CT + 1) + tx + 16 * q] = acc[p][q]; }
+      else if (i < n && j < n && j <= i) {
+        if (MODE == 0) C[(size_t)i * n + j] -= acc[p][q]; else { C[(size_t)i * n + j] = acc[p][q]; C[(size_t)j * n + i] = acc[p][q]; }
+      }
+    }
+}
+
 __global__ void __launch_bounds__(256) coarse_setup_kernel(double *__restrict__ E, int n, double *__restrict__ T, double *__restrict__ Einv, int *__restrict__ fail) {
   cg::grid_group grid = cg::this_grid();
-  extern __shared__ double csm[];            // max(CNB*CNB, 8*n) doubles
+  extern __shared__ double csm[];            // CNB*CNB + 2*CT*(CNB+1) + 2*CT*(CT+1) doubles
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gwarp = tid >> 5, nwarps = nt >> 5;
+  double *tsm = csm + CNB * CNB;
   __shared__ double s_ridge;
-  // symmetrise (lower <- average) ; ridge
   for (long long idx = tid; idx < (long long)n * n; idx += nt) { const int i = (int)(idx / n), j = (int)(idx % n); if (j < i) E[(size_t)i * n + j] = 0.5 * (E[(size_t)i * n + j] + E[(size_t)j * n + i]); }
   if (threadIdx.x == 0) { double mx = 0; for (int i = 0; i < n; ++i) mx = fmax(mx, E[(size_t)i * n + i]); s_ridge = 1e-15 * mx; }
   grid.sync();
   const double ridge = s_ridge;
   for (int kb = 0; kb < n; kb += CNB) {
     const int nb = min(CNB, n - kb);
-    // (1) every block factors the nb x nb diagonal block redundantly in shared memory (cheap, avoids a broadcast)
+    // (1) every block factors the nb x nb diagonal block redundantly in shared memory
     for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) { const int i = idx / nb, j = idx % nb; csm[i * CNB + j] = j <= i ? E[(size_t)(kb + i) * n + kb + j] + (i == j ? ridge : 0.0) : 0.0; }
     __syncthreads();
     if (wib == 0) {
@@ -1141,7 +1189,7 @@ __global__ void __launch_bounds__(256) coarse_setup_kernel(double *__restrict__ 
     }
     __syncthreads();
     if (blockIdx.x == 0) for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) { const int i = idx / nb, j = idx % nb; if (j <= i) E[(size_t)(kb + i) * n + kb + j] = csm[i * CNB + j]; }
-    // (2) panel: row i below the block solves  L[i, kb:kb+nb] D' = A[i, kb:kb+nb]   (thread per row)
+    // (2) panel: L[i, kb:kb+nb] = A[i, kb:kb+nb] D^-T, one thread per row below the block
     for (int i = kb + nb + tid; i < n; i += nt) {
       double x[CNB];
       #pragma unroll
@@ -1157,44 +1205,64 @@ __global__ void __launch_bounds__(256) coarse_setup_kernel(double *__restrict__ 
       for (int j = 0; j < CNB; ++j) if (j < nb) E[(size_t)i * n + kb + j] = x[j];
     }
     grid.sync();
-    // (3) trailing update of the lower triangle: A[i][j] -= L[i,kb:]. L[j,kb:]
-    const int r0 = kb + nb, m = n - r0;
-    for (long long idx = tid; idx < (long long)m * m; idx += nt) {
-      const int i = r0 + (int)(idx / m), j = r0 + (int)(idx % m);
-      if (j > i) continue;
-      const double *li = E + (size_t)i * n + kb, *lj = E + (size_t)j * n + kb;
-      double v = 0;
-      for (int q = 0; q < nb; ++q) v += li[q] * lj[q];
-      E[(size_t)i * n + j] -= v;
+    // (3) trailing update, lower-triangular CT x CT tiles:  A22 -= L21 L21'
+    const int r0 = kb + nb, mt = (n - r0 + CT - 1) / CT;
+    for (int t = blockIdx.x; t < mt * mt; t += gridDim.x) {
+      const int bi = t / mt, bj = t % mt;
+      if (bj > bi) continue;
+      tile_abt<0>(E, E, E, n, r0 + bi * CT, r0 + bj * CT, kb, kb + nb, tsm);
     }
     grid.sync();
   }
-  // T[c][i] = (L^-1)[i][c] : forward substitution, one warp per column, x in shared memory
-  for (int c = gwarp; c < n; c += nwarps) {
-    double *x = csm + (size_t)wib * n;
-    for (int i = lane; i < n; i += 32) x[i] = 0.0;
-    __syncwarp();
-    for (int i = c; i < n; ++i) {
-      double v = 0; for (int k = c + lane; k < i; k += 32) v += E[(size_t)i * n + k] * x[k];
-      #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) x[i] = ((i == c ? 1.0 : 0.0) - v) / E[(size_t)i * n + i];
-      __syncwarp();
+  // T = (L^-1)' by blocks of CT: (a) invert the diagonal blocks in shared memory, (b) block column j of L^-1
+  // by forward substitution over block rows, one CTA per block column (tiled products), T stored transposed.
+  const int nbk = (n + CT - 1) / CT;
+  double *Ls = tsm + 2 * CT * (CNB + 1);                 // [CT][CT+1] scratch: a diagonal block of L, then S
+  double *Ds = Ls + CT * (CT + 1);                        // [CT][CT+1] inverse of a diagonal block
+  for (long long idx = tid; idx < (long long)n * n; idx += nt) T[idx] = 0.0;
+  grid.sync();
+  for (int bq = blockIdx.x; bq < nbk; bq += gridDim.x) {
+    const int o = bq * CT, m = min(CT, n - o);
+    for (int idx = threadIdx.x; idx < CT * CT; idx += blockDim.x) { const int r = idx / CT, cc = idx % CT; Ls[r * (CT + 1) + cc] = (r < m && cc <= r) ? E[(size_t)(o + r) * n + o + cc] : (r == cc ? 1.0 : 0.0); }
+    __syncthreads();
+    if (threadIdx.x < CT) {                                // column c of inv(L_bb): x_i = (delta - sum_{k<i} L_ik x_k) / L_ii
+      const int c = threadIdx.x;
+      for (int i = 0; i < CT; ++i) {
+        double v = i == c ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) v -= Ls[i * (CT + 1) + k] * Ds[k * (CT + 1) + c];
+        Ds[i * (CT + 1) + c] = i < c ? 0.0 : v / Ls[i * (CT + 1) + i];
+      }
     }
-    for (int i = lane; i < n; i += 32) T[(size_t)c * n + i] = x[i];
-    __syncwarp();
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < CT * CT; idx += blockDim.x) { const int r = idx / CT, cc = idx % CT; if (r < m && cc < m && cc <= r) T[(size_t)(o + cc) * n + o + r] = Ds[r * (CT + 1) + cc]; }
+    __syncthreads();
   }
   grid.sync();
-  // Einv[i][j] = sum_k (L^-1)[k][i] (L^-1)[k][j] = T[i,:].T[j,:]   (entries with k < max(i,j) are zero)
-  for (long long p = gwarp; p < (long long)n * n; p += nwarps) {
-    const int i = (int)(p / n), j = (int)(p % n);
-    if (j > i) continue;
-    const double *ti = T + (size_t)i * n, *tj = T + (size_t)j * n;
-    double v = 0; for (int k = i + lane; k < n; k += 32) v += ti[k] * tj[k];
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) { Einv[(size_t)i * n + j] = v; Einv[(size_t)j * n + i] = v; }
+  for (int bj = blockIdx.x; bj < nbk; bj += gridDim.x) {
+    for (int bi = bj + 1; bi < nbk; ++bi) {
+      // S = sum_{k in [bj*CT, bi*CT)} L[bi rows][k] * Linv[k][bj cols]  ==  tile of  L . T'   (T holds Linv transposed)
+      tile_abt<2>(Ls, E, T, n, bi * CT, bj * CT, bj * CT, bi * CT, tsm);
+      __syncthreads();
+      // Linv_ij = -inv(L_ii) S ; inv(L_ii) is in T (transposed): Dinv[r][q] = T[o_i + q][o_i + r]
+      const int oi = bi * CT, oj = bj * CT, mi = min(CT, n - oi), mj = min(CT, n - oj);
+      for (int idx = threadIdx.x; idx < CT * CT; idx += blockDim.x) { const int r = idx / CT, q = idx % CT; Ds[r * (CT + 1) + q] = (r < mi && q <= r) ? T[(size_t)(oi + q) * n + oi + r] : 0.0; }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < CT * CT; idx += blockDim.x) {
+        const int r = idx / CT, cc = idx % CT;
+        if (r < mi && cc < mj) { double v = 0; for (int q = 0; q <= r; ++q) v += Ds[r * (CT + 1) + q] * Ls[q * (CT + 1) + cc]; T[(size_t)(oj + cc) * n + oi + r] = -v; }
+      }
+      __syncthreads();
+      __threadfence();                                      // later block rows of this column read T written above
+    }
   }
+  grid.sync();
+  // Einv = T T'  (T[i][k] = 0 for k < i, so the sum starts at the tile's first row index)
+  { const int mt = (n + CT - 1) / CT;
+    for (int t = blockIdx.x; t < mt * mt; t += gridDim.x) {
+      const int bi = t / mt, bj = t % mt;
+      if (bj > bi) continue;
+      tile_abt<1>(Einv, T, T, n, bi * CT, bj * CT, (bi * CT / CNB) * CNB, n, tsm);
+    } }
 }
 
 struct Pcg3Args {

@@ -30,17 +30,15 @@
 namespace omvg {
 
 constexpr int TILE_Q = 128;      // UMMA M  (queries  -> TMEM lanes)
-constexpr int TILE_DB = 128;     // UMMA N  (database -> TMEM columns)
+constexpr int TILE_DB = 256;     // UMMA N  (database -> TMEM columns)
 constexpr int ROW_PAD = 256;     // every image starts at a multiple of this many arena rows
-constexpr int ACC_STAGES = 4;    // TMEM: 4 accumulators x 128 columns; epilogue warpgroup w owns tiles g % 4 == w
-constexpr int A_STAGES = 2, B_STAGES = 6;
+constexpr int A_STAGES = 2, B_STAGES = 4;
 constexpr int A_BYTES = TILE_Q * OMVG_DESC_LEN;                 // 16 KB
-constexpr int B_BYTES = TILE_DB * OMVG_DESC_LEN;                // 16 KB
-constexpr int CK_BYTES = TILE_DB * 4;                           // 512 B of packed keys
-constexpr int B_STAGE_BYTES = B_BYTES + 1024;                   // keep every stage 1024-B aligned (SWIZZLE_128B)
-constexpr int MERGE_BYTES = 2 * (ACC_STAGES - 1) * TILE_Q * 8;
-constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align slack*/ + MERGE_BYTES + 256 /*barriers*/;
-constexpr int TC_THREADS = 64 + ACC_STAGES * 128;   // warp0 TMA, warp1 MMA, 4 epilogue warpgroups
+constexpr int B_BYTES = TILE_DB * OMVG_DESC_LEN;                // 32 KB
+constexpr int CK_BYTES = TILE_DB * 4;                           //  1 KB of packed keys
+constexpr int B_STAGE_BYTES = B_BYTES + CK_BYTES;
+constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align slack*/ + 2048 /*merge*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2-5 / 6-9 epilogue for even / odd tiles
 constexpr int KEY_MIN = INT_MIN;
 
 struct Unit { uint32_t q_row, db_row, n_db_tiles, out_off; };   // one (pair, 128-query tile)
@@ -107,11 +105,11 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *a_smem = smem;                                        // [A_STAGES][16 KB]
   uint8_t *b_smem = smem + A_STAGES * A_BYTES;                   // [B_STAGES][32 KB + 1 KB]
-  int2 *merge = reinterpret_cast<int2 *>(b_smem + B_STAGES * B_STAGE_BYTES);   // [2][ACC_STAGES-1][128]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(merge) + MERGE_BYTES);
-  uint64_t *full_a = bars, *empty_a = bars + 2, *full_b = bars + 4, *empty_b = bars + 4 + B_STAGES;
-  uint64_t *tmem_full = bars + 4 + 2 * B_STAGES, *tmem_empty = tmem_full + ACC_STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + ACC_STAGES);
+  int2 *merge = reinterpret_cast<int2 *>(b_smem + B_STAGES * B_STAGE_BYTES);   // [2][128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(merge + 2 * TILE_Q);
+  uint64_t *full_a = bars, *empty_a = bars + 2, *full_b = bars + 4, *empty_b = bars + 8;
+  uint64_t *tmem_full = bars + 12, *tmem_empty = bars + 14;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -119,7 +117,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
     prefetch_tmap(&tmap);
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1 + 4); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -141,10 +139,11 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
         for (uint32_t t = 0; t < un.n_db_tiles; ++t, ++g) {
           const uint32_t st = g % B_STAGES;
           mbar_wait(&empty_b[st], ((g / B_STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_b[st], B_BYTES + CK_BYTES);
+          mbar_arrive_expect_tx(&full_b[st], B_STAGE_BYTES);
           uint8_t *dst = b_smem + st * B_STAGE_BYTES;
           const uint32_t row = un.db_row + t * TILE_DB;
           tma_load_2d(dst, &tmap, 0, (int)row, &full_b[st]);
+          tma_load_2d(dst + A_BYTES, &tmap, 0, (int)(row + 128), &full_b[st]);
           bulk_load_1d(dst + B_BYTES, ckey + row, CK_BYTES, &full_b[st]);
         }
       }
@@ -160,9 +159,9 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
         mbar_wait(&full_a[as], (ul >> 1) & 1);
         const uint32_t a_addr = smem_u32(a_smem + as * A_BYTES);
         for (uint32_t t = 0; t < n_tiles; ++t, ++g) {
-          const uint32_t st = g % B_STAGES, acc = g % ACC_STAGES;
+          const uint32_t st = g % B_STAGES, acc = g & 1;
           mbar_wait(&full_b[st], (g / B_STAGES) & 1);
-          mbar_wait(&tmem_empty[acc], ((g / ACC_STAGES) & 1) ^ 1);
+          mbar_wait(&tmem_empty[acc], ((g >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(b_smem + st * B_STAGE_BYTES);
           const uint32_t d = tmem_base + acc * TILE_DB;
@@ -176,8 +175,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
       }
     }
   } else {
-    // ===================================================================== epilogue (4 warpgroups)
-    const uint32_t wg = (warp - 2) >> 2;                 // owns tiles g % ACC_STAGES == wg and accumulator wg
+    // ===================================================================== epilogue (8 warps)
+    const uint32_t wg = (warp - 2) >> 2;                 // 0: even tiles / acc 0, 1: odd tiles / acc 1
     const uint32_t quarter = warp & 3;                   // TMEM lane quarter this warp may access
     const uint32_t row_in_tile = quarter * 32 + lane;
     uint32_t g = 0, ul = 0;
@@ -185,10 +184,10 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
       const Unit un = units[u];
       int k1 = KEY_MIN, k2 = KEY_MIN;
       for (uint32_t t = 0; t < un.n_db_tiles; ++t, ++g) {
-        if ((g % ACC_STAGES) != wg) continue;
+        if ((g & 1) != wg) continue;
         const uint32_t st = g % B_STAGES, acc = wg;
         mbar_wait(&full_b[st], (g / B_STAGES) & 1);      // packed keys of this tile are in smem
-        mbar_wait(&tmem_full[acc], (g / ACC_STAGES) & 1);   // accumulator complete
+        mbar_wait(&tmem_full[acc], (g >> 1) & 1);        // accumulator complete
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + acc * TILE_DB;
         const uint32_t ck = smem_u32(b_smem + st * B_STAGE_BYTES + B_BYTES);
@@ -207,18 +206,14 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
         __syncwarp();
         if (lane == 0) { mbar_arrive(&tmem_empty[acc]); mbar_arrive(&empty_b[st]); }
       }
-      // merge the warpgroups' partial top-2 (disjoint chunks) and store
-      int2 *mb = merge + (ul & 1) * (ACC_STAGES - 1) * TILE_Q;
-      if (wg > 0) mb[(wg - 1) * TILE_Q + row_in_tile] = make_int2(k1, k2);
-      asm volatile("bar.sync 1, %0;" :: "n"(ACC_STAGES * 128) : "memory");
+      // merge the two warpgroups' partial top-2 (disjoint chunks) and store
+      int2 *mb = merge + (ul & 1) * TILE_Q;
+      if (wg == 1) mb[row_in_tile] = make_int2(k1, k2);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (wg == 0) {
-        int K1 = k1, K2 = k2;
-        #pragma unroll
-        for (int w = 0; w < ACC_STAGES - 1; ++w) {
-          const int2 o = mb[w * TILE_Q + row_in_tile];
-          K2 = max(min(K1, o.x), max(K2, o.y));
-          K1 = max(K1, o.x);
-        }
+        const int2 o = mb[row_in_tile];
+        const int K1 = max(k1, o.x);
+        const int K2 = max(min(k1, o.x), max(k2, o.y));
         k12[(size_t)un.out_off + row_in_tile] = make_int2(K1, K2);
       }
     }
