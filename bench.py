@@ -135,7 +135,7 @@ def run_ours(args):
     barrier()
     e_iters = 0; t0 = time.perf_counter(); e_steps = max(1, min(K, 3))
     for _ in range(e_steps):
-        g = ba.solve(scene); e_iters += g["iterations"]; launches += g["kernel_launches"]
+        g = ba.solve(scene, device=local); e_iters += g["iterations"]; launches += g["kernel_launches"]
     barrier()
     e_wall = allmax(time.perf_counter() - t0); e_iters_all = allsum(e_iters)
     h2d = sum(scene[k].nbytes for k in ("poses", "intrinsics", "points", "intr_model", "view_pose", "view_intr", "obs_view", "obs_point", "obs_xy"))

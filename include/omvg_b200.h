@@ -44,6 +44,7 @@ extern "C" {
 int         omvg_version(void);            /* 100 = round 1 */
 const char *omvg_last_error(void);         /* thread-local message of the last failing call */
 int         omvg_device_count(void);       /* >0 only if sm_100 devices are visible */
+void        omvg_trim_cache(void);         /* return cached device work buffers to the driver */
 
 /* ===================================================================== MATCH ============== */
 typedef struct omvg_match_ctx omvg_match_ctx;
@@ -153,6 +154,8 @@ typedef struct {
   double  pcg_tolerance;       /* relative residual |S z - b| / |b| <= tol ; default 1e-12 */
   int32_t pcg_max_iterations;  /* default 2000 */
   int32_t verbose;
+  int32_t device;              /* CUDA ordinal used by omvg_ba_solve (omvg_ba_create takes its own) ; default 0 */
+  int32_t reserved_;
 } omvg_ba_options;
 
 typedef struct {

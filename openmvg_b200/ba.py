@@ -33,7 +33,8 @@ class Options(ctypes.Structure):
                 ("initial_radius", ctypes.c_double), ("max_radius", ctypes.c_double), ("min_radius", ctypes.c_double),
                 ("min_relative_decrease", ctypes.c_double), ("min_lm_diagonal", ctypes.c_double),
                 ("max_lm_diagonal", ctypes.c_double), ("pcg_tolerance", ctypes.c_double),
-                ("pcg_max_iterations", ctypes.c_int32), ("verbose", ctypes.c_int32)]
+                ("pcg_max_iterations", ctypes.c_int32), ("verbose", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("reserved_", ctypes.c_int32)]
 
 
 class Summary(ctypes.Structure):

@@ -10,7 +10,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libomvg_b200.so")
 SOURCES = ["match.cu", "ba.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-fopenmp", "--use_fast_math=false"]
 
 
 def _nvcc() -> str:
@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.check_call(cmd)
         objs.append(o)
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs   # cudart is linked statically (nvcc default)
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lgomp"]   # cudart is linked statically (nvcc default)
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -29,8 +29,8 @@ int model_nparams(int m) {
 
 template <typename T> struct DevBuf {
   T *p = nullptr; size_t n = 0;
-  int alloc(size_t count) { release(); n = count; if (!count) return OMVG_OK; OMVG_CUDA(cudaMalloc(&p, count * sizeof(T))); return OMVG_OK; }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  int alloc(size_t count) { release(); n = count; if (!count) return OMVG_OK; OMVG_CUDA(pool_malloc(reinterpret_cast<void **>(&p), count * sizeof(T))); return OMVG_OK; }
+  void release() { if (p) pool_free(p); p = nullptr; n = 0; }
   ~DevBuf() { release(); }
 };
 
@@ -271,6 +271,8 @@ int build_structure(omvg_ba_ctx *c) {
 
 extern "C" {
 
+void omvg_trim_cache(void) { omvg::pool_trim(); }
+
 void omvg_ba_default_options(omvg_ba_options *o) {
   if (!o) return;
   std::memset(o, 0, sizeof *o);
@@ -287,10 +289,13 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   int rc = validate(P); if (rc) return rc;
   int n = 0; OMVG_CUDA(cudaGetDeviceCount(&n));
   if (device < 0 || device >= n) return fail(OMVG_E_CUDA, "no CUDA device %d (found %d)", device, n);
-  cudaDeviceProp prop; OMVG_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) return fail(OMVG_E_CUDA, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  int cc_major = 0, cc_minor = 0, n_sms = 0;                 // attributes: cudaGetDeviceProperties costs milliseconds
+  OMVG_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  OMVG_CUDA(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+  OMVG_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+  if (cc_major != 10) return fail(OMVG_E_CUDA, "device %d is sm_%d%d; this library is sm_100a only", device, cc_major, cc_minor);
   OMVG_CUDA(cudaSetDevice(device));
-  omvg_ba_ctx *c = new omvg_ba_ctx; c->device = device; c->n_sms = prop.multiProcessorCount;
+  omvg_ba_ctx *c = new omvg_ba_ctx; c->device = device; c->n_sms = n_sms;
   std::unique_ptr<omvg_ba_ctx, void (*)(omvg_ba_ctx *)> guard(c, [](omvg_ba_ctx *x) { omvg_ba_destroy(x); });
   OMVG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   OMVG_CUDA(cudaEventCreate(&c->ev0)); OMVG_CUDA(cudaEventCreate(&c->ev1)); OMVG_CUDA(cudaEventCreate(&c->evj0)); OMVG_CUDA(cudaEventCreate(&c->evj1));
@@ -307,9 +312,11 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   c->perm.resize(no);
   { std::vector<int> cur(pt_start.begin(), pt_start.end() - 1); for (long long o = 0; o < no; ++o) c->perm[cur[P->obs_point[o]]++] = (int)o; }
   std::vector<int> s_pose(no), s_intr(no), s_pt(no); std::vector<double> s_xy(2 * no);
+  #pragma omp parallel for schedule(static) if (no > 100000)
   for (long long t = 0; t < no; ++t) { const int o = c->perm[t], v = P->obs_view[o];
     s_pose[t] = P->view_pose[v]; s_intr[t] = P->view_intr[v]; s_pt[t] = P->obs_point[o]; s_xy[2 * t] = P->obs_xy[2 * o]; s_xy[2 * t + 1] = P->obs_xy[2 * o + 1]; }
   std::vector<unsigned char> pt_single(c->np, 1);
+  #pragma omp parallel for schedule(static) if (c->np > 100000)
   for (int j = 0; j < c->np; ++j) for (int t = pt_start[j] + 1; t < pt_start[j + 1]; ++t) if (s_intr[t] != s_intr[pt_start[j]]) { pt_single[j] = 0; break; }
   std::vector<int> cam_start(c->nc + 1, 0), cam_obs(no);
   for (long long t = 0; t < no; ++t) cam_start[s_pose[t] + 1]++;
@@ -402,6 +409,11 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   int n_free_intr = 0; for (unsigned mm : m.intr_mask) n_free_intr += __builtin_popcount(mm);
   const bool use_pcg2 = n_free_intr <= MAXRHS - 1 && !getenv("OMVG_BA_PCG1");
   const bool use_pcg3 = use_pcg2 && !getenv("OMVG_BA_PCG2") && c->nc >= 2;
+  // the per-observation kernels gather pose records (176 B x n_poses) and points through L1: give them all of it
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   OMVG_CUDA(cudaFuncSetAttribute(pcg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
   OMVG_CUDA(cudaFuncSetAttribute(pcg3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
   if ((rc = read_scalars(c))) return rc;
@@ -415,6 +427,8 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   bool step_is_successful = true, failure = false;
   double reference_cost = x_cost, accumulated_reference = 0.0, current_cost = x_cost;
   long long pcg_total = 0;
+  int coarse_age = -1; double last_pcg_its = 0, fresh_pcg_its = 1e30; bool fresh_pending = false;
+  static const int coarse_every = getenv("OMVG_BA_COARSE_EVERY") ? std::max(1, atoi(getenv("OMVG_BA_COARSE_EVERY"))) : 2;
   const int pcg_grid = c->n_sms;
 
   for (;;) {
@@ -453,7 +467,13 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       if (use_pcg3) {
         Pcg3Args P3{}; P3.base = P2; P3.C = Coarse{c->agg_of.p, c->agg_start.p, c->agg_cams.p, c->ng, nw, c->ng * nw}; P3.Einv = c->cEinv.p; P3.Cv = c->cCv.p; P3.Yv = c->cYv.p; P3.Pv2 = c->bP2.p;
         const int nco = P3.C.nco;
-        if (nco > 0) {
+        // The coarse operator is only a preconditioner: a slightly stale E^-1 (previous LM step, radius/3) costs a few
+        // extra PCG iterations (measured 38->40, 42->49, 43->43) but saves its O(nco^3) setup, so it is refreshed every
+        // `coarse_every` LM steps, or earlier if the last solve needed 1.5x the iterations seen right after a refresh.
+        const bool refresh = nco > 0 && (coarse_age < 0 || coarse_age >= coarse_every || last_pcg_its > 1.5 * fresh_pcg_its + 5);
+        if (refresh) { coarse_age = 0; fresh_pending = true; }
+        ++coarse_age;
+        if (refresh) {
           OMVG_CUDA(cudaMemsetAsync(c->cE.p, 0, (size_t)nco * nco * sizeof(double), c->stream));
           coarse_assemble_kernel<<<(c->nnzb + 127) / 128, 128, 0, c->stream>>>(c->Scc.p, c->brow.p, c->cols.p, c->nnzb, c->gW.p, c->nc, P3.C, c->cE.p); LAUNCH_CHECK();
           { const size_t sm = sizeof(double) * ((size_t)CNB * CNB + 2 * CT * (CNB + 1) + 2 * CT * (CT + 1));
@@ -493,6 +513,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     if ((rc = read_scalars(c))) return rc;
     const double *h = c->h_scal;
     pcg_total += (long long)h[S_PCG_IT];
+    last_pcg_its = h[S_PCG_IT]; if (fresh_pending) { fresh_pcg_its = last_pcg_its; fresh_pending = false; }
     int failflag; std::memcpy(&failflag, c->h_scal + S_COUNT + 192, sizeof(int));
     const double model_cost_change = h[S_MODEL];
     bool finite_step = std::isfinite(h[S_STEP2_PT]) && std::isfinite(h[S_STEP2_POSE]) && std::isfinite(h[S_STEP2_INTR]) && std::isfinite(model_cost_change);
@@ -572,7 +593,7 @@ int omvg_ba_solve(omvg_ba_problem *P, const omvg_ba_options *O, omvg_ba_summary 
   omvg_ba_options def; if (!O) { omvg_ba_default_options(&def); O = &def; }
   omvg_ba_summary local; if (!sum) sum = &local;
   omvg_ba_ctx *c = nullptr;
-  int rc = omvg_ba_create(&c, 0, P); if (rc) return rc;
+  int rc = omvg_ba_create(&c, O->device, P); if (rc) return rc;
   rc = omvg_ba_run(c, O, sum);
   if (rc == OMVG_OK) {                       // state is copied back only when usable (solver.cc:445-448)
     // Adjust's write-back rules (sfm_data_BA_ceres.cpp:528-568): poses only if extrinsics were refined,

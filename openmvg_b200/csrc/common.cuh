@@ -5,6 +5,9 @@
 #include <cstdio>
 #include <cstdarg>
 #include <string>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 
 #include "../../include/omvg_b200.h"
 
@@ -17,6 +20,50 @@ inline int fail(int code, const char *fmt, ...) {
 }
 #define OMVG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
   return ::omvg::fail(OMVG_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+
+// ----------------------------------------------------------------------------- caching device allocator
+// Adjust()/Match() are called many times by the SfM engines (BA / outlier-rejection / BA loops): cudaMalloc and
+// cudaFree of ~100 work buffers cost more than a whole solve, so released buffers are kept per device and
+// handed out again (best fit within 25 % slack).  omvg_trim_cache() returns everything to the driver.
+struct DevPool {
+  std::mutex mu;
+  std::multimap<size_t, void *> free_[16];
+  std::unordered_map<void *, std::pair<size_t, int>> live;
+  size_t cached = 0;
+};
+inline DevPool &dev_pool() { static DevPool p; return p; }
+inline cudaError_t pool_malloc(void **out, size_t bytes) {
+  int dev = 0; cudaGetDevice(&dev); dev &= 15;
+  bytes = (bytes + 511) & ~size_t(511);
+  DevPool &P = dev_pool();
+  { std::lock_guard<std::mutex> g(P.mu);
+    auto it = P.free_[dev].lower_bound(bytes);
+    if (it != P.free_[dev].end() && it->first <= bytes + bytes / 4 + 4096) {
+      *out = it->second; P.live[*out] = {it->first, dev}; P.cached -= it->first; P.free_[dev].erase(it); return cudaSuccess; } }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) {                                   // out of memory: drop the cache and retry once
+    { std::lock_guard<std::mutex> g(P.mu); for (auto &kv : P.free_[dev]) cudaFree(kv.second); for (auto &kv : P.free_[dev]) P.cached -= kv.first; P.free_[dev].clear(); }
+    cudaGetLastError(); e = cudaMalloc(out, bytes);
+  }
+  if (e == cudaSuccess) { std::lock_guard<std::mutex> g(P.mu); P.live[*out] = {bytes, dev}; }
+  return e;
+}
+inline void pool_free(void *p) {
+  if (!p) return;
+  DevPool &P = dev_pool();
+  std::lock_guard<std::mutex> g(P.mu);
+  auto it = P.live.find(p);
+  if (it == P.live.end()) { cudaFree(p); return; }
+  const size_t bytes = it->second.first; const int dev = it->second.second; P.live.erase(it);
+  if (P.cached + bytes > (size_t(16) << 30)) { cudaFree(p); return; }
+  P.free_[dev].emplace(bytes, p); P.cached += bytes;
+}
+inline void pool_trim() {
+  DevPool &P = dev_pool();
+  std::lock_guard<std::mutex> g(P.mu);
+  for (int d = 0; d < 16; ++d) { for (auto &kv : P.free_[d]) cudaFree(kv.second); P.free_[d].clear(); }
+  P.cached = 0;
+}
 
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -143,6 +143,7 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
     O.parameter_tolerance = options_.parameter_tolerance_;
     O.gradient_tolerance = options_.gradient_tolerance_;
     O.verbose = options_.bVerbose_ ? 1 : 0;
+    O.device = options_.device_;
 
     const int rc = omvg_ba_solve(&P, &O, &summary_);
     if (rc != OMVG_OK)
