@@ -37,10 +37,8 @@ constexpr int A_BYTES = TILE_Q * OMVG_DESC_LEN;                 // 16 KB
 constexpr int B_BYTES = TILE_DB * OMVG_DESC_LEN;                // 32 KB
 constexpr int CK_BYTES = TILE_DB * 4;                           //  1 KB of packed keys
 constexpr int B_STAGE_BYTES = B_BYTES + CK_BYTES;
-constexpr int EPI_WGS = 4;       // epilogue warpgroups: accumulator stage s is drained by WGs 2s (columns 0-127) and 2s+1 (128-255)
-constexpr int MERGE_BYTES = 2 * (EPI_WGS - 1) * TILE_Q * 8;
-constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align slack*/ + MERGE_BYTES + 256 /*barriers*/;
-constexpr int TC_THREADS = 64 + EPI_WGS * 128;  // warp0 TMA, warp1 MMA, 16 epilogue warps (4 per SM sub-partition)
+constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align slack*/ + 2048 /*merge*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2-5 / 6-9 epilogue for even / odd tiles
 constexpr int KEY_MIN = INT_MIN;
 
 struct Unit { uint32_t q_row, db_row, n_db_tiles, out_off; };   // one (pair, 128-query tile)
@@ -66,57 +64,41 @@ __global__ void prep_rows_kernel(const uint8_t *__restrict__ desc, const uint32_
 }
 
 // --------------------------------------------------------------------------------- tcgen05 kernel
-// Epilogue register layout: tcgen05.ld.16x256b (measured with tools/tmem_layout_probe.cu, see
-// profiles/r01_tmem_layout_16x256b.txt): a warp reads 16 TMEM lanes; thread t receives, per 8-column
-// group, lane t/4 columns 2(t%4), 2(t%4)+1 (regs 0,1) and lane t/4+8, same columns (regs 2,3).
-// With two such loads (lanes 0-15 and 16-31 of the warp's quadrant) a thread owns 4 query rows and a
-// quarter of the columns, so every per-column key it fetches from shared memory serves 4 rows:
-// 4x fewer shared-memory wavefronts than the one-row-per-thread 32x32b layout (which ran the
-// LSU/shared pipe at 63 % and, together with the MMA operand reads, saturated shared memory).
-__device__ __forceinline__ void tmem_ld_16x256_x4(uint32_t taddr, int32_t (&r)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-    : "r"(taddr) : "memory");
-}
-// tcgen05.wait::ld with the loaded registers as in/out operands: no use of them can be scheduled above it
-__device__ __forceinline__ void tmem_ld_wait_dep2(int32_t (&a)[16], int32_t (&b)[16]) {
+__device__ __forceinline__ void tmem_ld_wait_dep(int32_t (&r)[32]) {
+  // tcgen05.wait::ld, with the 32 registers as in/out operands so that no use of them can be
+  // scheduled above the wait.
   asm volatile("tcgen05.wait::ld.sync.aligned;"
-    : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
-      "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
-      "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
-      "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+    : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+      "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
     :: "memory");
 }
-__device__ __forceinline__ int2 lds64(uint32_t saddr) {
-  int2 v; asm("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr)); return v;
-}
-// one 32-column chunk: a = lanes 0-15 (rows t/4, t/4+8), b = lanes 16-31 (rows 16+t/4, 24+t/4);
-// ck = shared address of this thread's first key of the chunk (column 2(t%4)); groups are 8 columns apart.
-__device__ __forceinline__ void chunk_update4(const int32_t (&a)[16], const int32_t (&b)[16], uint32_t ck, int (&k1)[4], int (&k2)[4]) {
-  const int2 c0 = lds64(ck), c1 = lds64(ck + 32), c2 = lds64(ck + 64), c3 = lds64(ck + 96);
-  int g[4];
-  g[0] = max(max(a[0] * 512 + c0.x, a[1] * 512 + c0.y), a[4] * 512 + c1.x);
-  g[1] = max(max(a[2] * 512 + c0.x, a[3] * 512 + c0.y), a[6] * 512 + c1.x);
-  g[2] = max(max(b[0] * 512 + c0.x, b[1] * 512 + c0.y), b[4] * 512 + c1.x);
-  g[3] = max(max(b[2] * 512 + c0.x, b[3] * 512 + c0.y), b[6] * 512 + c1.x);
-  g[0] = max(max(g[0], a[5] * 512 + c1.y), a[8] * 512 + c2.x);
-  g[1] = max(max(g[1], a[7] * 512 + c1.y), a[10] * 512 + c2.x);
-  g[2] = max(max(g[2], b[5] * 512 + c1.y), b[8] * 512 + c2.x);
-  g[3] = max(max(g[3], b[7] * 512 + c1.y), b[10] * 512 + c2.x);
-  g[0] = max(max(g[0], a[9] * 512 + c2.y), a[12] * 512 + c3.x);
-  g[1] = max(max(g[1], a[11] * 512 + c2.y), a[14] * 512 + c3.x);
-  g[2] = max(max(g[2], b[9] * 512 + c2.y), b[12] * 512 + c3.x);
-  g[3] = max(max(g[3], b[11] * 512 + c2.y), b[14] * 512 + c3.x);
-  g[0] = max(g[0], a[13] * 512 + c3.y);
-  g[1] = max(g[1], a[15] * 512 + c3.y);
-  g[2] = max(g[2], b[13] * 512 + c3.y);
-  g[3] = max(g[3], b[15] * 512 + c3.y);
-  #pragma unroll
-  for (int i = 0; i < 4; ++i) { k2[i] = max(k2[i], min(k1[i], g[i])); k1[i] = max(k1[i], g[i]); }
+
+__device__ __forceinline__ int4 lds128(uint32_t saddr) {
+  int4 v;
+  asm("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
 }
 
+__device__ __forceinline__ void chunk_update(const int32_t (&r)[32], uint32_t ck, int &k1, int &k2) {
+  // four independent max chains (ILP) instead of one 16-deep dependent chain
+  int g0 = KEY_MIN, g1 = KEY_MIN, g2 = KEY_MIN, g3 = KEY_MIN;
+  #pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const int4 c = lds128(ck + 16 * j);                          // LDS.128, same address for all lanes (broadcast)
+    const int4 d = lds128(ck + 16 * j + 16);
+    g0 = max(max(g0, r[4 * j + 0] * 512 + c.x), r[4 * j + 1] * 512 + c.y);
+    g1 = max(max(g1, r[4 * j + 2] * 512 + c.z), r[4 * j + 3] * 512 + c.w);
+    g2 = max(max(g2, r[4 * j + 4] * 512 + d.x), r[4 * j + 5] * 512 + d.y);
+    g3 = max(max(g3, r[4 * j + 6] * 512 + d.z), r[4 * j + 7] * 512 + d.w);
+  }
+  const int gm = max(max(g0, g1), max(g2, g3));
+  k2 = max(k2, min(k1, gm));
+  k1 = max(k1, gm);
+}
+
+template <bool DRAIN_ONLY>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ ckey,
                 const Unit *__restrict__ units, uint32_t n_units, int2 *__restrict__ k12) {
@@ -124,8 +106,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *a_smem = smem;                                        // [A_STAGES][16 KB]
   uint8_t *b_smem = smem + A_STAGES * A_BYTES;                   // [B_STAGES][32 KB + 1 KB]
-  int2 *merge = reinterpret_cast<int2 *>(b_smem + B_STAGES * B_STAGE_BYTES);   // [2][EPI_WGS-1][128]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(merge) + MERGE_BYTES);
+  int2 *merge = reinterpret_cast<int2 *>(b_smem + B_STAGES * B_STAGE_BYTES);   // [2][128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(merge + 2 * TILE_Q);
   uint64_t *full_a = bars, *empty_a = bars + 2, *full_b = bars + 4, *empty_b = bars + 8;
   uint64_t *tmem_full = bars + 12, *tmem_empty = bars + 14;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
@@ -135,8 +117,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap);
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1 + 8); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1 + 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -194,65 +176,45 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
       }
     }
   } else {
-    // ===================================================================== epilogue (16 warps)
-    const uint32_t wg = (warp - 2) >> 2;                 // 0..3
-    const uint32_t stage_of_wg = wg >> 1, half = wg & 1;  // accumulator stage (tile parity) and column half of this warpgroup
+    // ===================================================================== epilogue (8 warps)
+    const uint32_t wg = (warp - 2) >> 2;                 // 0: even tiles / acc 0, 1: odd tiles / acc 1
     const uint32_t quarter = warp & 3;                   // TMEM lane quarter this warp may access
-    const uint32_t qrow = lane >> 2, qcol = lane & 3;    // 16x256b: lane t -> rows t/4 (+8), columns 2(t%4), +1 per 8-column group
+    const uint32_t row_in_tile = quarter * 32 + lane;
     uint32_t g = 0, ul = 0;
     for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
       const Unit un = units[u];
-      int k1[4] = {KEY_MIN, KEY_MIN, KEY_MIN, KEY_MIN}, k2[4] = {KEY_MIN, KEY_MIN, KEY_MIN, KEY_MIN};
+      int k1 = KEY_MIN, k2 = KEY_MIN;
       for (uint32_t t = 0; t < un.n_db_tiles; ++t, ++g) {
-        if ((g & 1) != stage_of_wg) continue;
-        const uint32_t st = g % B_STAGES, acc = stage_of_wg;
+        if ((g & 1) != wg) continue;
+        const uint32_t st = g % B_STAGES, acc = wg;
         mbar_wait(&full_b[st], (g / B_STAGES) & 1);      // packed keys of this tile are in smem
         mbar_wait(&tmem_full[acc], (g >> 1) & 1);        // accumulator complete
         tc_fence_after();
-        const uint32_t ta = tmem_base + ((quarter * 32) << 16) + acc * TILE_DB + half * (TILE_DB / 2);   // lanes 0-15 of the quarter
-        const uint32_t tb = ta + (16u << 16);                                           // lanes 16-31
-        const uint32_t ck = smem_u32(b_smem + st * B_STAGE_BYTES + B_BYTES) + half * (TILE_DB / 2) * 4 + 8 * qcol;
-        int32_t a0[16], b0[16], a1[16], b1[16];
-        tmem_ld_16x256_x4(ta, a0); tmem_ld_16x256_x4(tb, b0);
+        const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + acc * TILE_DB;
+        const uint32_t ck = smem_u32(b_smem + st * B_STAGE_BYTES + B_BYTES);
+        int32_t ra[32], rb[32];
+        tmem_ld_32x32(taddr, ra);
         #pragma unroll
-        for (int c = 0; c < TILE_DB / 64; c += 2) {
-          tmem_ld_wait_dep2(a0, b0);
-          tmem_ld_16x256_x4(ta + (c + 1) * 32, a1); tmem_ld_16x256_x4(tb + (c + 1) * 32, b1);
-          chunk_update4(a0, b0, ck + c * 128, k1, k2);
-          tmem_ld_wait_dep2(a1, b1);
-          if (c + 2 < TILE_DB / 64) { tmem_ld_16x256_x4(ta + (c + 2) * 32, a0); tmem_ld_16x256_x4(tb + (c + 2) * 32, b0); }
-          chunk_update4(a1, b1, ck + (c + 1) * 128, k1, k2);
+        for (int c = 0; c < TILE_DB / 32; c += 2) {
+          tmem_ld_wait_dep(ra);
+          tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+          if (!DRAIN_ONLY) chunk_update(ra, ck + c * 128, k1, k2);
+          tmem_ld_wait_dep(rb);
+          if (c + 2 < TILE_DB / 32) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+          if (!DRAIN_ONLY) chunk_update(rb, ck + (c + 1) * 128, k1, k2);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { mbar_arrive(&tmem_empty[acc]); mbar_arrive(&empty_b[st]); }
       }
-      // merge the 4 lanes of a quad (disjoint column subsets of the same rows)
-      #pragma unroll
-      for (int off = 1; off <= 2; off <<= 1) {
-        #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int o1 = __shfl_xor_sync(0xffffffffu, k1[i], off), o2 = __shfl_xor_sync(0xffffffffu, k2[i], off);
-          k2[i] = max(min(k1[i], o1), max(k2[i], o2));
-          k1[i] = max(k1[i], o1);
-        }
-      }
-      // lane qcol publishes row i == qcol of the quad's four rows: tile row = 32*quarter + 16*(i>>1) + 8*(i&1) + qrow
-      const int sk1 = qcol == 0 ? k1[0] : qcol == 1 ? k1[1] : qcol == 2 ? k1[2] : k1[3];
-      const int sk2 = qcol == 0 ? k2[0] : qcol == 1 ? k2[1] : qcol == 2 ? k2[2] : k2[3];
-      const uint32_t row_in_tile = quarter * 32 + 16 * (qcol >> 1) + 8 * (qcol & 1) + qrow;
-      // merge the warpgroups' partial top-2 (disjoint tiles / column halves) and store
-      int2 *mb = merge + (ul & 1) * (EPI_WGS - 1) * TILE_Q;
-      if (wg > 0) mb[(wg - 1) * TILE_Q + row_in_tile] = make_int2(sk1, sk2);
-      asm volatile("bar.sync 1, %0;" :: "n"(EPI_WGS * 128) : "memory");
+      // merge the two warpgroups' partial top-2 (disjoint chunks) and store
+      int2 *mb = merge + (ul & 1) * TILE_Q;
+      if (wg == 1) mb[row_in_tile] = make_int2(k1, k2);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (wg == 0) {
-        int K1 = sk1, K2 = sk2;
-        #pragma unroll
-        for (int w = 0; w < EPI_WGS - 1; ++w) {
-          const int2 o = mb[w * TILE_Q + row_in_tile];
-          K2 = max(min(K1, o.x), max(K2, o.y));
-          K1 = max(K1, o.x);
-        }
+        const int2 o = mb[row_in_tile];
+        const int K1 = max(k1, o.x);
+        const int K2 = max(min(k1, o.x), max(k2, o.y));
         k12[(size_t)un.out_off + row_in_tile] = make_int2(K1, K2);
       }
     }
@@ -544,7 +506,10 @@ int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_
     const uint32_t grid = (uint32_t)std::min<size_t>(units.size(), (size_t)c->n_sms);
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     OMVG_CUDA(cudaEventRecord(e0, c->stream));
-    match_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)units.size(), c->d_k12);
+    // OMVG_MATCH_DRAIN_ONLY=1 (measurement aid, results are garbage): epilogue reads TMEM but does no arithmetic
+    static const bool drain_only = getenv("OMVG_MATCH_DRAIN_ONLY") != nullptr;
+    if (drain_only) match_tc_kernel<true><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)units.size(), c->d_k12);
+    else match_tc_kernel<false><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)units.size(), c->d_k12);
     OMVG_CUDA(cudaGetLastError());
     OMVG_CUDA(cudaEventRecord(e1, c->stream));
     c->pending.emplace_back(e0, e1); c->tc_launches++; c->launches++;
@@ -597,7 +562,8 @@ int omvg_match_create(omvg_match_ctx **out, int device) {
   OMVG_CUDA(cudaSetDevice(device));
   omvg_match_ctx *c = new omvg_match_ctx; c->device = device; c->n_sms = n_sms;
   OMVG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   OMVG_CUDA(cudaMalloc(&c->d_total, sizeof(uint64_t)));
   if (const char *e = getenv("OMVG_MATCH_K12_MB")) c->k12_budget_bytes = size_t(atol(e)) << 20;
   *out = c; return OMVG_OK;
@@ -788,7 +754,7 @@ int omvg_match_debug_top2_tc(omvg_match_ctx *c, uint32_t I, uint32_t J, int32_t 
   if ((rc = ensure(c->d_k12, c->k12_cap, size_t(qt) * TILE_Q))) return rc;
   if ((rc = ensure(c->d_units, c->units_cap, units.size()))) return rc;
   OMVG_CUDA(cudaMemcpyAsync(c->d_units, units.data(), units.size() * sizeof(Unit), cudaMemcpyHostToDevice, c->stream));
-  match_tc_kernel<<<std::min<uint32_t>(qt, c->n_sms), TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, qt, c->d_k12);
+  match_tc_kernel<false><<<std::min<uint32_t>(qt, c->n_sms), TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, qt, c->d_k12);
   OMVG_CUDA(cudaGetLastError()); c->launches++;
   int32_t *dd1, *dd2; uint32_t *dg1;
   OMVG_CUDA(cudaMalloc(&dd1, nq * 4)); OMVG_CUDA(cudaMalloc(&dd2, nq * 4)); OMVG_CUDA(cudaMalloc(&dg1, nq * 4));
