@@ -187,6 +187,10 @@ int omvg_ba_reset(omvg_ba_ctx *ctx);      /* restore the parameters uploaded at 
 int omvg_ba_run(omvg_ba_ctx *ctx, const omvg_ba_options *options, omvg_ba_summary *summary);
 int omvg_ba_download(omvg_ba_ctx *ctx, double *poses, double *intrinsics, double *points);
 int omvg_ba_destroy(omvg_ba_ctx *ctx);
+/* |reprojection residual| (pixels, no loss) of every observation at the current device parameters, in the
+ * caller's observation order: the quantity RemoveOutliers_PixelResidualError (sfm/sfm_data_filters.cpp:40-73)
+ * thresholds after each Adjust of the BA / outlier-rejection loop (sequential_SfM.cpp:205-211). */
+int omvg_ba_residual_norms(omvg_ba_ctx *ctx, double *norms /* [n_obs] */);
 
 /* Validation aids (tests only): one evaluation at the uploaded parameters.
  * r[n_obs][2], J_intr[n_obs][2][8], J_pose[n_obs][2][6], J_point[n_obs][2][3] (row-major blocks,

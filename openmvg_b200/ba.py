@@ -127,6 +127,11 @@ class BAContext:
         check(lib().omvg_ba_download(self._h, poses.ctypes.data_as(_dp), intr.ctypes.data_as(_dp), pts.ctypes.data_as(_dp)))
         return poses, intr, pts
 
+    def residual_norms(self):
+        out = np.zeros(len(self._s["obs_view"]))
+        check(lib().omvg_ba_residual_norms(self._h, out.ctypes.data_as(_dp)))
+        return out
+
     def debug_eval(self, **opts):
         o = default_options(**opts)
         n = len(self._s["obs_view"])

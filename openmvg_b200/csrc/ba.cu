@@ -40,7 +40,7 @@ struct omvg_ba_ctx {
   int device = 0, n_sms = 0;
   cudaStream_t stream = nullptr;
   int nc = 0, ni = 0, np = 0, nv = 0; long long no = 0;
-  int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0, kiu = KI;
+  int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0, eval_grid = 0, kiu = KI;
   std::vector<int> perm;                    // sorted position -> caller's observation index
   std::vector<int> h_intr_model;
   // parameters: [0] current, [1] candidate, init = copy at create
@@ -124,9 +124,9 @@ int eval_cost(omvg_ba_ctx *c, const omvg_ba_options *o, int which, int slot) {
   EvalArgs A{}; A.poses = c->pose[which].p; A.intr = c->intr[which].p; A.pts = c->pt[which].p; A.camR = c->camR[which].p; A.camdR = c->camdR.p; A.camrec = c->camrec[which].p;
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = o->use_loss; A.huber_a = o->huber_a; A.cost_partial = c->part.p;
-  eval_kernel<false, 8><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  eval_kernel<false, 8><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
   c->launches += 2;
-  return reduce_to(c, c->part.p, c->eval_blocks, slot);
+  return reduce_to(c, c->part.p, c->eval_grid, slot);
 }
 
 int colsums(omvg_ba_ctx *c) {
@@ -149,13 +149,13 @@ int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which
   if (have_scale) { A.sc_pt = c->sc_pt.p; A.sc_cam = c->sc_cam.p; A.sc_intr = c->sc_intr.p; }
   if (time_it) OMVG_CUDA(cudaEventRecord(c->evj0, c->stream));
   static const int minb = getenv("OMVG_BA_EVAL_MINB") ? atoi(getenv("OMVG_BA_EVAL_MINB")) : 4;
-  if (minb >= 8) eval_kernel<true, 8><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A);
-  else if (minb >= 6) eval_kernel<true, 6><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A);
-  else eval_kernel<true, 4><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A);
+  if (minb >= 8) eval_kernel<true, 8><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
+  else if (minb >= 6) eval_kernel<true, 6><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
+  else eval_kernel<true, 4><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
   LAUNCH_CHECK();
   if (time_it) OMVG_CUDA(cudaEventRecord(c->evj1, c->stream));
   c->launches += 2;
-  int rc = reduce_to(c, c->part.p, c->eval_blocks, S_COST); if (rc) return rc;
+  int rc = reduce_to(c, c->part.p, c->eval_grid, S_COST); if (rc) return rc;
   if (!have_scale) {        // iteration 0: Jacobi scaling from the unscaled J (trust_region_minimizer.cc:239-253)
     if ((rc = colsums(c))) return rc;
     make_scale_kernel<<<(3 * c->np + 255) / 256, 256, 0, c->stream>>>(c->diag_pt.p, 3 * c->np, c->sc_pt.p); LAUNCH_CHECK();
@@ -302,6 +302,7 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   OMVG_CUDA(cudaMallocHost(&c->h_scal, (S_COUNT + 192 + 2) * sizeof(double)));
   c->nc = P->n_poses; c->ni = P->n_intrinsics; c->np = P->n_points; c->nv = P->n_views; c->no = P->n_obs;
   c->ni8 = KI * c->ni; c->nred = 6 * c->nc + c->ni8; c->eval_blocks = (int)std::max<long long>(1, (c->no + EVAL_THREADS - 1) / EVAL_THREADS);
+  c->eval_grid = std::min(c->eval_blocks, c->n_sms * (getenv("OMVG_BA_EVAL_WAVES") ? atoi(getenv("OMVG_BA_EVAL_WAVES")) : 4));   // persistent grid-stride evaluation
   c->h_intr_model.assign(P->intr_model, P->intr_model + c->ni);
   c->kiu = 0; for (int q = 0; q < c->ni; ++q) c->kiu = std::max(c->kiu, model_nparams(P->intr_model[q]));
   // ---- sort observations by point (counting sort); build per-pose lists
@@ -623,6 +624,26 @@ int omvg_ba_solve(omvg_ba_problem *P, const omvg_ba_options *O, omvg_ba_summary 
   return rc;
 }
 
+// Reprojection residual norms (pixels) of every observation at the current device parameters, in the
+// caller's observation order — what RemoveOutliers_PixelResidualError (sfm/sfm_data_filters.cpp:40-73)
+// recomputes on the host after every Adjust of the BA / reject loop (sequential_SfM.cpp:205-211).
+int omvg_ba_residual_norms(omvg_ba_ctx *c, double *norms) {
+  if (!c || !norms) return fail(OMVG_E_ARG, "null argument");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  omvg_ba_options O; omvg_ba_default_options(&O); O.use_loss = 0;
+  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[0].p, c->nc, c->camR[0].p, c->camdR.p, c->camrec[0].p); LAUNCH_CHECK();
+  EvalArgs A{}; A.poses = c->pose[0].p; A.intr = c->intr[0].p; A.pts = c->pt[0].p; A.camR = c->camR[0].p; A.camdR = c->camdR.p; A.camrec = c->camrec[0].p;
+  A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
+  A.n_obs = c->no; A.use_loss = 0; A.huber_a = O.huber_a; A.cost_partial = c->part.p; A.rnorm = c->r.p;   // r is scratch between solves
+  eval_kernel<false, 8><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  c->launches += 2;
+  std::vector<double> h(c->no);
+  OMVG_CUDA(cudaMemcpyAsync(h.data(), c->r.p, (size_t)c->no * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  for (long long t = 0; t < c->no; ++t) norms[c->perm[t]] = h[t];
+  return OMVG_OK;
+}
+
 int omvg_ba_debug_eval(omvg_ba_ctx *c, const omvg_ba_options *O, double *cost, double *r, double *J_intr, double *J_pose, double *J_point) {
   if (!c || !O) return fail(OMVG_E_ARG, "null argument");
   OMVG_CUDA(cudaSetDevice(c->device));
@@ -635,8 +656,8 @@ int omvg_ba_debug_eval(omvg_ba_ctx *c, const omvg_ba_options *O, double *cost, d
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = O->use_loss; A.huber_a = O->huber_a; A.r = c->r.p; A.Jp = c->Jp.p; A.Jc = c->Jc.p; A.Ji = c->Ji.p;
   A.cost_partial = c->part.p; A.kiu = c->kiu; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
-  eval_kernel<true, 4><<<c->eval_blocks, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
-  int rc = reduce_to(c, c->part.p, c->eval_blocks, S_COST); if (rc) return rc;
+  eval_kernel<true, 4><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  int rc = reduce_to(c, c->part.p, c->eval_grid, S_COST); if (rc) return rc;
   c->launches += 2;
   const long long n = c->no;
   std::vector<double> hr(2 * n), hp(6 * n), hc(12 * n), hi(2 * KI * n); double hcost = 0;

@@ -118,6 +118,7 @@ struct EvalArgs {
   // outputs (component-major: comp * n_obs + obs)
   double *r, *Jp, *Jc, *Ji;
   double *cost_partial;
+  double *rnorm;                            // optional: |r| (pixels, before the loss) per observation
   // scaling & masks
   const double *sc_pt, *sc_cam, *sc_intr;   // null => unscaled
   int kiu;                                  // intrinsic columns in use (max nparams over the groups)
@@ -181,10 +182,17 @@ constexpr int EVAL_THREADS = 128;
 template <bool WANT_J, int MINB>
 __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
   __shared__ double sh[EVAL_THREADS / 32];
-  const long long o = (long long)blockIdx.x * EVAL_THREADS + threadIdx.x;
+  // persistent grid-stride loop; the (DRAM-latency) index / observation loads of the NEXT observation are
+  // issued before the current one is processed
+  const long long stride = (long long)gridDim.x * EVAL_THREADS;
+  long long o = (long long)blockIdx.x * EVAL_THREADS + threadIdx.x;
   double cost = 0.0;
-  if (o < A.n_obs) {
-    const int ip = __ldcs(A.obs_pose + o), iq = __ldcs(A.obs_intr + o), j = __ldcs(A.obs_pt + o);
+  int ip = 0, iq = 0, j = 0; double2 xy = make_double2(0.0, 0.0);
+  if (o < A.n_obs) { ip = __ldcs(A.obs_pose + o); iq = __ldcs(A.obs_intr + o); j = __ldcs(A.obs_pt + o); xy = __ldcs(reinterpret_cast<const double2 *>(A.obs_xy) + o); }
+  while (o < A.n_obs) {
+    const long long o_next = o + stride;
+    int ipn = 0, iqn = 0, jn = 0; double2 xyn = make_double2(0.0, 0.0);
+    if (o_next < A.n_obs) { ipn = __ldcs(A.obs_pose + o_next); iqn = __ldcs(A.obs_intr + o_next); jn = __ldcs(A.obs_pt + o_next); xyn = __ldcs(reinterpret_cast<const double2 *>(A.obs_xy) + o_next); }
     double R[CAMREC];
     { const double2 *rp = reinterpret_cast<const double2 *>(A.camrec + (size_t)CAMREC * ip);
       #pragma unroll
@@ -200,13 +208,13 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
     double dx, dy, dd[4], dk[10];
     distort(model, K, x, y, dx, dy, dd, dk, WANT_J);
     const double f = K[0];
-    const double2 xy = __ldcs(reinterpret_cast<const double2 *>(A.obs_xy) + o);
     double r0 = K[1] + dx * f - xy.x, r1 = K[2] + dy * f - xy.y;
     const double s = r0 * r0 + r1 * r1;
+    if (!WANT_J && A.rnorm) A.rnorm[o] = sqrt(s);
     double rho0 = s, rho1 = 1.0;
     const double b = A.huber_a * A.huber_a;
     if (A.use_loss && s > b) { const double rr = sqrt(s); rho0 = 2.0 * A.huber_a * rr - b; rho1 = fmax(DBL_MIN, A.huber_a / rr); }
-    cost = 0.5 * rho0;
+    cost += 0.5 * rho0;
     if (WANT_J) {
       const double w = sqrt(rho1);                              // Huber: rho'' <= 0 => r, J scaled by sqrt(rho')
       const long long n = A.n_obs;
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
         if (k < A.kiu) { __stcs(A.Ji + (0 * KI + k) * n + o, sc * ji0[k]); __stcs(A.Ji + (1 * KI + k) * n + o, sc * ji1[k]); }
       }
     }
+    o = o_next; ip = ipn; iq = iqn; j = jn; xy = xyn;
   }
   const double t = block_sum<EVAL_THREADS>(cost, sh);
   if (threadIdx.x == 0) A.cost_partial[blockIdx.x] = t;

@@ -226,7 +226,15 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
 }
 
 // --------------------------------------------------------------------------------- finalize
-struct PairInfo { uint32_t db_row0, db_count, db_group, q_row0, q_count; uint32_t pad; uint64_t out_off; };
+struct PairInfo { uint32_t db_row0, db_count, db_group, q_row0, q_count; uint32_t unit0; uint64_t out_off; };
+
+// expand the per-pair table into the (pair, 128-query tile) work units on the device (one block per pair)
+__global__ void expand_units_kernel(const PairInfo *__restrict__ pairs, Unit *__restrict__ units) {
+  const PairInfo P = pairs[blockIdx.x];
+  const uint32_t qt = (P.q_count + TILE_Q - 1) / TILE_Q, dt = (P.db_count + TILE_DB - 1) / TILE_DB;
+  for (uint32_t t = threadIdx.x; t < qt; t += blockDim.x)
+    units[P.unit0 + t] = Unit{P.q_row0 + t * TILE_Q, P.db_row0, dt, (uint32_t)(P.out_off + t * TILE_Q)};
+}
 
 // exact top-2 of one query inside rows [r0, r1) of the database; whole warp cooperates.
 __device__ __forceinline__ void warp_rescan(const uint8_t *__restrict__ desc, const int32_t *__restrict__ norm,
@@ -475,7 +483,7 @@ cudaEvent_t get_event(omvg_match_ctx *c) {
 int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_t p0, uint64_t p1, float fratio,
               std::vector<Unit> &units, std::vector<PairInfo> &pinfo) {
   units.clear(); pinfo.clear();
-  size_t out = 0;
+  size_t out = 0, n_units = 0;
   for (uint64_t p = p0; p < p1; ++p) {
     const uint32_t I = pi[p], J = pj[p];
     PairInfo P{}; P.db_row0 = c->row0[I]; P.db_count = c->counts[I]; P.db_group = c->group[I];
@@ -486,14 +494,15 @@ int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_
     pinfo.push_back(P);
     if (!active) continue;
     const uint32_t qt = (P.q_count + TILE_Q - 1) / TILE_Q, dt = (P.db_count + TILE_DB - 1) / TILE_DB;
-    for (uint32_t t = 0; t < qt; ++t) units.push_back(Unit{P.q_row0 + t * TILE_Q, P.db_row0, dt, (uint32_t)(out + t * TILE_Q)});
+    (void)dt;
+    pinfo.back().unit0 = (uint32_t)n_units; n_units += qt;
     out += size_t(qt) * TILE_Q;
   }
   if (out > 0xffffffffull) return fail(OMVG_E_ARG, "batch too large");
   const uint32_t nb = (uint32_t)(p1 - p0);
   int rc;
   if ((rc = ensure(c->d_k12, c->k12_cap, std::max<size_t>(out, 1)))) return rc;
-  if ((rc = ensure(c->d_units, c->units_cap, std::max<size_t>(units.size(), 1)))) return rc;
+  if ((rc = ensure(c->d_units, c->units_cap, std::max<size_t>(n_units, 1)))) return rc;
   if (nb > c->pairs_cap) {
     if (c->d_pairs) cudaFree(c->d_pairs); if (c->d_counts) cudaFree(c->d_counts);
     c->d_pairs = nullptr; c->d_counts = nullptr; c->pairs_cap = 0;
@@ -501,15 +510,15 @@ int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_
     c->pairs_cap = nb;
   }
   OMVG_CUDA(cudaMemcpyAsync(c->d_pairs, pinfo.data(), nb * sizeof(PairInfo), cudaMemcpyHostToDevice, c->stream));
-  if (!units.empty()) {
-    OMVG_CUDA(cudaMemcpyAsync(c->d_units, units.data(), units.size() * sizeof(Unit), cudaMemcpyHostToDevice, c->stream));
-    const uint32_t grid = (uint32_t)std::min<size_t>(units.size(), (size_t)c->n_sms);
+  if (n_units) {
+    expand_units_kernel<<<nb, 64, 0, c->stream>>>(c->d_pairs, c->d_units); OMVG_CUDA(cudaGetLastError()); c->launches++;
+    const uint32_t grid = (uint32_t)std::min<size_t>(n_units, (size_t)c->n_sms);
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     OMVG_CUDA(cudaEventRecord(e0, c->stream));
     // OMVG_MATCH_DRAIN_ONLY=1 (measurement aid, results are garbage): epilogue reads TMEM but does no arithmetic
     static const bool drain_only = getenv("OMVG_MATCH_DRAIN_ONLY") != nullptr;
-    if (drain_only) match_tc_kernel<true><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)units.size(), c->d_k12);
-    else match_tc_kernel<false><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)units.size(), c->d_k12);
+    if (drain_only) match_tc_kernel<true><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)n_units, c->d_k12);
+    else match_tc_kernel<false><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)n_units, c->d_k12);
     OMVG_CUDA(cudaGetLastError());
     OMVG_CUDA(cudaEventRecord(e1, c->stream));
     c->pending.emplace_back(e0, e1); c->tc_launches++; c->launches++;

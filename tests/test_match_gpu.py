@@ -105,3 +105,48 @@ def test_matcher_interface(matching):
     out = matching.Matcher_Regions_B200(0.8).Match(provider, pairs)
     assert set(out.keys()) == {(10, 42)}
     assert np.array_equal(out[(10, 42)], ck.oracle_match_pair(d[0], d[1], 0.8))
+
+
+def test_reference_golden_hashes(matching):
+    """Golden outputs of the compiled reference (tests/golden): counts, CSR offsets and FNV-1a of the (i,j) list,
+    including the 5000 x 5000 pair of the survey probe shape."""
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.json")))
+    for case in gold["match"]:
+        descs = synth.descriptors(len(case["counts"]), case["counts"], seed=case["seed"])
+        pi, pj = synth.exhaustive_pairs(len(case["counts"]))
+        ctx = matching.MatchContext(0)
+        ctx.load(descs); ctx.run(pi, pj, case["ratio"]); off, ij = ctx.fetch(); ctx.close()
+        assert [int(x) for x in off] == case["offsets"]
+        ij = np.ascontiguousarray(ij)
+        fnv = int(ck.oracle().oracle_fnv1a_ij(ck._P(ij), ck.ctypes.c_int64(len(ij))))
+        assert str(fnv) == case["fnv1a"], case["name"]
+
+
+def test_full_size_properties(matching):
+    """BASELINE-size slice (40 images x 5000): size-independent properties — every kept match passes the ratio
+    test when re-evaluated exactly for its own query, rows are sorted by query index, and the self-pair (I,I)
+    matches nothing (d1 = 0 needs 0 < fratio*d2: true only if d2 > 0, then i == j)."""
+    descs = synth.descriptors(40, 5000, seed=1000)
+    pi, pj = synth.exhaustive_pairs(40)
+    ctx = matching.MatchContext(0)
+    ctx.load(descs); ctx.run(pi, pj, 0.8); off, ij = ctx.fetch()
+    assert len(ij) > 10000
+    rng = np.random.default_rng(0)
+    for p in rng.choice(len(pi), 12, replace=False):
+        rows = ij[int(off[p]):int(off[p + 1])]
+        assert np.all(np.diff(rows[:, 1].astype(np.int64)) > 0)              # ascending query index
+        if len(rows) == 0:
+            continue
+        I, J = descs[int(pi[p])].astype(np.int64), descs[int(pj[p])].astype(np.int64)
+        for i, j in rows[rng.choice(len(rows), min(5, len(rows)), replace=False)]:
+            d = ((I - J[int(j)]) ** 2).sum(1)
+            o = np.argsort(d, kind="stable")
+            assert o[0] == i and np.float32(d[o[0]]) < np.float32(0.8) * np.float32(0.8) * np.float32(d[o[1]])
+    # a pair sample bit-exact against the oracle
+    for p in (0, len(pi) // 2, len(pi) - 1):
+        want = ck.oracle_match_pair(descs[int(pi[p])], descs[int(pj[p])], 0.8)
+        assert np.array_equal(ij[int(off[p]):int(off[p + 1])], want)
+    ctx.run(np.array([3], np.uint32), np.array([3], np.uint32), 0.8); o2, ij2 = ctx.fetch()
+    assert np.array_equal(ij2[:, 0], ij2[:, 1])                                   # self pair: only i == j can survive
+    ctx.close()
