@@ -131,6 +131,25 @@ typedef struct {
   const int32_t *obs_view;
   const int32_t *obs_point;
   const double *obs_xy;
+  /* ---- optional extensions (NULL / 0 = absent) -------------------------------------------------
+   * Ground control points (sfm_data_BA_ceres.cpp:398-452): extra landmarks with point_fixed = 1
+   * (SetParameterBlockConstant, :447) whose observations carry obs_weight = Control_Point_Parameter
+   * ::weight (WeightedCostFunction multiplies the residual before the loss,
+   * sfm_data_BA_ceres_camera_functor.hpp:35-90) and obs_no_loss = 1 (loss nullptr, :424/:432).
+   * obs_weight = 0 removes an observation exactly (see omvg_ba_set_obs_weights). */
+  const double  *obs_weight;     /* [n_obs] */
+  const uint8_t *obs_no_loss;    /* [n_obs] */
+  const uint8_t *point_fixed;    /* [n_points] */
+  /* Pose-centre priors (PoseCenterConstraintCostFunction, sfm_data_BA_ceres.cpp:44-80, added at
+   * :455-472): residual prior_weight .* (C(pose) - prior_center) under HuberLoss(prior_huber_a),
+   * prior_huber_a = Square(pose_center_robust_fitting_error).  The similarity registration of the
+   * scene to the priors (:183-236) is host-side geometry done by the caller before this call
+   * (Bundle_Adjustment_B200.hpp does it with openMVG's own LeastMedianOfSquares/ApplySimilarity). */
+  int32_t n_priors, reserved_;
+  const int32_t *prior_pose;     /* [n_priors] pose index */
+  const double  *prior_center;   /* [n_priors][3] */
+  const double  *prior_weight;   /* [n_priors][3] */
+  double prior_huber_a;
 } omvg_ba_problem;
 
 /* Optimize_Options (sfm/sfm_data_BA.hpp:66-89) + BA_Ceres_options (sfm_data_BA_ceres.hpp:34-49)
@@ -191,6 +210,11 @@ int omvg_ba_destroy(omvg_ba_ctx *ctx);
  * caller's observation order: the quantity RemoveOutliers_PixelResidualError (sfm/sfm_data_filters.cpp:40-73)
  * thresholds after each Adjust of the BA / outlier-rejection loop (sequential_SfM.cpp:205-211). */
 int omvg_ba_residual_norms(omvg_ba_ctx *ctx, double *norms /* [n_obs] */);
+/* Replace the per-observation weights of the resident problem (caller's observation order; weight 0 =
+ * observation removed, exactly) — the rejection half of the loop above without rebuilding the scene. */
+int omvg_ba_set_obs_weights(omvg_ba_ctx *ctx, const double *weights /* [n_obs] */);
+/* Make the current (refined) parameters the state omvg_ba_reset() restores. */
+int omvg_ba_commit(omvg_ba_ctx *ctx);
 
 /* Validation aids (tests only): one evaluation at the uploaded parameters.
  * r[n_obs][2], J_intr[n_obs][2][8], J_pose[n_obs][2][6], J_point[n_obs][2][3] (row-major blocks,

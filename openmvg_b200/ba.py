@@ -16,13 +16,18 @@ from ._lib import OmvgError, check, lib
 _vp = ctypes.c_void_p
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
+_bp = ctypes.POINTER(ctypes.c_uint8)
 
 
 class Problem(ctypes.Structure):
     _fields_ = [("n_poses", ctypes.c_int32), ("n_intrinsics", ctypes.c_int32), ("n_points", ctypes.c_int32),
                 ("n_views", ctypes.c_int32), ("n_obs", ctypes.c_int64), ("poses", _dp), ("intrinsics", _dp),
                 ("intr_model", _ip), ("points", _dp), ("view_pose", _ip), ("view_intr", _ip), ("obs_view", _ip),
-                ("obs_point", _ip), ("obs_xy", _dp)]
+                ("obs_point", _ip), ("obs_xy", _dp),
+                # optional extensions (NULL / 0 = absent): GCP weights / flags / fixed landmarks, pose-centre priors
+                ("obs_weight", _dp), ("obs_no_loss", _bp), ("point_fixed", _bp),
+                ("n_priors", ctypes.c_int32), ("reserved_", ctypes.c_int32), ("prior_pose", _ip),
+                ("prior_center", _dp), ("prior_weight", _dp), ("prior_huber_a", ctypes.c_double)]
 
 
 class Options(ctypes.Structure):
@@ -67,6 +72,25 @@ def _problem(s, poses, intr, pts) -> Problem:
     P.poses, P.intrinsics, P.points = d(poses), d(intr), d(pts)
     P.intr_model, P.view_pose, P.view_intr = i(s["intr_model"]), i(s["view_pose"]), i(s["view_intr"])
     P.obs_view, P.obs_point, P.obs_xy = i(s["obs_view"]), i(s["obs_point"]), d(s["obs_xy"])
+    # optional extensions; the converted arrays are kept alive on the struct
+    keep = []
+
+    def opt(key, dtype, ptr):
+        a = s.get(key)
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype); keep.append(a)
+        return a.ctypes.data_as(ptr)
+    P.obs_weight = opt("obs_weight", np.float64, _dp)
+    P.obs_no_loss = opt("obs_no_loss", np.uint8, _bp)
+    P.point_fixed = opt("point_fixed", np.uint8, _bp)
+    if s.get("prior_pose") is not None and len(s["prior_pose"]):
+        P.n_priors = len(s["prior_pose"])
+        P.prior_pose = opt("prior_pose", np.int32, _ip)
+        P.prior_center = opt("prior_center", np.float64, _dp)
+        P.prior_weight = opt("prior_weight", np.float64, _dp)
+        P.prior_huber_a = float(s.get("prior_huber_a", 0.0))
+    P._keep = keep
     return P
 
 
@@ -131,6 +155,16 @@ class BAContext:
         out = np.zeros(len(self._s["obs_view"]))
         check(lib().omvg_ba_residual_norms(self._h, out.ctypes.data_as(_dp)))
         return out
+
+    def set_obs_weights(self, w):
+        """Per-observation weights of the resident problem (0 = observation removed)."""
+        w = np.ascontiguousarray(w, np.float64)
+        assert len(w) == len(self._s["obs_view"])
+        check(lib().omvg_ba_set_obs_weights(self._h, w.ctypes.data_as(_dp)))
+
+    def commit(self):
+        """Make the refined parameters the state reset() restores."""
+        check(lib().omvg_ba_commit(self._h))
 
     def debug_eval(self, **opts):
         o = default_options(**opts)

@@ -58,6 +58,9 @@ struct omvg_ba_ctx {
   DevBuf<int> agg_of, agg_start, agg_cams, brow; DevBuf<double> cE, cEinv, cT, cCv, cYv, bP2; int ng = 0;
   DevBuf<double> part, part2, part3, icol_part, scal;
   DevBuf<int> fail;
+  // optional extensions: GCP weights / flags / fixed landmarks, pose-centre priors
+  DevBuf<double> obs_w; DevBuf<unsigned char> obs_flags, pt_fixed; DevBuf<unsigned> pt_mask;
+  int npri = 0; double prior_huber_a = 0; DevBuf<int> prior_pose; DevBuf<double> prior_center, prior_weight, rP, JP;
   double *h_scal = nullptr;                 // pinned
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evj0 = nullptr, evj1 = nullptr;
   long long launches = 0;
@@ -79,6 +82,9 @@ int validate(const omvg_ba_problem *P) {
     if (P->view_pose[v] < 0 || P->view_pose[v] >= P->n_poses || P->view_intr[v] < 0 || P->view_intr[v] >= P->n_intrinsics) return fail(OMVG_E_ARG, "view %d out of range", v);
   for (long long o = 0; o < P->n_obs; ++o)
     if (P->obs_view[o] < 0 || P->obs_view[o] >= P->n_views || P->obs_point[o] < 0 || P->obs_point[o] >= P->n_points) return fail(OMVG_E_ARG, "observation %lld out of range", o);
+  if (P->n_priors < 0 || (P->n_priors > 0 && (!P->prior_pose || !P->prior_center || !P->prior_weight))) return fail(OMVG_E_ARG, "bad pose-centre prior arrays");
+  for (int k = 0; k < P->n_priors; ++k) if (P->prior_pose[k] < 0 || P->prior_pose[k] >= P->n_poses) return fail(OMVG_E_ARG, "prior %d: pose out of range", k);
+  if (P->n_priors > 0 && !(P->prior_huber_a >= 0.0)) return fail(OMVG_E_ARG, "prior_huber_a must be >= 0");
   if (P->n_poses > 32768) return fail(OMVG_E_UNSUPPORTED, "more than 32768 poses (camera-pair bitmap)");
   if (P->n_intrinsics > 32) return fail(OMVG_E_UNSUPPORTED, "more than 32 intrinsic groups (dense border)");
   return OMVG_OK;
@@ -124,15 +130,22 @@ int eval_cost(omvg_ba_ctx *c, const omvg_ba_options *o, int which, int slot) {
   EvalArgs A{}; A.poses = c->pose[which].p; A.intr = c->intr[which].p; A.pts = c->pt[which].p; A.camR = c->camR[which].p; A.camdR = c->camdR.p; A.camrec = c->camrec[which].p;
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = o->use_loss; A.huber_a = o->huber_a; A.cost_partial = c->part.p;
+  A.obs_w = c->obs_w.p; A.obs_flags = c->obs_flags.p; A.pt_fixed = c->pt_fixed.p;
   eval_kernel<false, 8><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
   c->launches += 2;
-  return reduce_to(c, c->part.p, c->eval_grid, slot);
+  if (c->npri) {
+    PriorArgs PA{}; PA.poses = c->pose[which].p; PA.camR = c->camR[which].p; PA.camdR = c->camdR.p; PA.prior_pose = c->prior_pose.p; PA.center = c->prior_center.p; PA.weight = c->prior_weight.p;
+    PA.n = c->npri; PA.huber_a = c->prior_huber_a; PA.cost_out = c->part.p + c->eval_grid;
+    prior_eval_kernel<false><<<1, PRIOR_THREADS, 0, c->stream>>>(PA); LAUNCH_CHECK(); c->launches++;
+  }
+  return reduce_to(c, c->part.p, c->eval_grid + (c->npri ? 1 : 0), slot);
 }
 
 int colsums(omvg_ba_ctx *c) {
   point_accum_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Ji.p, c->r.p, c->pt_start.p, c->pt_single.p, c->np, c->no, c->kiu, c->EtE.p, c->Etb.p, c->EtFi.p); LAUNCH_CHECK();
   point_diag_from_EtE_kernel<<<(c->np + 255) / 256, 256, 0, c->stream>>>(c->EtE.p, c->np, c->diag_pt.p); LAUNCH_CHECK();
   cam_colsum_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Jc.p, c->r.p, c->cam_start.p, c->cam_obs.p, c->nc, c->no, c->diag_cam.p, c->g_cam.p, c->FtF.p); LAUNCH_CHECK();
+  if (c->npri) { prior_accum_kernel<<<(c->npri + 127) / 128, 128, 0, c->stream>>>(c->JP.p, c->rP.p, c->prior_pose.p, c->npri, c->diag_cam.p, c->g_cam.p, c->FtF.p); LAUNCH_CHECK(); c->launches++; }
   const int chunks = 64;
   intr_colsum_kernel<<<dim3(chunks, c->ni), ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->kiu, c->icol_part.p); LAUNCH_CHECK();
   intr_colsum_final_kernel<<<(c->ni * 72 + 63) / 64, 64, 0, c->stream>>>(c->icol_part.p, chunks, c->ni, c->diag_intr.p, c->g_intr.p, c->FiFi.p); LAUNCH_CHECK();
@@ -146,6 +159,7 @@ int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = o->use_loss; A.huber_a = o->huber_a; A.r = c->r.p; A.Jp = c->Jp.p; A.Jc = c->Jc.p; A.Ji = c->Ji.p;
   A.cost_partial = c->part.p; A.kiu = c->kiu; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
+  A.obs_w = c->obs_w.p; A.obs_flags = c->obs_flags.p; A.pt_fixed = c->pt_fixed.p;
   if (have_scale) { A.sc_pt = c->sc_pt.p; A.sc_cam = c->sc_cam.p; A.sc_intr = c->sc_intr.p; }
   if (time_it) OMVG_CUDA(cudaEventRecord(c->evj0, c->stream));
   static const int minb = getenv("OMVG_BA_EVAL_MINB") ? atoi(getenv("OMVG_BA_EVAL_MINB")) : 4;
@@ -155,7 +169,12 @@ int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which
   LAUNCH_CHECK();
   if (time_it) OMVG_CUDA(cudaEventRecord(c->evj1, c->stream));
   c->launches += 2;
-  int rc = reduce_to(c, c->part.p, c->eval_grid, S_COST); if (rc) return rc;
+  if (c->npri) {
+    PriorArgs PA{}; PA.poses = c->pose[which].p; PA.camR = c->camR[which].p; PA.camdR = c->camdR.p; PA.prior_pose = c->prior_pose.p; PA.center = c->prior_center.p; PA.weight = c->prior_weight.p;
+    PA.n = c->npri; PA.huber_a = c->prior_huber_a; PA.sc_cam = have_scale ? c->sc_cam.p : nullptr; PA.pose_mask = m.pose_mask; PA.rP = c->rP.p; PA.JP = c->JP.p; PA.cost_out = c->part.p + c->eval_grid;
+    prior_eval_kernel<true><<<1, PRIOR_THREADS, 0, c->stream>>>(PA); LAUNCH_CHECK(); c->launches++;
+  }
+  int rc = reduce_to(c, c->part.p, c->eval_grid + (c->npri ? 1 : 0), S_COST); if (rc) return rc;
   if (!have_scale) {        // iteration 0: Jacobi scaling from the unscaled J (trust_region_minimizer.cc:239-253)
     if ((rc = colsums(c))) return rc;
     make_scale_kernel<<<(3 * c->np + 255) / 256, 256, 0, c->stream>>>(c->diag_pt.p, 3 * c->np, c->sc_pt.p); LAUNCH_CHECK();
@@ -163,6 +182,7 @@ int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which
     make_scale_kernel<<<(c->ni8 + 255) / 256, 256, 0, c->stream>>>(c->diag_intr.p, c->ni8, c->sc_intr.p); LAUNCH_CHECK();
     scale_J_kernel<<<(unsigned)((c->no + 255) / 256), 256, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no, c->kiu,
                                                                           c->sc_pt.p, c->sc_cam.p, c->sc_intr.p); LAUNCH_CHECK();
+    if (c->npri) { prior_scale_kernel<<<(18 * c->npri + 127) / 128, 128, 0, c->stream>>>(c->JP.p, c->prior_pose.p, c->sc_cam.p, c->npri); LAUNCH_CHECK(); c->launches++; }
     c->launches += 4; have_scale = true;
   }
   if ((rc = colsums(c))) return rc;
@@ -316,6 +336,9 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   #pragma omp parallel for schedule(static) if (no > 100000)
   for (long long t = 0; t < no; ++t) { const int o = c->perm[t], v = P->obs_view[o];
     s_pose[t] = P->view_pose[v]; s_intr[t] = P->view_intr[v]; s_pt[t] = P->obs_point[o]; s_xy[2 * t] = P->obs_xy[2 * o]; s_xy[2 * t + 1] = P->obs_xy[2 * o + 1]; }
+  std::vector<double> s_w; std::vector<unsigned char> s_fl;
+  if (P->obs_weight) { s_w.resize(no); for (long long t = 0; t < no; ++t) s_w[t] = P->obs_weight[c->perm[t]]; }
+  if (P->obs_no_loss) { s_fl.resize(no); for (long long t = 0; t < no; ++t) s_fl[t] = P->obs_no_loss[c->perm[t]] ? 1 : 0; }
   std::vector<unsigned char> pt_single(c->np, 1);
   #pragma omp parallel for schedule(static) if (c->np > 100000)
   for (int j = 0; j < c->np; ++j) for (int t = pt_start[j] + 1; t < pt_start[j + 1]; ++t) if (s_intr[t] != s_intr[pt_start[j]]) { pt_single[j] = 0; break; }
@@ -331,6 +354,14 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   UP(c->pose0, P->poses, 6 * c->nc); UP(c->intr0, h_intr.data(), c->ni8); UP(c->pt0, P->points, 3 * (size_t)c->np);
   UP(c->intr_model, P->intr_model, c->ni); UP(c->obs_pose, s_pose.data(), no); UP(c->obs_intr, s_intr.data(), no); UP(c->obs_pt, s_pt.data(), no);
   UP(c->pt_single, pt_single.data(), c->np); UP(c->pt_start, pt_start.data(), c->np + 1); UP(c->cam_start, cam_start.data(), c->nc + 1); UP(c->cam_obs, cam_obs.data(), no); UP(c->obs_xy, s_xy.data(), 2 * no);
+  if (P->obs_weight) UP(c->obs_w, s_w.data(), no);
+  if (P->obs_no_loss) UP(c->obs_flags, s_fl.data(), no);
+  if (P->point_fixed) {
+    std::vector<unsigned> pm(c->np); for (int j = 0; j < c->np; ++j) pm[j] = P->point_fixed[j] ? 0u : 7u;
+    UP(c->pt_fixed, P->point_fixed, c->np); UP(c->pt_mask, pm.data(), c->np);
+  }
+  c->npri = P->n_priors; c->prior_huber_a = P->prior_huber_a;
+  if (c->npri) { UP(c->prior_pose, P->prior_pose, c->npri); UP(c->prior_center, P->prior_center, 3 * c->npri); UP(c->prior_weight, P->prior_weight, 3 * c->npri); }
 #undef UP
 #define AL(buf, cnt) if ((rc = buf.alloc((size_t)(cnt)))) return rc
   for (int w = 0; w < 2; ++w) { AL(c->pose[w], 6 * c->nc); AL(c->intr[w], c->ni8); AL(c->pt[w], 3 * (size_t)c->np); AL(c->camR[w], 9 * c->nc); AL(c->camrec[w], (size_t)CAMREC * c->nc); }
@@ -348,7 +379,8 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   AL(c->bX, (size_t)MAXRHS * 6 * c->nc); AL(c->bR, (size_t)MAXRHS * 6 * c->nc); AL(c->bP, (size_t)MAXRHS * 6 * c->nc); AL(c->bW, (size_t)MAXRHS * 6 * c->nc); AL(c->bZ, (size_t)MAXRHS * 6 * c->nc);
   AL(c->pcg2_part, (size_t)c->n_sms * PCG2_V);
   AL(c->z, c->nred); AL(c->res, c->nred); AL(c->pvec, c->nred); AL(c->w, c->nred); AL(c->zeta, c->nred); AL(c->pcg_part, 3 * (size_t)c->n_sms * 2);
-  AL(c->part, std::max(c->eval_blocks, 1024)); AL(c->part2, 1024); AL(c->part3, 1024); AL(c->icol_part, (size_t)c->ni * 64 * ICS_W); AL(c->scal, S_COUNT); AL(c->fail, 1);
+  if (c->npri) { AL(c->rP, 3 * c->npri); AL(c->JP, 18 * c->npri); }
+  AL(c->part, std::max(c->eval_blocks, 1024) + 2); AL(c->part2, 1024); AL(c->part3, 1024); AL(c->icol_part, (size_t)c->ni * 64 * ICS_W); AL(c->scal, S_COUNT); AL(c->fail, 1);
 #undef AL
   OMVG_CUDA(cudaMemsetAsync(c->scal.p, 0, S_COUNT * sizeof(double), s));
   if ((rc = build_structure(c))) return rc;
@@ -500,10 +532,11 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     // ---- model cost change
     model_kernel<<<c->eval_blocks, MODEL_THREADS, 0, c->stream>>>(c->r.p, c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no, c->nc, c->kiu, c->step_pt.p, c->step_red.p, c->part.p); LAUNCH_CHECK();
     c->launches += 10;
-    if ((rc = reduce_to(c, c->part.p, c->eval_blocks, S_MODEL))) return rc;
+    if (c->npri) { prior_model_kernel<<<1, PRIOR_THREADS, 0, c->stream>>>(c->JP.p, c->rP.p, c->prior_pose.p, c->npri, c->step_red.p, c->part.p + c->eval_blocks); LAUNCH_CHECK(); c->launches++; }
+    if ((rc = reduce_to(c, c->part.p, c->eval_blocks + (c->npri ? 1 : 0), S_MODEL))) return rc;
     // ---- candidate = Plus(x, step * scale)
     const int ub = 64;
-    update_kernel<<<ub, 256, 0, c->stream>>>(c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, nullptr, 0, c->pt[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
+    update_kernel<<<ub, 256, 0, c->stream>>>(c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, m.pts_free ? c->pt_mask.p : nullptr, 0, c->pt[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
     if ((rc = reduce_to(c, c->part2.p, ub, S_STEP2_PT))) return rc; if ((rc = reduce_to(c, c->part3.p, ub, S_X2_PT))) return rc;
     update_kernel<<<ub, 256, 0, c->stream>>>(c->pose[0].p, c->step_red.p, c->sc_cam.p, 6 * c->nc, 6, m.pose_mask, nullptr, 0, c->pose[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
     if ((rc = reduce_to(c, c->part2.p, ub, S_STEP2_POSE))) return rc; if ((rc = reduce_to(c, c->part3.p, ub, S_X2_POSE))) return rc;
@@ -541,7 +574,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
       if ((rc = make_gauge(c, m, nw))) return rc;
       // x_norm of the new x: update_kernel measures |x| of its input; run the three norm passes on the new x
-      update_kernel<<<ub, 256, 0, c->stream>>>(c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, nullptr, 0, c->pt[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
+      update_kernel<<<ub, 256, 0, c->stream>>>(c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, m.pts_free ? c->pt_mask.p : nullptr, 0, c->pt[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
       if ((rc = reduce_to(c, c->part3.p, ub, S_X2_PT))) return rc;
       update_kernel<<<ub, 256, 0, c->stream>>>(c->pose[0].p, c->step_red.p, c->sc_cam.p, 6 * c->nc, 6, m.pose_mask, nullptr, 0, c->pose[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
       if ((rc = reduce_to(c, c->part3.p, ub, S_X2_POSE))) return rc;
@@ -635,12 +668,39 @@ int omvg_ba_residual_norms(omvg_ba_ctx *c, double *norms) {
   EvalArgs A{}; A.poses = c->pose[0].p; A.intr = c->intr[0].p; A.pts = c->pt[0].p; A.camR = c->camR[0].p; A.camdR = c->camdR.p; A.camrec = c->camrec[0].p;
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = 0; A.huber_a = O.huber_a; A.cost_partial = c->part.p; A.rnorm = c->r.p;   // r is scratch between solves
+  A.pt_fixed = c->pt_fixed.p;                              // (weights deliberately not applied: pixels)
   eval_kernel<false, 8><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
   c->launches += 2;
   std::vector<double> h(c->no);
   OMVG_CUDA(cudaMemcpyAsync(h.data(), c->r.p, (size_t)c->no * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   OMVG_CUDA(cudaStreamSynchronize(c->stream));
   for (long long t = 0; t < c->no; ++t) norms[c->perm[t]] = h[t];
+  return OMVG_OK;
+}
+
+// Replaces the per-observation weights of a resident problem (caller's observation order).  Weight 0
+// removes the observation exactly (zero residual and Jacobian rows) while the sparsity structure stays
+// a superset: the BA -> RemoveOutliers_PixelResidualError -> BA loop (sequential_SfM.cpp:1226-1243,
+// sfm_filters.hpp:49-79) runs without rebuilding or re-uploading the scene.
+int omvg_ba_set_obs_weights(omvg_ba_ctx *c, const double *w) {
+  if (!c || !w) return fail(OMVG_E_ARG, "null argument");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  std::vector<double> s_w(c->no);
+  for (long long t = 0; t < c->no; ++t) { const double v = w[c->perm[t]]; if (!(v >= 0.0) || !std::isfinite(v)) return fail(OMVG_E_ARG, "weight %d is negative or not finite", c->perm[t]); s_w[t] = v; }
+  if (!c->obs_w.p) { int rc = c->obs_w.alloc(c->no); if (rc) return rc; }
+  OMVG_CUDA(cudaMemcpyAsync(c->obs_w.p, s_w.data(), (size_t)c->no * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  return OMVG_OK;
+}
+
+// Makes the current (refined) parameters the state omvg_ba_reset() returns to: the next run of the
+// BA / reject loop starts from the previous solution.
+int omvg_ba_commit(omvg_ba_ctx *c) {
+  if (!c) return fail(OMVG_E_ARG, "null ctx");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  OMVG_CUDA(cudaMemcpyAsync(c->pose0.p, c->pose[0].p, 6 * c->nc * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(c->intr0.p, c->intr[0].p, c->ni8 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  OMVG_CUDA(cudaMemcpyAsync(c->pt0.p, c->pt[0].p, 3 * (size_t)c->np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   return OMVG_OK;
 }
 
@@ -656,6 +716,7 @@ int omvg_ba_debug_eval(omvg_ba_ctx *c, const omvg_ba_options *O, double *cost, d
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = O->use_loss; A.huber_a = O->huber_a; A.r = c->r.p; A.Jp = c->Jp.p; A.Jc = c->Jc.p; A.Ji = c->Ji.p;
   A.cost_partial = c->part.p; A.kiu = c->kiu; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
+  A.obs_w = c->obs_w.p; A.obs_flags = c->obs_flags.p; A.pt_fixed = c->pt_fixed.p;      // (prior rows are not part of this dump)
   eval_kernel<true, 4><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
   int rc = reduce_to(c, c->part.p, c->eval_grid, S_COST); if (rc) return rc;
   c->launches += 2;

@@ -118,7 +118,10 @@ struct EvalArgs {
   // outputs (component-major: comp * n_obs + obs)
   double *r, *Jp, *Jc, *Ji;
   double *cost_partial;
-  double *rnorm;                            // optional: |r| (pixels, before the loss) per observation
+  double *rnorm;                            // optional: |r| (pixels, before weight and loss) per observation
+  // optional per-observation weight / flags and fixed landmarks (ground control points, sfm_data_BA_ceres.cpp:398-452;
+  // weight 0 removes an observation without rebuilding the structure: the outlier-rejection loop)
+  const double *obs_w; const unsigned char *obs_flags; const unsigned char *pt_fixed;
   // scaling & masks
   const double *sc_pt, *sc_cam, *sc_intr;   // null => unscaled
   int kiu;                                  // intrinsic columns in use (max nparams over the groups)
@@ -202,23 +205,29 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
     const double p0 = R[0] * X0 + R[1] * X1 + R[2] * X2 + T[0];
     const double p1 = R[3] * X0 + R[4] * X1 + R[5] * X2 + T[1];
     const double p2 = R[6] * X0 + R[7] * X1 + R[8] * X2 + T[2];
-    const double iz = 1.0 / p2, x = p0 * iz, y = p1 * iz;
+    const double wg = A.obs_w ? __ldcs(A.obs_w + o) : 1.0;      // WeightedCostFunction (functor.hpp:35-90)
+    const bool dead = wg == 0.0;                               // removed observation: contributes exact zeros
+    const bool safe = dead && WANT_J;                          // keep every Jacobian factor finite so that 0 * J == 0
+    const double iz = safe ? 1.0 : 1.0 / p2, x = safe ? 0.0 : p0 * iz, y = safe ? 0.0 : p1 * iz;
     const double *K = A.intr + KI * iq;
     const int model = A.intr_model[iq];
     double dx, dy, dd[4], dk[10];
     distort(model, K, x, y, dx, dy, dd, dk, WANT_J);
     const double f = K[0];
     double r0 = K[1] + dx * f - xy.x, r1 = K[2] + dy * f - xy.y;
+    if (!WANT_J && A.rnorm) A.rnorm[o] = sqrt(r0 * r0 + r1 * r1);
+    r0 = dead ? 0.0 : r0 * wg; r1 = dead ? 0.0 : r1 * wg;
     const double s = r0 * r0 + r1 * r1;
-    if (!WANT_J && A.rnorm) A.rnorm[o] = sqrt(s);
     double rho0 = s, rho1 = 1.0;
     const double b = A.huber_a * A.huber_a;
-    if (A.use_loss && s > b) { const double rr = sqrt(s); rho0 = 2.0 * A.huber_a * rr - b; rho1 = fmax(DBL_MIN, A.huber_a / rr); }
+    const bool lossy = A.use_loss && !(A.obs_flags && (A.obs_flags[o] & 1));   // GCP blocks carry no loss (:424)
+    if (lossy && s > b) { const double rr = sqrt(s); rho0 = 2.0 * A.huber_a * rr - b; rho1 = fmax(DBL_MIN, A.huber_a / rr); }
     cost += 0.5 * rho0;
     if (WANT_J) {
-      const double w = sqrt(rho1);                              // Huber: rho'' <= 0 => r, J scaled by sqrt(rho')
+      const double wl = sqrt(rho1);                             // Huber: rho'' <= 0 => r, J scaled by sqrt(rho')
+      const double w = wl * wg;                                 // Jacobian of the weighted residual
       const long long n = A.n_obs;
-      __stcs(A.r + o, w * r0); __stcs(A.r + n + o, w * r1);
+      __stcs(A.r + o, wl * r0); __stcs(A.r + n + o, wl * r1);
       // d r / d u = f * dd ; d u / d p = [[iz,0,-x iz],[0,iz,-y iz]]
       const double a00 = w * f * dd[0], a01 = w * f * dd[1], a10 = w * f * dd[2], a11 = w * f * dd[3];
       double g[6];                                              // d r / d p (2x3)
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
       // point block: g * R
       #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const double sc = A.pts_free ? (A.sc_pt ? A.sc_pt[3 * j + c] : 1.0) : 0.0;
+        const double sc = (A.pts_free && !(A.pt_fixed && A.pt_fixed[j])) ? (A.sc_pt ? A.sc_pt[3 * j + c] : 1.0) : 0.0;
         __stcs(A.Jp + (0 * 3 + c) * n + o, sc * (g[0] * R[c] + g[1] * R[3 + c] + g[2] * R[6 + c]));
         __stcs(A.Jp + (1 * 3 + c) * n + o, sc * (g[3] * R[c] + g[4] * R[3 + c] + g[5] * R[6 + c]));
       }
@@ -263,6 +272,81 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
   }
   const double t = block_sum<EVAL_THREADS>(cost, sh);
   if (threadIdx.x == 0) A.cost_partial[blockIdx.x] = t;
+}
+
+// ------------------------------------------------------------------------------ pose-centre priors
+// PoseCenterConstraintCostFunction (sfm_data_BA_ceres.cpp:44-80), added with HuberLoss(a = fit^2) at :455-472:
+// r = w .* (C - c0), C = -R' t.  A few hundred rows touching one pose block each: one block does them all.
+struct PriorArgs {
+  const double *poses, *camR, *camdR; const int *prior_pose; const double *center, *weight; int n; double huber_a;
+  const double *sc_cam; unsigned pose_mask;
+  double *rP, *JP;            // corrected residuals [n][3], Jacobians [n][3][6] (scaled, masked)
+  double *cost_out;           // one partial
+};
+constexpr int PRIOR_THREADS = 128;
+template <bool WANT_J>
+__global__ void __launch_bounds__(PRIOR_THREADS) prior_eval_kernel(PriorArgs A) {
+  __shared__ double sh[PRIOR_THREADS / 32];
+  double cost = 0.0;
+  for (int k = threadIdx.x; k < A.n; k += PRIOR_THREADS) {
+    const int p = A.prior_pose[k];
+    const double *R = A.camR + 9 * p, *t = A.poses + 6 * p + 3, *w = A.weight + 3 * k, *c0 = A.center + 3 * k;
+    double r[3];
+    #pragma unroll
+    for (int i = 0; i < 3; ++i) r[i] = w[i] * (-(R[i] * t[0] + R[3 + i] * t[1] + R[6 + i] * t[2]) - c0[i]);
+    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2], b = A.huber_a * A.huber_a;
+    double rho0 = s, rho1 = 1.0;
+    if (s > b) { const double rr = sqrt(s); rho0 = 2.0 * A.huber_a * rr - b; rho1 = fmax(DBL_MIN, A.huber_a / rr); }
+    cost += 0.5 * rho0;
+    if (WANT_J) {
+      const double wl = sqrt(rho1);
+      const double *dR = A.camdR + 27 * p;
+      #pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        A.rP[3 * k + i] = wl * r[i];
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const double d = c < 3 ? -(dR[9 * c + i] * t[0] + dR[9 * c + 3 + i] * t[1] + dR[9 * c + 6 + i] * t[2]) : -R[3 * (c - 3) + i];
+          const double sc = ((A.pose_mask >> c) & 1) ? (A.sc_cam ? A.sc_cam[6 * p + c] : 1.0) : 0.0;
+          A.JP[18 * k + 6 * i + c] = sc * wl * w[i] * d;
+        }
+      }
+    }
+  }
+  const double tsum = block_sum<PRIOR_THREADS>(cost, sh);
+  if (threadIdx.x == 0) A.cost_out[0] = tsum;
+}
+// iteration 0: the Jacobi scale is known only after the unscaled column norms
+__global__ void prior_scale_kernel(double *__restrict__ JP, const int *__restrict__ prior_pose, const double *__restrict__ sc_cam, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 18 * n) JP[i] *= sc_cam[6 * prior_pose[i / 18] + i % 6];
+}
+// adds the prior rows to the pose-diagonal blocks, column norms and gradient (run after cam_colsum_kernel)
+__global__ void prior_accum_kernel(const double *__restrict__ JP, const double *__restrict__ rP, const int *__restrict__ prior_pose, int n,
+                                   double *__restrict__ diag_cam, double *__restrict__ g_cam, double *__restrict__ FtF) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int p = prior_pose[k]; const double *J = JP + 18 * k, *r = rP + 3 * k;
+  for (int a = 0; a < 6; ++a) {
+    atomicAdd(g_cam + 6 * p + a, J[a] * r[0] + J[6 + a] * r[1] + J[12 + a] * r[2]);
+    for (int b = 0; b < 6; ++b) {
+      const double v = J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b];
+      atomicAdd(FtF + 36 * (size_t)p + a * 6 + b, v);
+      if (a == b) atomicAdd(diag_cam + 6 * p + a, v);
+    }
+  }
+}
+// model-cost partial of the prior rows
+__global__ void __launch_bounds__(PRIOR_THREADS) prior_model_kernel(const double *__restrict__ JP, const double *__restrict__ rP, const int *__restrict__ prior_pose, int n,
+                                                                     const double *__restrict__ step_red, double *__restrict__ out) {
+  __shared__ double sh[PRIOR_THREADS / 32];
+  double v = 0.0;
+  for (int k = threadIdx.x; k < n; k += PRIOR_THREADS) {
+    const double *st = step_red + 6 * prior_pose[k];
+    for (int i = 0; i < 3; ++i) { double m = 0; for (int c = 0; c < 6; ++c) m += JP[18 * k + 6 * i + c] * st[c]; v += -m * (rP[3 * k + i] + m / 2.0); }
+  }
+  const double t = block_sum<PRIOR_THREADS>(v, sh);
+  if (threadIdx.x == 0) out[0] = t;
 }
 
 // fixed-order final reduction of per-block partials -> out[0]

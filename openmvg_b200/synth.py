@@ -112,7 +112,50 @@ def ba_scene(n_cams: int, n_points: int, obs_per_point: int, seed: int = 42,
         intr_model=intr_model, points=np.ascontiguousarray(points),
         view_pose=view_pose, view_intr=view_intr,
         obs_view=np.ascontiguousarray(obs_view), obs_point=np.ascontiguousarray(obs_point),
-        obs_xy=np.ascontiguousarray(xy), gt_dist=gt_dist)
+        obs_xy=np.ascontiguousarray(xy), gt_dist=gt_dist, gt_R=gtR, gt_C=gtC)
+
+
+def add_gcp(scene: dict, n_gcp: int, weight: float = 20.0, views_per_gcp: int = 4, seed: int = 7) -> dict:
+    """Ground control points as Adjust adds them (sfm_data_BA_ceres.cpp:398-452): landmarks held
+    constant at their surveyed position, observed with residuals multiplied by ``weight`` and no
+    robust loss.  In the flat layout they are extra points (``point_fixed`` = 1) whose observations
+    carry ``obs_weight`` = weight and ``obs_no_loss`` = 1; appended after the regular ones."""
+    rng = np.random.default_rng(seed)
+    s = dict(scene)
+    n_cams = len(s["poses"]); n_pts = len(s["points"]); n_obs = len(s["obs_view"])
+    Xg = rng.uniform(-0.5, 0.5, (n_gcp, 3))
+    first = rng.integers(0, n_cams, n_gcp)
+    cam = ((first[:, None] + np.arange(views_per_gcp)[None, :] * max(1, n_cams // (2 * views_per_gcp))) % n_cams).astype(np.int32)
+    ov = cam.reshape(-1)
+    op = np.repeat(np.arange(n_gcp, dtype=np.int32), views_per_gcp)
+    Xc = np.einsum('oij,oj->oi', s["gt_R"][ov], Xg[op] - s["gt_C"][ov])
+    u = _distort(Xc[:, :2] / Xc[:, 2:3], int(s["intr_model"][0]), s["gt_dist"])
+    f, cx, cy = 1000.0, 500.0, 500.0
+    xy = np.stack([cx + f * u[:, 0], cy + f * u[:, 1]], 1) + rng.normal(0, 0.3, (len(ov), 2))
+    s["points"] = np.ascontiguousarray(np.concatenate([s["points"], Xg]))
+    s["obs_view"] = np.ascontiguousarray(np.concatenate([s["obs_view"], ov]).astype(np.int32))
+    s["obs_point"] = np.ascontiguousarray(np.concatenate([s["obs_point"], op + n_pts]).astype(np.int32))
+    s["obs_xy"] = np.ascontiguousarray(np.concatenate([s["obs_xy"], xy]))
+    s["obs_weight"] = np.concatenate([np.ones(n_obs), np.full(len(ov), float(weight))])
+    s["obs_no_loss"] = np.concatenate([np.zeros(n_obs, np.uint8), np.ones(len(ov), np.uint8)])
+    s["point_fixed"] = np.concatenate([np.zeros(n_pts, np.uint8), np.ones(n_gcp, np.uint8)])
+    return s
+
+
+def add_priors(scene: dict, sigma: float = 0.01, weight=(1.0, 1.0, 1.0), seed: int = 11,
+               offset=(0.0, 0.0, 0.0), scale: float = 1.0) -> dict:
+    """Pose-centre (GPS) priors on every view (sfm_view_priors.hpp:27-80): prior centre =
+    scale * ground-truth centre + offset + N(0, sigma), per-axis weight.  ``prior_huber_a`` is the
+    squared median fitting error and is filled by the registration step (host-side geometry, done by
+    the C++ shim with openMVG's own functions)."""
+    rng = np.random.default_rng(seed)
+    s = dict(scene)
+    n = len(s["poses"])
+    s["prior_pose"] = np.arange(n, dtype=np.int32)
+    s["prior_center"] = np.ascontiguousarray(scale * s["gt_C"] + np.asarray(offset) + rng.normal(0, sigma, (n, 3)))
+    s["prior_weight"] = np.ascontiguousarray(np.tile(np.asarray(weight, np.float64), (n, 1)))
+    s["prior_huber_a"] = 0.0
+    return s
 
 
 def _distort(u: np.ndarray, model: int, d: np.ndarray) -> np.ndarray:

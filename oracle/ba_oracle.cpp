@@ -158,6 +158,11 @@ struct Problem {
   int n_poses, n_intr, n_points, n_views; long n_obs;
   const int *intr_model, *view_pose, *view_intr, *obs_view, *obs_point;
   const double *obs_xy;
+  // optional (all may be null / 0): ground control points and pose-centre priors
+  const double *obs_weight;          // WeightedCostFunction weight per observation (functor.hpp:35-90)
+  const unsigned char *obs_no_loss;  // residual block added with loss == nullptr (sfm_data_BA_ceres.cpp:418-435)
+  const unsigned char *point_fixed;  // SetParameterBlockConstant on the landmark (:447)
+  int n_priors; const int *prior_pose; const double *prior_center, *prior_weight; double prior_huber_a;  // :455-472
 };
 
 struct Options {   // mirrors include/omvg_b200.h omvg_ba_options
@@ -176,10 +181,13 @@ double eval_obs(const Problem &P, const Options &O, const double *poses, const d
   const int v = P.obs_view[o], ip = P.view_pose[v], iq = P.view_intr[v], j = P.obs_point[o];
   const int model = P.intr_model[iq];
   double rho[3];
+  const double wgt = P.obs_weight ? P.obs_weight[o] : 1.0;
+  const bool use_loss = O.use_loss && !(P.obs_no_loss && P.obs_no_loss[o]);
   if (!J) {
     residual_functor<double>(model, intr + KI * iq, poses + 6 * ip, pts + 3 * j, P.obs_xy + 2 * o, r);
+    if (P.obs_weight) { r[0] *= wgt; r[1] *= wgt; }
     const double s = r[0] * r[0] + r[1] * r[1];
-    loss_eval(O.use_loss, O.huber_a, s, rho);
+    loss_eval(use_loss, O.huber_a, s, rho);
     return 0.5 * rho[0];                       // cost-only: no correction (residual_block.cc:170-172)
   }
   Jet K[KI], E[6], X[3], R[2];
@@ -187,9 +195,10 @@ double eval_obs(const Problem &P, const Options &O, const double *poses, const d
   for (int k = 0; k < 6; ++k) E[k] = Jet(poses[6 * ip + k], KI + k);
   for (int k = 0; k < 3; ++k) X[k] = Jet(pts[3 * j + k], KI + 6 + k);
   residual_functor<Jet>(model, K, E, X, P.obs_xy + 2 * o, R);
+  if (P.obs_weight) { R[0] = R[0] * Jet(wgt); R[1] = R[1] * Jet(wgt); }
   r[0] = R[0].a; r[1] = R[1].a;
   const double s = r[0] * r[0] + r[1] * r[1];
-  loss_eval(O.use_loss, O.huber_a, s, rho);
+  loss_eval(use_loss, O.huber_a, s, rho);
   // corrector.cc:41-110 — Huber has rho'' <= 0 everywhere, so the common case applies; the general
   // branch is kept for completeness.
   const double sqrt_rho1 = std::sqrt(rho[1]);
@@ -209,6 +218,39 @@ double eval_obs(const Problem &P, const Options &O, const double *poses, const d
     }
   }
   r[0] *= residual_scaling; r[1] *= residual_scaling;
+  return 0.5 * rho[0];
+}
+
+// Pose-centre prior (sfm_data_BA_ceres.cpp:44-80 PoseCenterConstraintCostFunction, added at :455-472
+// with its own HuberLoss(Square(fitting_error))):  r = w .* (-R(-aa) t - c0).  J: [3][6] (pose lanes).
+double eval_prior(const Problem &P, const double *poses, int k, double r[3], double (*J)[6]) {
+  const double *pose = poses + 6 * P.prior_pose[k];
+  const double *c0 = P.prior_center + 3 * k, *w = P.prior_weight + 3 * k;
+  double rho[3];
+  if (!J) {
+    const double naa[3] = {-pose[0], -pose[1], -pose[2]};
+    double c[3]; angle_axis_rotate_point<double>(naa, pose + 3, c);
+    for (int i = 0; i < 3; ++i) r[i] = w[i] * (c[i] * -1.0 - c0[i]);
+    loss_eval(true, P.prior_huber_a, r[0] * r[0] + r[1] * r[1] + r[2] * r[2], rho);
+    return 0.5 * rho[0];
+  }
+  Jet E[6], naa[3], c[3], R[3];
+  for (int i = 0; i < 6; ++i) E[i] = Jet(pose[i], KI + i);
+  for (int i = 0; i < 3; ++i) naa[i] = -E[i];
+  angle_axis_rotate_point<Jet>(naa, E + 3, c);
+  for (int i = 0; i < 3; ++i) { R[i] = Jet(w[i]) * (c[i] * Jet(-1.0) - Jet(c0[i])); r[i] = R[i].a; }
+  const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  loss_eval(true, P.prior_huber_a, s, rho);
+  const double sqrt_rho1 = std::sqrt(rho[1]);
+  double residual_scaling, alpha_sq_norm;
+  if (s == 0.0 || rho[2] <= 0.0) { residual_scaling = sqrt_rho1; alpha_sq_norm = 0.0; }
+  else { const double D = 1.0 + 2.0 * s * rho[2] / rho[1]; const double alpha = 1.0 - std::sqrt(D);
+    residual_scaling = sqrt_rho1 / (1 - alpha); alpha_sq_norm = alpha / s; }
+  for (int c6 = 0; c6 < 6; ++c6) {
+    const double rtj = R[0].v[KI + c6] * r[0] + R[1].v[KI + c6] * r[1] + R[2].v[KI + c6] * r[2];
+    for (int i = 0; i < 3; ++i) J[i][c6] = sqrt_rho1 * (R[i].v[KI + c6] - alpha_sq_norm * r[i] * rtj);
+  }
+  for (int i = 0; i < 3; ++i) r[i] *= residual_scaling;
   return 0.5 * rho[0];
 }
 
@@ -360,11 +402,11 @@ double oracle_ba_eval(int n_poses, const double *poses, int n_intr, const double
 // [5]=termination (0 CONVERGENCE fn-tol, 1 param-tol, 2 gradient-tol, 3 NO_CONVERGENCE max iters,
 // 4 min radius, -1 FAILURE) [6]=usable (1/0)
 // trace (optional, may be NULL): per LM iteration 4 doubles {cost, cost_change, radius, rho}, cap trace_cap rows.
-int oracle_ba_solve(int n_poses, double *poses, int n_intr, double *intr, const int *intr_model,
-                    int n_points, double *points, int n_views, const int *view_pose, const int *view_intr,
-                    long n_obs, const int *obs_view, const int *obs_point, const double *obs_xy,
-                    const double *opts, double *summary, double *trace, int trace_cap) {
-  Problem P{n_poses, n_intr, n_points, n_views, n_obs, intr_model, view_pose, view_intr, obs_view, obs_point, obs_xy};
+static int solve_impl(const Problem &P, double *poses, double *intr, double *points,
+                      const double *opts, double *summary, double *trace, int trace_cap) {
+  const int n_poses = P.n_poses, n_intr = P.n_intr, n_points = P.n_points; const long n_obs = P.n_obs;
+  const int *intr_model = P.intr_model, *view_pose = P.view_pose, *view_intr = P.view_intr, *obs_view = P.obs_view, *obs_point = P.obs_point;
+  const int n_pri = P.n_priors;
   Options O;
   O.intrinsics_opt = (int)opts[0]; O.extrinsics_opt = (int)opts[1]; O.structure_opt = (int)opts[2];
   O.use_loss = (int)opts[3]; O.huber_a = opts[4]; O.max_num_iterations = (int)opts[5];
@@ -395,8 +437,13 @@ int oracle_ba_solve(int n_poses, double *poses, int n_intr, double *intr, const 
       const auto &f = L.intr_free[q]; for (size_t t = 0; t < f.size(); ++t) if (f[t] == lane) return L.pt_cols + L.intr_col[q] + (int)t; return -1; }
     if (lane < KI + 6) { const int p = view_pose[v]; if (L.pose_col[p] < 0) return -1;
       for (int t = 0; t < npf; ++t) if (L.pose_free[t] == lane - KI) return L.pt_cols + L.pose_col[p] + t; return -1; }
-    return L.pts_var ? 3 * obs_point[o] + (lane - KI - 6) : -1;
+    return (L.pts_var && !(P.point_fixed && P.point_fixed[obs_point[o]])) ? 3 * obs_point[o] + (lane - KI - 6) : -1;
   };
+  // pose-centre priors: residual rows appended after the observations; they touch pose columns only
+  std::vector<double> resP(3 * (size_t)n_pri), JP((size_t)n_pri * 18);
+  std::vector<int> colP((size_t)n_pri * 6, -1);
+  for (int k = 0; k < n_pri; ++k) { const int p = P.prior_pose[k]; if (L.pose_col[p] < 0) continue;
+    for (int t = 0; t < npf; ++t) colP[6 * k + L.pose_free[t]] = L.pt_cols + L.pose_col[p] + t; }
   std::vector<int> colmap((size_t)n_obs * NJ);
   for (long o = 0; o < n_obs; ++o) for (int l = 0; l < NJ; ++l) colmap[o * NJ + l] = col_of(o, l);
 
@@ -410,26 +457,39 @@ int oracle_ba_solve(int n_poses, double *poses, int n_intr, double *intr, const 
       c += eval_obs(P, O, xp, xi, xq, o, &res[2 * o], J);
       for (int l = 0; l < NJ; ++l) {
         const int col = colmap[o * NJ + l];
-        Jall[(o * 2 + 0) * NJ + l] = J[0][l]; Jall[(o * 2 + 1) * NJ + l] = J[1][l];
+        Jall[(o * 2 + 0) * NJ + l] = col >= 0 ? J[0][l] : 0.0; Jall[(o * 2 + 1) * NJ + l] = col >= 0 ? J[1][l] : 0.0;   // constant lanes have no column
         if (col >= 0) grad[col] += J[0][l] * res[2 * o] + J[1][l] * res[2 * o + 1];   // program_evaluator.h:239-256 (unscaled J)
       }
+    }
+    for (int k = 0; k < n_pri; ++k) {
+      double J[3][6];
+      c += eval_prior(P, xp, k, &resP[3 * k], J);
+      for (int l = 0; l < 6; ++l) { const int col = colP[6 * k + l];
+        for (int i = 0; i < 3; ++i) JP[(k * 3 + i) * 6 + l] = J[i][l];
+        if (col >= 0) grad[col] += J[0][l] * resP[3 * k] + J[1][l] * resP[3 * k + 1] + J[2][l] * resP[3 * k + 2]; }
     }
     x_cost = (double)c;
     if (!have_scale) {            // trust_region_minimizer.cc:239-250, iteration 0 only
       std::vector<double> n2(n_eff, 0.0);
       for (long o = 0; o < n_obs; ++o) for (int l = 0; l < NJ; ++l) { const int col = colmap[o * NJ + l];
         if (col >= 0) n2[col] += Jall[(o * 2) * NJ + l] * Jall[(o * 2) * NJ + l] + Jall[(o * 2 + 1) * NJ + l] * Jall[(o * 2 + 1) * NJ + l]; }
+      for (int k = 0; k < n_pri; ++k) for (int l = 0; l < 6; ++l) { const int col = colP[6 * k + l];
+        if (col >= 0) for (int i = 0; i < 3; ++i) n2[col] += JP[(k * 3 + i) * 6 + l] * JP[(k * 3 + i) * 6 + l]; }
       for (int i = 0; i < n_eff; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(n2[i]));
       have_scale = true;
     }
     for (long o = 0; o < n_obs; ++o) for (int l = 0; l < NJ; ++l) { const int col = colmap[o * NJ + l];   // :253 ScaleColumns
       if (col >= 0) { Jall[(o * 2) * NJ + l] *= scale[col]; Jall[(o * 2 + 1) * NJ + l] *= scale[col]; } }
+    for (int k = 0; k < n_pri; ++k) for (int l = 0; l < 6; ++l) { const int col = colP[6 * k + l];
+      if (col >= 0) for (int i = 0; i < 3; ++i) JP[(k * 3 + i) * 6 + l] *= scale[col]; }
   };
   auto cost_only = [&](const double *xp, const double *xi, const double *xq) {
-    long double c = 0; for (long o = 0; o < n_obs; ++o) { double r[2]; c += eval_obs(P, O, xp, xi, xq, o, r, nullptr); } return (double)c; };
+    long double c = 0; for (long o = 0; o < n_obs; ++o) { double r[2]; c += eval_obs(P, O, xp, xi, xq, o, r, nullptr); }
+    for (int k = 0; k < n_pri; ++k) { double r[3]; c += eval_prior(P, xp, k, r, nullptr); }
+    return (double)c; };
   auto x_norm_of = [&]() {    // norm over the reduced program's parameter vector (constant blocks are removed)
     long double s = 0;
-    if (L.pts_var) for (double v : x_pt) s += v * v;
+    if (L.pts_var) for (int j = 0; j < n_points; ++j) if (!(P.point_fixed && P.point_fixed[j])) for (int a = 0; a < 3; ++a) s += x_pt[3 * j + a] * x_pt[3 * j + a];
     if (npf) for (double v : x_pose) s += v * v;
     for (int q = 0; q < n_intr; ++q) if (L.intr_col[q] >= 0) for (int k = 0; k < model_nparams(intr_model[q]); ++k) s += x_intr[KI * q + k] * x_intr[KI * q + k];
     return std::sqrt((double)s); };
@@ -501,6 +561,10 @@ int oracle_ba_solve(int n_poses, double *poses, int n_intr, double *intr, const 
           S[(size_t)ci * n_red + cj] += Jall[(o * 2) * NJ + l] * Jall[(o * 2) * NJ + m] + Jall[(o * 2 + 1) * NJ + l] * Jall[(o * 2 + 1) * NJ + m]; } }
     }
     if (!ok) return false;
+    for (int k = 0; k < n_pri; ++k) for (int l = 0; l < 6; ++l) { const int ci = colP[6 * k + l]; if (ci < 0) continue;   // rows without an e-block
+      for (int i = 0; i < 3; ++i) rhs[ci - base] += JP[(k * 3 + i) * 6 + l] * resP[3 * k + i];
+      for (int m = 0; m < 6; ++m) { const int cj = colP[6 * k + m]; if (cj < 0) continue;
+        for (int i = 0; i < 3; ++i) S[(size_t)(ci - base) * n_red + (cj - base)] += JP[(k * 3 + i) * 6 + l] * JP[(k * 3 + i) * 6 + m]; } }
     for (int i = 0; i < n_red; ++i) S[(size_t)i * n_red + i] += lmD[base + i] * lmD[base + i];
     std::vector<double> z(rhs);
     if (n_red > 0) { if (!cholesky(S, n_red)) return false; chol_solve(S, n_red, z.data()); }
@@ -552,6 +616,8 @@ int oracle_ba_solve(int n_poses, double *poses, int n_intr, double *intr, const 
       std::fill(diag.begin(), diag.end(), 0.0);
       for (long o = 0; o < n_obs; ++o) for (int l = 0; l < NJ; ++l) { const int col = colmap[o * NJ + l];
         if (col >= 0) diag[col] += Jall[(o * 2) * NJ + l] * Jall[(o * 2) * NJ + l] + Jall[(o * 2 + 1) * NJ + l] * Jall[(o * 2 + 1) * NJ + l]; }
+      for (int k = 0; k < n_pri; ++k) for (int l = 0; l < 6; ++l) { const int col = colP[6 * k + l];
+        if (col >= 0) for (int i = 0; i < 3; ++i) diag[col] += JP[(k * 3 + i) * 6 + l] * JP[(k * 3 + i) * 6 + l]; }
       for (int i = 0; i < n_eff; ++i) diag[i] = std::min(std::max(diag[i], O.min_lm_diagonal), O.max_lm_diagonal);
     }
     for (int i = 0; i < n_eff; ++i) lmD[i] = std::sqrt(diag[i] / radius);
@@ -563,6 +629,9 @@ int oracle_ba_solve(int n_poses, double *poses, int n_intr, double *intr, const 
       for (long o = 0; o < n_obs; ++o) for (int row = 0; row < 2; ++row) {
         double mr = 0; for (int l = 0; l < NJ; ++l) { const int col = colmap[o * NJ + l]; if (col >= 0) mr += Jall[(o * 2 + row) * NJ + l] * step[col]; }
         m += -mr * (res[2 * o + row] + mr / 2.0); }
+      for (int k = 0; k < n_pri; ++k) for (int i = 0; i < 3; ++i) {
+        double mr = 0; for (int l = 0; l < 6; ++l) { const int col = colP[6 * k + l]; if (col >= 0) mr += JP[(k * 3 + i) * 6 + l] * step[col]; }
+        m += -mr * (resP[3 * k + i] + mr / 2.0); }
       model_cost_change = (double)m;
       step_is_valid = model_cost_change > 0.0;
     }
@@ -621,5 +690,43 @@ int oracle_ba_solve(int n_poses, double *poses, int n_intr, double *intr, const 
   summary[8] = iteration;   // linear solves attempted (includes the terminating iteration)
   return usable ? 0 : 1;
 }
+
+extern "C" {
+int oracle_ba_solve(int n_poses, double *poses, int n_intr, double *intr, const int *intr_model,
+                    int n_points, double *points, int n_views, const int *view_pose, const int *view_intr,
+                    long n_obs, const int *obs_view, const int *obs_point, const double *obs_xy,
+                    const double *opts, double *summary, double *trace, int trace_cap) {
+  Problem P{n_poses, n_intr, n_points, n_views, n_obs, intr_model, view_pose, view_intr, obs_view, obs_point, obs_xy};
+  return solve_impl(P, poses, intr, points, opts, summary, trace, trace_cap);
+}
+
+// Same with ground control points (per-observation weight / no-loss flag, fixed landmarks) and
+// pose-centre priors.  Any of the extension pointers may be NULL.
+int oracle_ba_solve_ex(int n_poses, double *poses, int n_intr, double *intr, const int *intr_model,
+                       int n_points, double *points, int n_views, const int *view_pose, const int *view_intr,
+                       long n_obs, const int *obs_view, const int *obs_point, const double *obs_xy,
+                       const double *obs_weight, const unsigned char *obs_no_loss, const unsigned char *point_fixed,
+                       int n_priors, const int *prior_pose, const double *prior_center, const double *prior_weight, double prior_huber_a,
+                       const double *opts, double *summary, double *trace, int trace_cap) {
+  Problem P{n_poses, n_intr, n_points, n_views, n_obs, intr_model, view_pose, view_intr, obs_view, obs_point, obs_xy,
+            obs_weight, obs_no_loss, point_fixed, n_priors, prior_pose, prior_center, prior_weight, prior_huber_a};
+  return solve_impl(P, poses, intr, points, opts, summary, trace, trace_cap);
+}
+
+double oracle_ba_cost_ex(int n_poses, const double *poses, int n_intr, const double *intr, const int *intr_model,
+                         int n_points, const double *points, int n_views, const int *view_pose, const int *view_intr,
+                         long n_obs, const int *obs_view, const int *obs_point, const double *obs_xy,
+                         const double *obs_weight, const unsigned char *obs_no_loss,
+                         int n_priors, const int *prior_pose, const double *prior_center, const double *prior_weight, double prior_huber_a,
+                         int use_loss, double huber_a) {
+  Problem P{n_poses, n_intr, n_points, n_views, n_obs, intr_model, view_pose, view_intr, obs_view, obs_point, obs_xy,
+            obs_weight, obs_no_loss, nullptr, n_priors, prior_pose, prior_center, prior_weight, prior_huber_a};
+  Options O{}; O.use_loss = use_loss; O.huber_a = huber_a;
+  long double c = 0;
+  for (long o = 0; o < n_obs; ++o) { double r[2]; c += eval_obs(P, O, poses, intr, points, o, r, nullptr); }
+  for (int k = 0; k < n_priors; ++k) { double r[3]; c += eval_prior(P, poses, k, r, nullptr); }
+  return (double)c;
+}
+}  // extern "C"
 
 }  // extern "C"

@@ -13,6 +13,7 @@
 #include "openMVG/numeric/numeric.h"
 #include "openMVG/sfm/sfm_data.hpp"
 #include "openMVG/sfm/sfm_data_BA_ceres.hpp"
+#include "openMVG/sfm/sfm_view_priors.hpp"
 
 #include "../openmvg_b200/host/Bundle_Adjustment_B200.hpp"
 #include "../openmvg_b200/host/Matcher_Regions_B200.hpp"
@@ -65,7 +66,9 @@ double huber_cost(const SfM_Data & s)
   return double(c);
 }
 
-SfM_Data make_scene(int C, int P, int K)
+// priors_and_gcp: views become ViewPriors (GPS = true centre * 3 + offset + noise; id_pose == id_view as in
+// every openMVG loader) and 6 ground control points, surveyed in the GPS frame, are observed by 4 views each.
+SfM_Data make_scene(int C, int P, int K, bool priors_and_gcp = false)
 {
   std::mt19937 g(42);
   std::uniform_real_distribution<double> U(-0.6, 0.6);
@@ -79,10 +82,16 @@ SfM_Data make_scene(int C, int P, int K)
     const Vec3 c(1.5 * std::sin(th), 0.2 * std::sin(3 * th), 1.5 * std::cos(th));
     const Mat3 R = LookAt(Vec3(-c));
     gt[i] = Pose3(R, c);
+    const IndexT pose_id = priors_and_gcp ? 10 + i : 100 + i;
+    if (priors_and_gcp) {
+      auto vp = std::make_shared<ViewPriors>("", 10 + i, 7, pose_id, 1000, 1000);
+      vp->SetPoseCenterPrior(3.0 * c + Vec3(50, -20, 10) + Vec3(N(g), N(g), N(g)) * 0.03, Vec3(1, 1, 1));
+      s.views[10 + i] = vp;
+    } else
     s.views[10 + i] = std::make_shared<View>("", 10 + i, 7, 100 + i, 1000, 1000);
     const Vec3 aa(N(g) * 0.005, N(g) * 0.005, N(g) * 0.005);
     const Mat3 dR = Eigen::AngleAxisd(aa.norm(), aa.normalized()).toRotationMatrix();
-    s.poses[100 + i] = Pose3(dR * R, c + Vec3(N(g), N(g), N(g)) * 0.005);
+    s.poses[pose_id] = Pose3(dR * R, c + Vec3(N(g), N(g), N(g)) * 0.005);
   }
   std::uniform_int_distribution<int> start(0, C - 1);
   for (int j = 0; j < P; ++j) {
@@ -97,6 +106,18 @@ SfM_Data make_scene(int C, int P, int K)
     L.X = X + Vec3(N(g), N(g), N(g)) * 0.01;
     s.structure[1000 + j] = L;
   }
+  if (priors_and_gcp)
+    for (int q = 0; q < 6; ++q) {
+      const Vec3 X(U(g), U(g), U(g));
+      Landmark L;
+      for (int k = 0; k < 4; ++k) {
+        const int i = (5 * q + 6 * k) % C;
+        const Vec3 Xc = gt[i](X);
+        L.obs[10 + i] = Observation(Vec2(cx + f * Xc(0) / Xc(2) + 0.3 * N(g), cy + f * Xc(1) / Xc(2) + 0.3 * N(g)), q);
+      }
+      L.X = 3.0 * X + Vec3(50, -20, 10);        // surveyed position, GPS frame
+      s.control_points[q] = L;
+    }
   return s;
 }
 
@@ -146,6 +167,28 @@ int main()
     const double rel = std::fabs(ca - cb) / ca;
     std::printf("BA drop-in: initial %.6f  reference %.9f  B200 %.9f  rel %.3e  ok %d/%d\n", c0, ca, cb, rel, int(ok_ref), int(ok_b200));
     if (!ok_ref || !ok_b200 || !(rel <= 1e-6) || !(ca < c0)) ++failures;
+  }
+  // ------------------------------------------------------------------ BA with control points + motion priors
+  {
+    SfM_Data a = make_scene(24, 1200, 6, /*priors_and_gcp=*/true), b = a;
+    b.intrinsics[7] = std::shared_ptr<IntrinsicBase>(a.intrinsics.at(7)->clone());
+    for (auto & v : b.views)        // deep-copy the views too: the registration step rewrites the priors in place
+      v.second = std::make_shared<ViewPriors>(*dynamic_cast<ViewPriors *>(a.views.at(v.first).get()));
+    const double c0 = huber_cost(a);
+    std::unique_ptr<Bundle_Adjustment> ba_ref(new Bundle_Adjustment_Ceres(Bundle_Adjustment_Ceres::BA_Ceres_options(false, true)));
+    std::unique_ptr<Bundle_Adjustment> ba_b200(new Bundle_Adjustment_B200());
+    const Optimize_Options opt(Intrinsic_Parameter_Type::ADJUST_ALL, Extrinsic_Parameter_Type::ADJUST_ALL, Structure_Parameter_Type::ADJUST_ALL,
+                               Control_Point_Parameter(20.0, true), true);
+    const bool ok_ref = ba_ref->Adjust(a, opt);
+    const bool ok_b200 = ba_b200->Adjust(b, opt);
+    const double ca = huber_cost(a), cb = huber_cost(b);
+    const double rel = std::fabs(ca - cb) / ca;
+    double dc = 0, dg = 0;
+    for (const auto & p : a.poses) dc = std::max(dc, (p.second.center() - b.poses.at(p.first).center()).norm());
+    for (const auto & g : a.control_points) dg = std::max(dg, (g.second.X - b.control_points.at(g.first).X).norm());
+    std::printf("BA+GCP+priors drop-in: initial %.6f  reference %.9f  B200 %.9f  rel %.3e  max centre diff %.3e  gcp diff %.3e  ok %d/%d\n",
+                c0, ca, cb, rel, dc, dg, int(ok_ref), int(ok_b200));
+    if (!ok_ref || !ok_b200 || !(rel <= 1e-6) || !(dc <= 1e-6) || !(dg <= 1e-12)) ++failures;
   }
   std::printf(failures ? "DROPIN FAILED\n" : "DROPIN OK\n");
   return failures;

@@ -46,6 +46,7 @@ def oracle():
         lib.oracle_fnv1a_ij.restype = ctypes.c_uint64
         lib.oracle_ba_cost.restype = ctypes.c_double
         lib.oracle_ba_eval.restype = ctypes.c_double
+        lib.oracle_ba_cost_ex.restype = ctypes.c_double
         _cache["o"] = lib
     return _cache["o"]
 
@@ -127,10 +128,32 @@ def _ba_args(s, poses, intr, pts):
             _P(s["obs_view"]), _P(s["obs_point"]), _P(s["obs_xy"]))
 
 
+def _opt(s, key, dtype):
+    a = s.get(key)
+    return None if a is None else np.ascontiguousarray(a, dtype)
+
+
+def has_ext(s):
+    return any(s.get(k) is not None for k in ("obs_weight", "obs_no_loss", "point_fixed", "prior_pose"))
+
+
+def _ba_ext_args(s, with_fixed=True):
+    """Extension arrays of a scene (GCP weights / flags / fixed landmarks, pose-centre priors)."""
+    keep = [_opt(s, "obs_weight", np.float64), _opt(s, "obs_no_loss", np.uint8), _opt(s, "point_fixed", np.uint8),
+            _opt(s, "prior_pose", np.int32), _opt(s, "prior_center", np.float64), _opt(s, "prior_weight", np.float64)]
+    p = lambda a: None if a is None else _P(a)  # noqa: E731
+    npri = 0 if keep[3] is None else len(keep[3])
+    head = [p(keep[0]), p(keep[1])] + ([p(keep[2])] if with_fixed else [])
+    return keep, head + [npri, p(keep[3]), p(keep[4]), p(keep[5]), ctypes.c_double(float(s.get("prior_huber_a", 0.0)))]
+
+
 def oracle_ba_cost(s, poses=None, intr=None, pts=None, use_loss=1, huber_a=16.0):
     poses = s["poses"] if poses is None else poses
     intr = s["intrinsics"] if intr is None else intr
     pts = s["points"] if pts is None else pts
+    if has_ext(s):
+        keep, ext = _ba_ext_args(s, with_fixed=False)
+        return oracle().oracle_ba_cost_ex(*_ba_args(s, poses, intr, pts), *ext, int(use_loss), ctypes.c_double(huber_a))
     return oracle().oracle_ba_cost(*_ba_args(s, poses, intr, pts), int(use_loss), ctypes.c_double(huber_a))
 
 
@@ -147,7 +170,11 @@ def oracle_ba_solve(s, **kw):
     opts = np.array([float(o[k]) for k in BA_OPT_ORDER])
     poses = s["poses"].copy(); intr = s["intrinsics"].copy(); pts = s["points"].copy()
     summ = np.zeros(16); trace = np.zeros((128, 4))
-    rc = oracle().oracle_ba_solve(*_ba_args(s, poses, intr, pts), _P(opts), _P(summ), _P(trace), 128)
+    if has_ext(s):
+        keep, ext = _ba_ext_args(s)
+        rc = oracle().oracle_ba_solve_ex(*_ba_args(s, poses, intr, pts), *ext, _P(opts), _P(summ), _P(trace), 128)
+    else:
+        rc = oracle().oracle_ba_solve(*_ba_args(s, poses, intr, pts), _P(opts), _P(summ), _P(trace), 128)
     return dict(rc=rc, poses=poses, intrinsics=intr, points=pts, initial_cost=summ[0], final_cost=summ[1],
                 iterations=int(summ[2]), successful=int(summ[3]), unsuccessful=int(summ[4]),
                 termination=int(summ[5]), usable=bool(summ[6]), trace=trace[:int(summ[7])], lm_steps=int(summ[8]))
@@ -175,3 +202,94 @@ def ref_ba_adjust(s, intrinsics_opt=14, extrinsics_opt=6, structure_opt=1, threa
                 residual_s=grab(r"Residual evaluation\s+([0-9.]+)"),
                 threads=grab(r"\nThreads\s+\d+\s+(\d+)", int),
                 termination=grab(r"Termination:\s+(.*)", str))
+
+
+def _split_gcp(s):
+    """Flat scene with fixed landmarks -> (regular scene view, GCP arrays) for the reference driver:
+    fixed landmarks become SfM_Data::control_points, their observations the GCP observations."""
+    fixed = np.asarray(s.get("point_fixed", np.zeros(len(s["points"]), np.uint8))).astype(bool)
+    reg_idx = np.flatnonzero(~fixed); gcp_idx = np.flatnonzero(fixed)
+    remap = np.full(len(fixed), -1, np.int64); remap[reg_idx] = np.arange(len(reg_idx))
+    gmap = np.full(len(fixed), -1, np.int64); gmap[gcp_idx] = np.arange(len(gcp_idx))
+    og = fixed[s["obs_point"]]
+    reg = dict(s)
+    reg["points"] = np.ascontiguousarray(s["points"][reg_idx])
+    reg["obs_view"] = np.ascontiguousarray(s["obs_view"][~og]); reg["obs_xy"] = np.ascontiguousarray(s["obs_xy"][~og])
+    reg["obs_point"] = np.ascontiguousarray(remap[s["obs_point"][~og]].astype(np.int32))
+    w = 20.0
+    if og.any():
+        ws = np.asarray(s["obs_weight"])[og]
+        assert np.all(ws == ws[0]) and np.all(np.asarray(s["obs_no_loss"])[og] == 1), "GCP observations: one weight, no loss"
+        w = float(ws[0])
+    if "obs_weight" in s:
+        assert np.all(np.asarray(s["obs_weight"])[~og] == 1.0) and np.all(np.asarray(s["obs_no_loss"])[~og] == 0)
+    gcp = dict(X=np.ascontiguousarray(s["points"][gcp_idx]), obs_view=np.ascontiguousarray(s["obs_view"][og]),
+               obs_gcp=np.ascontiguousarray(gmap[s["obs_point"][og]].astype(np.int32)),
+               obs_xy=np.ascontiguousarray(s["obs_xy"][og]), weight=w)
+    return reg, gcp, reg_idx, gcp_idx
+
+
+def _prior_views(s):
+    """The reference hangs a prior on a VIEW; scenes here use view v <-> pose v."""
+    if s.get("prior_pose") is None:
+        return 0, None, None, None
+    assert np.array_equal(s["view_pose"], np.arange(len(s["view_pose"]))), "prior tests need view_pose = identity"
+    pv = np.ascontiguousarray(s["prior_pose"], np.int32)
+    return len(pv), pv, np.ascontiguousarray(s["prior_center"], np.float64).copy(), np.ascontiguousarray(s["prior_weight"], np.float64)
+
+
+def ref_ba_adjust_ex(s, intrinsics_opt=14, extrinsics_opt=6, structure_opt=1, threads=0, use_loss=1):
+    """The reference Adjust with control points and/or pose-centre priors."""
+    reg, g, reg_idx, gcp_idx = _split_gcp(s)
+    opts = np.array([intrinsics_opt, extrinsics_opt, structure_opt, threads, use_loss], np.int32)
+    poses = s["poses"].copy(); intr = s["intrinsics"].copy(); pts = reg["points"].copy(); gX = g["X"].copy()
+    npri, pv, pc, pw = _prior_views(s)
+    out = np.zeros(8); rep = ctypes.create_string_buffer(1 << 16)
+    rc = ref_ba().ref_ba_adjust_ex(*_ba_args(reg, poses, intr, pts), len(gX), _P(gX), ctypes.c_long(len(g["obs_view"])),
+                                   _P(g["obs_view"]), _P(g["obs_gcp"]), _P(g["obs_xy"]), ctypes.c_double(g["weight"]),
+                                   npri, None if pv is None else _P(pv), None if pc is None else _P(pc),
+                                   None if pw is None else _P(pw), _P(opts), _P(out), rep, 1 << 16)
+    text = rep.value.decode(errors="replace")
+    allpts = s["points"].copy(); allpts[reg_idx] = pts; allpts[gcp_idx] = gX
+    m = re.search(r"Minimizer iterations\s+(\d+)", text)
+    return dict(rc=rc, ok=bool(out[0]), initial_cost=out[1], final_cost=out[2], wall_s=out[3], prior_fit=out[4],
+                poses=poses, intrinsics=intr, points=allpts, prior_center=pc, report=text,
+                iterations=int(m.group(1)) if m else None)
+
+
+def ref_ba_register_priors(s):
+    """The registration Adjust performs before its solve when priors are used, done by the
+    reference's own functions; returns the registered scene (prior_huber_a = fit^2) and the centroid."""
+    reg, g, reg_idx, gcp_idx = _split_gcp(s)
+    poses = s["poses"].copy(); intr = s["intrinsics"].copy(); pts = reg["points"].copy(); gX = g["X"].copy()
+    npri, pv, pc, pw = _prior_views(s)
+    out = np.zeros(4)
+    rc = ref_ba().ref_ba_register_priors(*_ba_args(reg, poses, intr, pts), len(gX), _P(gX), ctypes.c_long(len(g["obs_view"])),
+                                         _P(g["obs_view"]), _P(g["obs_gcp"]), _P(g["obs_xy"]),
+                                         npri, _P(pv), _P(pc), _P(pw), _P(out))
+    assert rc == 0
+    t = dict(s)
+    if out[0] >= 0:
+        allpts = s["points"].copy(); allpts[reg_idx] = pts; allpts[gcp_idx] = gX
+        t.update(poses=poses, points=allpts, prior_center=pc, prior_huber_a=float(out[0]) ** 2)
+    return t, float(out[0]), out[1:4].copy()
+
+
+# ----------------------------------------------------------------------------- golden GCP / prior cases
+def golden_ext_scene(case, registered=True):
+    """Scene of a tests/golden 'ba_ext' case from its seeds.  With registered=True the prior cases come
+    back in the frame the reference's LM solved in (its own LMedS registration + centring, stored in
+    tests/golden/reference_ba_ext.npz) with prior_huber_a = fit^2."""
+    from openmvg_b200 import synth
+    s = synth.ba_scene(**case["scene"])
+    if case.get("gcp"):
+        s = synth.add_gcp(s, **case["gcp"])
+    if case.get("priors"):
+        s = synth.add_priors(s, **case["priors"])
+        if registered:
+            z = np.load(os.path.join(ROOT, "tests", "golden", "reference_ba_ext.npz"))
+            s["poses"] = np.ascontiguousarray(z[case["name"] + "_poses"])
+            s["points"] = np.ascontiguousarray(z[case["name"] + "_points"])
+            s["prior_center"] = np.ascontiguousarray(z[case["name"] + "_prior_center"])
+            s["prior_huber_a"] = float(case["prior_fit"]) ** 2
+    return s

@@ -38,6 +38,48 @@ BA_CASES = [
     dict(name="config2_1000_100k_1M", scene=dict(n_cams=1000, n_points=100000, obs_per_point=10), opts={}),
 ]
 
+# Ground control points / pose-centre priors (sfm_data_BA_ceres.cpp:183-236, 398-472).  For prior cases the
+# reference's own pre-solve registration (LMedS similarity + centring) is stored too, so the tests can hand
+# the LM core the scene the reference's LM saw without the reference being present.
+BA_EXT_CASES = [
+    dict(name="gcp", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5), gcp=dict(n_gcp=8, weight=20.0), opts={}),
+    dict(name="gcp_radial3", scene=dict(n_cams=14, n_points=700, obs_per_point=6, seed=8, model=3), gcp=dict(n_gcp=6, weight=10.0), opts={}),
+    dict(name="priors", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5), priors=dict(sigma=0.01, offset=(5.0, -3.0, 2.0), scale=2.0), opts={}),
+    dict(name="priors_weighted", scene=dict(n_cams=20, n_points=600, obs_per_point=5, seed=9), priors=dict(sigma=0.02, weight=(4.0, 4.0, 0.5)), opts=dict(intrinsics_opt=1)),
+    dict(name="gcp_priors", scene=dict(n_cams=16, n_points=800, obs_per_point=6, seed=5), gcp=dict(n_gcp=8, weight=20.0), priors=dict(sigma=0.02), opts={}),
+]
+
+
+def ext_scene(c):
+    s = synth.ba_scene(**c["scene"])
+    if "gcp" in c:
+        s = synth.add_gcp(s, **c["gcp"])
+    if "priors" in c:
+        s = synth.add_priors(s, **c["priors"])
+    return s
+
+
+def main_ext():
+    path = os.path.join(HERE, "reference_outputs.json")
+    out = json.load(open(path))
+    out["ba_ext"] = []
+    arrays = {}
+    for c in BA_EXT_CASES:
+        s = ext_scene(c)
+        ref_opts = {k: v for k, v in c["opts"].items() if k in ("intrinsics_opt", "extrinsics_opt", "structure_opt", "use_loss")}
+        r = ck.ref_ba_adjust_ex(s, threads=8, **ref_opts)
+        e = dict(name=c["name"], scene=c["scene"], gcp=c.get("gcp"), priors=c.get("priors"), opts=c["opts"], ok=r["ok"],
+                 initial_cost=r["initial_cost"], final_cost=r["final_cost"], iterations=r["iterations"], prior_fit=r["prior_fit"])
+        if "priors" in c:
+            t, fit, cen = ck.ref_ba_register_priors(s)
+            assert fit == r["prior_fit"]
+            e["centroid"] = [float(x) for x in cen]
+            arrays[c["name"] + "_poses"] = t["poses"]; arrays[c["name"] + "_points"] = t["points"]; arrays[c["name"] + "_prior_center"] = t["prior_center"]
+        out["ba_ext"].append(e)
+        print("ba_ext", c["name"], r["initial_cost"], r["final_cost"], r["iterations"], r["prior_fit"])
+    json.dump(out, open(path, "w"), indent=1)
+    np.savez_compressed(os.path.join(HERE, "reference_ba_ext.npz"), **arrays)
+
 
 def main():
     out = {"match": [], "ba": []}
@@ -64,4 +106,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ext":      # only the GCP / prior section (keeps the rest untouched)
+        main_ext()
+    else:
+        main()
+        main_ext()

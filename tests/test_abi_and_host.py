@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_struct_layouts_match_header(lib):
     from openmvg_b200 import ba
-    assert ctypes.sizeof(ba.Options) == 128 and ctypes.sizeof(ba.Summary) == 80 and ctypes.sizeof(ba.Problem) == 96
+    assert ctypes.sizeof(ba.Options) == 128 and ctypes.sizeof(ba.Summary) == 80 and ctypes.sizeof(ba.Problem) == 160
     o = ba.default_options()
     assert (o.intrinsics_opt, o.extrinsics_opt, o.structure_opt, o.use_loss) == (14, 6, 1, 1)
     assert o.huber_a == 16.0 and o.max_num_iterations == 50 and o.function_tolerance == 1e-6

@@ -65,3 +65,44 @@ def test_against_compiled_reference(kw):
     from scipy.spatial.transform import Rotation   # angle-axis is ambiguous at theta ~ pi: compare the rotations
     Ro = Rotation.from_rotvec(o["poses"][:, :3]).as_matrix(); Rr = Rotation.from_rotvec(r["poses"][:, :3]).as_matrix()
     assert np.abs(Ro - Rr).max() < 1e-7
+
+
+# ---- ground control points and pose-centre priors
+@pytest.mark.parametrize("case", GOLD.get("ba_ext", []), ids=lambda c: c["name"])
+def test_golden_gcp_and_priors(case):
+    """Oracle vs the reference Adjust with control points / motion priors (golden = cost of the scene
+    the reference returned, GCP and prior terms included)."""
+    s = ck.golden_ext_scene(case)
+    o = ck.oracle_ba_solve(s, **case["opts"])
+    assert o["usable"] and case["ok"]
+    assert abs(o["final_cost"] - case["final_cost"]) <= 1e-9 * case["final_cost"], (o["final_cost"], case["final_cost"])
+    assert o["iterations"] == case["iterations"]
+    if s.get("point_fixed") is not None:                      # GCP landmarks are constant
+        f = s["point_fixed"].astype(bool)
+        assert np.array_equal(o["points"][f], s["points"][f])
+    ret = dict(s); ret.update(poses=o["poses"], intrinsics=o["intrinsics"], points=o["points"])
+    assert abs(ck.oracle_ba_cost(ret, use_loss=case["opts"].get("use_loss", 1)) - o["final_cost"]) <= 1e-12 * o["final_cost"]
+
+
+@pytest.mark.skipif(not ck.have_ref_ba(), reason="oracle/_ref not built")
+def test_gcp_and_priors_against_compiled_reference():
+    s = synth.add_priors(synth.add_gcp(synth.ba_scene(12, 300, 5, seed=3), 6, weight=15.0), sigma=0.02)   # GCPs live in the priors' frame
+    r = ck.ref_ba_adjust_ex(s)
+    t, fit, cen = ck.ref_ba_register_priors(s)
+    assert fit == r["prior_fit"] and fit > 0
+    o = ck.oracle_ba_solve(t)
+    assert abs(o["final_cost"] - r["final_cost"]) <= 1e-9 * r["final_cost"]
+    assert o["iterations"] == r["iterations"]
+    # the reference undoes only the centring (sfm_data_BA_ceres.cpp:572): same for the oracle's result
+    assert np.abs((o["points"] + cen) - r["points"]).max() <= 1e-7
+
+
+def test_zero_weight_removes_observation_exactly():
+    """Weight 0 must equal deleting the observation (the rejection loop relies on it)."""
+    s = synth.ba_scene(10, 300, 5, seed=4, outlier_frac=0.05)
+    rng = np.random.default_rng(0)
+    keep = rng.random(len(s["obs_view"])) > 0.1
+    w = dict(s); w["obs_weight"] = keep.astype(np.float64)
+    d = dict(s); d["obs_view"] = np.ascontiguousarray(s["obs_view"][keep]); d["obs_point"] = np.ascontiguousarray(s["obs_point"][keep]); d["obs_xy"] = np.ascontiguousarray(s["obs_xy"][keep])
+    a = ck.oracle_ba_solve(w); b = ck.oracle_ba_solve(d)
+    assert abs(a["final_cost"] - b["final_cost"]) <= 1e-9 * b["final_cost"] and a["iterations"] == b["iterations"]   # (OpenMP atomics reorder sums)
