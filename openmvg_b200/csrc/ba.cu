@@ -7,12 +7,14 @@
 // All arithmetic runs in the kernels of ba_kernels.cuh; the host only takes the accept/reject and
 // termination decisions from a handful of scalars read back once per LM iteration.
 #include "ba_kernels.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <chrono>
 #include <vector>
 
 using namespace omvg;
@@ -36,12 +38,19 @@ template <typename T> struct DevBuf {
 
 }  // namespace
 
+// stream / events / pinned scalars of a context: creating and destroying them costs ~2.5 ms per Adjust, so
+// released sets are kept per device and reused (omvg_trim_cache() frees them)
+struct CtxRes { cudaStream_t stream = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; double *h_scal = nullptr; };
+struct ResPool { std::mutex mu; std::vector<CtxRes> free_[16]; };
+static ResPool &res_pool() { static ResPool p; return p; }
+
 struct omvg_ba_ctx {
   int device = 0, n_sms = 0;
   cudaStream_t stream = nullptr;
   int nc = 0, ni = 0, np = 0, nv = 0; long long no = 0;
-  int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0, eval_grid = 0, kiu = KI;
-  std::vector<int> perm;                    // sorted position -> caller's observation index
+  int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0, eval_grid = 0, kiu = KI, gj_grid = 0;
+  std::vector<int> perm;                    // sorted position -> caller's observation index (fetched on first use)
+  DevBuf<int> d_perm;
   std::vector<int> h_intr_model;
   // parameters: [0] current, [1] candidate, init = copy at create
   DevBuf<double> pose[2], intr[2], pt[2], pose0, intr0, pt0;
@@ -60,7 +69,7 @@ struct omvg_ba_ctx {
   DevBuf<int> fail;
   // optional extensions: GCP weights / flags / fixed landmarks, pose-centre priors
   DevBuf<double> obs_w; DevBuf<unsigned char> obs_flags, pt_fixed; DevBuf<unsigned> pt_mask;
-  int npri = 0; double prior_huber_a = 0; DevBuf<int> prior_pose; DevBuf<double> prior_center, prior_weight, rP, JP;
+  bool has_ext = false; int npri = 0; double prior_huber_a = 0; DevBuf<int> prior_pose; DevBuf<double> prior_center, prior_weight, rP, JP;
   double *h_scal = nullptr;                 // pinned
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evj0 = nullptr, evj1 = nullptr;
   long long launches = 0;
@@ -69,6 +78,14 @@ struct omvg_ba_ctx {
 namespace {
 
 #define LAUNCH_CHECK() OMVG_CUDA(cudaGetLastError())
+
+// OMVG_BA_TIMING=1: host wall-clock of the phases around the solve (where the end-to-end time goes)
+struct PhaseTimer {
+  bool on = getenv("OMVG_BA_TIMING") != nullptr; const char *what;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit PhaseTimer(const char *w) : what(w) {}
+  void lap(const char *name) { if (!on) return; const auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[omvg_ba timing] %s/%s %.3f ms\n", what, name, std::chrono::duration<double, std::milli>(t1 - t0).count()); t0 = t1; }
+};
 
 int validate(const omvg_ba_problem *P) {
   if (!P) return fail(OMVG_E_ARG, "null problem");
@@ -80,8 +97,7 @@ int validate(const omvg_ba_problem *P) {
     return fail(OMVG_E_UNSUPPORTED, "camera model %d is not implemented on the GPU path", P->intr_model[q]);
   for (int v = 0; v < P->n_views; ++v)
     if (P->view_pose[v] < 0 || P->view_pose[v] >= P->n_poses || P->view_intr[v] < 0 || P->view_intr[v] >= P->n_intrinsics) return fail(OMVG_E_ARG, "view %d out of range", v);
-  for (long long o = 0; o < P->n_obs; ++o)
-    if (P->obs_view[o] < 0 || P->obs_view[o] >= P->n_views || P->obs_point[o] < 0 || P->obs_point[o] >= P->n_points) return fail(OMVG_E_ARG, "observation %lld out of range", o);
+  // (observation indices are range-checked on the device by setup_check_kernel)
   if (P->n_priors < 0 || (P->n_priors > 0 && (!P->prior_pose || !P->prior_center || !P->prior_weight))) return fail(OMVG_E_ARG, "bad pose-centre prior arrays");
   for (int k = 0; k < P->n_priors; ++k) if (P->prior_pose[k] < 0 || P->prior_pose[k] >= P->n_poses) return fail(OMVG_E_ARG, "prior %d: pose out of range", k);
   if (P->n_priors > 0 && !(P->prior_huber_a >= 0.0)) return fail(OMVG_E_ARG, "prior_huber_a must be >= 0");
@@ -131,7 +147,9 @@ int eval_cost(omvg_ba_ctx *c, const omvg_ba_options *o, int which, int slot) {
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = o->use_loss; A.huber_a = o->huber_a; A.cost_partial = c->part.p;
   A.obs_w = c->obs_w.p; A.obs_flags = c->obs_flags.p; A.pt_fixed = c->pt_fixed.p;
-  eval_kernel<false, 8><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  if (c->has_ext) eval_kernel<false, 8, true><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
+  else eval_kernel<false, 8, false><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
+  LAUNCH_CHECK();
   c->launches += 2;
   if (c->npri) {
     PriorArgs PA{}; PA.poses = c->pose[which].p; PA.camR = c->camR[which].p; PA.camdR = c->camdR.p; PA.prior_pose = c->prior_pose.p; PA.center = c->prior_center.p; PA.weight = c->prior_weight.p;
@@ -163,9 +181,10 @@ int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which
   if (have_scale) { A.sc_pt = c->sc_pt.p; A.sc_cam = c->sc_cam.p; A.sc_intr = c->sc_intr.p; }
   if (time_it) OMVG_CUDA(cudaEventRecord(c->evj0, c->stream));
   static const int minb = getenv("OMVG_BA_EVAL_MINB") ? atoi(getenv("OMVG_BA_EVAL_MINB")) : 4;
-  if (minb >= 8) eval_kernel<true, 8><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
-  else if (minb >= 6) eval_kernel<true, 6><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
-  else eval_kernel<true, 4><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
+  if (c->has_ext) eval_kernel<true, 4, true><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
+  else if (minb >= 8) eval_kernel<true, 8, false><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
+  else if (minb >= 6) eval_kernel<true, 6, false><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
+  else eval_kernel<true, 4, false><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A);
   LAUNCH_CHECK();
   if (time_it) OMVG_CUDA(cudaEventRecord(c->evj1, c->stream));
   c->launches += 2;
@@ -279,7 +298,7 @@ int build_structure(omvg_ba_ctx *c) {
   const size_t nco_max = (size_t)ng * MAXW;
   if ((rc = c->cE.alloc(nco_max * nco_max))) return rc;
   if ((rc = c->cEinv.alloc(nco_max * nco_max))) return rc;
-  if ((rc = c->cT.alloc(nco_max * nco_max))) return rc;
+  if ((rc = c->cT.alloc(std::max(nco_max * nco_max, 3 * (size_t)GJ_B * nco_max)))) return rc;   // Cholesky route: T; Gauss-Jordan: Cold/H/Gn
   if ((rc = c->cCv.alloc((size_t)MAXRHS * nco_max))) return rc;
   if ((rc = c->cYv.alloc((size_t)MAXRHS * nco_max))) return rc;
   if ((rc = c->bP2.alloc((size_t)MAXRHS * 6 * c->nc))) return rc;
@@ -291,7 +310,15 @@ int build_structure(omvg_ba_ctx *c) {
 
 extern "C" {
 
-void omvg_trim_cache(void) { omvg::pool_trim(); }
+void omvg_trim_cache(void) {
+  omvg::pool_trim();
+  ResPool &rp = res_pool(); std::lock_guard<std::mutex> g(rp.mu);
+  int cur = 0; cudaGetDevice(&cur);
+  for (int d = 0; d < 16; ++d) { if (rp.free_[d].empty()) continue; cudaSetDevice(d);
+    for (CtxRes &r : rp.free_[d]) { cudaFreeHost(r.h_scal); for (cudaEvent_t e : r.ev) cudaEventDestroy(e); cudaStreamDestroy(r.stream); }
+    rp.free_[d].clear(); }
+  cudaSetDevice(cur);
+}
 
 void omvg_ba_default_options(omvg_ba_options *o) {
   if (!o) return;
@@ -306,7 +333,9 @@ void omvg_ba_default_options(omvg_ba_options *o) {
 
 int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   if (!out) return fail(OMVG_E_ARG, "null ctx");
+  PhaseTimer tm("create");
   int rc = validate(P); if (rc) return rc;
+  tm.lap("validate");
   int n = 0; OMVG_CUDA(cudaGetDeviceCount(&n));
   if (device < 0 || device >= n) return fail(OMVG_E_CUDA, "no CUDA device %d (found %d)", device, n);
   int cc_major = 0, cc_minor = 0, n_sms = 0;                 // attributes: cudaGetDeviceProperties costs milliseconds
@@ -317,49 +346,68 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   OMVG_CUDA(cudaSetDevice(device));
   omvg_ba_ctx *c = new omvg_ba_ctx; c->device = device; c->n_sms = n_sms;
   std::unique_ptr<omvg_ba_ctx, void (*)(omvg_ba_ctx *)> guard(c, [](omvg_ba_ctx *x) { omvg_ba_destroy(x); });
-  OMVG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  OMVG_CUDA(cudaEventCreate(&c->ev0)); OMVG_CUDA(cudaEventCreate(&c->ev1)); OMVG_CUDA(cudaEventCreate(&c->evj0)); OMVG_CUDA(cudaEventCreate(&c->evj1));
-  OMVG_CUDA(cudaMallocHost(&c->h_scal, (S_COUNT + 192 + 2) * sizeof(double)));
+  { CtxRes r; bool have = false;
+    { ResPool &rp = res_pool(); std::lock_guard<std::mutex> g(rp.mu); auto &v = rp.free_[device & 15]; if (!v.empty()) { r = v.back(); v.pop_back(); have = true; } }
+    if (!have) {
+      OMVG_CUDA(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 4; ++i) OMVG_CUDA(cudaEventCreate(&r.ev[i]));
+      OMVG_CUDA(cudaMallocHost(&r.h_scal, (S_COUNT + 192 + 2) * sizeof(double)));
+    }
+    c->stream = r.stream; c->ev0 = r.ev[0]; c->ev1 = r.ev[1]; c->evj0 = r.ev[2]; c->evj1 = r.ev[3]; c->h_scal = r.h_scal; }
   c->nc = P->n_poses; c->ni = P->n_intrinsics; c->np = P->n_points; c->nv = P->n_views; c->no = P->n_obs;
   c->ni8 = KI * c->ni; c->nred = 6 * c->nc + c->ni8; c->eval_blocks = (int)std::max<long long>(1, (c->no + EVAL_THREADS - 1) / EVAL_THREADS);
   c->eval_grid = std::min(c->eval_blocks, c->n_sms * (getenv("OMVG_BA_EVAL_WAVES") ? atoi(getenv("OMVG_BA_EVAL_WAVES")) : 4));   // persistent grid-stride evaluation
+  tm.lap("stream+events+pinned");
   c->h_intr_model.assign(P->intr_model, P->intr_model + c->ni);
   c->kiu = 0; for (int q = 0; q < c->ni; ++q) c->kiu = std::max(c->kiu, model_nparams(P->intr_model[q]));
-  // ---- sort observations by point (counting sort); build per-pose lists
   const long long no = c->no;
-  std::vector<int> pt_start(c->np + 1, 0);
-  for (long long o = 0; o < no; ++o) pt_start[P->obs_point[o] + 1]++;
-  for (int j = 0; j < c->np; ++j) pt_start[j + 1] += pt_start[j];
-  c->perm.resize(no);
-  { std::vector<int> cur(pt_start.begin(), pt_start.end() - 1); for (long long o = 0; o < no; ++o) c->perm[cur[P->obs_point[o]]++] = (int)o; }
-  std::vector<int> s_pose(no), s_intr(no), s_pt(no); std::vector<double> s_xy(2 * no);
-  #pragma omp parallel for schedule(static) if (no > 100000)
-  for (long long t = 0; t < no; ++t) { const int o = c->perm[t], v = P->obs_view[o];
-    s_pose[t] = P->view_pose[v]; s_intr[t] = P->view_intr[v]; s_pt[t] = P->obs_point[o]; s_xy[2 * t] = P->obs_xy[2 * o]; s_xy[2 * t + 1] = P->obs_xy[2 * o + 1]; }
-  std::vector<double> s_w; std::vector<unsigned char> s_fl;
-  if (P->obs_weight) { s_w.resize(no); for (long long t = 0; t < no; ++t) s_w[t] = P->obs_weight[c->perm[t]]; }
-  if (P->obs_no_loss) { s_fl.resize(no); for (long long t = 0; t < no; ++t) s_fl[t] = P->obs_no_loss[c->perm[t]] ? 1 : 0; }
-  std::vector<unsigned char> pt_single(c->np, 1);
-  #pragma omp parallel for schedule(static) if (c->np > 100000)
-  for (int j = 0; j < c->np; ++j) for (int t = pt_start[j] + 1; t < pt_start[j + 1]; ++t) if (s_intr[t] != s_intr[pt_start[j]]) { pt_single[j] = 0; break; }
-  std::vector<int> cam_start(c->nc + 1, 0), cam_obs(no);
-  for (long long t = 0; t < no; ++t) cam_start[s_pose[t] + 1]++;
-  for (int p = 0; p < c->nc; ++p) cam_start[p + 1] += cam_start[p];
-  { std::vector<int> cur(cam_start.begin(), cam_start.end() - 1); for (long long t = 0; t < no; ++t) cam_obs[cur[s_pose[t]]++] = (int)t; }
   // intrinsics with the unused tail zeroed (so block norms only see real parameters)
   std::vector<double> h_intr((size_t)c->ni8, 0.0);
   for (int q = 0; q < c->ni; ++q) for (int k = 0; k < model_nparams(P->intr_model[q]); ++k) h_intr[KI * q + k] = P->intrinsics[KI * q + k];
   cudaStream_t s = c->stream;
 #define UP(buf, ptr, cnt) if ((rc = upload(buf, ptr, (size_t)(cnt), s))) return rc
   UP(c->pose0, P->poses, 6 * c->nc); UP(c->intr0, h_intr.data(), c->ni8); UP(c->pt0, P->points, 3 * (size_t)c->np);
-  UP(c->intr_model, P->intr_model, c->ni); UP(c->obs_pose, s_pose.data(), no); UP(c->obs_intr, s_intr.data(), no); UP(c->obs_pt, s_pt.data(), no);
-  UP(c->pt_single, pt_single.data(), c->np); UP(c->pt_start, pt_start.data(), c->np + 1); UP(c->cam_start, cam_start.data(), c->nc + 1); UP(c->cam_obs, cam_obs.data(), no); UP(c->obs_xy, s_xy.data(), 2 * no);
-  if (P->obs_weight) UP(c->obs_w, s_w.data(), no);
-  if (P->obs_no_loss) UP(c->obs_flags, s_fl.data(), no);
+  UP(c->intr_model, P->intr_model, c->ni);
+  // ---- observations: upload as given, then sort by landmark / build the per-pose lists on the device
+  { DevBuf<int> raw_view, raw_point, d_view_pose, d_view_intr, keys, iota, keys2, bad; DevBuf<double> raw_xy, raw_w; DevBuf<unsigned char> raw_fl, cubtmp;
+    UP(raw_view, P->obs_view, no); UP(raw_point, P->obs_point, no); UP(raw_xy, P->obs_xy, 2 * no);
+    UP(d_view_pose, P->view_pose, c->nv); UP(d_view_intr, P->view_intr, c->nv);
+    if (P->obs_weight) { UP(raw_w, P->obs_weight, no); if ((rc = c->obs_w.alloc(no))) return rc; }
+    if (P->obs_no_loss) { UP(raw_fl, P->obs_no_loss, no); if ((rc = c->obs_flags.alloc(no))) return rc; }
+    if (tm.on) cudaStreamSynchronize(s);
+    tm.lap("uploads");
+    if ((rc = keys.alloc(no)) || (rc = iota.alloc(no)) || (rc = keys2.alloc(no)) || (rc = bad.alloc(1))) return rc;
+    if ((rc = c->d_perm.alloc(no)) || (rc = c->obs_pose.alloc(no)) || (rc = c->obs_intr.alloc(no)) || (rc = c->obs_pt.alloc(no)) || (rc = c->obs_xy.alloc(2 * no))) return rc;
+    if ((rc = c->pt_start.alloc(c->np + 1)) || (rc = c->cam_start.alloc(c->nc + 1)) || (rc = c->cam_obs.alloc(no)) || (rc = c->pt_single.alloc(c->np))) return rc;
+    const int h_big = 0x7fffffff; OMVG_CUDA(cudaMemcpyAsync(bad.p, &h_big, sizeof(int), cudaMemcpyHostToDevice, s));
+    const unsigned gb = (unsigned)((no + 255) / 256);
+    setup_check_kernel<<<gb, 256, 0, s>>>(raw_view.p, raw_point.p, no, c->nv, c->np, keys.p, iota.p, bad.p); LAUNCH_CHECK();
+    int pbits = 1; while ((1ll << pbits) < c->np) ++pbits;
+    int cbits = 1; while ((1ll << cbits) < c->nc) ++cbits;
+    size_t tb1 = 0, tb2 = 0;                                  // stable LSD radix sorts (CUB): by landmark, then by pose
+    OMVG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb1, keys.p, c->obs_pt.p, iota.p, c->d_perm.p, (int)no, 0, pbits, s));
+    OMVG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, c->obs_pose.p, keys2.p, iota.p, c->cam_obs.p, (int)no, 0, cbits, s));
+    if ((rc = cubtmp.alloc(std::max(tb1, tb2)))) return rc;
+    size_t tb = cubtmp.n;
+    OMVG_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, keys.p, c->obs_pt.p, iota.p, c->d_perm.p, (int)no, 0, pbits, s));
+    setup_gather_kernel<<<gb, 256, 0, s>>>(c->d_perm.p, raw_view.p, d_view_pose.p, d_view_intr.p, reinterpret_cast<const double2 *>(raw_xy.p), raw_w.p, raw_fl.p, no, c->nv,
+                                           c->obs_pose.p, c->obs_intr.p, reinterpret_cast<double2 *>(c->obs_xy.p), c->obs_w.p, c->obs_flags.p, iota.p); LAUNCH_CHECK();
+    setup_starts_kernel<<<(unsigned)((no + 256) / 256), 256, 0, s>>>(c->obs_pt.p, no, c->np, c->pt_start.p); LAUNCH_CHECK();
+    tb = cubtmp.n;
+    OMVG_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, c->obs_pose.p, keys2.p, iota.p, c->cam_obs.p, (int)no, 0, cbits, s));
+    setup_starts_kernel<<<(unsigned)((no + 256) / 256), 256, 0, s>>>(keys2.p, no, c->nc, c->cam_start.p); LAUNCH_CHECK();
+    setup_single_kernel<<<(c->np + 255) / 256, 256, 0, s>>>(c->obs_intr.p, c->pt_start.p, c->np, c->pt_single.p); LAUNCH_CHECK();
+    int h_bad = 0; OMVG_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    OMVG_CUDA(cudaStreamSynchronize(s));                      // the temporaries above are released at the end of this scope
+    c->launches += 9;
+    if (h_bad != h_big) return fail(OMVG_E_ARG, "observation %d out of range", h_bad);
+    tm.lap("device sort / lists");
+  }
   if (P->point_fixed) {
     std::vector<unsigned> pm(c->np); for (int j = 0; j < c->np; ++j) pm[j] = P->point_fixed[j] ? 0u : 7u;
     UP(c->pt_fixed, P->point_fixed, c->np); UP(c->pt_mask, pm.data(), c->np);
   }
+  c->has_ext = P->obs_weight || P->obs_no_loss || P->point_fixed;
   c->npri = P->n_priors; c->prior_huber_a = P->prior_huber_a;
   if (c->npri) { UP(c->prior_pose, P->prior_pose, c->npri); UP(c->prior_center, P->prior_center, 3 * c->npri); UP(c->prior_weight, P->prior_weight, 3 * c->npri); }
 #undef UP
@@ -383,7 +431,9 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   AL(c->part, std::max(c->eval_blocks, 1024) + 2); AL(c->part2, 1024); AL(c->part3, 1024); AL(c->icol_part, (size_t)c->ni * 64 * ICS_W); AL(c->scal, S_COUNT); AL(c->fail, 1);
 #undef AL
   OMVG_CUDA(cudaMemsetAsync(c->scal.p, 0, S_COUNT * sizeof(double), s));
+  tm.lap("allocations");
   if ((rc = build_structure(c))) return rc;
+  tm.lap("structure");
   if ((rc = omvg_ba_reset(c))) return rc;
   OMVG_CUDA(cudaStreamSynchronize(s));
   guard.release();
@@ -403,11 +453,11 @@ int omvg_ba_destroy(omvg_ba_ctx *c) {
   if (!c) return OMVG_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->h_scal) cudaFreeHost(c->h_scal);
-  for (cudaEvent_t e : {c->ev0, c->ev1, c->evj0, c->evj1}) if (e) cudaEventDestroy(e);
-  cudaStream_t s = c->stream;
-  delete c;                                   // DevBuf destructors free device memory
-  if (s) cudaStreamDestroy(s);
+  CtxRes r; r.stream = c->stream; r.ev[0] = c->ev0; r.ev[1] = c->ev1; r.ev[2] = c->evj0; r.ev[3] = c->evj1; r.h_scal = c->h_scal;
+  const int dev = c->device & 15;
+  delete c;                                   // DevBuf destructors hand device memory back to the pool
+  if (r.stream && r.ev[3] && r.h_scal) { ResPool &rp = res_pool(); std::lock_guard<std::mutex> g(rp.mu); rp.free_[dev].push_back(r); }
+  else { if (r.h_scal) cudaFreeHost(r.h_scal); for (cudaEvent_t e : r.ev) if (e) cudaEventDestroy(e); if (r.stream) cudaStreamDestroy(r.stream); }
   return OMVG_OK;
 }
 
@@ -443,10 +493,12 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   const bool use_pcg2 = n_free_intr <= MAXRHS - 1 && !getenv("OMVG_BA_PCG1");
   const bool use_pcg3 = use_pcg2 && !getenv("OMVG_BA_PCG2") && c->nc >= 2;
   // the per-observation kernels gather pose records (176 B x n_poses) and points through L1: give them all of it
-  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
-  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
-  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
-  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<false, 8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<false, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   OMVG_CUDA(cudaFuncSetAttribute(pcg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
   OMVG_CUDA(cudaFuncSetAttribute(pcg3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
   if ((rc = read_scalars(c))) return rc;
@@ -463,6 +515,10 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   int coarse_age = -1; double last_pcg_its = 0, fresh_pcg_its = 1e30; bool fresh_pending = false;
   static const int coarse_every = getenv("OMVG_BA_COARSE_EVERY") ? std::max(1, atoi(getenv("OMVG_BA_COARSE_EVERY"))) : 2;
   const int pcg_grid = c->n_sms;
+  if (!c->gj_grid) {                                        // as many co-resident CTAs as the tile count can use
+    int per_sm = 1; OMVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_invert_kernel, 256, 0));
+    c->gj_grid = c->n_sms * std::max(1, std::min(per_sm, 2));
+  }
 
   for (;;) {
     if (step_is_successful) ++n_success; else ++n_fail;
@@ -498,7 +554,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       P2.W = c->gW.p; P2.intr_mask = c->intr_mask.p; P2.n_poses = c->nc; P2.ni8 = c->ni8; P2.nw = nw; P2.X = c->bX.p; P2.Rv = c->bR.p; P2.Pv = c->bP.p; P2.Wv = c->bW.p; P2.Zv = c->bZ.p;
       P2.AW = c->gAW.p; P2.part = c->pcg2_part.p; P2.z = c->z.p; P2.tol = O->pcg_tolerance; P2.max_iter = O->pcg_max_iterations; P2.out = c->scal.p + S_PCG_IT;
       if (use_pcg3) {
-        Pcg3Args P3{}; P3.base = P2; P3.C = Coarse{c->agg_of.p, c->agg_start.p, c->agg_cams.p, c->ng, nw, c->ng * nw}; P3.Einv = c->cEinv.p; P3.Cv = c->cCv.p; P3.Yv = c->cYv.p; P3.Pv2 = c->bP2.p;
+        Pcg3Args P3{}; P3.base = P2; P3.C = Coarse{c->agg_of.p, c->agg_start.p, c->agg_cams.p, c->ng, nw, c->ng * nw}; P3.Einv = getenv("OMVG_BA_COARSE_CHOL") ? c->cEinv.p : c->cE.p; P3.Cv = c->cCv.p; P3.Yv = c->cYv.p; P3.Pv2 = c->bP2.p;
         const int nco = P3.C.nco;
         // The coarse operator is only a preconditioner: a slightly stale E^-1 (previous LM step, radius/3) costs a few
         // extra PCG iterations (measured 38->40, 42->49, 43->43) but saves its O(nco^3) setup, so it is refreshed every
@@ -509,6 +565,13 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
         if (refresh) {
           OMVG_CUDA(cudaMemsetAsync(c->cE.p, 0, (size_t)nco * nco * sizeof(double), c->stream));
           coarse_assemble_kernel<<<(c->nnzb + 127) / 128, 128, 0, c->stream>>>(c->Scc.p, c->brow.p, c->cols.p, c->nnzb, c->gW.p, c->nc, P3.C, c->cE.p); LAUNCH_CHECK();
+          static const bool use_chol = getenv("OMVG_BA_COARSE_CHOL") != nullptr;
+          if (!use_chol) {                                        // blocked Gauss-Jordan, in place: cE becomes E^-1
+            double *Ep = c->cE.p, *Tp = c->cT.p; int nn = nco; int *fp = c->fail.p;
+            void *cargs[] = {&Ep, &nn, &Tp, &fp};
+            OMVG_CUDA(cudaLaunchCooperativeKernel((void *)coarse_invert_kernel, dim3(c->gj_grid), dim3(256), cargs, 0, c->stream));
+            P3.Einv = c->cE.p;
+          } else
           { const size_t sm = sizeof(double) * ((size_t)CNB * CNB + 2 * CT * (CNB + 1) + 2 * CT * (CT + 1));
             OMVG_CUDA(cudaFuncSetAttribute(coarse_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             double *Ep = c->cE.p, *Tp = c->cT.p, *Ip = c->cEinv.p; int nn = nco; int *fp = c->fail.p;
@@ -626,9 +689,12 @@ static void aa_to_R(const double *aa, double R[9]) {
 int omvg_ba_solve(omvg_ba_problem *P, const omvg_ba_options *O, omvg_ba_summary *sum) {
   omvg_ba_options def; if (!O) { omvg_ba_default_options(&def); O = &def; }
   omvg_ba_summary local; if (!sum) sum = &local;
+  PhaseTimer tm("solve");
   omvg_ba_ctx *c = nullptr;
   int rc = omvg_ba_create(&c, O->device, P); if (rc) return rc;
+  tm.lap("create");
   rc = omvg_ba_run(c, O, sum);
+  tm.lap("run");
   if (rc == OMVG_OK) {                       // state is copied back only when usable (solver.cc:445-448)
     // Adjust's write-back rules (sfm_data_BA_ceres.cpp:528-568): poses only if extrinsics were refined,
     // intrinsics only if intrinsics were refined; ADJUST_ROTATION keeps the pose CENTRE (t = -R_new C_old).
@@ -653,23 +719,33 @@ int omvg_ba_solve(omvg_ba_problem *P, const omvg_ba_options *O, omvg_ba_summary 
       if (!(O->intrinsics_opt & 1)) std::memcpy(P->intrinsics, ni_.data(), ni_.size() * sizeof(double));
     }
   }
+  tm.lap("download+write-back");
   omvg_ba_destroy(c);
+  tm.lap("destroy");
   return rc;
 }
 
 // Reprojection residual norms (pixels) of every observation at the current device parameters, in the
 // caller's observation order — what RemoveOutliers_PixelResidualError (sfm/sfm_data_filters.cpp:40-73)
 // recomputes on the host after every Adjust of the BA / reject loop (sequential_SfM.cpp:205-211).
+static int ensure_perm(omvg_ba_ctx *c) {
+  if (!c->perm.empty() || !c->no) return OMVG_OK;
+  c->perm.resize(c->no);
+  OMVG_CUDA(cudaMemcpyAsync(c->perm.data(), c->d_perm.p, (size_t)c->no * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  return OMVG_OK;
+}
+
 int omvg_ba_residual_norms(omvg_ba_ctx *c, double *norms) {
   if (!c || !norms) return fail(OMVG_E_ARG, "null argument");
   OMVG_CUDA(cudaSetDevice(c->device));
+  { const int prc = ensure_perm(c); if (prc) return prc; }
   omvg_ba_options O; omvg_ba_default_options(&O); O.use_loss = 0;
   cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[0].p, c->nc, c->camR[0].p, c->camdR.p, c->camrec[0].p); LAUNCH_CHECK();
   EvalArgs A{}; A.poses = c->pose[0].p; A.intr = c->intr[0].p; A.pts = c->pt[0].p; A.camR = c->camR[0].p; A.camdR = c->camdR.p; A.camrec = c->camrec[0].p;
   A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
   A.n_obs = c->no; A.use_loss = 0; A.huber_a = O.huber_a; A.cost_partial = c->part.p; A.rnorm = c->r.p;   // r is scratch between solves
-  A.pt_fixed = c->pt_fixed.p;                              // (weights deliberately not applied: pixels)
-  eval_kernel<false, 8><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  eval_kernel<false, 8, false><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();   // (weights deliberately not applied: pixels)
   c->launches += 2;
   std::vector<double> h(c->no);
   OMVG_CUDA(cudaMemcpyAsync(h.data(), c->r.p, (size_t)c->no * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -685,9 +761,11 @@ int omvg_ba_residual_norms(omvg_ba_ctx *c, double *norms) {
 int omvg_ba_set_obs_weights(omvg_ba_ctx *c, const double *w) {
   if (!c || !w) return fail(OMVG_E_ARG, "null argument");
   OMVG_CUDA(cudaSetDevice(c->device));
+  { const int prc = ensure_perm(c); if (prc) return prc; }
   std::vector<double> s_w(c->no);
   for (long long t = 0; t < c->no; ++t) { const double v = w[c->perm[t]]; if (!(v >= 0.0) || !std::isfinite(v)) return fail(OMVG_E_ARG, "weight %d is negative or not finite", c->perm[t]); s_w[t] = v; }
   if (!c->obs_w.p) { int rc = c->obs_w.alloc(c->no); if (rc) return rc; }
+  c->has_ext = true;
   OMVG_CUDA(cudaMemcpyAsync(c->obs_w.p, s_w.data(), (size_t)c->no * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   OMVG_CUDA(cudaStreamSynchronize(c->stream));
   return OMVG_OK;
@@ -707,6 +785,7 @@ int omvg_ba_commit(omvg_ba_ctx *c) {
 int omvg_ba_debug_eval(omvg_ba_ctx *c, const omvg_ba_options *O, double *cost, double *r, double *J_intr, double *J_pose, double *J_point) {
   if (!c || !O) return fail(OMVG_E_ARG, "null argument");
   OMVG_CUDA(cudaSetDevice(c->device));
+  { const int prc = ensure_perm(c); if (prc) return prc; }
   Masks m = make_masks(c, O);
   OMVG_CUDA(cudaMemcpyAsync(c->intr_mask.p, m.intr_mask.data(), c->ni * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
   // unscaled evaluation (intrinsic columns >= kiu are never written: present them as zeros)
@@ -717,7 +796,7 @@ int omvg_ba_debug_eval(omvg_ba_ctx *c, const omvg_ba_options *O, double *cost, d
   A.n_obs = c->no; A.use_loss = O->use_loss; A.huber_a = O->huber_a; A.r = c->r.p; A.Jp = c->Jp.p; A.Jc = c->Jc.p; A.Ji = c->Ji.p;
   A.cost_partial = c->part.p; A.kiu = c->kiu; A.pose_mask = m.pose_mask; A.intr_mask = c->intr_mask.p; A.pts_free = m.pts_free;
   A.obs_w = c->obs_w.p; A.obs_flags = c->obs_flags.p; A.pt_fixed = c->pt_fixed.p;      // (prior rows are not part of this dump)
-  eval_kernel<true, 4><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  eval_kernel<true, 4, true><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
   int rc = reduce_to(c, c->part.p, c->eval_grid, S_COST); if (rc) return rc;
   c->launches += 2;
   const long long n = c->no;

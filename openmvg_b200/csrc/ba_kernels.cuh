@@ -109,6 +109,44 @@ __global__ void cam_prep_kernel(const double *__restrict__ poses, int n_poses, d
   rec[18] = poses[6 * p + 3]; rec[19] = poses[6 * p + 4]; rec[20] = poses[6 * p + 5]; rec[21] = 0.0;
 }
 
+// ------------------------------------------------------------------------------ problem setup on the device
+// (the caller's observation arrays are uploaded as they are; sorting by landmark, the per-pose lists and the
+// range checks run here instead of on the host: at 1M observations the host version cost more than the solve)
+__global__ void setup_check_kernel(const int *__restrict__ obs_view, const int *__restrict__ obs_point, long long n, int n_views, int n_points,
+                                   int *__restrict__ keys, int *__restrict__ iota, int *__restrict__ bad) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  const int v = obs_view[o], j = obs_point[o];
+  if (v < 0 || v >= n_views || j < 0 || j >= n_points) { atomicMin(bad, (int)o); keys[o] = 0; } else keys[o] = j;
+  iota[o] = (int)o;
+}
+__global__ void setup_gather_kernel(const int *__restrict__ perm, const int *__restrict__ obs_view, const int *__restrict__ view_pose, const int *__restrict__ view_intr,
+                                    const double2 *__restrict__ xy, const double *__restrict__ w_in, const unsigned char *__restrict__ fl_in, long long n, int n_views,
+                                    int *__restrict__ s_pose, int *__restrict__ s_intr, double2 *__restrict__ s_xy, double *__restrict__ s_w, unsigned char *__restrict__ s_fl,
+                                    int *__restrict__ iota) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int o = perm[t]; int v = obs_view[o]; v = min(max(v, 0), n_views - 1);
+  s_pose[t] = view_pose[v]; s_intr[t] = view_intr[v]; s_xy[t] = xy[o];
+  if (s_w) s_w[t] = w_in[o];
+  if (s_fl) s_fl[t] = fl_in[o] ? 1 : 0;
+  iota[t] = (int)t;
+}
+// segment starts of a sorted key array: start[k] = first t with key[t] >= k, start[n_keys] = n (empty keys included)
+__global__ void setup_starts_kernel(const int *__restrict__ key, long long n, int n_keys, int *__restrict__ start) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n) return;
+  const int lo = t == 0 ? -1 : key[t - 1], hi = t == n ? n_keys : key[t];
+  for (int k = lo + 1; k <= hi; ++k) start[k] = (int)t;
+}
+__global__ void setup_single_kernel(const int *__restrict__ s_intr, const int *__restrict__ pt_start, int n_points, unsigned char *__restrict__ pt_single) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_points) return;
+  unsigned char one = 1;
+  for (int t = pt_start[j] + 1; t < pt_start[j + 1]; ++t) if (s_intr[t] != s_intr[pt_start[j]]) { one = 0; break; }
+  pt_single[j] = one;
+}
+
 // ------------------------------------------------------------------------------ residual / Jacobian
 struct EvalArgs {
   const double *poses, *intr, *pts, *camR, *camdR, *camrec, *obs_xy;
@@ -182,7 +220,8 @@ __device__ __forceinline__ void distort(int model, const double *K, double x, do
 }
 
 constexpr int EVAL_THREADS = 128;
-template <bool WANT_J, int MINB>
+// EXT = false compiles the weight / flag / fixed-landmark handling out (the common problem has none)
+template <bool WANT_J, int MINB, bool EXT>
 __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
   __shared__ double sh[EVAL_THREADS / 32];
   // persistent grid-stride loop; the (DRAM-latency) index / observation loads of the NEXT observation are
@@ -205,8 +244,8 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
     const double p0 = R[0] * X0 + R[1] * X1 + R[2] * X2 + T[0];
     const double p1 = R[3] * X0 + R[4] * X1 + R[5] * X2 + T[1];
     const double p2 = R[6] * X0 + R[7] * X1 + R[8] * X2 + T[2];
-    const double wg = A.obs_w ? __ldcs(A.obs_w + o) : 1.0;      // WeightedCostFunction (functor.hpp:35-90)
-    const bool dead = wg == 0.0;                               // removed observation: contributes exact zeros
+    const double wg = (EXT && A.obs_w) ? __ldcs(A.obs_w + o) : 1.0;   // WeightedCostFunction (functor.hpp:35-90)
+    const bool dead = EXT && wg == 0.0;                        // removed observation: contributes exact zeros
     const bool safe = dead && WANT_J;                          // keep every Jacobian factor finite so that 0 * J == 0
     const double iz = safe ? 1.0 : 1.0 / p2, x = safe ? 0.0 : p0 * iz, y = safe ? 0.0 : p1 * iz;
     const double *K = A.intr + KI * iq;
@@ -216,16 +255,16 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
     const double f = K[0];
     double r0 = K[1] + dx * f - xy.x, r1 = K[2] + dy * f - xy.y;
     if (!WANT_J && A.rnorm) A.rnorm[o] = sqrt(r0 * r0 + r1 * r1);
-    r0 = dead ? 0.0 : r0 * wg; r1 = dead ? 0.0 : r1 * wg;
+    if (EXT) { r0 = dead ? 0.0 : r0 * wg; r1 = dead ? 0.0 : r1 * wg; }
     const double s = r0 * r0 + r1 * r1;
     double rho0 = s, rho1 = 1.0;
     const double b = A.huber_a * A.huber_a;
-    const bool lossy = A.use_loss && !(A.obs_flags && (A.obs_flags[o] & 1));   // GCP blocks carry no loss (:424)
+    const bool lossy = A.use_loss && !(EXT && A.obs_flags && (A.obs_flags[o] & 1));   // GCP blocks carry no loss (:424)
     if (lossy && s > b) { const double rr = sqrt(s); rho0 = 2.0 * A.huber_a * rr - b; rho1 = fmax(DBL_MIN, A.huber_a / rr); }
     cost += 0.5 * rho0;
     if (WANT_J) {
       const double wl = sqrt(rho1);                             // Huber: rho'' <= 0 => r, J scaled by sqrt(rho')
-      const double w = wl * wg;                                 // Jacobian of the weighted residual
+      const double w = EXT ? wl * wg : wl;                      // Jacobian of the weighted residual
       const long long n = A.n_obs;
       __stcs(A.r + o, wl * r0); __stcs(A.r + n + o, wl * r1);
       // d r / d u = f * dd ; d u / d p = [[iz,0,-x iz],[0,iz,-y iz]]
@@ -236,7 +275,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
       // point block: g * R
       #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const double sc = (A.pts_free && !(A.pt_fixed && A.pt_fixed[j])) ? (A.sc_pt ? A.sc_pt[3 * j + c] : 1.0) : 0.0;
+        const double sc = (A.pts_free && !(EXT && A.pt_fixed && A.pt_fixed[j])) ? (A.sc_pt ? A.sc_pt[3 * j + c] : 1.0) : 0.0;
         __stcs(A.Jp + (0 * 3 + c) * n + o, sc * (g[0] * R[c] + g[1] * R[3 + c] + g[2] * R[6 + c]));
         __stcs(A.Jp + (1 * 3 + c) * n + o, sc * (g[3] * R[c] + g[4] * R[3 + c] + g[5] * R[6 + c]));
       }
@@ -1356,6 +1395,113 @@ __global__ void __launch_bounds__(256) coarse_setup_kernel(double *__restrict__ 
       if (bj > bi) continue;
       tile_abt<1>(Einv, T, T, n, bi * CT, bj * CT, (bi * CT / CNB) * CNB, n, tsm);
     } }
+}
+
+// Coarse operator inverse by blocked Gauss-Jordan, in place, ONE cooperative kernel (default).  The Cholesky route above
+// serialises on its triangular inverse (one CTA per block column); Gauss-Jordan does twice the flops but every
+// pivot step is a rank-32 update of the WHOLE matrix — 196 independent 64x64 tiles — between two grid syncs:
+//   phase 1 (every CTA): B = inv(A_KK) redundantly in shared memory; slices of  Cold = A[:,K] (copy),
+//                        H = B A[K,:],  Gn = -A[:,K] B  into scratch
+//   phase 2 (tiles):     A_ij <- A_ij - Cold_i H_j  (i,j not in K);  A_Kj <- H_j;  A_iK <- Gn_i;  A_KK <- B
+// A is symmetrised (+ tiny ridge) first; SPD input needs no pivoting (every pivot block is a Schur complement).
+constexpr int GJ_B = 32;
+__global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__ A, int n, double *__restrict__ tmp, int *__restrict__ fail) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double Bs[GJ_B][GJ_B + 1];
+  __shared__ double As[CT][GJ_B + 1];
+  __shared__ double Hs[GJ_B][CT + 1];
+  __shared__ double s_red[8];
+  __shared__ double s_row[GJ_B], s_col[GJ_B];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  double *Cold = tmp, *H = tmp + (size_t)GJ_B * n, *Gn = tmp + 2 * (size_t)GJ_B * n;     // [n][32], [32][n], [n][32]
+  // ridge = 1e-15 * max diagonal (every CTA computes it: no extra sync)
+  { double mx = 0; for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, A[(size_t)i * n + i]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = 0; for (int w = 0; w < 8; ++w) mx = fmax(mx, s_red[w]);
+    const double ridge = 1e-15 * mx;
+    grid.sync();                                           // everyone has read the diagonal before it changes
+    for (long long idx = tid; idx < (long long)n * n; idx += nt) {
+      const int i = (int)(idx / n), j = (int)(idx % n);
+      if (j < i) { const double v = 0.5 * (A[(size_t)i * n + j] + A[(size_t)j * n + i]); A[(size_t)i * n + j] = v; A[(size_t)j * n + i] = v; }
+      else if (j == i) A[idx] += ridge;
+    } }
+  grid.sync();
+  const int mt = (n + CT - 1) / CT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  for (int k0 = 0; k0 < n; k0 += GJ_B) {
+    const int nb = min(GJ_B, n - k0);
+    // ---- phase 1: B = inv(A_KK) (Gauss-Jordan in shared memory, 256 threads), identity-padded to 32
+    for (int idx = threadIdx.x; idx < GJ_B * GJ_B; idx += 256) { const int r = idx >> 5, c = idx & 31; Bs[r][c] = (r < nb && c < nb) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0); }
+    __syncthreads();
+    for (int k = 0; k < GJ_B; ++k) {
+      if (threadIdx.x < GJ_B) { s_col[threadIdx.x] = Bs[threadIdx.x][k]; s_row[threadIdx.x] = Bs[k][threadIdx.x]; }
+      __syncthreads();
+      const double piv = s_row[k];
+      if (!(piv > 0.0) || !isfinite(piv)) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(fail, 4); }
+      const double ip = 1.0 / piv;
+      for (int idx = threadIdx.x; idx < GJ_B * GJ_B; idx += 256) {
+        const int r = idx >> 5, c = idx & 31;
+        double v;
+        if (r == k) v = c == k ? ip : s_row[c] * ip;
+        else { const double f = s_col[r]; v = c == k ? -f * ip : Bs[r][c] - f * (s_row[c] * ip); }
+        Bs[r][c] = v;
+      }
+      __syncthreads();
+    }
+    // slices of Cold / H / Gn
+    for (long long idx = tid; idx < (long long)n * GJ_B; idx += nt) {
+      const int i = (int)(idx >> 5), q = (int)(idx & 31);
+      double g = 0.0;
+      if (q < nb) { for (int p2 = 0; p2 < nb; ++p2) g += A[(size_t)i * n + k0 + p2] * Bs[p2][q]; }
+      Cold[idx] = q < nb ? A[(size_t)i * n + k0 + q] : 0.0;
+      Gn[idx] = -g;
+    }
+    for (long long idx = tid; idx < (long long)n * GJ_B; idx += nt) {
+      const int q = (int)(idx / n), j = (int)(idx % n);
+      double h = 0.0;
+      if (q < nb) { for (int p2 = 0; p2 < nb; ++p2) h += Bs[q][p2] * A[(size_t)(k0 + p2) * n + j]; }
+      H[idx] = h;
+    }
+    grid.sync();
+    // ---- phase 2: tiles
+    for (int t = blockIdx.x; t < mt * mt; t += gridDim.x) {
+      const int i0 = (t / mt) * CT, j0 = (t % mt) * CT;
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < CT * GJ_B; idx += 256) { const int r = idx >> 5, q = idx & 31; As[r][q] = i0 + r < n ? Cold[(size_t)(i0 + r) * GJ_B + q] : 0.0; }
+      for (int idx = threadIdx.x; idx < CT * GJ_B; idx += 256) { const int q = idx / CT, c2 = idx % CT; Hs[q][c2] = j0 + c2 < n ? H[(size_t)q * n + j0 + c2] : 0.0; }
+      __syncthreads();
+      double acc[4][4];
+      #pragma unroll
+      for (int p2 = 0; p2 < 4; ++p2)
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p2][q] = 0.0;
+      #pragma unroll 8
+      for (int kk = 0; kk < GJ_B; ++kk) {
+        double av[4], bv[4];
+        #pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) { av[p2] = As[ty + 16 * p2][kk]; bv[p2] = Hs[kk][tx + 16 * p2]; }
+        #pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2)
+          #pragma unroll
+          for (int q = 0; q < 4; ++q) acc[p2][q] += av[p2] * bv[q];
+      }
+      #pragma unroll
+      for (int p2 = 0; p2 < 4; ++p2)
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = i0 + ty + 16 * p2, c2 = j0 + tx + 16 * q;
+          if (r >= n || c2 >= n) continue;
+          const bool rk = r >= k0 && r < k0 + nb, ck = c2 >= k0 && c2 < k0 + nb;
+          double v;
+          if (rk) v = ck ? Bs[r - k0][c2 - k0] : Hs[r - k0][tx + 16 * q];
+          else v = ck ? Gn[(size_t)r * GJ_B + (c2 - k0)] : A[(size_t)r * n + c2] - acc[p2][q];
+          A[(size_t)r * n + c2] = v;
+        }
+    }
+    grid.sync();
+  }
 }
 
 struct Pcg3Args {
