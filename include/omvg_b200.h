@@ -170,7 +170,7 @@ typedef struct {
   double  min_relative_decrease;                        /* 1e-3 */
   double  min_lm_diagonal, max_lm_diagonal;             /* 1e-6, 1e32 */
   /* reduced-camera-system solve (block-Jacobi PCG standing in for SimplicialLDLT) */
-  double  pcg_tolerance;       /* relative residual |S z - b| / |b| <= tol ; default 1e-12 */
+  double  pcg_tolerance;       /* relative residual |S z - b| / |b| <= tol ; default 1e-8 (final cost within ~3e-9 of the exact solve) */
   int32_t pcg_max_iterations;  /* default 2000 */
   int32_t verbose;
   int32_t device;              /* CUDA ordinal used by omvg_ba_solve (omvg_ba_create takes its own) ; default 0 */

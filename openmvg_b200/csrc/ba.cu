@@ -69,6 +69,7 @@ struct omvg_ba_ctx {
   DevBuf<int> fail;
   // optional extensions: GCP weights / flags / fixed landmarks, pose-centre priors
   DevBuf<double> obs_w; DevBuf<unsigned char> obs_flags, pt_fixed; DevBuf<unsigned> pt_mask;
+  int n_slow = 0;                           // landmarks left to the per-observation Schur kernel
   bool has_ext = false; int npri = 0; double prior_huber_a = 0; DevBuf<int> prior_pose; DevBuf<double> prior_center, prior_weight, rP, JP;
   double *h_scal = nullptr;                 // pinned
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evj0 = nullptr, evj1 = nullptr;
@@ -328,7 +329,7 @@ void omvg_ba_default_options(omvg_ba_options *o) {
   o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
   o->initial_radius = 1e4; o->max_radius = 1e16; o->min_radius = 1e-32; o->min_relative_decrease = 1e-3;
   o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
-  o->pcg_tolerance = 1e-10; o->pcg_max_iterations = 2000; o->verbose = 0;
+  o->pcg_tolerance = 1e-8; o->pcg_max_iterations = 2000; o->verbose = 0;
 }
 
 int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
@@ -396,8 +397,11 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
     tb = cubtmp.n;
     OMVG_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, c->obs_pose.p, keys2.p, iota.p, c->cam_obs.p, (int)no, 0, cbits, s));
     setup_starts_kernel<<<(unsigned)((no + 256) / 256), 256, 0, s>>>(keys2.p, no, c->nc, c->cam_start.p); LAUNCH_CHECK();
-    setup_single_kernel<<<(c->np + 255) / 256, 256, 0, s>>>(c->obs_intr.p, c->pt_start.p, c->np, c->pt_single.p); LAUNCH_CHECK();
+    DevBuf<int> slow; if ((rc = slow.alloc(1))) return rc;
+    OMVG_CUDA(cudaMemsetAsync(slow.p, 0, sizeof(int), s));
+    setup_single_kernel<<<(c->np + 255) / 256, 256, 0, s>>>(c->obs_intr.p, c->pt_start.p, c->np, c->pt_single.p, slow.p); LAUNCH_CHECK();
     int h_bad = 0; OMVG_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    OMVG_CUDA(cudaMemcpyAsync(&c->n_slow, slow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     OMVG_CUDA(cudaStreamSynchronize(s));                      // the temporaries above are released at the end of this scope
     c->launches += 9;
     if (h_bad != h_big) return fail(OMVG_E_ARG, "observation %d out of range", h_bad);
@@ -540,7 +544,16 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     SA.pts_free = m.pts_free; SA.kiu = c->kiu; SA.bsr = Bsr{c->bitmap.p, c->wprefix.p, c->rowptr.p, c->words}; SA.Scc = c->Scc.p; SA.Sci = c->Sci.p; SA.Sii = c->Sii.p; SA.rhs = c->rhs.p;
     SA.Einv = c->Einv.p; SA.fail = c->fail.p;
     { const int ninit = std::max(std::max(36 * c->nc, 64 * c->ni), c->nred); s_init_kernel<<<(ninit + 255) / 256, 256, 0, c->stream>>>(SA); LAUNCH_CHECK(); }
-    schur_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA); LAUNCH_CHECK();
+    static const bool schur1 = getenv("OMVG_BA_SCHUR1") != nullptr;
+    SA.n_points = c->np;
+    if (m.pts_free && !schur1) {
+      static const int minb = getenv("OMVG_BA_SCHUR2_MINB") ? atoi(getenv("OMVG_BA_SCHUR2_MINB")) : 5;
+      void (*kern)(SchurArgs) = minb >= 6 ? schur_point_kernel<6> : (minb >= 5 ? schur_point_kernel<5> : schur_point_kernel<3>);
+      static int occ = 0; if (!occ) { OMVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * SCHUR2_WARPS, 0)); occ = std::max(1, occ); }
+      kern<<<c->n_sms * occ, 32 * SCHUR2_WARPS, 0, c->stream>>>(SA); LAUNCH_CHECK(); c->launches++;   // one resident wave, grid-stride over landmarks
+      SA.skip_fast = 1;
+    }
+    if (!m.pts_free || schur1 || c->n_slow > 0) { schur_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA); LAUNCH_CHECK(); }
     mirror_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Scc.p, SA.bsr, c->cols.p, c->nc); LAUNCH_CHECK();
     c->launches += 2;
     finish_cam_kernel<<<(c->nc + 63) / 64, 64, 0, c->stream>>>(c->Scc.p, SA.bsr, c->lmD_cam.p, m.pose_mask, c->nc, c->Minv_c.p, c->fail.p); LAUNCH_CHECK();

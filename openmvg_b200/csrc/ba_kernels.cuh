@@ -139,12 +139,17 @@ __global__ void setup_starts_kernel(const int *__restrict__ key, long long n, in
   const int lo = t == 0 ? -1 : key[t - 1], hi = t == n ? n_keys : key[t];
   for (int k = lo + 1; k <= hi; ++k) start[k] = (int)t;
 }
-__global__ void setup_single_kernel(const int *__restrict__ s_intr, const int *__restrict__ pt_start, int n_points, unsigned char *__restrict__ pt_single) {
+// pt_single[j] = all observations of landmark j go through one intrinsic group; n_slow counts the landmarks the
+// warp-per-landmark Schur kernel does not take (several groups, or more than 32 observations)
+__global__ void setup_single_kernel(const int *__restrict__ s_intr, const int *__restrict__ pt_start, int n_points, unsigned char *__restrict__ pt_single,
+                                    int *__restrict__ n_slow) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_points) return;
   unsigned char one = 1;
   for (int t = pt_start[j] + 1; t < pt_start[j + 1]; ++t) if (s_intr[t] != s_intr[pt_start[j]]) { one = 0; break; }
   pt_single[j] = one;
+  const int K = pt_start[j + 1] - pt_start[j];
+  if (K > 0 && (!one || K > 32)) atomicAdd(n_slow, 1);
 }
 
 // ------------------------------------------------------------------------------ residual / Jacobian
@@ -571,6 +576,8 @@ struct SchurArgs {
   const int *obs_pose, *obs_intr, *obs_pt, *pt_start; const unsigned char *pt_single;
   const double *FtF, *FiFi, *g_cam, *g_intr;
   long long n; int n_poses, n_intr, pts_free, kiu;
+  int n_points;     // schur_point_kernel: landmarks
+  int skip_fast;    // schur_kernel: leave the landmarks schur_point_kernel handles (pt_single and <= 32 observations) alone
   Bsr bsr;
   double *Scc;      // [nnzb][36]
   double *Sci;      // [KI*n_intr][6*n_poses]
@@ -605,7 +612,9 @@ __global__ void __launch_bounds__(SCHUR_THREADS) schur_kernel(SchurArgs A) {
   __syncthreads();
   const int q0 = s_q0;
   const int nred_c = 6 * A.n_poses, ni8 = KI * A.n_intr;
-  if (t < n) {
+  bool mine = t < n;
+  if (mine && A.skip_fast && A.pts_free) { const int j = A.obs_pt[t]; mine = !(A.pt_single[j] != 0 && A.pt_start[j + 1] - A.pt_start[j] <= 32); }
+  if (mine) {
     const int j = A.obs_pt[t], ct = A.obs_pose[t], qt = A.obs_intr[t];
     double jc[12], ji[2 * KI], jp[6];
     #pragma unroll
@@ -733,6 +742,125 @@ __global__ void __launch_bounds__(SCHUR_THREADS) schur_kernel(SchurArgs A) {
 }
 
 // lower triangle of Scc from the upper one: block (a,b), a > b, = block (b,a)'
+// One WARP per landmark (the common case: all its observations through one intrinsic group, at most 32 of
+// them).  Lane l stages Einv E'Fc and E'Fc of observation l in shared memory and does the per-observation
+// border / right-hand-side terms; then the warp walks the camera pairs (cam(u) >= cam(t)) TOGETHER, lane e
+// adding element e of the 6x6 block: one RED instruction touches the 9 sectors of one block instead of 32
+// sectors of 32 different blocks.  Measured on B200 (tools/atomic_bench.cu): 565 vs 222 G FP64 atomics/s.
+constexpr int SCHUR2_WARPS = 4;
+template <int MINB>
+__global__ void __launch_bounds__(32 * SCHUR2_WARPS, MINB) schur_point_kernel(SchurArgs A) {
+  __shared__ double s_gt[SCHUR2_WARPS][32][18];
+  __shared__ double s_ef[SCHUR2_WARPS][32][18];
+  __shared__ int s_cam[SCHUR2_WARPS][32];
+  __shared__ double s_ii[KI * KI + KI];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * SCHUR2_WARPS + wib, nwarps = gridDim.x * SCHUR2_WARPS;
+  const long long n = A.n;
+  const int nred_c = 6 * A.n_poses, ni8 = KI * A.n_intr;
+  if (threadIdx.x < KI * KI + KI) s_ii[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int q0 = A.obs_intr[0];                               // the corner of this group is reduced per CTA in shared memory
+  for (int j = gwarp; j < A.n_points; j += nwarps) {
+    const int t0 = A.pt_start[j], K = A.pt_start[j + 1] - t0;
+    if (K == 0 || K > 32 || !A.pt_single[j]) continue;         // schur_kernel (skip_fast) takes the others
+    double inv[9], ie[3], m[6];
+    { const double *E = A.EtE + 6 * (size_t)j;
+      const double d0 = A.lmD_pt[3 * j], d1 = A.lmD_pt[3 * j + 1], d2 = A.lmD_pt[3 * j + 2];
+      m[0] = E[0] + d0 * d0; m[1] = E[1]; m[2] = E[2] + d1 * d1; m[3] = E[3]; m[4] = E[4]; m[5] = E[5] + d2 * d2; }
+    if (!inv3_spd(m, inv)) { if (lane == 0) atomicExch(A.fail, 1); }
+    { const double *eb = A.Etb + 3 * (size_t)j;
+      #pragma unroll
+      for (int a = 0; a < 3; ++a) ie[a] = inv[a * 3] * eb[0] + inv[a * 3 + 1] * eb[1] + inv[a * 3 + 2] * eb[2]; }
+    if (lane < 9) A.Einv[9 * (size_t)j + lane] = inv[lane];
+    __syncwarp();
+    if (lane < K) {
+      const long long t = t0 + lane;
+      const int ct = A.obs_pose[t], qt = A.obs_intr[t];
+      double jc[12], ji[2 * KI], jp[6];
+      #pragma unroll
+      for (int k = 0; k < 12; ++k) jc[k] = A.Jc[k * n + t];
+      #pragma unroll
+      for (int k = 0; k < 2 * KI; ++k) ji[k] = (k % KI) < A.kiu ? A.Ji[k * n + t] : 0.0;
+      #pragma unroll
+      for (int k = 0; k < 6; ++k) jp[k] = A.Jp[k * n + t];
+      double efc[18];                                          // E'Fc of this observation (3x6)
+      #pragma unroll
+      for (int a = 0; a < 3; ++a)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) efc[a * 6 + c] = jp[a] * jc[c] + jp[3 + a] * jc[6 + c];
+      #pragma unroll
+      for (int c = 0; c < 6; ++c) atomicAdd(&A.rhs[6 * ct + c], -(efc[c] * ie[0] + efc[6 + c] * ie[1] + efc[12 + c] * ie[2]));
+      // border with the point-summed E'Fi:  Sci(qt; ct) += Fi'Fc - (Einv E'Fi_pt)' E'Fc
+      double *sci_row0 = A.Sci + (size_t)(KI * qt) * nred_c + 6 * ct;
+      const double *fi = A.EtFi + (size_t)j * 3 * KI;
+      #pragma unroll
+      for (int a = 0; a < KI; ++a) {
+        const double f0 = fi[a], f1 = fi[KI + a], f2 = fi[2 * KI + a];
+        if (f0 == 0.0 && f1 == 0.0 && f2 == 0.0 && ji[a] == 0.0 && ji[KI + a] == 0.0) continue;   // constant parameter
+        const double g0 = inv[0] * f0 + inv[1] * f1 + inv[2] * f2, g1 = inv[3] * f0 + inv[4] * f1 + inv[5] * f2, g2 = inv[6] * f0 + inv[7] * f1 + inv[8] * f2;
+        #pragma unroll
+        for (int b = 0; b < 6; ++b)
+          atomicAdd(&sci_row0[(size_t)a * nred_c + b], ji[a] * jc[b] + ji[KI + a] * jc[6 + b] - (g0 * efc[b] + g1 * efc[6 + b] + g2 * efc[12 + b]));
+        if (lane == 0) {                                        // once per point: corner and its right-hand side
+          const double rv = -(f0 * ie[0] + f1 * ie[1] + f2 * ie[2]);
+          if (qt == q0) atomicAdd(&s_ii[KI * KI + a], rv); else atomicAdd(&A.rhs[nred_c + KI * qt + a], rv);
+          #pragma unroll
+          for (int b = 0; b < KI; ++b) {
+            const double v = -(g0 * fi[b] + g1 * fi[KI + b] + g2 * fi[2 * KI + b]);
+            if (v == 0.0) continue;
+            if (qt == q0) atomicAdd(&s_ii[a * KI + b], v); else atomicAdd(&A.Sii[(size_t)(KI * qt + a) * ni8 + KI * qt + b], v);
+          }
+        }
+      }
+      #pragma unroll
+      for (int a = 0; a < 3; ++a)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          s_ef[wib][lane][a * 6 + c] = efc[a * 6 + c];
+          s_gt[wib][lane][a * 6 + c] = inv[a * 3] * efc[c] + inv[a * 3 + 1] * efc[6 + c] + inv[a * 3 + 2] * efc[12 + c];   // Einv * E'Fc_t
+        }
+      s_cam[wib][lane] = ct;
+    }
+    __syncwarp();
+    // camera pairs: Scc(ct, cu) -= (Einv E'Fc_t)' E'Fc_u  for cam(u) >= cam(t)
+    const int ea = lane / 6, eb2 = lane % 6, fa = (32 + lane) / 6, fb = (32 + lane) % 6;   // element lane, and 32 + lane (lanes 0..3)
+    // block index of (cam(tt), cam(lane)): looked up by all lanes at once, one row ahead of its use, so the
+    // dependent bitmap loads never sit between two atomics
+    // block index of (cam(tt), cam(lane)): the three bitmap-BSR words are LOADED one row ahead (before the
+    // atomics of the current row) and only combined after them, so their latency hides behind the inner loop
+    const int cam_l = lane < K ? s_cam[wib][lane] : 0;
+    const unsigned lowmask = (1u << (cam_l & 31)) - 1u;
+    int rp = 0, wp = 0; unsigned bm = 0;
+    { const int c0 = s_cam[wib][0]; const size_t w = (size_t)c0 * A.bsr.words + (cam_l >> 5); rp = A.bsr.rowptr[c0]; wp = A.bsr.wprefix[w]; bm = A.bsr.bitmap[w]; }
+    for (int tt = 0; tt < K; ++tt) {
+      const int ctt = s_cam[wib][tt];
+      const int cur = (lane < K && cam_l >= ctt) ? rp + wp + __popc(bm & lowmask) : -1;
+      if (tt + 1 < K) { const int cn = s_cam[wib][tt + 1]; const size_t w = (size_t)cn * A.bsr.words + (cam_l >> 5); rp = A.bsr.rowptr[cn]; wp = A.bsr.wprefix[w]; bm = A.bsr.bitmap[w]; }
+      const double g0 = s_gt[wib][tt][ea], g1 = s_gt[wib][tt][6 + ea], g2 = s_gt[wib][tt][12 + ea];
+      const double h0 = lane < 4 ? s_gt[wib][tt][fa] : 0.0, h1 = lane < 4 ? s_gt[wib][tt][6 + fa] : 0.0, h2 = lane < 4 ? s_gt[wib][tt][12 + fa] : 0.0;
+      unsigned todo = __ballot_sync(0xffffffffu, cur >= 0);
+      while (todo) {
+        const int u = __ffs(todo) - 1; todo &= todo - 1;
+        const int bi = __shfl_sync(0xffffffffu, cur, u);
+        double *blk = A.Scc + 36 * (size_t)bi;
+        const double *ef = s_ef[wib][u];
+        atomicAdd(blk + lane, -(g0 * ef[eb2] + g1 * ef[6 + eb2] + g2 * ef[12 + eb2]));
+        if (lane < 4) atomicAdd(blk + 32 + lane, -(h0 * ef[fb] + h1 * ef[6 + fb] + h2 * ef[12 + fb]));
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < KI * KI + KI) {
+    const double v = s_ii[threadIdx.x];
+    if (v != 0.0) {
+      if (threadIdx.x < KI * KI) atomicAdd(&A.Sii[(size_t)(KI * q0 + threadIdx.x / KI) * ni8 + KI * q0 + threadIdx.x % KI], v);
+      else atomicAdd(&A.rhs[nred_c + KI * q0 + (threadIdx.x - KI * KI)], v);
+    }
+  }
+}
+
 __global__ void mirror_kernel(double *__restrict__ Scc, Bsr B, const int *__restrict__ cols, int n_poses) {
   const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (a >= n_poses) return;
@@ -1582,9 +1710,11 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
   double *Pcur = A.Pv, *Pnext = P.Pv2;
   // ---- init (aggregate-owned elements): X = 0, P = 0, R = B, |b|^2, coarse residual
   vsum_begin(S, nrhs);
-  for (int g = gwarp; g < C.ng; g += nwarps) {
+  // (aggregate, right-hand side) pairs are the unit of work of the vector phases: ng * nrhs warp tasks
+  for (int task = gwarp; task < C.ng * nrhs; task += nwarps) {
+    const int g = task / nrhs, j = task - g * nrhs;
     const int c0 = C.agg_start[g], ne = 6 * (C.agg_start[g + 1] - c0);
-    for (int j = 0; j < nrhs; ++j) {
+    {
       const double *src = j == 0 ? A.rhs : A.Sci + (size_t)S.rhs_col[j] * nc6;
       double v = 0;
       double cm[MAXW];
@@ -1632,9 +1762,10 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
     }
     // (b) z = Minv r + Wa y ;  r'z
     vsum_begin(S, nrhs);
-    for (int g = gwarp; g < C.ng; g += nwarps) {
+    for (int task = gwarp; task < C.ng * nrhs; task += nwarps) {
+      const int g = task / nrhs, j = task - g * nrhs;
       const int c0 = C.agg_start[g], ne = 6 * (C.agg_start[g + 1] - c0);
-      for (int j = 0; j < nrhs; ++j) {
+      {
         if (S.done[j]) continue;
         double y[MAXW];
         #pragma unroll
@@ -1664,9 +1795,10 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
     __syncthreads();
     // (e) x += alpha p ; r -= alpha w ; |r|^2 ; coarse residual of the new r
     vsum_begin(S, nrhs);
-    for (int g = gwarp; g < C.ng; g += nwarps) {
+    for (int task = gwarp; task < C.ng * nrhs; task += nwarps) {
+      const int g = task / nrhs, j = task - g * nrhs;
       const int c0 = C.agg_start[g], ne = 6 * (C.agg_start[g + 1] - c0);
-      for (int j = 0; j < nrhs; ++j) {
+      {
         if (S.done[j]) continue;
         const double al = S.alpha[j]; double v = 0;
         double cm[MAXW];
