@@ -48,7 +48,7 @@ struct omvg_ba_ctx {
   int device = 0, n_sms = 0;
   cudaStream_t stream = nullptr;
   int nc = 0, ni = 0, np = 0, nv = 0; long long no = 0;
-  int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0, eval_grid = 0, kiu = KI, gj_grid = 0;
+  int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0, eval_grid = 0, kiu = KI, gj_grid = 0, ics_chunks = 64;
   std::vector<int> perm;                    // sorted position -> caller's observation index (fetched on first use)
   DevBuf<int> d_perm;
   std::vector<int> h_intr_model;
@@ -67,6 +67,7 @@ struct omvg_ba_ctx {
   DevBuf<int> agg_of, agg_start, agg_cams, brow; DevBuf<double> cE, cEinv, cT, cCv, cYv, bP2; int ng = 0;
   DevBuf<double> part, part2, part3, icol_part, scal;
   DevBuf<int> fail;
+  DevBuf<unsigned long long> pcg_tim;
   // optional extensions: GCP weights / flags / fixed landmarks, pose-centre priors
   DevBuf<double> obs_w; DevBuf<unsigned char> obs_flags, pt_fixed; DevBuf<unsigned> pt_mask;
   int n_slow = 0;                           // landmarks left to the per-observation Schur kernel
@@ -165,9 +166,17 @@ int colsums(omvg_ba_ctx *c) {
   point_diag_from_EtE_kernel<<<(c->np + 255) / 256, 256, 0, c->stream>>>(c->EtE.p, c->np, c->diag_pt.p); LAUNCH_CHECK();
   cam_colsum_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Jc.p, c->r.p, c->cam_start.p, c->cam_obs.p, c->nc, c->no, c->diag_cam.p, c->g_cam.p, c->FtF.p); LAUNCH_CHECK();
   if (c->npri) { prior_accum_kernel<<<(c->npri + 127) / 128, 128, 0, c->stream>>>(c->JP.p, c->rP.p, c->prior_pose.p, c->npri, c->diag_cam.p, c->g_cam.p, c->FtF.p); LAUNCH_CHECK(); c->launches++; }
-  const int chunks = 64;
-  intr_colsum_kernel<<<dim3(chunks, c->ni), ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->kiu, c->icol_part.p); LAUNCH_CHECK();
-  intr_colsum_final_kernel<<<(c->ni * 72 + 63) / 64, 64, 0, c->stream>>>(c->icol_part.p, chunks, c->ni, c->diag_intr.p, c->g_intr.p, c->FiFi.p); LAUNCH_CHECK();
+  const int chunks = c->ics_chunks;
+  { const dim3 g(chunks, c->ni);
+    switch (c->kiu) {          // columns in use = max getParams() size over the intrinsic groups (3, 4, 6, 7 or 8)
+      case 3: intr_colsum_kernel<3><<<g, ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->icol_part.p); break;
+      case 4: intr_colsum_kernel<4><<<g, ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->icol_part.p); break;
+      case 6: intr_colsum_kernel<6><<<g, ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->icol_part.p); break;
+      case 7: intr_colsum_kernel<7><<<g, ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->icol_part.p); break;
+      default: intr_colsum_kernel<8><<<g, ICS_THREADS, 0, c->stream>>>(c->Ji.p, c->r.p, c->obs_intr.p, c->no, chunks, c->icol_part.p); break;
+    } }
+  LAUNCH_CHECK();
+  intr_colsum_final_kernel<<<c->ni * 72, 128, 0, c->stream>>>(c->icol_part.p, chunks, c->ni, c->diag_intr.p, c->g_intr.p, c->FiFi.p); LAUNCH_CHECK();
   c->launches += 5; return OMVG_OK;
 }
 
@@ -432,7 +441,8 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   AL(c->pcg2_part, (size_t)c->n_sms * PCG2_V);
   AL(c->z, c->nred); AL(c->res, c->nred); AL(c->pvec, c->nred); AL(c->w, c->nred); AL(c->zeta, c->nred); AL(c->pcg_part, 3 * (size_t)c->n_sms * 2);
   if (c->npri) { AL(c->rP, 3 * c->npri); AL(c->JP, 18 * c->npri); }
-  AL(c->part, std::max(c->eval_blocks, 1024) + 2); AL(c->part2, 1024); AL(c->part3, 1024); AL(c->icol_part, (size_t)c->ni * 64 * ICS_W); AL(c->scal, S_COUNT); AL(c->fail, 1);
+  AL(c->part, std::max(c->eval_blocks, 1024) + 2); AL(c->part2, 1024); AL(c->part3, 1024); c->ics_chunks = (int)std::max<long long>(1, std::min<long long>(4ll * c->n_sms / std::max(1, c->ni), (c->no + 2047) / 2048));
+  AL(c->icol_part, (size_t)c->ni * c->ics_chunks * ICS_W); AL(c->scal, S_COUNT); AL(c->fail, 1);
 #undef AL
   OMVG_CUDA(cudaMemsetAsync(c->scal.p, 0, S_COUNT * sizeof(double), s));
   tm.lap("allocations");
@@ -504,7 +514,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<true, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<false, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   OMVG_CUDA(cudaFuncSetAttribute(pcg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
-  OMVG_CUDA(cudaFuncSetAttribute(pcg3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
+  OMVG_CUDA(cudaFuncSetAttribute(pcg3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Pcg2Smem) + 4 * PCG3_NCO_MAX * sizeof(double))));
   if ((rc = read_scalars(c))) return rc;
   account_jac();
   double x_cost = c->h_scal[S_COST];
@@ -517,7 +527,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   double reference_cost = x_cost, accumulated_reference = 0.0, current_cost = x_cost;
   long long pcg_total = 0;
   int coarse_age = -1; double last_pcg_its = 0, fresh_pcg_its = 1e30; bool fresh_pending = false;
-  static const int coarse_every = getenv("OMVG_BA_COARSE_EVERY") ? std::max(1, atoi(getenv("OMVG_BA_COARSE_EVERY"))) : 2;
+  static const int coarse_every = getenv("OMVG_BA_COARSE_EVERY") ? std::max(1, atoi(getenv("OMVG_BA_COARSE_EVERY"))) : 3;
   const int pcg_grid = c->n_sms;
   if (!c->gj_grid) {                                        // as many co-resident CTAs as the tile count can use
     int per_sm = 1; OMVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_invert_kernel, 256, 0));
@@ -557,7 +567,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     mirror_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Scc.p, SA.bsr, c->cols.p, c->nc); LAUNCH_CHECK();
     c->launches += 2;
     finish_cam_kernel<<<(c->nc + 63) / 64, 64, 0, c->stream>>>(c->Scc.p, SA.bsr, c->lmD_cam.p, m.pose_mask, c->nc, c->Minv_c.p, c->fail.p); LAUNCH_CHECK();
-    finish_intr_kernel<<<1, 32, 0, c->stream>>>(c->Sii.p, c->lmD_intr.p, c->intr_mask.p, c->ni8, c->Minv_i.p, c->work_i.p, c->fail.p); LAUNCH_CHECK();
+    finish_intr_kernel<<<1, 256, 0, c->stream>>>(c->Sii.p, c->lmD_intr.p, c->intr_mask.p, c->ni8, c->Minv_i.p, c->work_i.p, c->fail.p, use_pcg2 ? 0 : 1); LAUNCH_CHECK();
     // ---- PCG on S z = rhs
     PcgArgs PA{}; PA.Scc = c->Scc.p; PA.rowptr = c->rowptr.p; PA.cols = c->cols.p; PA.Sci = c->Sci.p; PA.Sii = c->Sii.p; PA.rhs = c->rhs.p; PA.Minv_c = c->Minv_c.p; PA.Minv_i = c->Minv_i.p;
     PA.n_poses = c->nc; PA.ni8 = c->ni8; PA.z = c->z.p; PA.res = c->res.p; PA.p = c->pvec.p; PA.w = c->w.p; PA.zeta = c->zeta.p; PA.part = c->pcg_part.p;
@@ -571,7 +581,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
         const int nco = P3.C.nco;
         // The coarse operator is only a preconditioner: a slightly stale E^-1 (previous LM step, radius/3) costs a few
         // extra PCG iterations (measured 38->40, 42->49, 43->43) but saves its O(nco^3) setup, so it is refreshed every
-        // `coarse_every` LM steps, or earlier if the last solve needed 1.5x the iterations seen right after a refresh.
+        // `coarse_every` LM steps (measured at 1000 cameras, ms per solve: every step 17.9, 2: 16.0, 3: 15.2, 5: 15.9), or earlier if the last solve needed 1.5x the iterations seen right after a refresh.
         const bool refresh = nco > 0 && (coarse_age < 0 || coarse_age >= coarse_every || last_pcg_its > 1.5 * fresh_pcg_its + 5);
         if (refresh) { coarse_age = 0; fresh_pending = true; }
         ++coarse_age;
@@ -592,8 +602,12 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
             OMVG_CUDA(cudaLaunchCooperativeKernel((void *)coarse_setup_kernel, dim3(pcg_grid), dim3(256), cargs, sm, c->stream)); }
           c->launches += 2;
         }
+        static const bool pcg_timing = getenv("OMVG_BA_PCG_TIMING") != nullptr;
+        if (pcg_timing) { if (!c->pcg_tim.p) { if ((rc = c->pcg_tim.alloc(8))) return rc; } OMVG_CUDA(cudaMemsetAsync(c->pcg_tim.p, 0, 64, c->stream)); P3.tim = c->pcg_tim.p; }
         void *args[] = {&P3};
-        OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg3_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem), c->stream));
+        OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg3_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem) + 4 * PCG3_NCO_MAX * sizeof(double), c->stream));
+        if (pcg_timing) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
+          fprintf(stderr, "[omvg_ba pcg timing] us: coarse (stage %.1f rows %.1f sync %.1f) z %.1f spmv %.1f update %.1f tail %.1f border %.1f\n", h[6] * 1e-3, h[7] * 1e-3, h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, h[4] * 1e-3, h[5] * 1e-3); }
       } else {
         void *args[] = {&P2};
         OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg2_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem), c->stream));
@@ -602,8 +616,16 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       void *args[] = {&PA}; OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(pcg_grid), dim3(256), args, 0, c->stream));
     }
     // ---- back substitution, step = -y
-    backsub_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->Etb.p, c->Einv.p, c->obs_pose.p, c->obs_intr.p, c->pt_start.p, c->np, c->nc, c->no, c->kiu,
-                                                             c->z.p, m.pts_free, c->step_pt.p); LAUNCH_CHECK();
+    static const bool backsub1 = getenv("OMVG_BA_BACKSUB1") != nullptr;
+    if (backsub1 || !m.pts_free) {
+      backsub_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->Etb.p, c->Einv.p, c->obs_pose.p, c->obs_intr.p, c->pt_start.p, c->np, c->nc, c->no, c->kiu,
+                                                               c->z.p, m.pts_free, c->step_pt.p); LAUNCH_CHECK();
+    } else {
+      OMVG_CUDA(cudaMemsetAsync(c->step_pt.p, 0, 3 * (size_t)c->np * sizeof(double), c->stream));
+      backsub_obs_kernel<<<(unsigned)((c->no + 255) / 256), 256, 0, c->stream>>>(c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->nc, c->no, c->kiu, c->z.p, c->step_pt.p); LAUNCH_CHECK();
+      backsub_point_kernel<<<(c->np + 255) / 256, 256, 0, c->stream>>>(c->Etb.p, c->Einv.p, c->pt_start.p, c->np, m.pts_free, c->step_pt.p); LAUNCH_CHECK();
+      c->launches++;
+    }
     negate_kernel<<<(c->nred + 255) / 256, 256, 0, c->stream>>>(c->z.p, c->nred, c->step_red.p); LAUNCH_CHECK();
     // ---- model cost change
     model_kernel<<<c->eval_blocks, MODEL_THREADS, 0, c->stream>>>(c->r.p, c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no, c->nc, c->kiu, c->step_pt.p, c->step_red.p, c->part.p); LAUNCH_CHECK();

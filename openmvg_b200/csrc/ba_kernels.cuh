@@ -469,48 +469,61 @@ __global__ void cam_colsum_kernel(const double *__restrict__ Jc, const double *_
 // (chunks x blocks, then a final pass): part[q][chunk][80] = {64 FiFi, 8 g, 8 unused}
 constexpr int ICS_THREADS = 256;
 constexpr int ICS_W = 80;
+// KIU = number of intrinsic columns in use (3 pinhole .. 8 Brown): only those products are formed, which keeps the
+// kernel at a few dozen registers (the generic 8-column version needed 166 and ran one CTA per SM: 105 us)
+template <int KIU>
 __global__ void __launch_bounds__(ICS_THREADS) intr_colsum_kernel(const double *__restrict__ Ji, const double *__restrict__ r, const int *__restrict__ obs_intr,
-                                   long long n, int chunks, int kiu, double *__restrict__ part) {
+                                   long long n, int chunks, double *__restrict__ part) {
   __shared__ double sh[ICS_THREADS / 32];
   const int q = blockIdx.y, chunk = blockIdx.x;
-  double m[36], g[KI];
+  constexpr int NM = KIU * (KIU + 1) / 2;
+  double m[NM], g[KIU];
   #pragma unroll
-  for (int k = 0; k < 36; ++k) m[k] = 0;
+  for (int k = 0; k < NM; ++k) m[k] = 0;
   #pragma unroll
-  for (int k = 0; k < KI; ++k) g[k] = 0;
+  for (int k = 0; k < KIU; ++k) g[k] = 0;
   const long long per = (n + chunks - 1) / chunks, lo = per * chunk, hi = lo + per < n ? lo + per : n;
   for (long long o = lo + threadIdx.x; o < hi; o += ICS_THREADS) {
-    if (obs_intr[o] != q) continue;
-    const double r0 = r[o], r1 = r[n + o];
-    double a[KI], b[KI];
+    const bool mine = __ldcs(obs_intr + o) == q;
+    const double r0 = __ldcs(r + o), r1 = __ldcs(r + n + o);
+    double a[KIU], b[KIU];
     #pragma unroll
-    for (int k = 0; k < KI; ++k) { a[k] = k < kiu ? Ji[k * n + o] : 0.0; b[k] = k < kiu ? Ji[(KI + k) * n + o] : 0.0; g[k] += a[k] * r0 + b[k] * r1; }
+    for (int k = 0; k < KIU; ++k) { a[k] = __ldcs(Ji + k * n + o); b[k] = __ldcs(Ji + (KI + k) * n + o); }
+    if (!mine) continue;
+    #pragma unroll
+    for (int k = 0; k < KIU; ++k) g[k] += a[k] * r0 + b[k] * r1;
     int t = 0;
     #pragma unroll
-    for (int i = 0; i < KI; ++i)
+    for (int i = 0; i < KIU; ++i)
       #pragma unroll
       for (int k = 0; k <= i; ++k) m[t++] += a[i] * a[k] + b[i] * b[k];
   }
   double *dst = part + ((size_t)q * chunks + chunk) * ICS_W;
+  for (int e = threadIdx.x; e < ICS_W; e += ICS_THREADS) dst[e] = 0.0;
+  __syncthreads();
   int t = 0;
-  for (int i = 0; i < KI; ++i) for (int k = 0; k <= i; ++k) {
-    const double v = block_sum<ICS_THREADS>(m[t++], sh);
-    if (threadIdx.x == 0) { dst[i * KI + k] = v; dst[k * KI + i] = v; }
-  }
-  for (int k = 0; k < KI; ++k) { const double v = block_sum<ICS_THREADS>(g[k], sh); if (threadIdx.x == 0) dst[64 + k] = v; }
+  #pragma unroll
+  for (int i = 0; i < KIU; ++i)
+    #pragma unroll
+    for (int k = 0; k <= i; ++k) {
+      const double v = block_sum<ICS_THREADS>(m[t++], sh);
+      if (threadIdx.x == 0) { dst[i * KI + k] = v; dst[k * KI + i] = v; }
+    }
+  #pragma unroll
+  for (int k = 0; k < KIU; ++k) { const double v = block_sum<ICS_THREADS>(g[k], sh); if (threadIdx.x == 0) dst[64 + k] = v; }
 }
-__global__ void intr_colsum_final_kernel(const double *__restrict__ part, int chunks, int n_intr, double *__restrict__ diag_intr, double *__restrict__ g_intr,
+// one CTA per (intrinsic group, element): strided partial sums over the chunks, then a fixed-order block reduction
+__global__ void __launch_bounds__(128) intr_colsum_final_kernel(const double *__restrict__ part, int chunks, int n_intr, double *__restrict__ diag_intr, double *__restrict__ g_intr,
                                          double *__restrict__ FiFi) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_intr * 72) return;
-  const int q = t / 72, e = t % 72;
+  __shared__ double sh[4];
+  const int q = blockIdx.x / 72, e = blockIdx.x % 72;
   double v = 0;
-  for (int c = 0; c < chunks; ++c) v += part[((size_t)q * chunks + c) * ICS_W + e];
+  for (int c = threadIdx.x; c < chunks; c += 128) v += part[((size_t)q * chunks + c) * ICS_W + e];
+  v = block_sum<128>(v, sh);
+  if (threadIdx.x != 0) return;
   if (e < 64) { FiFi[(size_t)q * 64 + e] = v; if (e / KI == e % KI) diag_intr[q * KI + e / KI] = v; }
   else g_intr[q * KI + (e - 64)] = v;
 }
-
-// scale[i] = 1 / (1 + sqrt(colnorm2[i]))    (trust_region_minimizer.cc:239-250)
 __global__ void make_scale_kernel(const double *__restrict__ n2, int n, double *__restrict__ scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) scale[i] = 1.0 / (1.0 + sqrt(n2[i]));
 }
@@ -895,14 +908,21 @@ __global__ void finish_cam_kernel(double *__restrict__ Scc, Bsr B, const double 
 }
 // intrinsics corner: add D^2 / identity, dense Cholesky inverse by one thread block (ni*8 <= 256)
 __global__ void finish_intr_kernel(double *__restrict__ Sii, const double *__restrict__ lmD_intr, const unsigned *__restrict__ intr_mask,
-                                   int ni8, double *__restrict__ Minv_i, double *__restrict__ work, int *__restrict__ fail) {
-  // single thread does the (tiny) factorisation; ni8 is typically 8
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  for (int i = 0; i < ni8; ++i) {
+                                   int ni8, double *__restrict__ Minv_i, double *__restrict__ work, int *__restrict__ fail, int need_inverse) {
+  // LM diagonal / identity rows: one thread per row (off-diagonal zeroing first, diagonals after the barrier)
+  for (int i = threadIdx.x; i < ni8; i += blockDim.x) {
     const bool free_ = (intr_mask[i / KI] >> (i % KI)) & 1;
-    if (free_) Sii[(size_t)i * ni8 + i] += lmD_intr[i] * lmD_intr[i];
-    else { for (int k = 0; k < ni8; ++k) { Sii[(size_t)i * ni8 + k] = 0.0; Sii[(size_t)k * ni8 + i] = 0.0; } Sii[(size_t)i * ni8 + i] = 1.0; }
+    if (!free_) for (int k = 0; k < ni8; ++k) { Sii[(size_t)i * ni8 + k] = 0.0; Sii[(size_t)k * ni8 + i] = 0.0; }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ni8; i += blockDim.x) {
+    const bool free_ = (intr_mask[i / KI] >> (i % KI)) & 1;
+    if (free_) Sii[(size_t)i * ni8 + i] += lmD_intr[i] * lmD_intr[i]; else Sii[(size_t)i * ni8 + i] = 1.0;
+  }
+  __syncthreads();
+  // the explicit inverse is only the block-Jacobi preconditioner of the single-vector PCG fallback: a single thread
+  // does the (tiny) factorisation
+  if (!need_inverse || threadIdx.x != 0) return;
   double *L = work;
   for (int i = 0; i < ni8 * ni8; ++i) L[i] = Sii[i];
   for (int k = 0; k < ni8; ++k) {
@@ -1095,6 +1115,7 @@ struct Pcg2Args {
 constexpr int PCG2_V = 320;   // max reduction width: nrhs*(1+nw) <= 33*8 = 264, border 32*33 handled in chunks
 constexpr int PCG2_THREADS = 256;
 
+constexpr int PCG3_NCO_MAX = 1024;          // coarse dimension bound (aggregation keeps 7 * n_aggregates below it)
 struct Pcg2Smem {
   double wpart[PCG2_THREADS / 32][PCG2_V];   // per-warp partials
   double bv[PCG2_V], tot[PCG2_V];
@@ -1579,18 +1600,28 @@ __global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__
       __syncthreads();
     }
     // slices of Cold / H / Gn
+    // (all 32 operand loads of a slice element are issued before the first FMA: L1 is cold after a grid sync and a
+    // dependent L2 round trip costs ~0.5 us; Bs is identity-padded, so out-of-range pivots contribute zeros)
     for (long long idx = tid; idx < (long long)n * GJ_B; idx += nt) {
       const int i = (int)(idx >> 5), q = (int)(idx & 31);
+      double av[GJ_B];
+      #pragma unroll
+      for (int p2 = 0; p2 < GJ_B; ++p2) av[p2] = p2 < nb ? __ldcg(A + (size_t)i * n + k0 + p2) : 0.0;
       double g = 0.0;
-      if (q < nb) { for (int p2 = 0; p2 < nb; ++p2) g += A[(size_t)i * n + k0 + p2] * Bs[p2][q]; }
-      Cold[idx] = q < nb ? A[(size_t)i * n + k0 + q] : 0.0;
-      Gn[idx] = -g;
+      #pragma unroll
+      for (int p2 = 0; p2 < GJ_B; ++p2) g += av[p2] * Bs[p2][q];
+      Cold[idx] = q < nb ? __ldcg(A + (size_t)i * n + k0 + q) : 0.0;
+      Gn[idx] = q < nb ? -g : 0.0;
     }
     for (long long idx = tid; idx < (long long)n * GJ_B; idx += nt) {
       const int q = (int)(idx / n), j = (int)(idx % n);
+      double av[GJ_B];
+      #pragma unroll
+      for (int p2 = 0; p2 < GJ_B; ++p2) av[p2] = p2 < nb ? __ldcg(A + (size_t)(k0 + p2) * n + j) : 0.0;
       double h = 0.0;
-      if (q < nb) { for (int p2 = 0; p2 < nb; ++p2) h += Bs[q][p2] * A[(size_t)(k0 + p2) * n + j]; }
-      H[idx] = h;
+      #pragma unroll
+      for (int p2 = 0; p2 < GJ_B; ++p2) h += Bs[q][p2] * av[p2];
+      H[idx] = q < nb ? h : 0.0;
     }
     grid.sync();
     // ---- phase 2: tiles
@@ -1639,8 +1670,16 @@ struct Pcg3Args {
   double *Cv;             // [MAXRHS][nco] coarse residuals  W_a' r
   double *Yv;             // [MAXRHS][nco] coarse corrections Einv c
   double *Pv2;            // second direction buffer (ping-pong with base.Pv)
+  unsigned long long *tim; // optional (OMVG_BA_PCG_TIMING): ns spent by CTA 0 in [coarse, z, spmv, update, other]
 };
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PCG_LAP(k) do { if (P.tim && tid == 0) { const unsigned long long now_ = gtimer(); P.tim[k] += now_ - tlast; tlast = now_; } } while (0)
 
+// 32-byte read-only load (LDG.E.256, sm_100): a 6x6 block is 9 of these instead of 36 8-byte loads, which at the
+// 288-byte lane stride cost one L1 wavefront per lane per instruction (the SpMV was L1-wavefront bound)
+__device__ __forceinline__ void ldg256(const double *p, double &a, double &b, double &c, double &d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 // w_j = Scc p_j with p_j = z_j + beta_j * pold_j formed ON THE FLY for the gathered columns (so the
 // direction update needs no grid sync of its own); the owner warp of row a stores p_j(a) into pnew and
 // accumulates p_j.w_j over its rows into this warp's reduction slot j.
@@ -1659,7 +1698,7 @@ __device__ __forceinline__ void spmv_pcg(const Pcg2Args &A, Pcg2Smem &S, const d
         const double *blk = A.Scc + 36 * (size_t)e; const int cb = 6 * A.cols[e];
         double b[36];
         #pragma unroll
-        for (int i = 0; i < 36; ++i) b[i] = blk[i];
+        for (int i = 0; i < 9; ++i) ldg256(blk + 4 * i, b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]);
         #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (j0 + j < nv && !S.done[j0 + j]) {
@@ -1739,27 +1778,53 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
   if (threadIdx.x == 0) { S.worst = 0; S.all_done = 0; }
   __syncthreads();
   int it = 0;
+  unsigned long long tlast = P.tim ? gtimer() : 0ull;
   for (;;) {
-    // (y) coarse solve  Y_j = Einv C_j, rows distributed over all warps (Einv row read once for all j)
+    // (y) coarse solve  Y_j = Einv C_j, one row per warp.  The phase is pure latency (L1 is cold after a grid sync,
+    // every operand comes from L2): the right-hand sides are staged once per CTA in shared memory and each lane
+    // issues ALL its row loads back to back before the first FMA (the naive k-loop paid one L2 round trip per
+    // 5 loads: 13 us per iteration).
     if (nco > 0) {
-      for (int row = gwarp; row < nco; row += nwarps) {
-        const double *er = P.Einv + (size_t)row * nco;
-        for (int j0 = 0; j0 < nrhs; j0 += 4) {
-          double acc[4] = {0, 0, 0, 0};
-          for (int k = lane; k < nco; k += 32) {
-            const double ev = er[k];
+      double *sCv = reinterpret_cast<double *>(pcg2_smem_raw + sizeof(Pcg2Smem));     // [4][PCG3_NCO_MAX]
+      for (int j0 = 0; j0 < nrhs; j0 += 4) {
+        const int nj = min(4, nrhs - j0);
+        for (int kc = 0; kc < nco; kc += PCG3_NCO_MAX) {       // (one chunk unless the coarse space exceeds 1024)
+          const int nk = min(PCG3_NCO_MAX, nco - kc);
+          { double tv[4][(PCG3_NCO_MAX + PCG2_THREADS - 1) / PCG2_THREADS];      // all loads in flight before the first store
             #pragma unroll
-            for (int j = 0; j < 4; ++j) if (j0 + j < nrhs) acc[j] += ev * P.Cv[(size_t)(j0 + j) * nco + k];
+            for (int j = 0; j < 4; ++j)
+              #pragma unroll
+              for (int q = 0; q < (PCG3_NCO_MAX + PCG2_THREADS - 1) / PCG2_THREADS; ++q) { const int k = threadIdx.x + PCG2_THREADS * q; tv[j][q] = (j < nj && k < nk) ? __ldcg(P.Cv + (size_t)(j0 + j) * nco + kc + k) : 0.0; }
+            #pragma unroll
+            for (int j = 0; j < 4; ++j)
+              #pragma unroll
+              for (int q = 0; q < (PCG3_NCO_MAX + PCG2_THREADS - 1) / PCG2_THREADS; ++q) { const int k = threadIdx.x + PCG2_THREADS * q; if (k < nk) sCv[j * PCG3_NCO_MAX + k] = tv[j][q]; } }
+          __syncthreads();
+          PCG_LAP(6);
+          for (int row = gwarp; row < nco; row += nwarps) {
+            const double *er = P.Einv + (size_t)row * nco + kc;
+            double ev[PCG3_NCO_MAX / 32];
+            #pragma unroll
+            for (int q = 0; q < PCG3_NCO_MAX / 32; ++q) { const int k = lane + 32 * q; ev[q] = k < nk ? __ldcg(er + k) : 0.0; }
+            double acc[4] = {0, 0, 0, 0};
+            #pragma unroll
+            for (int q = 0; q < PCG3_NCO_MAX / 32; ++q) { const int k = lane + 32 * q;
+              if (k < nk) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < nj) acc[j] += ev[q] * sCv[j * PCG3_NCO_MAX + k]; } }
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              double v = acc[j]; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              if (lane == 0 && j < nj) { double *dst = P.Yv + (size_t)(j0 + j) * nco + row; *dst = kc == 0 ? v : *dst + v; }
+            }
           }
-          #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            double v = acc[j]; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && j0 + j < nrhs) P.Yv[(size_t)(j0 + j) * nco + row] = v;
-          }
+          __syncthreads();
+          PCG_LAP(7);
         }
       }
       grid.sync();
     }
+    PCG_LAP(0);
     // (b) z = Minv r + Wa y ;  r'z
     vsum_begin(S, nrhs);
     for (int task = gwarp; task < C.ng * nrhs; task += nwarps) {
@@ -1785,11 +1850,13 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
     vsum_end(grid, S, nrhs, A.part);
     if (threadIdx.x < nrhs) { const int j = threadIdx.x; if (!S.done[j]) { const double rzn = S.tot[j]; S.beta[j] = it == 0 ? 0.0 : rzn / S.rz[j]; S.rz[j] = rzn; } }
     __syncthreads();
+    PCG_LAP(1);
     if (it >= A.max_iter) break;
     // (c+d) p = z + beta p (on the fly) ; w = Scc p ; p'w
     vsum_begin(S, nrhs);
     spmv_pcg(A, S, A.Zv, Pcur, Pnext, A.Wv, nrhs);
     vsum_end(grid, S, nrhs, A.part);
+    PCG_LAP(2);
     { double *t2 = Pcur; Pcur = Pnext; Pnext = t2; }
     if (threadIdx.x < nrhs) { const int j = threadIdx.x; S.alpha[j] = S.done[j] ? 0.0 : S.rz[j] / S.tot[j]; }
     __syncthreads();
@@ -1820,6 +1887,7 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
       }
     }
     vsum_end(grid, S, nrhs, A.part);                // its grid.sync publishes Cv as well
+    PCG_LAP(3);
     ++it;
     if (threadIdx.x == 0) {
       int ad = 1; double wmax = 0;
@@ -1830,6 +1898,7 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
     if (S.all_done) break;
   }
   // ---- border: (Sii - Sci Y2) zi = bi - Sci y1 ; zc = y1 - Y2 zi
+  PCG_LAP(4);
   const int k = nrhs - 1;
   if (k > 0) {
     for (int a = 0; a < k; ++a) {
@@ -1861,6 +1930,7 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
   }
   for (size_t i = tid; i < nc6; i += nt) { double v = A.X[i]; for (int a = 0; a < k; ++a) v -= A.X[(size_t)(1 + a) * nc6 + i] * S.zi[a]; A.z[i] = v; }
   for (int q = tid; q < A.ni8; q += nt) { double v = 0; for (int a = 0; a < k; ++a) if (S.rhs_col[1 + a] == q) v = S.zi[a]; A.z[nc6 + q] = v; }
+  PCG_LAP(5);
   if (tid == 0) { A.out[0] = (double)it; A.out[1] = sqrt(S.worst); A.out[2] = sqrt(S.bb[0]); }
 }
 
@@ -1885,6 +1955,47 @@ __global__ void backsub_kernel(const double *__restrict__ Jp, const double *__re
   const double *I = Einv + 9 * (size_t)j;
   step_pt[3 * j] = -(I[0] * b0 + I[1] * b1 + I[2] * b2); step_pt[3 * j + 1] = -(I[3] * b0 + I[4] * b1 + I[5] * b2); step_pt[3 * j + 2] = -(I[6] * b0 + I[7] * b1 + I[8] * b2);
 }
+// Coalesced form (default): thread per OBSERVATION computes its E'F z 3-vector with contiguous component-major
+// loads; observations are sorted by landmark, so a segmented warp scan sums each landmark's run and the last lane
+// of a run adds it to acc[landmark] (one atomic per landmark per warp).  backsub_point_kernel finishes
+// step = -Einv (Etb - acc) in place.  The thread-per-landmark kernel above re-fetched every sector ~4x (280 us).
+__global__ void backsub_obs_kernel(const double *__restrict__ Jp, const double *__restrict__ Jc, const double *__restrict__ Ji,
+                                   const int *__restrict__ obs_pose, const int *__restrict__ obs_intr, const int *__restrict__ obs_pt,
+                                   int n_poses, long long n, int kiu, const double *__restrict__ z, double *__restrict__ acc) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool valid = o < n;
+  int j = -1; double v0 = 0, v1 = 0, v2 = 0;
+  if (valid) {
+    j = obs_pt[o];
+    const double *zc = z + 6 * obs_pose[o]; const double *zi = z + 6 * n_poses + KI * obs_intr[o];
+    double f0 = 0, f1 = 0;
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) { f0 += __ldcs(Jc + k * n + o) * zc[k]; f1 += __ldcs(Jc + (6 + k) * n + o) * zc[k]; }
+    #pragma unroll
+    for (int k = 0; k < KI; ++k) if (k < kiu) { f0 += __ldcs(Ji + k * n + o) * zi[k]; f1 += __ldcs(Ji + (KI + k) * n + o) * zi[k]; }
+    v0 = __ldcs(Jp + 0 * n + o) * f0 + __ldcs(Jp + 3 * n + o) * f1;
+    v1 = __ldcs(Jp + 1 * n + o) * f0 + __ldcs(Jp + 4 * n + o) * f1;
+    v2 = __ldcs(Jp + 2 * n + o) * f0 + __ldcs(Jp + 5 * n + o) * f1;
+  }
+  #pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int jv = __shfl_up_sync(0xffffffffu, j, off);
+    const double a0 = __shfl_up_sync(0xffffffffu, v0, off), a1 = __shfl_up_sync(0xffffffffu, v1, off), a2 = __shfl_up_sync(0xffffffffu, v2, off);
+    if (lane >= off && jv == j) { v0 += a0; v1 += a1; v2 += a2; }
+  }
+  const int jn = __shfl_down_sync(0xffffffffu, j, 1);
+  if (valid && (lane == 31 || jn != j)) { atomicAdd(acc + 3 * (size_t)j, v0); atomicAdd(acc + 3 * (size_t)j + 1, v1); atomicAdd(acc + 3 * (size_t)j + 2, v2); }
+}
+__global__ void backsub_point_kernel(const double *__restrict__ Etb, const double *__restrict__ Einv, const int *__restrict__ pt_start, int n_points,
+                                     int pts_free, double *__restrict__ step_pt /* in: acc, out: step */) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n_points) return;
+  if (!pts_free || pt_start[j] == pt_start[j + 1]) { step_pt[3 * j] = step_pt[3 * j + 1] = step_pt[3 * j + 2] = 0.0; return; }
+  const double b0 = Etb[3 * (size_t)j] - step_pt[3 * j], b1 = Etb[3 * (size_t)j + 1] - step_pt[3 * j + 1], b2 = Etb[3 * (size_t)j + 2] - step_pt[3 * j + 2];
+  const double *I = Einv + 9 * (size_t)j;
+  step_pt[3 * j] = -(I[0] * b0 + I[1] * b1 + I[2] * b2); step_pt[3 * j + 1] = -(I[3] * b0 + I[4] * b1 + I[5] * b2); step_pt[3 * j + 2] = -(I[6] * b0 + I[7] * b1 + I[8] * b2);
+}
+
 __global__ void negate_kernel(const double *__restrict__ z, int n, double *__restrict__ step) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) step[i] = -z[i]; }
 
 // model_cost_change partials: - m . (r + m/2), m = J step    (trust_region_minimizer.cc:402-405)
