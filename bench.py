@@ -141,7 +141,11 @@ def run_ours(args):
     h2d = sum(scene[k].nbytes for k in ("poses", "intrinsics", "points", "intr_model", "view_pose", "view_intr", "obs_view", "obs_point", "obs_xy"))
     d2h = sum(scene[k].nbytes for k in ("poses", "intrinsics", "points"))
     jac_s = jac_ms / 1e3 / max(jac_n, 1)
-    ba_roof = dict(bound="hbm", achieved=BA_BYTES_PER_OBS * n_obs / jac_s / 1e9, peak=pk["hbm_gbs"], unit="GB/s", traffic=None,
+    ba_roof = dict(bound="hbm", achieved=BA_BYTES_PER_OBS * n_obs / jac_s / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
+                   # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this scene (ncu --set full capture,
+                   # profiles/r01_ba_eval_kernel_full.md: 33.06 MB read + 150.79 MB written; less than the 232 MB of
+                   # algorithmic bytes because the tail of the write stream is still in the 126 MB L2 when the kernel ends)
+                   traffic=183.85e6 if n_obs == 1000000 else None, traffic_unit="bytes/launch",
                    kernel="eval_kernel<true> (residual+Jacobian+Huber+scaling)", launches=jac_n, avg_ms=jac_s * 1e3, peak_source=pk["src"])
     ba_roof["frac"] = ba_roof["achieved"] / ba_roof["peak"]
 

@@ -68,6 +68,8 @@ struct omvg_ba_ctx {
   DevBuf<double> part, part2, part3, icol_part, scal;
   DevBuf<int> fail;
   DevBuf<unsigned long long> pcg_tim;
+  DevBuf<double> corner_rep;
+  DevBuf<double> GE;                        // per observation { Einv E'Fc, E'Fc } of the split Schur step
   // optional extensions: GCP weights / flags / fixed landmarks, pose-centre priors
   DevBuf<double> obs_w; DevBuf<unsigned char> obs_flags, pt_fixed; DevBuf<unsigned> pt_mask;
   int n_slow = 0;                           // landmarks left to the per-observation Schur kernel
@@ -556,6 +558,17 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     { const int ninit = std::max(std::max(36 * c->nc, 64 * c->ni), c->nred); s_init_kernel<<<(ninit + 255) / 256, 256, 0, c->stream>>>(SA); LAUNCH_CHECK(); }
     static const bool schur1 = getenv("OMVG_BA_SCHUR1") != nullptr;
     SA.n_points = c->np;
+    static const bool schur2 = getenv("OMVG_BA_SCHUR2") != nullptr;      // fused warp-per-landmark kernel (A/B)
+    if (m.pts_free && !schur1 && !schur2) {
+      if (!c->GE.p) { if ((rc = c->GE.alloc(36 * (size_t)c->no))) return rc; }
+      if (!c->corner_rep.p) { if ((rc = c->corner_rep.alloc((size_t)CORNER_REPS * (KI * KI + KI)))) return rc; }
+      OMVG_CUDA(cudaMemsetAsync(c->corner_rep.p, 0, c->corner_rep.n * sizeof(double), c->stream));
+      schur_stage_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA, c->GE.p, c->corner_rep.p); LAUNCH_CHECK();
+      corner_fold_kernel<<<1, 96, 0, c->stream>>>(c->corner_rep.p, c->obs_intr.p, c->nc, c->ni, c->Sii.p, c->rhs.p); LAUNCH_CHECK(); c->launches++;
+      static int occ2 = 0; if (!occ2) { OMVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, schur_pair_kernel, 256, 0)); occ2 = std::max(1, occ2); }
+      schur_pair_kernel<<<c->n_sms * occ2, 256, 0, c->stream>>>(SA, c->GE.p); LAUNCH_CHECK(); c->launches += 2;
+      SA.skip_fast = 1;
+    } else
     if (m.pts_free && !schur1) {
       static const int minb = getenv("OMVG_BA_SCHUR2_MINB") ? atoi(getenv("OMVG_BA_SCHUR2_MINB")) : 5;
       void (*kern)(SchurArgs) = minb >= 6 ? schur_point_kernel<6> : (minb >= 5 ? schur_point_kernel<5> : schur_point_kernel<3>);

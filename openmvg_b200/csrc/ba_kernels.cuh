@@ -761,6 +761,7 @@ __global__ void __launch_bounds__(SCHUR_THREADS) schur_kernel(SchurArgs A) {
 // adding element e of the 6x6 block: one RED instruction touches the 9 sectors of one block instead of 32
 // sectors of 32 different blocks.  Measured on B200 (tools/atomic_bench.cu): 565 vs 222 G FP64 atomics/s.
 constexpr int SCHUR2_WARPS = 4;
+constexpr int CORNER_REPS = 64;
 template <int MINB>
 __global__ void __launch_bounds__(32 * SCHUR2_WARPS, MINB) schur_point_kernel(SchurArgs A) {
   __shared__ double s_gt[SCHUR2_WARPS][32][18];
@@ -870,6 +871,131 @@ __global__ void __launch_bounds__(32 * SCHUR2_WARPS, MINB) schur_point_kernel(Sc
     if (v != 0.0) {
       if (threadIdx.x < KI * KI) atomicAdd(&A.Sii[(size_t)(KI * q0 + threadIdx.x / KI) * ni8 + KI * q0 + threadIdx.x % KI], v);
       else atomicAdd(&A.rhs[nred_c + KI * q0 + (threadIdx.x - KI * KI)], v);
+    }
+  }
+}
+
+// ---- split form of the warp-per-landmark Schur step (default): the staging half needs ~160 registers, the pair
+// walk ~40; in one kernel the walk ran at 12-20 warps per SM and was latency-bound (0.94 ms).  Here
+//   schur_stage_kernel : thread per observation (coalesced component-major loads), per-observation border / rhs
+//                        terms, writes GE[obs] = { Einv E'Fc (18), E'Fc (18) }  (288 B per observation)
+//   schur_pair_kernel  : warp per landmark, lane e adds element e of block (cam_t, cam_u) reading GE through L1
+__global__ void __launch_bounds__(SCHUR_THREADS) schur_stage_kernel(SchurArgs A, double *__restrict__ GE, double *__restrict__ corner_rep) {
+  // The intrinsics corner (and its rhs) of group q0 is hit once per landmark: accumulate into CORNER_REPS replicas
+  // with native FP64 REDs (shared-memory double atomics are CAS loops: they cost 0.3 ms here) and fold them after.
+  const long long t = (long long)blockIdx.x * SCHUR_THREADS + threadIdx.x;
+  const long long n = A.n;
+  const int nred_c = 6 * A.n_poses, ni8 = KI * A.n_intr;
+  const int q0 = A.obs_intr[0];
+  double *s_ii = corner_rep + (size_t)(blockIdx.x % CORNER_REPS) * (KI * KI + KI);
+  bool mine = t < n;
+  int j = 0;
+  if (mine) { j = A.obs_pt[t]; const int K = A.pt_start[j + 1] - A.pt_start[j]; mine = A.pt_single[j] != 0 && K <= 32; }
+  if (mine) {
+    const int ct = A.obs_pose[t], qt = A.obs_intr[t];
+    double inv[9], ie[3], m[6];
+    { const double *E = A.EtE + 6 * (size_t)j;
+      const double d0 = A.lmD_pt[3 * j], d1 = A.lmD_pt[3 * j + 1], d2 = A.lmD_pt[3 * j + 2];
+      m[0] = E[0] + d0 * d0; m[1] = E[1]; m[2] = E[2] + d1 * d1; m[3] = E[3]; m[4] = E[4]; m[5] = E[5] + d2 * d2; }
+    if (!inv3_spd(m, inv)) atomicExch(A.fail, 1);
+    { const double *eb = A.Etb + 3 * (size_t)j;
+      #pragma unroll
+      for (int a = 0; a < 3; ++a) ie[a] = inv[a * 3] * eb[0] + inv[a * 3 + 1] * eb[1] + inv[a * 3 + 2] * eb[2]; }
+    const bool first = t == A.pt_start[j];
+    if (first) { for (int a = 0; a < 9; ++a) A.Einv[9 * (size_t)j + a] = inv[a]; }
+    double jc[12], ji[2 * KI], jp[6];
+    #pragma unroll
+    for (int k = 0; k < 12; ++k) jc[k] = A.Jc[k * n + t];
+    #pragma unroll
+    for (int k = 0; k < 2 * KI; ++k) ji[k] = (k % KI) < A.kiu ? A.Ji[k * n + t] : 0.0;
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) jp[k] = A.Jp[k * n + t];
+    double efc[18];
+    #pragma unroll
+    for (int a = 0; a < 3; ++a)
+      #pragma unroll
+      for (int c = 0; c < 6; ++c) efc[a * 6 + c] = jp[a] * jc[c] + jp[3 + a] * jc[6 + c];
+    #pragma unroll
+    for (int c = 0; c < 6; ++c) atomicAdd(&A.rhs[6 * ct + c], -(efc[c] * ie[0] + efc[6 + c] * ie[1] + efc[12 + c] * ie[2]));
+    double *sci_row0 = A.Sci + (size_t)(KI * qt) * nred_c + 6 * ct;
+    const double *fi = A.EtFi + (size_t)j * 3 * KI;
+    #pragma unroll
+    for (int a = 0; a < KI; ++a) {
+      const double f0 = fi[a], f1 = fi[KI + a], f2 = fi[2 * KI + a];
+      if (f0 == 0.0 && f1 == 0.0 && f2 == 0.0 && ji[a] == 0.0 && ji[KI + a] == 0.0) continue;   // constant parameter
+      const double g0 = inv[0] * f0 + inv[1] * f1 + inv[2] * f2, g1 = inv[3] * f0 + inv[4] * f1 + inv[5] * f2, g2 = inv[6] * f0 + inv[7] * f1 + inv[8] * f2;
+      #pragma unroll
+      for (int b = 0; b < 6; ++b)
+        atomicAdd(&sci_row0[(size_t)a * nred_c + b], ji[a] * jc[b] + ji[KI + a] * jc[6 + b] - (g0 * efc[b] + g1 * efc[6 + b] + g2 * efc[12 + b]));
+      if (first) {
+        const double rv = -(f0 * ie[0] + f1 * ie[1] + f2 * ie[2]);
+        if (qt == q0) atomicAdd(&s_ii[KI * KI + a], rv); else atomicAdd(&A.rhs[nred_c + KI * qt + a], rv);
+        #pragma unroll
+        for (int b = 0; b < KI; ++b) {
+          const double v = -(g0 * fi[b] + g1 * fi[KI + b] + g2 * fi[2 * KI + b]);
+          if (v == 0.0) continue;
+          if (qt == q0) atomicAdd(&s_ii[a * KI + b], v); else atomicAdd(&A.Sii[(size_t)(KI * qt + a) * ni8 + KI * qt + b], v);
+        }
+      }
+    }
+    double *ge = GE + 36 * (size_t)t;
+    #pragma unroll
+    for (int a = 0; a < 3; ++a)
+      #pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        ge[a * 6 + c] = inv[a * 3] * efc[c] + inv[a * 3 + 1] * efc[6 + c] + inv[a * 3 + 2] * efc[12 + c];
+        ge[18 + a * 6 + c] = efc[a * 6 + c];
+      }
+  }
+}
+// folds the corner replicas of schur_stage_kernel into Sii / rhs of group q0 (fixed order)
+__global__ void corner_fold_kernel(const double *__restrict__ corner_rep, const int *__restrict__ obs_intr, int n_poses, int n_intr, double *__restrict__ Sii, double *__restrict__ rhs) {
+  const int e = threadIdx.x; if (e >= KI * KI + KI) return;
+  const int q0 = obs_intr[0], ni8 = KI * n_intr;
+  double v = 0; for (int rp2 = 0; rp2 < CORNER_REPS; ++rp2) v += corner_rep[(size_t)rp2 * (KI * KI + KI) + e];
+  if (v == 0.0) return;
+  if (e < KI * KI) atomicAdd(&Sii[(size_t)(KI * q0 + e / KI) * ni8 + KI * q0 + e % KI], v);
+  else atomicAdd(&rhs[6 * n_poses + KI * q0 + (e - KI * KI)], v);
+}
+__global__ void __launch_bounds__(256) schur_pair_kernel(SchurArgs A, const double *__restrict__ GE) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int ea = lane / 6, eb2 = lane % 6, fa = (32 + lane) / 6, fb = (32 + lane) % 6;
+  // GE (288 MB at 1M observations) comes from DRAM: the lines of a landmark (K x 288 B) are prefetched into L1 one
+  // landmark ahead, otherwise every first touch inside the pair walk is an exposed ~1 us miss
+  int t0n = 0, Kn = 0;
+  if (gwarp < A.n_points) { t0n = A.pt_start[gwarp]; Kn = A.pt_start[gwarp + 1] - t0n; }
+  { const char *pf = reinterpret_cast<const char *>(GE + 36 * (size_t)t0n) + 128 * lane;
+    if (128 * lane < 288 * Kn) asm volatile("prefetch.global.L1 [%0];" :: "l"(pf)); if (128 * (lane + 32) < 288 * Kn) asm volatile("prefetch.global.L1 [%0];" :: "l"(pf + 4096)); }
+  for (int j = gwarp; j < A.n_points; j += nwarps) {
+    const int t0 = t0n, K = Kn;
+    if (j + nwarps < A.n_points) {
+      t0n = A.pt_start[j + nwarps]; Kn = A.pt_start[j + nwarps + 1] - t0n;
+      const char *pf = reinterpret_cast<const char *>(GE + 36 * (size_t)t0n) + 128 * lane;
+      if (128 * lane < 288 * Kn) asm volatile("prefetch.global.L1 [%0];" :: "l"(pf)); if (128 * (lane + 32) < 288 * Kn && Kn <= 32) asm volatile("prefetch.global.L1 [%0];" :: "l"(pf + 4096));
+    }
+    if (K == 0 || K > 32 || !A.pt_single[j]) continue;
+    const int cam_l = lane < K ? A.obs_pose[t0 + lane] : 0;
+    const unsigned lowmask = (1u << (cam_l & 31)) - 1u;
+    int rp = 0, wp = 0; unsigned bm = 0;
+    { const int c0 = __shfl_sync(0xffffffffu, cam_l, 0); const size_t w = (size_t)c0 * A.bsr.words + (cam_l >> 5); rp = A.bsr.rowptr[c0]; wp = A.bsr.wprefix[w]; bm = A.bsr.bitmap[w]; }
+    const double *ge = GE + 36 * (size_t)t0;
+    for (int tt = 0; tt < K; ++tt) {
+      const int ctt = __shfl_sync(0xffffffffu, cam_l, tt);
+      const int cur = (lane < K && cam_l >= ctt) ? rp + wp + __popc(bm & lowmask) : -1;
+      if (tt + 1 < K) { const int cn = __shfl_sync(0xffffffffu, cam_l, tt + 1); const size_t w = (size_t)cn * A.bsr.words + (cam_l >> 5); rp = A.bsr.rowptr[cn]; wp = A.bsr.wprefix[w]; bm = A.bsr.bitmap[w]; }
+      const double *gt = ge + 36 * tt;
+      const double g0 = gt[ea], g1 = gt[6 + ea], g2 = gt[12 + ea];
+      const double h0 = lane < 4 ? gt[fa] : 0.0, h1 = lane < 4 ? gt[6 + fa] : 0.0, h2 = lane < 4 ? gt[12 + fa] : 0.0;
+      unsigned todo = __ballot_sync(0xffffffffu, cur >= 0);
+      while (todo) {
+        const int u = __ffs(todo) - 1; todo &= todo - 1;
+        const int bi = __shfl_sync(0xffffffffu, cur, u);
+        double *blk = A.Scc + 36 * (size_t)bi;
+        const double *ef = ge + 36 * u + 18;
+        atomicAdd(blk + lane, -(g0 * ef[eb2] + g1 * ef[6 + eb2] + g2 * ef[12 + eb2]));
+        if (lane < 4) atomicAdd(blk + 32 + lane, -(h0 * ef[fb] + h1 * ef[6 + fb] + h2 * ef[12 + fb]));
+      }
     }
   }
 }
