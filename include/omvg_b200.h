@@ -92,6 +92,22 @@ uint64_t omvg_match_launch_count(const omvg_match_ctx *ctx);
  * kernel (the tcgen05 distance/top-2 kernel) accumulated since the last call with reset!=0. */
 int omvg_match_kernel_time(omvg_match_ctx *ctx, double *ms, uint64_t *launches, int reset);
 
+/* ---- cascade hashing: openMVG's default matcher for scalar descriptors ("FASTCASCADEHASHINGL2",
+ * matching/cascade_hasher.hpp, matching_image_collection/Cascade_Hashing_Matcher_Regions.cpp:38-226).
+ * primary[128][128] / secondary[6][10][128]: the Gaussian projections CascadeHasher::Init draws
+ * (cascade_hasher.hpp:142-162) — generated by the caller with the same std::mt19937 / std::normal_distribution
+ * so that they are the reference's (host/Cascade_Hashing_Matcher_Regions_B200.hpp does it).
+ * used[n_images] (or NULL = all): the images the pair list names; the zero-mean descriptor is the mean of their
+ * per-image means (:78-105).  Call after omvg_match_prepare. */
+int omvg_match_cascade_prepare(omvg_match_ctx *ctx, const float *primary, const float *secondary, const uint8_t *used);
+/* Pairs (I = database, J = queries) as in omvg_match_run; fetch with omvg_match_fetch.  Rows hold (i, j) in
+ * ascending j; the reference then sorts by (i, j) (IndMatch::getDeduplicated) and drops matches with equal
+ * coordinates (IndMatchDecorator) — host-side steps the shim performs with openMVG's own functions. */
+int omvg_match_cascade_run(omvg_match_ctx *ctx, const uint32_t *pair_i, const uint32_t *pair_j, uint64_t n_pairs, float dist_ratio);
+/* Validation aid (tests only): hash codes [count][4] (bit j = bit j&31 of word j>>5), bucket ids [count][6],
+ * zero-mean vector [128]; any pointer may be NULL. */
+int omvg_match_cascade_debug_hash(omvg_match_ctx *ctx, uint32_t image, uint32_t *codes, uint16_t *bucket_ids, float *zero_mean);
+
 /* Validation aid (tests only): exact 2-NN of every row of image q_image in image db_image by a
  * plain SIMT dp4a kernel.  d1/i1/d2: host arrays of counts[q_image] entries. */
 int omvg_match_debug_top2_simt(omvg_match_ctx *ctx, uint32_t db_image, uint32_t q_image,

@@ -20,6 +20,7 @@
 //   (i1, d2) exactly, applies  float(d1) < fratio*float(d2)  and compacts in ascending query order.
 //   All integer arithmetic is exact, so the output is bit-identical to the reference.
 #include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cuda.h>
 #include <algorithm>
@@ -403,6 +404,193 @@ __global__ void decode_k12_kernel(const int2 *__restrict__ k12, const int32_t *_
   ub2[q] = (K.y == KEY_MIN) ? INT_MAX : qn - (K.y >> 8);
 }
 
+
+// ================================================================================= cascade hashing (M9 / N2)
+// openMVG's default matcher for scalar descriptors (matching/cascade_hasher.hpp, Cascade_Hashing_Matcher_Regions.cpp):
+// 128-bit sign code + 6 x 10-bit bucket ids per descriptor, candidates = union of the query's 6 buckets in the
+// database image, first 10 by (Hamming, insertion order), exact L2 on those, top-2 by (distance, id), ratio test.
+// Everything after the hashing is exact integer work; the hashing is a float mat-vec whose summation order is
+// fixed here (k ascending, separate multiply and add) and mirrored by oracle/cascade_oracle.c.
+constexpr int CH_GROUPS = 6, CH_BITS = 10, CH_NB = 1 << CH_BITS, CH_OUT = OMVG_DESC_LEN + CH_GROUPS * CH_BITS, CH_TOP = 10;
+constexpr int CH_HASH_THREADS = 192, CH_HASH_ROWS = 16;
+
+// integer column sums of one image (exact): the float means are formed on the host from them
+__global__ void cascade_colsum_kernel(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ img_row0, const uint32_t *__restrict__ img_count,
+                                      unsigned long long *__restrict__ sums) {
+  const uint32_t img = blockIdx.x, k = threadIdx.x;
+  const uint8_t *base = desc + (size_t)img_row0[img] * OMVG_DESC_LEN;
+  unsigned long long s = 0;
+  for (uint32_t r = 0; r < img_count[img]; ++r) s += base[(size_t)r * OMVG_DESC_LEN + k];
+  sums[(size_t)img * OMVG_DESC_LEN + k] = s;
+}
+
+// code bit j = (P_j . (d - zm) > 0), bucket id of group g = 10 such signs of S_g, MSB first (cascade_hasher.hpp:203-232)
+__global__ void __launch_bounds__(CH_HASH_THREADS) cascade_hash_kernel(const uint8_t *__restrict__ desc, uint32_t total_rows, const float *__restrict__ zm,
+                                                                       const float *__restrict__ proj /*[188][128]: primary then secondary*/,
+                                                                       uint4 *__restrict__ code, uint4 *__restrict__ bid) {
+  __shared__ float sd[CH_HASH_ROWS][OMVG_DESC_LEN];
+  __shared__ uint32_t sbid[CH_HASH_ROWS][8];
+  __shared__ uint32_t scode[CH_HASH_ROWS][4];
+  const uint32_t row0 = blockIdx.x * CH_HASH_ROWS, t = threadIdx.x;
+  for (uint32_t idx = t; idx < CH_HASH_ROWS * OMVG_DESC_LEN; idx += CH_HASH_THREADS) {
+    const uint32_t r = idx >> 7, k = idx & 127;
+    sd[r][k] = row0 + r < total_rows ? __fsub_rn((float)desc[(size_t)(row0 + r) * OMVG_DESC_LEN + k], zm[k]) : 0.0f;
+  }
+  if (t < CH_HASH_ROWS * 8) sbid[t >> 3][t & 7] = 0;
+  __syncthreads();
+  if (t < CH_OUT) {
+    const float *pr = proj + (size_t)t * OMVG_DESC_LEN;
+    float acc[CH_HASH_ROWS];
+    #pragma unroll
+    for (int r = 0; r < CH_HASH_ROWS; ++r) acc[r] = 0.0f;
+    for (int k = 0; k < OMVG_DESC_LEN; ++k) {
+      const float pv = pr[k];
+      #pragma unroll
+      for (int r = 0; r < CH_HASH_ROWS; ++r) acc[r] = __fadd_rn(acc[r], __fmul_rn(pv, sd[r][k]));
+    }
+    #pragma unroll
+    for (int r = 0; r < CH_HASH_ROWS; ++r) {
+      const bool bit = acc[r] > 0.0f;
+      if (t < OMVG_DESC_LEN) { const uint32_t w = __ballot_sync(0xffffffffu, bit); if ((t & 31) == 0) scode[r][t >> 5] = w; }
+      else if (bit) { const int u = t - OMVG_DESC_LEN, g = u / CH_BITS, b = u % CH_BITS; atomicOr(&sbid[r][g], 1u << (CH_BITS - 1 - b)); }
+    }
+  }
+  __syncthreads();
+  if (t < CH_HASH_ROWS && row0 + t < total_rows) {
+    code[row0 + t] = make_uint4(scode[t][0], scode[t][1], scode[t][2], scode[t][3]);
+    bid[row0 + t] = make_uint4(sbid[t][0] | (sbid[t][1] << 16), sbid[t][2] | (sbid[t][3] << 16), sbid[t][4] | (sbid[t][5] << 16), 0u);
+  }
+}
+
+// sort keys (segment = image*6 + group | bucket | local id) for the bucket tables
+__global__ void cascade_keys_kernel(const uint4 *__restrict__ bid, const uint32_t *__restrict__ img_row0, const uint32_t *__restrict__ img_count,
+                                    const uint32_t *__restrict__ img_real0, uint32_t n_images, unsigned long long *__restrict__ keys) {
+  const uint32_t img = blockIdx.y;
+  for (uint32_t local = blockIdx.x * blockDim.x + threadIdx.x; local < img_count[img]; local += gridDim.x * blockDim.x) {
+    const uint4 b = bid[img_row0[img] + local];
+    const uint32_t ids[6] = {b.x & 0xffffu, b.x >> 16, b.y & 0xffffu, b.y >> 16, b.z & 0xffffu, b.z >> 16};
+    #pragma unroll
+    for (int g = 0; g < CH_GROUPS; ++g)
+      keys[(size_t)CH_GROUPS * (img_real0[img] + local) + g] = ((unsigned long long)(img * CH_GROUPS + g) << 34) | ((unsigned long long)ids[g] << 24) | local;
+  }
+}
+// bucket starts from the sorted keys (bucket index = key >> 24, dense: segment * 1024 + bucket id) and item ids
+__global__ void cascade_starts_kernel(const unsigned long long *__restrict__ keys, uint64_t n, uint32_t n_buckets, uint32_t *__restrict__ start, uint32_t *__restrict__ items) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n) return;
+  const long long lo = t == 0 ? -1 : (long long)(keys[t - 1] >> 24), hi = t == n ? (long long)n_buckets : (long long)(keys[t] >> 24);
+  for (long long k = lo + 1; k <= hi; ++k) start[k] = (uint32_t)t;
+  if (t < n) items[t] = (uint32_t)(keys[t] & 0xffffffull);
+}
+
+// one warp per query (4 queries per warp); writes out[out_off + q].x = matched database id or -1
+__global__ void __launch_bounds__(256) cascade_query_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ norm, const uint4 *__restrict__ code,
+                                                            const uint4 *__restrict__ bid, const uint32_t *__restrict__ bstart, const uint32_t *__restrict__ bitems,
+                                                            const PairInfo *__restrict__ pairs, int2 *__restrict__ out, float fratio) {
+  const PairInfo P = pairs[blockIdx.y];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int qq = 0; qq < 4; ++qq) {
+    const uint32_t q = blockIdx.x * 32 + warp * 4 + qq;
+    if (q >= P.q_count) return;
+    const uint32_t qrow = P.q_row0 + q;
+    const uint4 qc = code[qrow], qb4 = bid[qrow];
+    const uint32_t qb[6] = {qb4.x & 0xffffu, qb4.x >> 16, qb4.y & 0xffffu, qb4.y >> 16, qb4.z & 0xffffu, qb4.z >> 16};
+    uint32_t s[6], len[6], tot = 0;
+    #pragma unroll
+    for (int g = 0; g < CH_GROUPS; ++g) { const uint32_t b = (P.db_group * CH_GROUPS + g) * CH_NB + qb[g]; s[g] = bstart[b]; len[g] = bstart[b + 1] - s[g]; tot += len[g]; }
+    int result = -1;
+    if (tot > 2) {                                              // "not at least NN candidates" counts duplicates (:301-304)
+      // first CH_TOP unique candidates by (Hamming, position in the concatenated bucket lists): CH_TOP selection rounds
+      // over the (short) lists; a candidate is a duplicate iff it already sat in the query's bucket of an earlier group
+      uint32_t last = 0, my_sel = 0; int nsel = 0;
+      for (int r = 0; r < CH_TOP; ++r) {
+        uint32_t best = 0xffffffffu, base = 0;
+        #pragma unroll
+        for (int g = 0; g < CH_GROUPS; ++g) {
+          for (uint32_t off0 = 0; off0 < len[g]; off0 += 32) {
+            const uint32_t off = off0 + lane;
+            if (off < len[g]) {
+              const uint32_t row = P.db_row0 + bitems[s[g] + off];
+              const uint4 cb = bid[row];
+              const uint32_t cbv[6] = {cb.x & 0xffffu, cb.x >> 16, cb.y & 0xffffu, cb.y >> 16, cb.z & 0xffffu, cb.z >> 16};
+              bool dup = false;
+              #pragma unroll
+              for (int g2 = 0; g2 < CH_GROUPS; ++g2) if (g2 < g && cbv[g2] == qb[g2]) dup = true;
+              if (!dup) {
+                const uint4 cc = code[row];
+                const uint32_t ham = __popc(cc.x ^ qc.x) + __popc(cc.y ^ qc.y) + __popc(cc.z ^ qc.z) + __popc(cc.w ^ qc.w);
+                const uint32_t key = ((ham << 24) | (base + off)) + 1u;
+                if (key > last && key < best) best = key;
+              }
+            }
+          }
+          base += len[g];
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (best == 0xffffffffu) break;
+        last = best;
+        uint32_t pos = (best - 1u) & 0xffffffu, id = 0; bool found = false;
+        #pragma unroll
+        for (int g = 0; g < CH_GROUPS; ++g) if (!found) { if (pos < len[g]) { id = bitems[s[g] + pos]; found = true; } else pos -= len[g]; }
+        if (lane == r) my_sel = id;
+        ++nsel;
+      }
+      if (nsel >= 2) {
+        // exact L2 of the selected candidates: d = |q|^2 + |c|^2 - 2 q.c  (integers)
+        const uint32_t qv = reinterpret_cast<const uint32_t *>(desc + (size_t)qrow * OMVG_DESC_LEN)[lane];
+        const int qn = norm[qrow];
+        unsigned long long mine = 0xffffffffffffffffull;
+        for (int r = 0; r < nsel; ++r) {
+          const uint32_t id = __shfl_sync(0xffffffffu, my_sel, r), row = P.db_row0 + id;
+          uint32_t dot = __dp4a(qv, reinterpret_cast<const uint32_t *>(desc + (size_t)row * OMVG_DESC_LEN)[lane], 0u);
+          #pragma unroll
+          for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          const int d = qn + norm[row] - 2 * (int)dot;
+          if (lane == r) mine = ((unsigned long long)(uint32_t)d << 32) | id;
+        }
+        // top-2 of (distance, id) in lexicographic order (std::partial_sort of pair<dist,int>, :352-355)
+        unsigned long long b1 = mine;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b1 = min(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+        unsigned long long b2 = mine == b1 ? 0xffffffffffffffffull : mine;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+        const int d1 = (int)(b1 >> 32), d2 = (int)(b2 >> 32);
+        if (__int2float_rn(d1) < __fmul_rn(fratio, __int2float_rn(d2))) result = (int)(uint32_t)(b1 & 0xffffffffull);   // matching_filters.hpp:57
+      }
+    }
+    if (lane == 0) out[P.out_off + q].x = result;
+  }
+}
+
+// ordered compaction of one pair's results: (database id, query id) for the kept queries, ascending query
+__global__ void __launch_bounds__(FIN_THREADS) cascade_compact_kernel(const PairInfo *__restrict__ pairs, int2 *__restrict__ k12, uint32_t *__restrict__ counts) {
+  __shared__ uint32_t warp_tot[FIN_THREADS / 32];
+  __shared__ uint32_t running;
+  const PairInfo P = pairs[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  int2 *io = k12 + P.out_off;
+  for (uint32_t q0 = 0; q0 < P.q_count; q0 += FIN_THREADS) {
+    const uint32_t q = q0 + threadIdx.x;
+    const int v = q < P.q_count ? io[q].x : -1;
+    const bool keep = v >= 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    const uint32_t in_warp = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = running;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (keep) reinterpret_cast<uint2 *>(io)[before + in_warp] = make_uint2((uint32_t)v, q);
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < FIN_THREADS / 32; ++w) t += warp_tot[w]; running += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[blockIdx.x] = running;
+}
+
 }  // namespace omvg
 
 // ===================================================================================== host side
@@ -430,6 +618,9 @@ struct omvg_match_ctx {
   double tc_ms = 0; uint64_t tc_launches = 0; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   std::vector<cudaEvent_t> ev_pool;
   size_t k12_budget_bytes = size_t(2) << 30;
+  // cascade hashing state (omvg_match_cascade_prepare)
+  uint4 *d_code = nullptr, *d_bid = nullptr; uint32_t *d_bstart = nullptr, *d_bitems = nullptr; float *d_proj = nullptr, *d_zm = nullptr;
+  bool cascade_ready = false; std::vector<float> h_zm;
 };
 
 namespace {
@@ -454,6 +645,8 @@ int make_tmap(omvg_match_ctx *c) {
 }
 
 void free_images(omvg_match_ctx *c) {
+  cudaFree(c->d_code); cudaFree(c->d_bid); cudaFree(c->d_bstart); cudaFree(c->d_bitems); cudaFree(c->d_proj); cudaFree(c->d_zm);
+  c->d_code = c->d_bid = nullptr; c->d_bstart = c->d_bitems = nullptr; c->d_proj = c->d_zm = nullptr; c->cascade_ready = false;
   cudaFree(c->d_desc); cudaFree(c->d_norm); cudaFree(c->d_ckey); cudaFree(c->d_img_row0); cudaFree(c->d_img_count);
   cudaFree(c->d_img_group); cudaFree(c->d_row_img);
   c->d_desc = nullptr; c->d_norm = c->d_ckey = nullptr; c->d_img_row0 = c->d_img_count = c->d_img_group = c->d_row_img = nullptr;
@@ -729,6 +922,151 @@ int omvg_match_kernel_time(omvg_match_ctx *c, double *ms, uint64_t *launches, in
   const int rc = drain_timers(c); if (rc) return rc;
   if (ms) *ms = c->tc_ms; if (launches) *launches = c->tc_launches;
   if (reset) { c->tc_ms = 0; c->tc_launches = 0; }
+  return OMVG_OK;
+}
+
+// ---- cascade hashing ---------------------------------------------------------------------------------------
+// Hash every image (zero-mean vector over the USED images, Cascade_Hashing_Matcher_Regions.cpp:78-105), build the
+// 6 x 1024 bucket tables of every image with one radix sort.  Needs omvg_match_prepare (row norms).
+int omvg_match_cascade_prepare(omvg_match_ctx *c, const float *primary, const float *secondary, const uint8_t *used) {
+  if (!c || !primary || !secondary) return fail(OMVG_E_ARG, "bad arguments");
+  if (!c->prepared) return fail(OMVG_E_STATE, "omvg_match_prepare must come first");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const uint32_t ni = c->n_images;
+  for (uint32_t k = 0; k < ni; ++k) if (c->counts[k] >= (1u << 24)) return fail(OMVG_E_UNSUPPORTED, "image %u has more than 2^24 descriptors", k);
+  // zero-mean descriptor: exact integer column sums on the device, the two float reductions on the host
+  // (float(sum)/float(n) per image; sequential float sum over the used images, / n_used: cascade_hasher.hpp:166-176)
+  unsigned long long *d_sums = nullptr; OMVG_CUDA(cudaMalloc(&d_sums, std::max<size_t>(1, ni) * OMVG_DESC_LEN * sizeof(unsigned long long)));
+  if (ni) { cascade_colsum_kernel<<<ni, OMVG_DESC_LEN, 0, st>>>(c->d_desc, c->d_img_row0, c->d_img_count, d_sums); OMVG_CUDA(cudaGetLastError()); c->launches++; }
+  std::vector<unsigned long long> sums((size_t)ni * OMVG_DESC_LEN);
+  if (ni) OMVG_CUDA(cudaMemcpyAsync(sums.data(), d_sums, sums.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  OMVG_CUDA(cudaStreamSynchronize(st)); cudaFree(d_sums);
+  c->h_zm.assign(OMVG_DESC_LEN, 0.0f);
+  uint32_t n_used = 0; for (uint32_t k = 0; k < ni; ++k) if (!used || used[k]) ++n_used;
+  for (int col = 0; col < OMVG_DESC_LEN; ++col) {
+    float acc = 0.0f;
+    for (uint32_t k = 0; k < ni; ++k) { if (used && !used[k]) continue;
+      const float m = c->counts[k] ? (float)sums[(size_t)k * OMVG_DESC_LEN + col] / (float)c->counts[k] : 0.0f; acc = acc + m; }
+    c->h_zm[col] = n_used ? acc / (float)n_used : 0.0f;
+  }
+  if (!c->d_proj) OMVG_CUDA(cudaMalloc(&c->d_proj, (size_t)CH_OUT * OMVG_DESC_LEN * sizeof(float)));
+  if (!c->d_zm) OMVG_CUDA(cudaMalloc(&c->d_zm, OMVG_DESC_LEN * sizeof(float)));
+  OMVG_CUDA(cudaMemcpyAsync(c->d_proj, primary, (size_t)OMVG_DESC_LEN * OMVG_DESC_LEN * sizeof(float), cudaMemcpyHostToDevice, st));
+  OMVG_CUDA(cudaMemcpyAsync(c->d_proj + (size_t)OMVG_DESC_LEN * OMVG_DESC_LEN, secondary, (size_t)CH_GROUPS * CH_BITS * OMVG_DESC_LEN * sizeof(float), cudaMemcpyHostToDevice, st));
+  OMVG_CUDA(cudaMemcpyAsync(c->d_zm, c->h_zm.data(), OMVG_DESC_LEN * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (!c->d_code) { OMVG_CUDA(cudaMalloc(&c->d_code, (size_t)c->total_rows * sizeof(uint4))); OMVG_CUDA(cudaMalloc(&c->d_bid, (size_t)c->total_rows * sizeof(uint4))); }
+  cascade_hash_kernel<<<(c->total_rows + CH_HASH_ROWS - 1) / CH_HASH_ROWS, CH_HASH_THREADS, 0, st>>>(c->d_desc, c->total_rows, c->d_zm, c->d_proj, c->d_code, c->d_bid);
+  OMVG_CUDA(cudaGetLastError()); c->launches++;
+  // bucket tables
+  std::vector<uint32_t> real0(ni + 1, 0); for (uint32_t k = 0; k < ni; ++k) real0[k + 1] = real0[k] + c->counts[k];
+  const uint64_t n_real = real0[ni], n_keys = n_real * CH_GROUPS; const uint32_t n_buckets = ni * CH_GROUPS * CH_NB;
+  if (n_keys >= 0xffffffffull) return fail(OMVG_E_UNSUPPORTED, "collection too large for the bucket tables");
+  cudaFree(c->d_bstart); cudaFree(c->d_bitems); c->d_bstart = c->d_bitems = nullptr;
+  OMVG_CUDA(cudaMalloc(&c->d_bstart, ((size_t)n_buckets + 1) * sizeof(uint32_t))); OMVG_CUDA(cudaMalloc(&c->d_bitems, std::max<uint64_t>(1, n_keys) * sizeof(uint32_t)));
+  uint32_t *d_real0 = nullptr; unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; void *d_tmp = nullptr;
+  OMVG_CUDA(cudaMalloc(&d_real0, (ni + 1) * sizeof(uint32_t)));
+  OMVG_CUDA(cudaMemcpyAsync(d_real0, real0.data(), (ni + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  OMVG_CUDA(cudaMalloc(&d_keys, std::max<uint64_t>(1, n_keys) * 8)); OMVG_CUDA(cudaMalloc(&d_keys2, std::max<uint64_t>(1, n_keys) * 8));
+  if (n_keys) {
+    cascade_keys_kernel<<<dim3(32, ni), 256, 0, st>>>(c->d_bid, c->d_img_row0, c->d_img_count, d_real0, ni, d_keys); OMVG_CUDA(cudaGetLastError());
+    int seg_bits = 1; while ((1ull << seg_bits) < (unsigned long long)ni * CH_GROUPS) ++seg_bits;
+    size_t tb = 0; OMVG_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_keys, d_keys2, (int)n_keys, 0, 34 + seg_bits, st));
+    OMVG_CUDA(cudaMalloc(&d_tmp, tb));
+    OMVG_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp, tb, d_keys, d_keys2, (int)n_keys, 0, 34 + seg_bits, st));
+    c->launches += 2;
+  }
+  cascade_starts_kernel<<<(unsigned)((n_keys + 256) / 256), 256, 0, st>>>(d_keys2, n_keys, n_buckets, c->d_bstart, c->d_bitems); OMVG_CUDA(cudaGetLastError());
+  c->launches++;
+  OMVG_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_real0); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_tmp);
+  c->cascade_ready = true; return OMVG_OK;
+}
+
+// Cascade_Hashing_Matcher_Regions.cpp:110-189 for a list of pairs (I = database, J = queries).  The result is read
+// with omvg_match_fetch: CSR rows of (i, j) in ascending j (the caller sorts by (i, j) as IndMatch::getDeduplicated does).
+int omvg_match_cascade_run(omvg_match_ctx *c, const uint32_t *pair_i, const uint32_t *pair_j, uint64_t n_pairs, float dist_ratio) {
+  if (!c || ((!pair_i || !pair_j) && n_pairs)) return fail(OMVG_E_ARG, "bad arguments");
+  if (!c->cascade_ready) return fail(OMVG_E_STATE, "omvg_match_cascade_prepare first");
+  if (!(dist_ratio >= 0.f)) return fail(OMVG_E_ARG, "dist_ratio must be >= 0");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  for (uint64_t p = 0; p < n_pairs; ++p)
+    if (pair_i[p] >= c->n_images || pair_j[p] >= c->n_images) return fail(OMVG_E_ARG, "pair %llu out of range", (unsigned long long)p);
+  const float fratio = dist_ratio * dist_ratio;
+  if (n_pairs + 1 > c->offsets_cap) {
+    if (c->d_offsets) cudaFree(c->d_offsets);
+    c->d_offsets = nullptr; c->offsets_cap = 0;
+    OMVG_CUDA(cudaMalloc(&c->d_offsets, (n_pairs + 1) * sizeof(uint64_t))); c->offsets_cap = n_pairs + 1;
+  }
+  OMVG_CUDA(cudaMemsetAsync(c->d_total, 0, sizeof(uint64_t), c->stream));
+  OMVG_CUDA(cudaMemsetAsync(c->d_offsets, 0, sizeof(uint64_t), c->stream));
+  c->total_last = 0; c->n_pairs_last = n_pairs; c->have_result = false;
+  std::vector<PairInfo> pinfo;
+  const size_t budget = c->k12_budget_bytes / sizeof(int2);
+  uint64_t p0 = 0;
+  while (p0 < n_pairs) {
+    pinfo.clear(); size_t out = 0; uint64_t p1 = p0; uint32_t maxq = 0;
+    while (p1 < n_pairs && p1 - p0 < 65535) {
+      const uint32_t I = pair_i[p1], J = pair_j[p1];
+      if (p1 > p0 && out + c->counts[J] > budget) break;
+      PairInfo P{}; P.db_row0 = c->row0[I]; P.db_count = c->counts[I]; P.db_group = I; P.q_row0 = c->row0[J]; P.q_count = c->counts[J]; P.out_off = out;
+      if (P.db_count == 0) P.q_count = 0;                      // empty database image: nothing (:120-124)
+      out += P.q_count; maxq = std::max(maxq, P.q_count); pinfo.push_back(P); ++p1;
+    }
+    const uint32_t nb = (uint32_t)(p1 - p0);
+    int rc;
+    if ((rc = ensure(c->d_k12, c->k12_cap, std::max<size_t>(out, 1)))) return rc;
+    if (nb > c->pairs_cap) {
+      if (c->d_pairs) cudaFree(c->d_pairs); if (c->d_counts) cudaFree(c->d_counts);
+      c->d_pairs = nullptr; c->d_counts = nullptr; c->pairs_cap = 0;
+      OMVG_CUDA(cudaMalloc(&c->d_pairs, nb * sizeof(PairInfo))); OMVG_CUDA(cudaMalloc(&c->d_counts, nb * sizeof(uint32_t)));
+      c->pairs_cap = nb;
+    }
+    OMVG_CUDA(cudaMemcpyAsync(c->d_pairs, pinfo.data(), nb * sizeof(PairInfo), cudaMemcpyHostToDevice, c->stream));
+    if (maxq) {
+      cudaEvent_t e0 = get_event(c), e1 = get_event(c);
+      OMVG_CUDA(cudaEventRecord(e0, c->stream));
+      cascade_query_kernel<<<dim3((maxq + 31) / 32, nb), 256, 0, c->stream>>>(c->d_desc, c->d_norm, c->d_code, c->d_bid, c->d_bstart, c->d_bitems, c->d_pairs, c->d_k12, fratio);
+      OMVG_CUDA(cudaGetLastError());
+      OMVG_CUDA(cudaEventRecord(e1, c->stream));
+      c->pending.emplace_back(e0, e1); c->tc_launches++; c->launches++;
+    }
+    cascade_compact_kernel<<<nb, FIN_THREADS, 0, c->stream>>>(c->d_pairs, c->d_k12, c->d_counts); OMVG_CUDA(cudaGetLastError());
+    scan_counts_kernel<<<1, 1024, 0, c->stream>>>(c->d_counts, nb, c->d_offsets + p0, c->d_total); OMVG_CUDA(cudaGetLastError());
+    c->launches += 2;
+    uint64_t total = 0;
+    OMVG_CUDA(cudaMemcpyAsync(&total, c->d_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+    OMVG_CUDA(cudaStreamSynchronize(c->stream));
+    if (total > c->out_cap) {
+      const size_t ncap = std::max<size_t>(total, c->out_cap * 2 + 1024);
+      uint2 *n = nullptr; OMVG_CUDA(cudaMalloc(&n, ncap * sizeof(uint2)));
+      if (c->d_out && c->total_last) OMVG_CUDA(cudaMemcpyAsync(n, c->d_out, c->total_last * sizeof(uint2), cudaMemcpyDeviceToDevice, c->stream));
+      OMVG_CUDA(cudaStreamSynchronize(c->stream));
+      if (c->d_out) cudaFree(c->d_out);
+      c->d_out = n; c->out_cap = ncap;
+    }
+    compact_kernel<<<nb, 128, 0, c->stream>>>(c->d_k12, c->d_pairs, c->d_counts, c->d_offsets + p0, c->d_out); OMVG_CUDA(cudaGetLastError());
+    c->launches++; c->total_last = total;
+    p0 = p1;
+  }
+  c->have_result = true; return OMVG_OK;
+}
+
+// Validation aid (tests only): hash codes [count][4], bucket ids [count][6] and the zero-mean vector [128].
+int omvg_match_cascade_debug_hash(omvg_match_ctx *c, uint32_t image, uint32_t *codes, uint16_t *bids, float *zero_mean) {
+  if (!c || image >= c->n_images) return fail(OMVG_E_ARG, "bad arguments");
+  if (!c->cascade_ready) return fail(OMVG_E_STATE, "omvg_match_cascade_prepare first");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  const uint32_t n = c->counts[image];
+  std::vector<uint4> hc(n), hb(n);
+  if (n) { OMVG_CUDA(cudaMemcpyAsync(hc.data(), c->d_code + c->row0[image], n * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+           OMVG_CUDA(cudaMemcpyAsync(hb.data(), c->d_bid + c->row0[image], n * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream)); }
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  for (uint32_t r = 0; r < n; ++r) {
+    if (codes) { codes[4 * r] = hc[r].x; codes[4 * r + 1] = hc[r].y; codes[4 * r + 2] = hc[r].z; codes[4 * r + 3] = hc[r].w; }
+    if (bids) { bids[6 * r] = hb[r].x & 0xffff; bids[6 * r + 1] = hb[r].x >> 16; bids[6 * r + 2] = hb[r].y & 0xffff; bids[6 * r + 3] = hb[r].y >> 16; bids[6 * r + 4] = hb[r].z & 0xffff; bids[6 * r + 5] = hb[r].z >> 16; }
+  }
+  if (zero_mean) for (int k = 0; k < OMVG_DESC_LEN; ++k) zero_mean[k] = c->h_zm[k];
   return OMVG_OK;
 }
 

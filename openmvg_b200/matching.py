@@ -93,6 +93,25 @@ class MatchContext:
         return ms.value, n.value
 
     # ---- validation aids
+    # ---- cascade hashing (FASTCASCADEHASHINGL2; Cascade_Hashing_Matcher_Regions.cpp)
+    def cascade_prepare(self, primary, secondary, used=None):
+        P = np.ascontiguousarray(primary, np.float32).reshape(128, 128)
+        S = np.ascontiguousarray(secondary, np.float32).reshape(6, 10, 128)
+        u = None if used is None else np.ascontiguousarray(used, np.uint8)
+        check(lib().omvg_match_cascade_prepare(self._h, _p(P), _p(S), None if u is None else _p(u)))
+
+    def cascade_run(self, pair_i, pair_j, dist_ratio: float = 0.8):
+        self._pi = np.ascontiguousarray(pair_i, np.uint32)
+        self._pj = np.ascontiguousarray(pair_j, np.uint32)
+        check(lib().omvg_match_cascade_run(self._h, _p(self._pi), _p(self._pj), ctypes.c_uint64(len(self._pi)),
+                                           ctypes.c_float(dist_ratio)))
+
+    def cascade_debug_hash(self, image: int):
+        n = int(self.counts[image])
+        codes = np.zeros((n, 4), np.uint32); bids = np.zeros((n, 6), np.uint16); zm = np.zeros(128, np.float32)
+        check(lib().omvg_match_cascade_debug_hash(self._h, image, _p(codes), _p(bids), _p(zm)))
+        return codes, bids, zm
+
     def debug_top2_simt(self, db_image: int, q_image: int):
         n = int(self.counts[q_image])
         d1 = np.zeros(n, np.int32); i1 = np.zeros(n, np.uint32); d2 = np.zeros(n, np.int32)
@@ -133,6 +152,43 @@ class Matcher_Regions_B200:
             a, b = int(offsets[k]), int(offsets[k + 1])
             if b > a:                                                  # Matcher_Regions.cpp:99-102
                 out[pr] = ij[a:b].copy()
+            if progress is not None:
+                progress(1)
+        return out
+
+
+class Cascade_Hashing_Matcher_Regions_B200:
+    """Drop-in for Cascade_Hashing_Matcher_Regions(distRatio) on {image id: [n,128] uint8}: same pairs, same
+    per-pair content as the reference up to its two host-side clean-ups — rows are sorted by (i, j) here as
+    IndMatch::getDeduplicated does; the equal-coordinates filter needs feature positions and lives in the C++ shim."""
+
+    def __init__(self, dist_ratio: float = 0.8, primary=None, secondary=None, device: int = 0):
+        self.f_dist_ratio_ = float(dist_ratio)
+        self.primary, self.secondary, self.device = primary, secondary, device
+
+    def Match(self, regions_provider, pairs, map_PutativeMatches=None, progress=None):
+        out = {} if map_PutativeMatches is None else map_PutativeMatches
+        pairs = sorted(set((int(a), int(b)) for a, b in pairs))
+        ids = sorted(regions_provider.keys())
+        dense = {v: k for k, v in enumerate(ids)}
+        used = np.zeros(len(ids), np.uint8)
+        for a, b in pairs:
+            used[dense[a]] = 1; used[dense[b]] = 1
+        ctx = MatchContext(self.device)
+        try:
+            ctx.load([np.ascontiguousarray(regions_provider[v], np.uint8).reshape(-1, 128) for v in ids])
+            ctx.cascade_prepare(self.primary, self.secondary, used)
+            pi = np.array([dense[a] for a, _ in pairs], np.uint32)
+            pj = np.array([dense[b] for _, b in pairs], np.uint32)
+            ctx.cascade_run(pi, pj, self.f_dist_ratio_)
+            offsets, ij = ctx.fetch()
+        finally:
+            ctx.close()
+        for k, pr in enumerate(pairs):
+            a, b = int(offsets[k]), int(offsets[k + 1])
+            if b > a:
+                m = ij[a:b]
+                out[pr] = m[np.lexsort((m[:, 1], m[:, 0]))].copy()
             if progress is not None:
                 progress(1)
         return out

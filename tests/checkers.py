@@ -293,3 +293,94 @@ def golden_ext_scene(case, registered=True):
             s["prior_center"] = np.ascontiguousarray(z[case["name"] + "_prior_center"])
             s["prior_huber_a"] = float(case["prior_fit"]) ** 2
     return s
+
+
+# ----------------------------------------------------------------------------- cascade hashing (M9 / N2)
+def ref_cascade_projections():
+    P = np.zeros((128, 128), np.float32); S = np.zeros((6, 10, 128), np.float32)
+    ref_match().ref_cascade_projections(_P(P), _P(S))
+    return P, S
+
+
+def cascade_projections():
+    """The projections CascadeHasher::Init draws, from the committed fixture (generated with std::mt19937 +
+    std::normal_distribution by the compiled reference driver; tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cascade_projections.npz"))
+    return np.ascontiguousarray(z["primary"]), np.ascontiguousarray(z["secondary"])
+
+
+def oracle_cascade_zero_mean(descs, used):
+    means = np.zeros((len(used), 128), np.float32)
+    for t, k in enumerate(used):
+        d = np.ascontiguousarray(descs[int(k)].reshape(-1, 128))
+        oracle().oracle_cascade_image_mean(_P(d), len(d), _P(means[t]))
+    zm = np.zeros(128, np.float32)
+    oracle().oracle_cascade_zero_mean(_P(means), len(used), _P(zm))
+    return zm
+
+
+def oracle_cascade_hash(d, zm, P, S):
+    d = np.ascontiguousarray(d.reshape(-1, 128))
+    codes = np.zeros((len(d), 4), np.uint32); bids = np.zeros((len(d), 6), np.uint16)
+    oracle().oracle_cascade_hash(_P(d), len(d), _P(zm), _P(P), _P(S), _P(codes), _P(bids))
+    return codes, bids
+
+
+def oracle_cascade_match_pair(di, hi, dj, hj, ratio=0.8):
+    di = np.ascontiguousarray(di.reshape(-1, 128)); dj = np.ascontiguousarray(dj.reshape(-1, 128))
+    out = np.zeros(2 * max(len(dj), 1), np.uint32)
+    oracle().oracle_cascade_match_pair.restype = ctypes.c_int64
+    n = oracle().oracle_cascade_match_pair(_P(di), len(di), _P(hi[0]), _P(hi[1]), _P(dj), len(dj), _P(hj[0]), _P(hj[1]),
+                                           ctypes.c_float(ratio), _P(out))
+    return out[:2 * n].reshape(-1, 2).copy()
+
+
+def oracle_cascade_collection(descs, pi, pj, ratio=0.8, P=None, S=None):
+    """Cascade_Hashing_Matcher_Regions.cpp:38-226 over the oracle: CSR in the order of (pi, pj), each row in
+    ascending query (j) order."""
+    if P is None:
+        P, S = cascade_projections()
+    used = sorted(set(int(x) for x in pi) | set(int(x) for x in pj))
+    zm = oracle_cascade_zero_mean(descs, used)
+    hashed = {k: oracle_cascade_hash(descs[k], zm, P, S) for k in used}
+    offsets = [0]; rows = []
+    for i, j in zip(pi, pj):
+        i = int(i); j = int(j)
+        m = oracle_cascade_match_pair(descs[i], hashed[i], descs[j], hashed[j], ratio) if len(descs[i]) and len(descs[j]) else np.zeros((0, 2), np.uint32)
+        rows.append(m); offsets.append(offsets[-1] + len(m))
+    ij = np.concatenate(rows) if rows else np.zeros((0, 2), np.uint32)
+    return np.array(offsets, np.uint64), ij.astype(np.uint32), zm, hashed
+
+
+def _flat(descs):
+    counts = np.array([len(d) for d in descs], np.uint32)
+    row_start = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.uint64)
+    allrows = np.ascontiguousarray(np.concatenate([d.reshape(-1, 128) for d in descs]) if len(descs) else np.zeros((0, 128), np.uint8))
+    return counts, row_start, allrows
+
+
+def ref_cascade_collection(descs, pi, pj, ratio=0.8):
+    counts, row_start, allrows = _flat(descs)
+    pi = np.ascontiguousarray(pi, np.uint32); pj = np.ascontiguousarray(pj, np.uint32)
+    offsets = np.zeros(len(pi) + 1, np.uint64)
+    cap = int(sum(int(counts[j]) for j in pj)) + 1
+    ij = np.zeros(2 * cap, np.uint32)
+    ref_match().ref_cascade_collection.restype = ctypes.c_int64
+    n = ref_match().ref_cascade_collection(_P(allrows), _P(row_start), _P(counts), len(descs), _P(pi), _P(pj),
+                                           ctypes.c_uint64(len(pi)), ctypes.c_float(ratio), _P(offsets), _P(ij), ctypes.c_uint64(cap))
+    assert n >= 0
+    return offsets, ij[:2 * n].reshape(-1, 2).copy()
+
+
+def ref_cascade_zero_mean(descs, used):
+    counts, row_start, allrows = _flat(descs)
+    used = np.ascontiguousarray(used, np.uint32); zm = np.zeros(128, np.float32)
+    ref_match().ref_cascade_zero_mean(_P(allrows), _P(row_start), _P(counts), _P(used), len(used), _P(zm))
+    return zm
+
+
+def ref_cascade_hash(d, zm):
+    d = np.ascontiguousarray(d.reshape(-1, 128))
+    codes = np.zeros((len(d), 4), np.uint32); bids = np.zeros((len(d), 6), np.uint16)
+    ref_match().ref_cascade_hash(_P(d), len(d), _P(zm), _P(codes), _P(bids))
+    return codes, bids

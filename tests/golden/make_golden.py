@@ -81,6 +81,35 @@ def main_ext():
     np.savez_compressed(os.path.join(HERE, "reference_ba_ext.npz"), **arrays)
 
 
+CASCADE_CASES = [
+    dict(name="ragged5", counts=[300, 129, 2, 257, 1000], seed=11, ratio=0.8),
+    dict(name="three2k", counts=[2000, 1800, 1500], seed=4, ratio=0.8),
+    dict(name="ratio06", counts=[1500, 1200, 0, 900], seed=11, ratio=0.6),
+]
+
+
+def main_cascade():
+    """Cascade_Hashing_Matcher_Regions::Match (the reference's default matcher) on seeded collections, and the
+    projections CascadeHasher::Init draws (std::mt19937 + std::normal_distribution, via the reference driver)."""
+    path = os.path.join(HERE, "reference_outputs.json")
+    out = json.load(open(path))
+    out["cascade"] = []
+    P, S = ck.ref_cascade_projections()
+    np.savez_compressed(os.path.join(HERE, "cascade_projections.npz"), primary=P, secondary=S)
+    arrays = {}
+    for c in CASCADE_CASES:
+        descs = synth.descriptors(len(c["counts"]), c["counts"], seed=c["seed"])
+        pi, pj = synth.exhaustive_pairs(len(c["counts"]))
+        off, ij = ck.ref_cascade_collection(descs, pi, pj, c["ratio"])
+        fnv = int(ck.oracle().oracle_fnv1a_ij(ij.ctypes.data_as(ck.ctypes.c_void_p), ck.ctypes.c_int64(len(ij))))
+        out["cascade"].append(dict(name=c["name"], counts=c["counts"], seed=c["seed"], ratio=c["ratio"], n_matches=int(len(ij)), fnv1a=str(fnv),
+                                   offsets=[int(x) for x in off]))
+        arrays["cascade_" + c["name"]] = ij
+        print("cascade", c["name"], len(ij), fnv)
+    json.dump(out, open(path, "w"), indent=1)
+    np.savez_compressed(os.path.join(HERE, "reference_cascade_matches.npz"), **arrays)
+
+
 def main():
     out = {"match": [], "ba": []}
     arrays = {}
@@ -108,6 +137,9 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ext":      # only the GCP / prior section (keeps the rest untouched)
         main_ext()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cascade":
+        main_cascade()
     else:
         main()
         main_ext()
+        main_cascade()

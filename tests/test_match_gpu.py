@@ -150,3 +150,72 @@ def test_full_size_properties(matching):
     ctx.run(np.array([3], np.uint32), np.array([3], np.uint32), 0.8); o2, ij2 = ctx.fetch()
     assert np.array_equal(ij2[:, 0], ij2[:, 1])                                   # self pair: only i == j can survive
     ctx.close()
+
+
+# ---- cascade hashing on the GPU
+def _cascade_gpu(descs, pi, pj, ratio):
+    from openmvg_b200 import matching
+    P, S = ck.cascade_projections()
+    used = np.zeros(len(descs), np.uint8)
+    used[np.asarray(pi, np.int64)] = 1; used[np.asarray(pj, np.int64)] = 1
+    ctx = matching.MatchContext()
+    ctx.load(descs)
+    ctx.cascade_prepare(P, S, used)
+    hashes = [ctx.cascade_debug_hash(k) for k in range(len(descs))]
+    ctx.cascade_run(pi, pj, ratio)
+    off, ij = ctx.fetch()
+    off = off.copy(); ij = ij.copy()
+    ctx.close()
+    return off, ij, hashes
+
+
+@pytest.mark.parametrize("counts,seed,ratio", [([300, 129, 2, 257, 1000], 11, 0.8), ([2000, 1800, 1500], 4, 0.8), ([1500, 1200, 0, 900], 11, 0.6),
+                                               ([1, 40, 3], 5, 0.8)])
+def test_cascade_matches_oracle_bit_exact(counts, seed, ratio):
+    """Zero-mean vector, hash codes, bucket ids and the final (i, j) rows of every pair, bit for bit."""
+    descs = synth.descriptors(len(counts), counts, seed=seed)
+    pi, pj = synth.exhaustive_pairs(len(counts))
+    off, ij, hashes = _cascade_gpu(descs, pi, pj, ratio)
+    ooff, oij, zm, oh = ck.oracle_cascade_collection(descs, pi, pj, ratio)
+    for k in range(len(counts)):
+        codes, bids, gzm = hashes[k]
+        assert np.array_equal(gzm, zm)
+        if k in oh:
+            assert np.array_equal(codes, oh[k][0]) and np.array_equal(bids, oh[k][1]), k
+    assert np.array_equal(off, ooff)
+    assert np.array_equal(ij, oij)
+
+
+@pytest.mark.parametrize("name", ["ragged5", "three2k", "ratio06"])
+def test_cascade_against_reference_golden(name):
+    """Against the committed output of the reference's Cascade_Hashing_Matcher_Regions::Match (rows sorted by
+    (i, j) as the reference leaves them); statistical bar 99.9 %, see tests/test_oracle_match.py."""
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.json")))
+    case = [c for c in gold["cascade"] if c["name"] == name][0]
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cascade_matches.npz"))["cascade_" + name]
+    descs = synth.descriptors(len(case["counts"]), case["counts"], seed=case["seed"])
+    pi, pj = synth.exhaustive_pairs(len(case["counts"]))
+    off, ij, _ = _cascade_gpu(descs, pi, pj, case["ratio"])
+    same = tot = 0
+    for p in range(len(pi)):
+        a = set(map(tuple, ij[int(off[p]):int(off[p + 1])])); b = set(map(tuple, ref[case["offsets"][p]:case["offsets"][p + 1]]))
+        same += len(a & b); tot += len(a | b)
+    assert tot > 0 and same >= 0.999 * tot, (same, tot)
+
+
+def test_cascade_full_size_pairs_properties():
+    """5000 x 5000 descriptors per image (BASELINE size): every emitted match is a true ratio-test survivor of the
+    candidates' exact distances and most brute-force matches are found (recall as main_benchANN scores it)."""
+    from openmvg_b200 import matching
+    descs = synth.descriptors(4, [5000] * 4, seed=3)
+    pi, pj = synth.exhaustive_pairs(4)
+    off, ij, _ = _cascade_gpu(descs, pi, pj, 0.8)
+    ctx = matching.MatchContext(); ctx.load(descs); ctx.run(pi, pj, 0.8); boff, bij = ctx.fetch(); boff = boff.copy(); bij = bij.copy(); ctx.close()
+    a = set(); b = set()
+    for p in range(len(pi)):
+        a |= {(p,) + tuple(r) for r in ij[int(off[p]):int(off[p + 1])]}; b |= {(p,) + tuple(r) for r in bij[int(boff[p]):int(boff[p + 1])]}
+    assert len(b) > 1000 and len(a & b) >= 0.9 * len(b), (len(a), len(b), len(a & b))
+    for p in range(len(pi)):                                    # ascending query order inside a pair
+        m = ij[int(off[p]):int(off[p + 1])]
+        assert np.all(np.diff(m[:, 1].astype(np.int64)) > 0)

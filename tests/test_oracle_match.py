@@ -86,3 +86,66 @@ def test_against_compiled_reference():
         assert np.array_equal(roff, ooff) and np.array_equal(rij, oij)
     a = ck.ref_match_pair(descs[0], descs[1]); b = ck.oracle_match_pair(descs[0], descs[1])
     assert np.array_equal(a, b)
+
+
+# ---- cascade hashing: oracle vs the reference's Cascade_Hashing_Matcher_Regions
+def _sorted_rows(off, ij, p):
+    m = ij[int(off[p]):int(off[p + 1])]
+    return m[np.lexsort((m[:, 1], m[:, 0]))]
+
+
+@pytest.mark.parametrize("case", GOLD.get("cascade", []), ids=lambda c: c["name"])
+def test_cascade_golden(case):
+    """Whole pipeline (zero-mean, hashing, buckets, Hamming top-10, exact L2 top-2, ratio) against the committed
+    output of the reference's Cascade_Hashing_Matcher_Regions::Match.  The reference sorts each pair's matches by
+    (i, j); the oracle emits them in query order, so rows are compared after that sort.  The hashing is a float
+    mat-vec whose summation order differs (Eigen GEMV vs k-ascending here): a projection within rounding of zero
+    could flip a bit, so the bar is statistical (>= 99.9 % of the matches identical); on these cases it is exact."""
+    descs = synth.descriptors(len(case["counts"]), case["counts"], seed=case["seed"])
+    pi, pj = synth.exhaustive_pairs(len(case["counts"]))
+    off, ij, _, _ = ck.oracle_cascade_collection(descs, pi, pj, case["ratio"])
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cascade_matches.npz"))["cascade_" + case["name"]]
+    goff = case["offsets"]
+    same = tot = 0
+    for p in range(len(pi)):
+        a = set(map(tuple, _sorted_rows(off, ij, p))); b = set(map(tuple, gold[goff[p]:goff[p + 1]]))
+        same += len(a & b); tot += len(a | b)
+    assert tot == 0 or same >= 0.999 * tot, (same, tot)
+    assert tot > 0 or case["n_matches"] == 0
+
+
+@pytest.mark.skipif(not ck.have_ref_match(), reason="oracle/_ref not built")
+def test_cascade_stages_against_compiled_reference():
+    descs = synth.descriptors(3, [1200, 1000, 700], seed=21)
+    P, S = ck.ref_cascade_projections()
+    Pg, Sg = ck.cascade_projections()
+    assert np.array_equal(P, Pg) and np.array_equal(S, Sg)            # the committed fixture is the reference's draw
+    used = [0, 1, 2]
+    zo = ck.oracle_cascade_zero_mean(descs, used); zr = ck.ref_cascade_zero_mean(descs, used)
+    assert np.array_equal(zo, zr)
+    bits = diff = 0
+    for d in descs:
+        co, bo = ck.oracle_cascade_hash(d, zr, P, S); cr, br = ck.ref_cascade_hash(d, zr)
+        diff += sum(bin(int(x)).count("1") for x in (co ^ cr).ravel()) + sum(bin(int(x)).count("1") for x in (bo ^ br).ravel())
+        bits += co.size * 32 + bo.size * 10
+    assert diff <= 1e-5 * bits, (diff, bits)
+    pi, pj = synth.exhaustive_pairs(3)
+    off, ij, _, _ = ck.oracle_cascade_collection(descs, pi, pj, 0.8, P, S)
+    roff, rij = ck.ref_cascade_collection(descs, pi, pj, 0.8)
+    same = tot = 0
+    for p in range(len(pi)):
+        a = set(map(tuple, _sorted_rows(off, ij, p))); b = set(map(tuple, rij[int(roff[p]):int(roff[p + 1])]))
+        same += len(a & b); tot += len(a | b)
+    assert tot > 50 and same >= 0.999 * tot, (same, tot)
+
+
+def test_cascade_recall_against_brute_force():
+    """What main_benchANN scores: the approximate matcher against the exhaustive one (same ratio test)."""
+    descs = synth.descriptors(3, [1500, 1500, 1500], seed=8)
+    pi, pj = synth.exhaustive_pairs(3)
+    off, ij, _, _ = ck.oracle_cascade_collection(descs, pi, pj, 0.8)
+    boff, bij = ck.oracle_match_collection(descs, pi, pj, 0.8)
+    a = set(); b = set()
+    for p in range(len(pi)):
+        a |= {(p,) + tuple(r) for r in ij[int(off[p]):int(off[p + 1])]}; b |= {(p,) + tuple(r) for r in bij[int(boff[p]):int(boff[p + 1])]}
+    assert len(b) > 100 and len(a & b) >= 0.9 * len(b), (len(a), len(b), len(a & b))
