@@ -410,7 +410,7 @@ __global__ void decode_k12_kernel(const int2 *__restrict__ k12, const int32_t *_
 // 128-bit sign code + 6 x 10-bit bucket ids per descriptor, candidates = union of the query's 6 buckets in the
 // database image, first 10 by (Hamming, insertion order), exact L2 on those, top-2 by (distance, id), ratio test.
 // Everything after the hashing is exact integer work; the hashing is a float mat-vec whose summation order is
-// fixed here (k ascending, separate multiply and add) and mirrored by oracle/cascade_oracle.c.
+// fixed here (k ascending, separate multiply and add); the CPU checker used by the tests mirrors it.
 constexpr int CH_GROUPS = 6, CH_BITS = 10, CH_NB = 1 << CH_BITS, CH_OUT = OMVG_DESC_LEN + CH_GROUPS * CH_BITS, CH_TOP = 10;
 constexpr int CH_HASH_THREADS = 192, CH_HASH_ROWS = 16;
 
@@ -905,7 +905,7 @@ int omvg_match_fetch(omvg_match_ctx *c, const uint64_t **offsets, const uint32_t
   OMVG_CUDA(cudaMemcpyAsync(c->h_offsets, c->d_offsets, no * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
   if (c->n_pairs_last == 0) { OMVG_CUDA(cudaStreamSynchronize(c->stream)); c->h_offsets[0] = 0; }
   const size_t nm = c->total_last;
-  if (nm > c->h_ij_cap) { if (c->h_ij) cudaFreeHost(c->h_ij); c->h_ij = nullptr; c->h_ij_cap = 0;
+  if (nm > c->h_ij_cap || !c->h_ij) { if (c->h_ij) cudaFreeHost(c->h_ij); c->h_ij = nullptr; c->h_ij_cap = 0;
     OMVG_CUDA(cudaMallocHost(&c->h_ij, std::max<size_t>(nm, 1) * 2 * sizeof(uint32_t))); c->h_ij_cap = std::max<size_t>(nm, 1); }
   if (nm) OMVG_CUDA(cudaMemcpyAsync(c->h_ij, c->d_out, nm * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
   OMVG_CUDA(cudaStreamSynchronize(c->stream));

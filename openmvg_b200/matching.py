@@ -81,7 +81,7 @@ class MatchContext:
         check(lib().omvg_match_fetch(self._h, ctypes.byref(off), ctypes.byref(ij), ctypes.byref(n)))
         npairs = len(self._pi)
         offsets = np.ctypeslib.as_array(off, (npairs + 1,)).copy()
-        m = np.ctypeslib.as_array(ij, (max(n.value, 1) * 2,))[: 2 * n.value].reshape(-1, 2).copy()
+        m = (np.ctypeslib.as_array(ij, (n.value * 2,)).reshape(-1, 2).copy() if n.value else np.zeros((0, 2), np.uint32))
         return offsets, m
 
     def launch_count(self) -> int:

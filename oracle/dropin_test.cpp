@@ -16,12 +16,15 @@
 #include "openMVG/sfm/sfm_view_priors.hpp"
 
 #include "../openmvg_b200/host/Bundle_Adjustment_B200.hpp"
+#include "../openmvg_b200/host/Cascade_Hashing_Matcher_Regions_B200.hpp"
+#include "openMVG/matching_image_collection/Cascade_Hashing_Matcher_Regions.hpp"
 #include "../openmvg_b200/host/Matcher_Regions_B200.hpp"
 
 #include <cmath>
 #include <cstdio>
 #include <memory>
 #include <random>
+#include <set>
 
 using namespace openMVG;
 using namespace openMVG::cameras;
@@ -151,6 +154,36 @@ int main()
     }
     std::printf("MATCH drop-in: %zu pairs with matches, %zu matches, %s\n", ref.size(), total, same ? "IDENTICAL" : "DIFFERENT");
     if (!same || total == 0) ++failures;
+  }
+  // ------------------------------------------------------------------ MATCH, cascade hashing (the CLI default)
+  {
+    auto provider = std::make_shared<InMemory_Regions_Provider>();
+    provider->set_type(new features::SIFT_Regions);
+    const int counts[5] = {1400, 1250, 0, 900, 3};
+    std::shared_ptr<features::SIFT_Regions> prev;
+    for (int k = 0; k < 5; ++k) { auto r = random_regions(counts[k], 300 + k, prev.get()); provider->set(3 * k + 1, r); if (counts[k] > 3) prev = r; }
+    Pair_Set pairs;
+    for (int a = 0; a < 5; ++a) for (int b = a + 1; b < 5; ++b) pairs.insert({3 * a + 1, 3 * b + 1});
+    matching::PairWiseMatches ref, ours;
+    std::unique_ptr<matching_image_collection::Matcher> m_ref(new matching_image_collection::Cascade_Hashing_Matcher_Regions(0.8f));
+    std::unique_ptr<matching_image_collection::Matcher> m_b200(new matching_image_collection::Cascade_Hashing_Matcher_Regions_B200(0.8f));
+    m_ref->Match(provider, pairs, ref, nullptr);
+    m_b200->Match(provider, pairs, ours, nullptr);
+    size_t total = 0, same = 0, uni = 0;
+    for (const auto & kv : ref) {
+      total += kv.second.size();
+      const auto it = ours.find(kv.first);
+      std::set<std::pair<IndexT, IndexT>> a, b;
+      for (const auto & m : kv.second) a.insert({m.i_, m.j_});
+      if (it != ours.end()) for (const auto & m : it->second) b.insert({m.i_, m.j_});
+      for (const auto & x : a) if (b.count(x)) ++same;
+      std::set<std::pair<IndexT, IndexT>> u(a); u.insert(b.begin(), b.end()); uni += u.size();
+    }
+    for (const auto & kv : ours) if (!ref.count(kv.first)) uni += kv.second.size();
+    std::printf("MATCH cascade drop-in: %zu pairs with matches, %zu reference matches, %zu identical of %zu in the union (%s)\n",
+                ref.size(), total, same, uni, same == uni ? "IDENTICAL" : "statistical");
+    // the hashing is a float mat-vec whose summation order differs from Eigen's: identical up to rare sign flips
+    if (total == 0 || same < 0.999 * uni) ++failures;
   }
   // ------------------------------------------------------------------ BA
   {
