@@ -503,6 +503,43 @@ __global__ void __launch_bounds__(256) cascade_query_kernel(const uint8_t *__res
       // first CH_TOP unique candidates by (Hamming, position in the concatenated bucket lists): CH_TOP selection rounds
       // over the (short) lists; a candidate is a duplicate iff it already sat in the query's bucket of an earlier group
       uint32_t last = 0, my_sel = 0; int nsel = 0;
+      if (tot <= 128) {
+        // common case: every candidate's (Hamming, position | id) key is formed ONCE into 4 registers per lane, then
+        // CH_TOP rounds of warp-min pick the winners (the streaming form below re-reads the lists every round)
+        unsigned long long kk[4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          kk[i] = 0xffffffffffffffffull;
+          uint32_t pp = lane + 32 * i;
+          if (pp < tot) {
+            const uint32_t pos = pp; int g = 0; uint32_t sg = 0;
+            bool found = false;
+            #pragma unroll
+            for (int g2 = 0; g2 < CH_GROUPS; ++g2) if (!found) { if (pp < len[g2]) { g = g2; sg = s[g2]; found = true; } else pp -= len[g2]; }
+            const uint32_t id = bitems[sg + pp], row = P.db_row0 + id;
+            const uint4 cb = bid[row];
+            const uint32_t cbv[6] = {cb.x & 0xffffu, cb.x >> 16, cb.y & 0xffffu, cb.y >> 16, cb.z & 0xffffu, cb.z >> 16};
+            bool dup = false;
+            #pragma unroll
+            for (int g2 = 0; g2 < CH_GROUPS; ++g2) if (g2 < g && cbv[g2] == qb[g2]) dup = true;
+            if (!dup) {
+              const uint4 cc = code[row];
+              const uint32_t ham = __popc(cc.x ^ qc.x) + __popc(cc.y ^ qc.y) + __popc(cc.z ^ qc.z) + __popc(cc.w ^ qc.w);
+              kk[i] = ((unsigned long long)((ham << 24) | pos) << 32) | id;
+            }
+          }
+        }
+        for (int r = 0; r < CH_TOP; ++r) {
+          unsigned long long m = min(min(kk[0], kk[1]), min(kk[2], kk[3]));
+          #pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+          if (m == 0xffffffffffffffffull) break;
+          #pragma unroll
+          for (int i = 0; i < 4; ++i) if (kk[i] == m) kk[i] = 0xffffffffffffffffull;
+          if (lane == r) my_sel = (uint32_t)(m & 0xffffffffull);
+          ++nsel;
+        }
+      } else
       for (int r = 0; r < CH_TOP; ++r) {
         uint32_t best = 0xffffffffu, base = 0;
         #pragma unroll

@@ -219,3 +219,22 @@ def test_cascade_full_size_pairs_properties():
     for p in range(len(pi)):                                    # ascending query order inside a pair
         m = ij[int(off[p]):int(off[p + 1])]
         assert np.all(np.diff(m[:, 1].astype(np.int64)) > 0)
+
+
+def test_cascade_large_buckets_take_the_streaming_path():
+    """More than 128 candidates per query (many near-identical descriptors share buckets): the streaming selection
+    rounds, duplicate suppression across groups and the (Hamming, insertion order) tie-breaks, bit for bit."""
+    rng = np.random.default_rng(5)
+    descs = synth.descriptors(3, [900, 800, 700], seed=9)
+    for d in descs:                                            # 300 rows of each image collapse onto 3 prototypes +-1
+        for k in range(3):
+            rows = slice(100 * k, 100 * k + 100)
+            d[rows] = np.clip(d[100 * k].astype(np.int16) + rng.integers(-1, 2, (100, 128)), 0, 255).astype(np.uint8)
+    descs[1][:300] = descs[0][:300]                            # and the same prototypes across images
+    pi, pj = synth.exhaustive_pairs(3)
+    off, ij, hashes = _cascade_gpu(descs, pi, pj, 0.8)
+    ooff, oij, zm, oh = ck.oracle_cascade_collection(descs, pi, pj, 0.8)
+    assert np.array_equal(off, ooff) and np.array_equal(ij, oij)
+    # the case really exercises more than 128 candidates per query (query 0 of image 1 against image 0)
+    tot = sum(int((oh[0][1][:, g] == oh[1][1][0, g]).sum()) for g in range(6))
+    assert tot > 128, tot
