@@ -199,6 +199,23 @@ def run_ours(args):
                   kernel="match_tc_kernel (tcgen05 kind::i8 + fused top-2)", launches=tc_n, avg_ms=tc_s * 1e3,
                   peak_source=f"2 x {pk['src']} bf16 sustained (INT8 dense rate = 2 x bf16)")
     m_roof["frac"] = m_roof["achieved"] / m_roof["peak"]
+    # cascade hashing (openMVG's default matcher) on the same pair shard: reported next to the
+    # exhaustive matcher, not part of the headline (its parity against the reference is statistical)
+    cascade = None
+    try:
+        z_ = np.load(os.path.join(ROOT, "tests", "golden", "cascade_projections.npz"))      # CascadeHasher::Init's draw (fixture)
+        P_, S_ = z_["primary"], z_["secondary"]
+        mctx.cascade_prepare(P_, S_, None); mctx.cascade_run(mpi, mpj, 0.8); mctx.sync()
+        barrier(); t0 = time.perf_counter()
+        for _ in range(K):
+            mctx.cascade_run(mpi, mpj, 0.8)
+        mctx.sync(); barrier()
+        c_wall = allmax(time.perf_counter() - t0)
+        cascade = {"ms_per_step": c_wall * 1e3 / K, "pairs_per_s": allsum(float(len(mpi))) * K / c_wall,
+                   "matches_rank0": int(len(mctx.fetch()[1])), "exhaustive_matches_rank0": int(n_matches),
+                   "note": "same pairs through omvg_match_cascade_run (hash tables resident); reference = Cascade_Hashing_Matcher_Regions"}
+    except Exception as e:                                     # the fixture with the reference's projections is test data
+        cascade = {"unavailable": str(e)[:120]}
     mctx.close()
 
     if rank == 0:
@@ -216,7 +233,7 @@ def run_ours(args):
                                  "l2": "descriptor arena 128 MB + per-pair results 815 MB: larger than L2", "matches_rank0": int(n_matches)},
                       "e2e": {"value": total_pairs * me_steps / me_wall, "unit": "desc-pairs/s", "h2d_bytes_per_step": n_img * MATCH_DESC * 128 + 8 * len(mpi),
                               "d2h_bytes_per_step": int(8 * (len(mpi) + 1) + 8 * n_matches), "ms_per_step": me_wall * 1e3 / me_steps},
-                      "roofline": m_roof},
+                      "roofline": m_roof, "cascade_hashing": cascade},
         }
         if not args.no_cpu and world == 1:
             line["cpu_baseline"], line["match"]["cpu_baseline"] = cpu_baselines(scene, args)
