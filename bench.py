@@ -289,7 +289,7 @@ def run_reference(args):
     ba_cpu, m_cpu = cpu_baselines(scene, args)
     line = {"impl": "reference", "metric": "BA LM-iters/sec", "value": ba_cpu["value"], "unit": "LM-iter/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ba_cpu.get("minimizer_s", 0) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BA 1000 cams / 100k pts / 1M obs, 1 shared pinhole intrinsic, Huber(16), refine all (BASELINE configs[1])"},
+            "config": {"workload": "BA 1000 cams / 100k pts / 1M obs, 1 shared pinhole intrinsic, Huber(16), refine all (BASELINE configs[1]); replica per GPU"},
             "cpu_baseline": ba_cpu, "e2e": {"value": ba_cpu["value"], "unit": "LM-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "match": {"metric": "desc-pairs/sec", "value": m_cpu["value"], "unit": "desc-pairs/s", "cpu_baseline": m_cpu,
