@@ -14,7 +14,9 @@ for C in sizes:
     s = synth.ba_scene(C, 50 * C, 10)
     ctx = ba.BAContext(s); ctx.run(); ctx.reset()
     g = ctx.run(); ctx.close()
-    t0 = time.perf_counter(); e = ba.solve(s); e2e = time.perf_counter() - t0
+    e2e = 1e9
+    for _ in range(2):                                     # best of two: the first call at a new size may pay cudaMalloc
+        t0 = time.perf_counter(); e = ba.solve(s); e2e = min(e2e, time.perf_counter() - t0)
     best = None
     for th in (8, 32):
         r = ck.ref_ba_adjust(s, threads=th)
