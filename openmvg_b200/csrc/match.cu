@@ -1002,6 +1002,7 @@ int omvg_match_cascade_prepare(omvg_match_ctx *c, const float *primary, const fl
   cudaFree(c->d_bstart); cudaFree(c->d_bitems); c->d_bstart = c->d_bitems = nullptr;
   OMVG_CUDA(cudaMalloc(&c->d_bstart, ((size_t)n_buckets + 1) * sizeof(uint32_t))); OMVG_CUDA(cudaMalloc(&c->d_bitems, std::max<uint64_t>(1, n_keys) * sizeof(uint32_t)));
   uint32_t *d_real0 = nullptr; unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; void *d_tmp = nullptr;
+  struct Scratch { uint32_t *&a; unsigned long long *&b, *&c; void *&d; ~Scratch() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); } } scratch{d_real0, d_keys, d_keys2, d_tmp};   // freed on every exit
   OMVG_CUDA(cudaMalloc(&d_real0, (ni + 1) * sizeof(uint32_t)));
   OMVG_CUDA(cudaMemcpyAsync(d_real0, real0.data(), (ni + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   OMVG_CUDA(cudaMalloc(&d_keys, std::max<uint64_t>(1, n_keys) * 8)); OMVG_CUDA(cudaMalloc(&d_keys2, std::max<uint64_t>(1, n_keys) * 8));
@@ -1016,7 +1017,6 @@ int omvg_match_cascade_prepare(omvg_match_ctx *c, const float *primary, const fl
   cascade_starts_kernel<<<(unsigned)((n_keys + 256) / 256), 256, 0, st>>>(d_keys2, n_keys, n_buckets, c->d_bstart, c->d_bitems); OMVG_CUDA(cudaGetLastError());
   c->launches++;
   OMVG_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_real0); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_tmp);
   c->cascade_ready = true; return OMVG_OK;
 }
 
