@@ -604,8 +604,13 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
           static const bool use_chol = getenv("OMVG_BA_COARSE_CHOL") != nullptr;
           if (!use_chol) {                                        // blocked Gauss-Jordan, in place: cE becomes E^-1
             double *Ep = c->cE.p, *Tp = c->cT.p; int nn = nco; int *fp = c->fail.p;
-            void *cargs[] = {&Ep, &nn, &Tp, &fp};
+            static const bool gj_timing = getenv("OMVG_BA_GJ_TIMING") != nullptr;
+            unsigned long long *tp = nullptr;
+            if (gj_timing) { if (!c->pcg_tim.p) { if ((rc = c->pcg_tim.alloc(8))) return rc; } OMVG_CUDA(cudaMemsetAsync(c->pcg_tim.p, 0, 64, c->stream)); tp = c->pcg_tim.p; }
+            void *cargs[] = {&Ep, &nn, &Tp, &fp, &tp};
             OMVG_CUDA(cudaLaunchCooperativeKernel((void *)coarse_invert_kernel, dim3(c->gj_grid), dim3(256), cargs, 0, c->stream));
+            if (gj_timing) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
+              fprintf(stderr, "[omvg_ba gj timing] us: pivot inverse %.1f slices %.1f sync %.1f tiles %.1f sync %.1f (n %d, %d CTAs)\n", h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, h[4] * 1e-3, nco, c->gj_grid); }
             P3.Einv = c->cE.p;
           } else
           { const size_t sm = sizeof(double) * ((size_t)CNB * CNB + 2 * CT * (CNB + 1) + 2 * CT * (CT + 1));

@@ -1680,7 +1680,9 @@ __global__ void __launch_bounds__(256) coarse_setup_kernel(double *__restrict__ 
 //   phase 2 (tiles):     A_ij <- A_ij - Cold_i H_j  (i,j not in K);  A_Kj <- H_j;  A_iK <- Gn_i;  A_KK <- B
 // A is symmetrised (+ tiny ridge) first; SPD input needs no pivoting (every pivot block is a Schur complement).
 constexpr int GJ_B = 32;
-__global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__ A, int n, double *__restrict__ tmp, int *__restrict__ fail) {
+__device__ __forceinline__ unsigned long long gtimer2() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define GJ_LAP(k) do { if (tim && tid == 0) { const unsigned long long now_ = gtimer2(); tim[k] += now_ - tlast; tlast = now_; } } while (0)
+__global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__ A, int n, double *__restrict__ tmp, int *__restrict__ fail, unsigned long long *__restrict__ tim) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double Bs[GJ_B][GJ_B + 1];
   __shared__ double As[CT][GJ_B + 1];
@@ -1705,6 +1707,7 @@ __global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__
   grid.sync();
   const int mt = (n + CT - 1) / CT;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  unsigned long long tlast = tim ? gtimer2() : 0ull;
   for (int k0 = 0; k0 < n; k0 += GJ_B) {
     const int nb = min(GJ_B, n - k0);
     // ---- phase 1: B = inv(A_KK) (Gauss-Jordan in shared memory, 256 threads), identity-padded to 32
@@ -1726,6 +1729,7 @@ __global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__
       __syncthreads();
     }
     // slices of Cold / H / Gn
+    GJ_LAP(0);
     // (all 32 operand loads of a slice element are issued before the first FMA: L1 is cold after a grid sync and a
     // dependent L2 round trip costs ~0.5 us; Bs is identity-padded, so out-of-range pivots contribute zeros)
     for (long long idx = tid; idx < (long long)n * GJ_B; idx += nt) {
@@ -1749,7 +1753,9 @@ __global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__
       for (int p2 = 0; p2 < GJ_B; ++p2) h += Bs[q][p2] * av[p2];
       H[idx] = q < nb ? h : 0.0;
     }
+    GJ_LAP(1);
     grid.sync();
+    GJ_LAP(2);
     // ---- phase 2: tiles
     for (int t = blockIdx.x; t < mt * mt; t += gridDim.x) {
       const int i0 = (t / mt) * CT, j0 = (t % mt) * CT;
@@ -1785,7 +1791,9 @@ __global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__
           A[(size_t)r * n + c2] = v;
         }
     }
+    GJ_LAP(3);
     grid.sync();
+    GJ_LAP(4);
   }
 }
 
