@@ -1682,7 +1682,10 @@ __global__ void __launch_bounds__(256) coarse_setup_kernel(double *__restrict__ 
 constexpr int GJ_B = 32;
 __device__ __forceinline__ unsigned long long gtimer2() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define GJ_LAP(k) do { if (tim && tid == 0) { const unsigned long long now_ = gtimer2(); tim[k] += now_ - tlast; tlast = now_; } } while (0)
-__global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__ A, int n, double *__restrict__ tmp, int *__restrict__ fail, unsigned long long *__restrict__ tim) {
+// Measured per inversion at n = 875 (28 pivot steps, us): pivot-block inverse 533, slices 64, tiles 172, grid syncs 145.
+// The 32 sequential pivots of a block (an FP64 reciprocal and two barriers each) are the critical path; a one-warp
+// register-resident variant with shuffle broadcasts was twice slower (1050 us) and was dropped.
+__global__ void __launch_bounds__(256, 2) coarse_invert_kernel(double *__restrict__ A, int n, double *__restrict__ tmp, int *__restrict__ fail, unsigned long long *__restrict__ tim) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double Bs[GJ_B][GJ_B + 1];
   __shared__ double As[CT][GJ_B + 1];
@@ -1763,11 +1766,15 @@ __global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__
       for (int idx = threadIdx.x; idx < CT * GJ_B; idx += 256) { const int r = idx >> 5, q = idx & 31; As[r][q] = i0 + r < n ? Cold[(size_t)(i0 + r) * GJ_B + q] : 0.0; }
       for (int idx = threadIdx.x; idx < CT * GJ_B; idx += 256) { const int q = idx / CT, c2 = idx % CT; Hs[q][c2] = j0 + c2 < n ? H[(size_t)q * n + j0 + c2] : 0.0; }
       __syncthreads();
-      double acc[4][4];
+      double acc[4][4], aold[4][4];                            // the tile's old values are fetched under the product
       #pragma unroll
       for (int p2 = 0; p2 < 4; ++p2)
         #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[p2][q] = 0.0;
+        for (int q = 0; q < 4; ++q) {
+          acc[p2][q] = 0.0;
+          const int r = i0 + ty + 16 * p2, c2 = j0 + tx + 16 * q;
+          aold[p2][q] = (r < n && c2 < n) ? __ldcg(A + (size_t)r * n + c2) : 0.0;
+        }
       #pragma unroll 8
       for (int kk = 0; kk < GJ_B; ++kk) {
         double av[4], bv[4];
@@ -1787,7 +1794,7 @@ __global__ void __launch_bounds__(256) coarse_invert_kernel(double *__restrict__
           const bool rk = r >= k0 && r < k0 + nb, ck = c2 >= k0 && c2 < k0 + nb;
           double v;
           if (rk) v = ck ? Bs[r - k0][c2 - k0] : Hs[r - k0][tx + 16 * q];
-          else v = ck ? Gn[(size_t)r * GJ_B + (c2 - k0)] : A[(size_t)r * n + c2] - acc[p2][q];
+          else v = ck ? Gn[(size_t)r * GJ_B + (c2 - k0)] : aold[p2][q] - acc[p2][q];
           A[(size_t)r * n + c2] = v;
         }
     }
