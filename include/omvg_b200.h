@@ -117,6 +117,18 @@ int omvg_match_debug_top2_simt(omvg_match_ctx *ctx, uint32_t db_image, uint32_t 
 int omvg_match_debug_top2_tc(omvg_match_ctx *ctx, uint32_t db_image, uint32_t q_image,
                              int32_t *d1, uint32_t *group1, int32_t *d2_upper);
 
+/* ---- descriptor / match file IO feeding the matcher ----------------------------------
+ * omvg_match_load_desc_files = omvg_match_set_images + uploads + omvg_match_prepare from openMVG ".desc" files
+ * (features/descriptor.hpp:182-203: size_t count, then count x 128 bytes), read by a pool of host threads into
+ * one page-locked buffer and uploaded as each read completes — what Regions_Provider::load
+ * (sfm/pipelines/sfm_regions_provider.hpp:88-138) does one std::vector at a time.  counts_out may be NULL. */
+int omvg_match_load_desc_files(omvg_match_ctx *ctx, uint32_t n_images, const char *const *desc_paths, uint32_t *counts_out);
+/* Writes a CSR result (omvg_match_fetch layout; pair_I / pair_J = the view ids to record) as openMVG's
+ * "matches.*.txt" or "matches.*.bin" (matching::Save, matching/indMatch_utils.cpp:80-131; the extension picks the
+ * format).  Pairs are written in std::map<Pair,...> order, pairs without matches are skipped. */
+int omvg_matches_save(const char *path, uint64_t n_pairs, const uint32_t *pair_I, const uint32_t *pair_J,
+                      const uint64_t *offsets, const uint32_t *ij);
+
 /* ===================================================================== BA ================= */
 #define OMVG_BA_INTR_STRIDE 8   /* doubles reserved per intrinsic block */
 

@@ -9,6 +9,7 @@ regions provider (image id -> [n,128] uint8 descriptors), a set of pairs, an out
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -62,6 +63,14 @@ class MatchContext:
         for k, d in enumerate(descs):
             self.upload_host(k, d)
         self.prepare()
+
+    def load_desc_files(self, paths):
+        """set_images + parallel read of openMVG '.desc' files into pinned memory + upload + prepare (N3)."""
+        arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        counts = np.zeros(len(paths), np.uint32)
+        check(lib().omvg_match_load_desc_files(self._h, len(paths), arr, _p(counts)))
+        self.counts = counts
+        return counts
 
     # ---- matching
     def run(self, pair_i, pair_j, dist_ratio: float = 0.8):
@@ -192,3 +201,17 @@ class Cascade_Hashing_Matcher_Regions_B200:
             if progress is not None:
                 progress(1)
         return out
+
+
+def save_matches(path: str, pair_I, pair_J, offsets, ij) -> None:
+    """Write a CSR result as openMVG's matches.*.txt / matches.*.bin (matching::Save; extension picks the format)."""
+    pI = np.ascontiguousarray(pair_I, np.uint32); pJ = np.ascontiguousarray(pair_J, np.uint32)
+    off = np.ascontiguousarray(offsets, np.uint64); m = np.ascontiguousarray(ij, np.uint32).reshape(-1)
+    check(lib().omvg_matches_save(os.fsencode(path), ctypes.c_uint64(len(pI)), _p(pI), _p(pJ), _p(off), _p(m)))
+
+
+def write_desc_file(path: str, desc: np.ndarray) -> None:
+    """openMVG '.desc' layout (features/descriptor.hpp:206-228): size_t count, then count x 128 bytes."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 128)
+    with open(path, "wb") as f:
+        f.write(np.uint64(len(d)).tobytes()); f.write(d.tobytes())

@@ -14,6 +14,8 @@
 // Built by oracle/Makefile into oracle/_ref/libref_match.so (git-ignored; shipped by gpurun).
 #include "openMVG/features/regions_factory.hpp"
 #include "openMVG/matching/indMatch.hpp"
+#include "openMVG/matching/indMatch_utils.hpp"
+#include "openMVG/features/descriptor.hpp"
 #include "openMVG/matching/metric.hpp"
 #include "openMVG/matching/regions_matcher.hpp"
 #include "openMVG/matching_image_collection/Matcher_Regions.hpp"
@@ -176,6 +178,42 @@ int64_t ref_cascade_collection(const uint8_t * desc, const uint64_t * row_start,
   }
   offsets[n_pairs] = w;
   return int64_t(total);
+}
+
+// ---- file formats: the reference's own writers / readers
+int ref_save_descs(const char * path, const uint8_t * desc, uint32_t n)
+{
+  std::vector<features::Descriptor<unsigned char, 128>, Eigen::aligned_allocator<features::Descriptor<unsigned char, 128>>> v(n);
+  for (uint32_t i = 0; i < n; ++i) std::memcpy(v[i].data(), desc + size_t(i) * 128, 128);
+  return features::saveDescsToBinFile(path, v) ? 0 : 1;                // features/descriptor.hpp:206-228
+}
+
+int ref_save_matches(const char * path, uint64_t n_pairs, const uint32_t * pI, const uint32_t * pJ, const uint64_t * offsets, const uint32_t * ij)
+{
+  matching::PairWiseMatches m;
+  for (uint64_t p = 0; p < n_pairs; ++p) {
+    if (offsets[p + 1] == offsets[p]) continue;
+    matching::IndMatches v;
+    for (uint64_t k = offsets[p]; k < offsets[p + 1]; ++k) v.emplace_back(ij[2 * k], ij[2 * k + 1]);
+    m[{pI[p], pJ[p]}] = std::move(v);
+  }
+  return matching::Save(m, path) ? 0 : 1;                              // matching/indMatch_utils.cpp:80-131
+}
+
+// matching::Load (indMatch_utils.cpp:31-78); returns the number of pairs or -1.
+int64_t ref_load_matches(const char * path, uint64_t cap_pairs, uint32_t * pI, uint32_t * pJ, uint64_t * offsets, uint64_t cap_m, uint32_t * ij)
+{
+  matching::PairWiseMatches m;
+  if (!matching::Load(m, path)) return -1;
+  uint64_t p = 0, w = 0;
+  for (const auto & kv : m) {
+    if (p >= cap_pairs || w + kv.second.size() > cap_m) return -2;
+    pI[p] = kv.first.first; pJ[p] = kv.first.second; offsets[p] = w;
+    for (const auto & x : kv.second) { ij[2 * w] = x.i_; ij[2 * w + 1] = x.j_; ++w; }
+    ++p;
+  }
+  offsets[p] = w;
+  return int64_t(p);
 }
 
 }  // extern "C"

@@ -384,3 +384,23 @@ def ref_cascade_hash(d, zm):
     codes = np.zeros((len(d), 4), np.uint32); bids = np.zeros((len(d), 6), np.uint16)
     ref_match().ref_cascade_hash(_P(d), len(d), _P(zm), _P(codes), _P(bids))
     return codes, bids
+
+
+# ----------------------------------------------------------------------------- file formats (N3)
+def ref_save_descs(path, d):
+    d = np.ascontiguousarray(d, np.uint8).reshape(-1, 128)
+    assert ref_match().ref_save_descs(os.fsencode(path), _P(d), len(d)) == 0
+
+
+def ref_save_matches(path, pI, pJ, offsets, ij):
+    pI = np.ascontiguousarray(pI, np.uint32); pJ = np.ascontiguousarray(pJ, np.uint32)
+    off = np.ascontiguousarray(offsets, np.uint64); m = np.ascontiguousarray(ij, np.uint32).reshape(-1)
+    assert ref_match().ref_save_matches(os.fsencode(path), ctypes.c_uint64(len(pI)), _P(pI), _P(pJ), _P(off), _P(m)) == 0
+
+
+def ref_load_matches(path, cap_pairs=100000, cap_m=10000000):
+    pI = np.zeros(cap_pairs, np.uint32); pJ = np.zeros(cap_pairs, np.uint32); off = np.zeros(cap_pairs + 1, np.uint64); ij = np.zeros(2 * cap_m, np.uint32)
+    ref_match().ref_load_matches.restype = ctypes.c_int64
+    n = ref_match().ref_load_matches(os.fsencode(path), ctypes.c_uint64(cap_pairs), _P(pI), _P(pJ), _P(off), ctypes.c_uint64(cap_m), _P(ij))
+    assert n >= 0, n
+    return pI[:n].copy(), pJ[:n].copy(), off[:n + 1].copy(), ij[:2 * int(off[n])].reshape(-1, 2).copy()

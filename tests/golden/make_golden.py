@@ -110,6 +110,16 @@ def main_cascade():
     np.savez_compressed(os.path.join(HERE, "reference_cascade_matches.npz"), **arrays)
 
 
+def main_io():
+    """File-format fixtures written by the reference's own writers (matching::Save, saveDescsToBinFile)."""
+    pI = np.array([7, 2, 2, 9, 4], np.uint32); pJ = np.array([9, 5, 3, 11, 6], np.uint32)
+    off = np.concatenate([[0], np.cumsum([3, 2, 4, 0, 1])]).astype(np.uint64)
+    ij = np.random.default_rng(0).integers(0, 5000, (int(off[-1]), 2)).astype(np.uint32)
+    for ext in ("txt", "bin"):
+        ck.ref_save_matches(os.path.join(HERE, f"matches_fixture.{ext}"), pI, pJ, off, ij)
+    ck.ref_save_descs(os.path.join(HERE, "desc_fixture.desc"), synth.descriptors(1, [37], seed=3)[0])
+
+
 def main():
     out = {"match": [], "ba": []}
     arrays = {}
@@ -139,7 +149,10 @@ if __name__ == "__main__":
         main_ext()
     elif len(sys.argv) > 1 and sys.argv[1] == "cascade":
         main_cascade()
+    elif len(sys.argv) > 1 and sys.argv[1] == "io":
+        main_io()
     else:
         main()
         main_ext()
         main_cascade()
+        main_io()

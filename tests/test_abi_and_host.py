@@ -101,3 +101,44 @@ def test_pair_sharding_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+# ---- file formats: host-side, no GPU needed
+def _sample_csr():
+    pI = np.array([7, 2, 2, 9, 4], np.uint32); pJ = np.array([9, 5, 3, 11, 6], np.uint32)      # unsorted, one empty pair
+    counts = [3, 2, 4, 0, 1]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+    rng = np.random.default_rng(0)
+    ij = rng.integers(0, 5000, (int(off[-1]), 2)).astype(np.uint32)
+    return pI, pJ, off, ij
+
+
+@pytest.mark.parametrize("ext", ["txt", "bin"])
+def test_matches_file_matches_reference_fixture(tmp_path, ext):
+    """omvg_matches_save writes byte for byte what matching::Save writes (fixtures generated by the reference,
+    tests/golden/make_golden.py): std::map order, empty pairs dropped."""
+    from openmvg_b200 import matching
+    pI, pJ, off, ij = _sample_csr()
+    out = tmp_path / f"matches.putative.{ext}"
+    matching.save_matches(str(out), pI, pJ, off, ij)
+    want = open(os.path.join(ROOT, "tests", "golden", f"matches_fixture.{ext}"), "rb").read()
+    assert out.read_bytes() == want
+
+
+def test_matches_save_rejects_bad_arguments(tmp_path):
+    from openmvg_b200 import matching
+    from openmvg_b200._lib import OmvgError
+    pI, pJ, off, ij = _sample_csr()
+    with pytest.raises(OmvgError):
+        matching.save_matches(str(tmp_path / "m.json"), pI, pJ, off, ij)
+    with pytest.raises(OmvgError):
+        matching.save_matches(str(tmp_path / "m.txt"), np.array([1, 1], np.uint32), np.array([2, 2], np.uint32), np.array([0, 1, 2], np.uint64), ij[:2])
+
+
+def test_desc_file_layout_is_the_reference_one(tmp_path):
+    """The '.desc' writer the GPU loader test uses produces the reference's bytes (fixture from saveDescsToBinFile)."""
+    from openmvg_b200 import matching, synth
+    d = synth.descriptors(1, [37], seed=3)[0]
+    p = tmp_path / "a.desc"
+    matching.write_desc_file(str(p), d)
+    assert p.read_bytes() == open(os.path.join(ROOT, "tests", "golden", "desc_fixture.desc"), "rb").read()

@@ -238,3 +238,33 @@ def test_cascade_large_buckets_take_the_streaming_path():
     # the case really exercises more than 128 candidates per query (query 0 of image 1 against image 0)
     tot = sum(int((oh[0][1][:, g] == oh[1][1][0, g]).sum()) for g in range(6))
     assert tot > 128, tot
+
+
+def test_load_desc_files_equals_in_memory_upload(tmp_path):
+    """N3: '.desc' files read by the library's thread pool into pinned memory give the same matches as uploading the
+    arrays, and the result written by omvg_matches_save reads back identically (text format parsed here)."""
+    from openmvg_b200 import matching
+    counts = [700, 0, 650, 300]
+    descs = synth.descriptors(len(counts), counts, seed=1)
+    paths = []
+    for k, d in enumerate(descs):
+        p = tmp_path / f"img{k}.desc"; matching.write_desc_file(str(p), d); paths.append(str(p))
+    pi, pj = synth.exhaustive_pairs(len(counts))
+    a = matching.MatchContext(); got = a.load_desc_files(paths); a.run(pi, pj, 0.8); aoff, aij = a.fetch(); aoff = aoff.copy(); aij = aij.copy(); a.close()
+    assert list(got) == counts
+    b = matching.MatchContext(); b.load(descs); b.run(pi, pj, 0.8); boff, bij = b.fetch()
+    assert np.array_equal(aoff, boff) and np.array_equal(aij, bij)
+    b.close()
+    out = tmp_path / "matches.putative.txt"
+    matching.save_matches(str(out), pi * 10 + 1, pj * 10 + 1, aoff, aij)        # arbitrary view ids
+    tok = out.read_text().split()
+    t = 0; seen = {}
+    while t < len(tok):
+        I, J, n = int(tok[t]), int(tok[t + 1]), int(tok[t + 2]); t += 3
+        seen[(I, J)] = np.array(tok[t:t + 2 * n], np.uint32).reshape(-1, 2); t += 2 * n
+    for p in range(len(pi)):
+        m = aij[int(aoff[p]):int(aoff[p + 1])]
+        key = (int(pi[p]) * 10 + 1, int(pj[p]) * 10 + 1)
+        assert (key in seen) == (len(m) > 0)
+        if len(m):
+            assert np.array_equal(seen[key], m)
