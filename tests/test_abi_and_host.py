@@ -142,3 +142,31 @@ def test_desc_file_layout_is_the_reference_one(tmp_path):
     p = tmp_path / "a.desc"
     matching.write_desc_file(str(p), d)
     assert p.read_bytes() == open(os.path.join(ROOT, "tests", "golden", "desc_fixture.desc"), "rb").read()
+
+
+def _build_c_example(tmp_path):
+    exe = str(tmp_path / "minimal_c_abi")
+    lib_dir = os.path.join(ROOT, "openmvg_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", os.path.join(ROOT, "examples", "minimal_c_abi.c"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + lib_dir, "-lomvg_b200", "-Wl,-rpath," + lib_dir, "-lm", "-o", exe])
+    return exe
+
+
+def test_header_is_plain_c_and_example_fails_loudly_without_gpu(tmp_path):
+    """include/omvg_b200.h compiles as strict C99; without a B200 the first call reports OMVG_E_CUDA."""
+    from openmvg_b200 import build
+    build.build()
+    exe = _build_c_example(tmp_path)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked variant")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "no B200" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_gpu(tmp_path):
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MATCH: 50 matches" in r.stdout and "BA: rc 0" in r.stdout
