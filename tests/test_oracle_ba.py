@@ -106,3 +106,19 @@ def test_zero_weight_removes_observation_exactly():
     d = dict(s); d["obs_view"] = np.ascontiguousarray(s["obs_view"][keep]); d["obs_point"] = np.ascontiguousarray(s["obs_point"][keep]); d["obs_xy"] = np.ascontiguousarray(s["obs_xy"][keep])
     a = ck.oracle_ba_solve(w); b = ck.oracle_ba_solve(d)
     assert abs(a["final_cost"] - b["final_cost"]) <= 1e-9 * b["final_cost"] and a["iterations"] == b["iterations"]   # (OpenMP atomics reorder sums)
+
+
+@pytest.mark.skipif(not ck.have_ref_ba(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kw", [dict(intrinsics_opt=1), dict(extrinsics_opt=4), dict(structure_opt=0), dict(use_loss=0), dict(model=3)],
+                         ids=lambda k: "_".join(f"{a}{b}" for a, b in k.items()))
+def test_gcp_priors_option_mixes_against_compiled_reference(kw):
+    """Control points + motion priors under the option mixes of Optimize_Options and another camera model."""
+    kw = dict(kw); model = kw.pop("model", 1)
+    s = synth.add_priors(synth.add_gcp(synth.ba_scene(14, 400, 5, seed=6, model=model), 5, weight=12.0), sigma=0.015)
+    ref_kw = {k: v for k, v in kw.items() if k in ("intrinsics_opt", "extrinsics_opt", "structure_opt", "use_loss")}
+    r = ck.ref_ba_adjust_ex(s, **ref_kw)
+    t, fit, cen = ck.ref_ba_register_priors(s)
+    o = ck.oracle_ba_solve(t, **kw)
+    assert r["ok"] and o["usable"]
+    assert abs(o["final_cost"] - r["final_cost"]) <= 1e-8 * r["final_cost"], (o["final_cost"], r["final_cost"])
+    assert o["iterations"] == r["iterations"]
