@@ -170,3 +170,20 @@ def test_c_example_runs_on_gpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "MATCH: 50 matches" in r.stdout and "BA: rc 0" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_ba.so")), reason="oracle/_ref not built")
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the same metric,
+    unit and workload string as our arm, impl == "reference", a cpu_baseline of kind "reference" and zero-copy e2e."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "BA LM-iters/sec" and line["unit"] == "LM-iter/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    ours = open(os.path.join(ROOT, "bench.py")).read()
+    assert ours.count(line["config"]["workload"]) == 2          # the very string our arm prints
+    assert line["match"]["cpu_baseline"]["kind"] == "reference" and line["match"]["value"] > 0
