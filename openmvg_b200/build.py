@@ -31,7 +31,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(os.path.dirname(PKG), "include", "omvg_b200.h"))
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         if not os.path.exists(s):
@@ -41,8 +41,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd = [nvcc] + [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
-            subprocess.check_call(cmd)
+            jobs.append(cmd)
         objs.append(o)
+    if jobs:                                                # the translation units compile side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            for _ in ex.map(subprocess.check_call, jobs):
+                pass
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lgomp"]   # cudart is linked statically (nvcc default)
         if verbose:
