@@ -234,6 +234,10 @@ int omvg_ba_reset(omvg_ba_ctx *ctx);      /* restore the parameters uploaded at 
 int omvg_ba_run(omvg_ba_ctx *ctx, const omvg_ba_options *options, omvg_ba_summary *summary);
 int omvg_ba_download(omvg_ba_ctx *ctx, double *poses, double *intrinsics, double *points);
 int omvg_ba_destroy(omvg_ba_ctx *ctx);
+/* Adjust's write-back rules (sfm_data_BA_ceres.cpp:528-568) from the device state into the caller's arrays (which hold
+ * the caller's previous values on entry): poses only if extrinsics were refined, ADJUST_ROTATION keeps the pose
+ * centre, intrinsics only if intrinsics were refined.  Any pointer may be NULL (that block is skipped). */
+int omvg_ba_writeback(omvg_ba_ctx *ctx, const omvg_ba_options *options, double *poses, double *intrinsics, double *points);
 /* |reprojection residual| (pixels, no loss) of every observation at the current device parameters, in the
  * caller's observation order: the quantity RemoveOutliers_PixelResidualError (sfm/sfm_data_filters.cpp:40-73)
  * thresholds after each Adjust of the BA / outlier-rejection loop (sequential_SfM.cpp:205-211). */
@@ -241,6 +245,19 @@ int omvg_ba_residual_norms(omvg_ba_ctx *ctx, double *norms /* [n_obs] */);
 /* Replace the per-observation weights of the resident problem (caller's observation order; weight 0 =
  * observation removed, exactly) — the rejection half of the loop above without rebuilding the scene. */
 int omvg_ba_set_obs_weights(omvg_ba_ctx *ctx, const double *weights /* [n_obs] */);
+/* The rejection half of `do { BundleAdjustment(); } while (badTrackRejector(4.0, 50))` (sequential_SfM.cpp:205-211,
+ * 1237-1243) on the resident scene.  omvg_ba_reject_outliers = RemoveOutliers_PixelResidualError(threshold_px,
+ * min_track_length) (sfm/sfm_data_filters.cpp:40-73) at the current device parameters: live observations with
+ * |residual| > threshold_px are removed and counted (*n_outliers), then tracks left with fewer than
+ * min_track_length observations are removed whole (*n_tracks; their observations are not counted, as in the
+ * reference).  Removal = weight 0 (exact) and the track becomes a constant block; control points are left alone.
+ * obs_removed_bits[(n_obs+31)/32]: bit o set = observation o (CALLER's order) was removed by THIS call;
+ * point_removed[n_points]: 1 = track removed by this call.  Either may be NULL.  Only a bit mask and two counters
+ * cross the bus.  omvg_ba_remove_points removes the tracks the caller names (point_mask[n_points] != 0): the
+ * angle test RemoveOutliers_AngleError stays host geometry in the shim. */
+int omvg_ba_reject_outliers(omvg_ba_ctx *ctx, double threshold_px, int32_t min_track_length,
+                            uint32_t *obs_removed_bits, uint8_t *point_removed, int64_t *n_outliers, int64_t *n_tracks);
+int omvg_ba_remove_points(omvg_ba_ctx *ctx, const uint8_t *point_mask, uint32_t *obs_removed_bits, int64_t *n_tracks);
 /* Make the current (refined) parameters the state omvg_ba_reset() restores. */
 int omvg_ba_commit(omvg_ba_ctx *ctx);
 

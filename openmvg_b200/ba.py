@@ -162,6 +162,25 @@ class BAContext:
         assert len(w) == len(self._s["obs_view"])
         check(lib().omvg_ba_set_obs_weights(self._h, w.ctypes.data_as(_dp)))
 
+    def reject_outliers(self, threshold_px: float = 4.0, min_track_length: int = 2):
+        """RemoveOutliers_PixelResidualError(threshold, minTrackLength) on the device (sfm_data_filters.cpp:40-73).
+        -> (obs_removed[n_obs] bool in the caller's order, point_removed[n_points] bool, n_outliers, n_tracks)"""
+        n = len(self._s["obs_view"]); npts = len(self._keep[2])
+        bits = np.zeros((n + 31) // 32, np.uint32); pr = np.zeros(npts, np.uint8)
+        no = ctypes.c_int64(); nt = ctypes.c_int64()
+        check(lib().omvg_ba_reject_outliers(self._h, ctypes.c_double(threshold_px), int(min_track_length), bits.ctypes.data_as(_vp),
+                                            pr.ctypes.data_as(_vp), ctypes.byref(no), ctypes.byref(nt)))
+        removed = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
+        return removed, pr.astype(bool), no.value, nt.value
+
+    def remove_points(self, mask):
+        """Remove whole tracks (the host-side angle test's verdict).  -> (obs_removed[n_obs] bool, n_tracks)"""
+        n = len(self._s["obs_view"])
+        m = np.ascontiguousarray(mask, np.uint8); assert len(m) == len(self._keep[2])
+        bits = np.zeros((n + 31) // 32, np.uint32); nt = ctypes.c_int64()
+        check(lib().omvg_ba_remove_points(self._h, m.ctypes.data_as(_vp), bits.ctypes.data_as(_vp), ctypes.byref(nt)))
+        return np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool), nt.value
+
     def commit(self):
         """Make the refined parameters the state reset() restores."""
         check(lib().omvg_ba_commit(self._h))

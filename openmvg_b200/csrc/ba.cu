@@ -72,6 +72,8 @@ struct omvg_ba_ctx {
   DevBuf<double> GE;                        // per observation { Einv E'Fc, E'Fc } of the split Schur step
   // optional extensions: GCP weights / flags / fixed landmarks, pose-centre priors
   DevBuf<double> obs_w; DevBuf<unsigned char> obs_flags, pt_fixed; DevBuf<unsigned> pt_mask;
+  DevBuf<unsigned char> pt_gcp, pt_removed, pt_now; DevBuf<unsigned> rej_bits; DevBuf<unsigned long long> rej_cnt;   // outlier rejection (omvg_ba_reject_outliers)
+  bool reject_ready = false;
   int n_slow = 0;                           // landmarks left to the per-observation Schur kernel
   bool has_ext = false; int npri = 0; double prior_huber_a = 0; DevBuf<int> prior_pose; DevBuf<double> prior_center, prior_weight, rP, JP;
   double *h_scal = nullptr;                 // pinned
@@ -739,6 +741,33 @@ static void aa_to_R(const double *aa, double R[9]) {
   }
 }
 
+// Adjust's write-back rules (sfm_data_BA_ceres.cpp:528-568) applied to the caller's flat arrays: poses only if
+// extrinsics were refined, ADJUST_ROTATION keeps the pose CENTRE (t = -R_new C_old), intrinsics only if intrinsics
+// were refined, points as they are on the device.  `poses` / `intrinsics` hold the caller's previous values on entry.
+int omvg_ba_writeback(omvg_ba_ctx *c, const omvg_ba_options *O, double *poses, double *intrinsics, double *points) {
+  if (!c || !O) return fail(OMVG_E_ARG, "null argument");
+  std::vector<double> np_(poses ? (size_t)6 * c->nc : 0), ni_(intrinsics ? (size_t)KI * c->ni : 0);
+  if (intrinsics) std::memcpy(ni_.data(), intrinsics, ni_.size() * sizeof(double));
+  int rc = omvg_ba_download(c, poses ? np_.data() : nullptr, intrinsics ? ni_.data() : nullptr, points);
+  if (rc) return rc;
+  if (poses && O->extrinsics_opt != 1) {
+    for (int p = 0; p < c->nc; ++p) {
+      double *dst = poses + 6 * p; const double *src = np_.data() + 6 * p;
+      if (O->extrinsics_opt == 2) {
+        double Ro[9], Rn[9], C[3];
+        aa_to_R(dst, Ro); aa_to_R(src, Rn);
+        for (int i = 0; i < 3; ++i) C[i] = -(Ro[0 * 3 + i] * dst[3] + Ro[1 * 3 + i] * dst[4] + Ro[2 * 3 + i] * dst[5]);
+        for (int i = 0; i < 3; ++i) dst[i] = src[i];
+        for (int i = 0; i < 3; ++i) dst[3 + i] = -(Rn[i * 3] * C[0] + Rn[i * 3 + 1] * C[1] + Rn[i * 3 + 2] * C[2]);
+      } else {
+        for (int i = 0; i < 6; ++i) dst[i] = src[i];
+      }
+    }
+  }
+  if (intrinsics && !(O->intrinsics_opt & 1)) std::memcpy(intrinsics, ni_.data(), ni_.size() * sizeof(double));
+  return OMVG_OK;
+}
+
 int omvg_ba_solve(omvg_ba_problem *P, const omvg_ba_options *O, omvg_ba_summary *sum) {
   omvg_ba_options def; if (!O) { omvg_ba_default_options(&def); O = &def; }
   omvg_ba_summary local; if (!sum) sum = &local;
@@ -748,30 +777,7 @@ int omvg_ba_solve(omvg_ba_problem *P, const omvg_ba_options *O, omvg_ba_summary 
   tm.lap("create");
   rc = omvg_ba_run(c, O, sum);
   tm.lap("run");
-  if (rc == OMVG_OK) {                       // state is copied back only when usable (solver.cc:445-448)
-    // Adjust's write-back rules (sfm_data_BA_ceres.cpp:528-568): poses only if extrinsics were refined,
-    // intrinsics only if intrinsics were refined; ADJUST_ROTATION keeps the pose CENTRE (t = -R_new C_old).
-    std::vector<double> np_((size_t)6 * P->n_poses), ni_((size_t)KI * P->n_intrinsics);
-    std::memcpy(ni_.data(), P->intrinsics, ni_.size() * sizeof(double));
-    rc = omvg_ba_download(c, np_.data(), ni_.data(), P->points);
-    if (rc == OMVG_OK) {
-      if (O->extrinsics_opt != 1) {
-        for (int p = 0; p < P->n_poses; ++p) {
-          double *dst = P->poses + 6 * p; const double *src = np_.data() + 6 * p;
-          if (O->extrinsics_opt == 2) {
-            double Ro[9], Rn[9], C[3];
-            aa_to_R(dst, Ro); aa_to_R(src, Rn);
-            for (int i = 0; i < 3; ++i) C[i] = -(Ro[0 * 3 + i] * dst[3] + Ro[1 * 3 + i] * dst[4] + Ro[2 * 3 + i] * dst[5]);
-            for (int i = 0; i < 3; ++i) dst[i] = src[i];
-            for (int i = 0; i < 3; ++i) dst[3 + i] = -(Rn[i * 3] * C[0] + Rn[i * 3 + 1] * C[1] + Rn[i * 3 + 2] * C[2]);
-          } else {
-            for (int i = 0; i < 6; ++i) dst[i] = src[i];
-          }
-        }
-      }
-      if (!(O->intrinsics_opt & 1)) std::memcpy(P->intrinsics, ni_.data(), ni_.size() * sizeof(double));
-    }
-  }
+  if (rc == OMVG_OK) rc = omvg_ba_writeback(c, O, P->poses, P->intrinsics, P->points);   // state is copied back only when usable (solver.cc:445-448)
   tm.lap("download+write-back");
   omvg_ba_destroy(c);
   tm.lap("destroy");
@@ -822,6 +828,70 @@ int omvg_ba_set_obs_weights(omvg_ba_ctx *c, const double *w) {
   OMVG_CUDA(cudaMemcpyAsync(c->obs_w.p, s_w.data(), (size_t)c->no * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   OMVG_CUDA(cudaStreamSynchronize(c->stream));
   return OMVG_OK;
+}
+
+// Device-side RemoveOutliers_PixelResidualError (sfm/sfm_data_filters.cpp:40-73) + the track-length rule, and the
+// removal of tracks named by the caller (the angle test of badTrackRejector, sequential_SfM.cpp:1237-1243, is host
+// geometry): observations get weight 0 (exact removal, structure unchanged), removed tracks become constant blocks.
+static int ensure_reject_state(omvg_ba_ctx *c) {
+  if (c->reject_ready) return OMVG_OK;
+  int rc;
+  const unsigned gb = (unsigned)((c->no + 255) / 256), gp = (unsigned)((c->np + 255) / 256);
+  if ((rc = c->pt_gcp.alloc(c->np)) || (rc = c->pt_removed.alloc(c->np)) || (rc = c->pt_now.alloc(c->np)) || (rc = c->rej_bits.alloc((size_t)(c->no + 31) / 32 + 1)) || (rc = c->rej_cnt.alloc(2))) return rc;
+  if (c->pt_fixed.p) OMVG_CUDA(cudaMemcpyAsync(c->pt_gcp.p, c->pt_fixed.p, c->np, cudaMemcpyDeviceToDevice, c->stream));   // fixed at create = control points
+  else OMVG_CUDA(cudaMemsetAsync(c->pt_gcp.p, 0, c->np, c->stream));
+  OMVG_CUDA(cudaMemsetAsync(c->pt_removed.p, 0, c->np, c->stream));
+  if (!c->obs_w.p) { if ((rc = c->obs_w.alloc(c->no))) return rc; fill_kernel<<<gb, 256, 0, c->stream>>>(c->obs_w.p, c->no, 1.0); LAUNCH_CHECK(); c->launches++; }
+  if (!c->pt_fixed.p) { if ((rc = c->pt_fixed.alloc(c->np))) return rc; OMVG_CUDA(cudaMemsetAsync(c->pt_fixed.p, 0, c->np, c->stream)); }
+  if (!c->pt_mask.p) { if ((rc = c->pt_mask.alloc(c->np))) return rc; fill_u32_kernel<<<gp, 256, 0, c->stream>>>(c->pt_mask.p, c->np, 7u); LAUNCH_CHECK(); c->launches++; }
+  c->has_ext = true; c->reject_ready = true;
+  return OMVG_OK;
+}
+
+static int reject_finish(omvg_ba_ctx *c, uint32_t *obs_removed_bits, uint8_t *point_removed, int64_t *n_outliers, int64_t *n_tracks) {
+  unsigned long long h[2] = {0, 0};
+  OMVG_CUDA(cudaMemcpyAsync(h, c->rej_cnt.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  if (obs_removed_bits) OMVG_CUDA(cudaMemcpyAsync(obs_removed_bits, c->rej_bits.p, ((size_t)(c->no + 31) / 32) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (point_removed) OMVG_CUDA(cudaMemcpyAsync(point_removed, c->pt_now.p, c->np, cudaMemcpyDeviceToHost, c->stream));
+  OMVG_CUDA(cudaStreamSynchronize(c->stream));
+  if (n_outliers) *n_outliers = (int64_t)h[0];
+  if (n_tracks) *n_tracks = (int64_t)h[1];
+  return OMVG_OK;
+}
+
+int omvg_ba_reject_outliers(omvg_ba_ctx *c, double threshold_px, int32_t min_track_length, uint32_t *obs_removed_bits, uint8_t *point_removed,
+                            int64_t *n_outliers, int64_t *n_tracks) {
+  if (!c) return fail(OMVG_E_ARG, "null ctx");
+  if (!(threshold_px >= 0.0) || min_track_length < 0) return fail(OMVG_E_ARG, "bad threshold / track length");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_reject_state(c); if (rc) return rc;
+  OMVG_CUDA(cudaMemsetAsync(c->rej_bits.p, 0, c->rej_bits.n * 4, c->stream));
+  OMVG_CUDA(cudaMemsetAsync(c->rej_cnt.p, 0, 16, c->stream));
+  // |r| in pixels at the current parameters (no weight, no loss): r is scratch between solves
+  cam_prep_kernel<<<(c->nc + 127) / 128, 128, 0, c->stream>>>(c->pose[0].p, c->nc, c->camR[0].p, c->camdR.p, c->camrec[0].p); LAUNCH_CHECK();
+  EvalArgs A{}; A.poses = c->pose[0].p; A.intr = c->intr[0].p; A.pts = c->pt[0].p; A.camR = c->camR[0].p; A.camdR = c->camdR.p; A.camrec = c->camrec[0].p;
+  A.obs_xy = c->obs_xy.p; A.intr_model = c->intr_model.p; A.obs_pose = c->obs_pose.p; A.obs_intr = c->obs_intr.p; A.obs_pt = c->obs_pt.p;
+  A.n_obs = c->no; A.use_loss = 0; A.huber_a = 16.0; A.cost_partial = c->part.p; A.rnorm = c->r.p;
+  eval_kernel<false, 8, false><<<c->eval_grid, EVAL_THREADS, 0, c->stream>>>(A); LAUNCH_CHECK();
+  reject_obs_kernel<<<(unsigned)((c->no + 255) / 256), 256, 0, c->stream>>>(c->r.p, c->obs_w.p, c->obs_pt.p, c->pt_gcp.p, c->no, threshold_px, c->d_perm.p, c->rej_bits.p, c->rej_cnt.p); LAUNCH_CHECK();
+  reject_tracks_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->pt_start.p, c->np, c->obs_w.p, min_track_length, nullptr, c->pt_gcp.p, c->d_perm.p, c->rej_bits.p,
+                                                                 c->pt_fixed.p, c->pt_mask.p, c->pt_removed.p, c->pt_now.p, c->rej_cnt.p); LAUNCH_CHECK();
+  c->launches += 4;
+  return reject_finish(c, obs_removed_bits, point_removed, n_outliers, n_tracks);
+}
+
+int omvg_ba_remove_points(omvg_ba_ctx *c, const uint8_t *point_mask, uint32_t *obs_removed_bits, int64_t *n_tracks) {
+  if (!c || !point_mask) return fail(OMVG_E_ARG, "null argument");
+  OMVG_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_reject_state(c); if (rc) return rc;
+  DevBuf<unsigned char> kill; if ((rc = kill.alloc(c->np))) return rc;
+  OMVG_CUDA(cudaMemcpyAsync(kill.p, point_mask, c->np, cudaMemcpyHostToDevice, c->stream));
+  OMVG_CUDA(cudaMemsetAsync(c->rej_bits.p, 0, c->rej_bits.n * 4, c->stream));
+  OMVG_CUDA(cudaMemsetAsync(c->rej_cnt.p, 0, 16, c->stream));
+  reject_tracks_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->pt_start.p, c->np, c->obs_w.p, 0, kill.p, c->pt_gcp.p, c->d_perm.p, c->rej_bits.p,
+                                                                 c->pt_fixed.p, c->pt_mask.p, c->pt_removed.p, c->pt_now.p, c->rej_cnt.p); LAUNCH_CHECK();
+  c->launches++;
+  return reject_finish(c, obs_removed_bits, nullptr, nullptr, n_tracks);      // (synchronises: `kill` may be released)
 }
 
 // Makes the current (refined) parameters the state omvg_ba_reset() returns to: the next run of the

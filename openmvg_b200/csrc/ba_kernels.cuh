@@ -152,6 +152,43 @@ __global__ void setup_single_kernel(const int *__restrict__ s_intr, const int *_
   if (K > 0 && (!one || K > 32)) atomicAdd(n_slow, 1);
 }
 
+// ------------------------------------------------------------------------------ outlier rejection on the resident scene
+// RemoveOutliers_PixelResidualError (sfm/sfm_data_filters.cpp:40-73) on the device: an observation whose reprojection
+// residual norm exceeds the threshold is removed (weight 0, counted); then a track left with fewer than min_len
+// observations is removed as a whole (its observations are not counted, as in the reference).  Removed bits are
+// returned in the CALLER's observation order.  Ground control points (fixed landmarks that were fixed at create) and
+// observations that are already removed are left alone.
+__global__ void reject_obs_kernel(const double *__restrict__ rnorm, double *__restrict__ obs_w, const int *__restrict__ obs_pt, const unsigned char *__restrict__ pt_gcp,
+                                  long long n, double thr, const int *__restrict__ perm, unsigned *__restrict__ removed_bits, unsigned long long *__restrict__ counters) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool out = false;
+  if (t < n && obs_w[t] != 0.0 && !(pt_gcp && pt_gcp[obs_pt[t]]) && rnorm[t] > thr) {
+    obs_w[t] = 0.0; const int o = perm[t]; atomicOr(&removed_bits[o >> 5], 1u << (o & 31)); out = true;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, out);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&counters[0], (unsigned long long)__popc(b));
+}
+// mode 0: tracks with fewer than min_len live observations; mode 1: tracks named by kill[] (the host-side angle test)
+__global__ void reject_tracks_kernel(const int *__restrict__ pt_start, int n_points, double *__restrict__ obs_w, int min_len, const unsigned char *__restrict__ kill,
+                                     const unsigned char *__restrict__ pt_gcp, const int *__restrict__ perm, unsigned *__restrict__ removed_bits,
+                                     unsigned char *__restrict__ pt_fixed, unsigned *__restrict__ pt_mask, unsigned char *__restrict__ pt_removed,
+                                     unsigned char *__restrict__ removed_now, unsigned long long *__restrict__ counters) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_points) return;
+  if (removed_now) removed_now[j] = 0;
+  if (pt_removed[j] || (pt_gcp && pt_gcp[j])) return;
+  int alive = 0;
+  for (int t = pt_start[j]; t < pt_start[j + 1]; ++t) alive += obs_w[t] != 0.0;
+  const bool gone = kill ? kill[j] != 0 : alive < min_len;
+  if (!gone) return;
+  for (int t = pt_start[j]; t < pt_start[j + 1]; ++t) if (obs_w[t] != 0.0) { obs_w[t] = 0.0; const int o = perm[t]; atomicOr(&removed_bits[o >> 5], 1u << (o & 31)); }
+  pt_removed[j] = 1; pt_fixed[j] = 1; pt_mask[j] = 0u;       // a removed track is no longer a parameter block
+  if (removed_now) removed_now[j] = 1;
+  atomicAdd(&counters[1], 1ull);
+}
+__global__ void fill_kernel(double *__restrict__ p, long long n, double v) { const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void fill_u32_kernel(unsigned *__restrict__ p, long long n, unsigned v) { const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
 // ------------------------------------------------------------------------------ residual / Jacobian
 struct EvalArgs {
   const double *poses, *intr, *pts, *camR, *camdR, *camrec, *obs_xy;

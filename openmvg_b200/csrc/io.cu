@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -25,10 +26,12 @@ using namespace omvg;
 
 namespace {
 
+// header count, checked against the file size (a corrupt header must not size a page-locked allocation)
 bool read_count(const char *path, uint64_t &n) {
   FILE *f = std::fopen(path, "rb");
   if (!f) return false;
-  const bool ok = std::fread(&n, sizeof(uint64_t), 1, f) == 1;          // std::size_t on the platforms openMVG builds on
+  bool ok = std::fread(&n, sizeof(uint64_t), 1, f) == 1;                // std::size_t on the platforms openMVG builds on
+  if (ok && std::fseek(f, 0, SEEK_END) == 0) { const long long sz = ftello(f); ok = n < (1ull << 40) && sz == (long long)(8 + n * OMVG_DESC_LEN); } else ok = false;
   std::fclose(f);
   return ok;
 }
@@ -42,7 +45,7 @@ int omvg_match_load_desc_files(omvg_match_ctx *ctx, uint32_t n_images, const cha
   std::vector<uint32_t> counts(n_images, 0);
   for (uint32_t k = 0; k < n_images; ++k) {
     uint64_t n = 0;
-    if (!desc_paths[k] || !read_count(desc_paths[k], n)) return fail(OMVG_E_ARG, "cannot read descriptor file %u: %s", k, desc_paths[k] ? desc_paths[k] : "(null)");
+    if (!desc_paths[k] || !read_count(desc_paths[k], n)) return fail(OMVG_E_ARG, "cannot read descriptor file %u (missing, or its size is not 8 + count x 128 bytes): %s", k, desc_paths[k] ? desc_paths[k] : "(null)");
     if (n >= (1ull << 31)) return fail(OMVG_E_ARG, "descriptor file %u claims %llu descriptors", k, (unsigned long long)n);
     counts[k] = (uint32_t)n;
   }
@@ -55,6 +58,7 @@ int omvg_match_load_desc_files(omvg_match_ctx *ctx, uint32_t n_images, const cha
   // reader pool: files are claimed in order; every image is uploaded by the thread that read it (the async copy is
   // queued on the context's stream from page-locked memory, so reads and H2D overlap)
   std::atomic<uint32_t> next{0}; std::atomic<int> err{OMVG_OK}; std::atomic<uint32_t> bad{0};
+  std::string worker_msg;                                     // omvg_last_error() is thread-local: carried over by hand
   const unsigned nthreads = std::max(1u, std::min<unsigned>(std::min<unsigned>(16u, std::thread::hardware_concurrency()), n_images));
   std::vector<std::thread> pool;
   std::mutex up;
@@ -71,7 +75,7 @@ int omvg_match_load_desc_files(omvg_match_ctx *ctx, uint32_t n_images, const cha
         if (!ok) { bad = k; err = OMVG_E_ARG; return; }
         std::lock_guard<std::mutex> g(up);                      // the C ABI of one context is not re-entrant
         const int r = omvg_match_upload_host(ctx, k, stage + off[k]);
-        if (r) { bad = k; err = r; return; }
+        if (r) { worker_msg = omvg_last_error(); bad = k; err = r; return; }      // (still under the lock)
       }
     });
   for (auto &th : pool) th.join();
@@ -80,7 +84,7 @@ int omvg_match_load_desc_files(omvg_match_ctx *ctx, uint32_t n_images, const cha
   else omvg_match_sync(ctx);
   if (stage) cudaFreeHost(stage);
   if (err.load() == OMVG_E_ARG) return fail(OMVG_E_ARG, "short read in descriptor file %u: %s", bad.load(), desc_paths[bad.load()]);
-  if (err.load() != OMVG_OK) return err.load();
+  if (err.load() != OMVG_OK) return fail(err.load(), "upload of descriptor file %u failed: %s", bad.load(), worker_msg.c_str());
   if (rc) return rc;
   if (counts_out) std::memcpy(counts_out, counts.data(), n_images * sizeof(uint32_t));
   return OMVG_OK;

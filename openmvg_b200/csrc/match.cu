@@ -860,7 +860,7 @@ int omvg_match_upload_host(omvg_match_ctx *c, uint32_t image, const uint8_t *des
   if (c->counts[image])
     OMVG_CUDA(cudaMemcpyAsync(c->d_desc + (size_t)c->row0[image] * OMVG_DESC_LEN, desc, (size_t)c->counts[image] * OMVG_DESC_LEN,
                               cudaMemcpyHostToDevice, c->stream));
-  c->uploaded = true; c->prepared = false; return OMVG_OK;
+  c->uploaded = true; c->prepared = false; c->cascade_ready = false; return OMVG_OK;
 }
 
 int omvg_match_upload_device(omvg_match_ctx *c, uint32_t image, const void *desc_dev) {
@@ -869,7 +869,7 @@ int omvg_match_upload_device(omvg_match_ctx *c, uint32_t image, const void *desc
   if (c->counts[image])
     OMVG_CUDA(cudaMemcpyAsync(c->d_desc + (size_t)c->row0[image] * OMVG_DESC_LEN, desc_dev, (size_t)c->counts[image] * OMVG_DESC_LEN,
                               cudaMemcpyDeviceToDevice, c->stream));
-  c->uploaded = true; c->prepared = false; return OMVG_OK;
+  c->uploaded = true; c->prepared = false; c->cascade_ready = false; return OMVG_OK;
 }
 
 int omvg_match_upload_device_packed(omvg_match_ctx *c, const void *desc_dev) {
@@ -890,7 +890,7 @@ int omvg_match_prepare(omvg_match_ctx *c) {
   prep_rows_kernel<<<(c->total_rows + rows_per_block - 1) / rows_per_block, threads, 0, c->stream>>>(
       c->d_desc, c->d_img_row0, c->d_img_count, c->d_img_group, c->d_row_img, c->d_norm, c->d_ckey, c->total_rows);
   OMVG_CUDA(cudaGetLastError());
-  c->launches++; c->prepared = true; return OMVG_OK;
+  c->launches++; c->prepared = true; c->cascade_ready = false; return OMVG_OK;
 }
 
 int omvg_match_run(omvg_match_ctx *c, const uint32_t *pair_i, const uint32_t *pair_j, uint64_t n_pairs, float dist_ratio) {
@@ -998,7 +998,7 @@ int omvg_match_cascade_prepare(omvg_match_ctx *c, const float *primary, const fl
   // bucket tables
   std::vector<uint32_t> real0(ni + 1, 0); for (uint32_t k = 0; k < ni; ++k) real0[k + 1] = real0[k] + c->counts[k];
   const uint64_t n_real = real0[ni], n_keys = n_real * CH_GROUPS; const uint32_t n_buckets = ni * CH_GROUPS * CH_NB;
-  if (n_keys >= 0xffffffffull) return fail(OMVG_E_UNSUPPORTED, "collection too large for the bucket tables");
+  if (n_keys >= (1ull << 31)) return fail(OMVG_E_UNSUPPORTED, "collection too large for the bucket tables (%llu keys; CUB radix sort takes int counts)", (unsigned long long)n_keys);
   cudaFree(c->d_bstart); cudaFree(c->d_bitems); c->d_bstart = c->d_bitems = nullptr;
   OMVG_CUDA(cudaMalloc(&c->d_bstart, ((size_t)n_buckets + 1) * sizeof(uint32_t))); OMVG_CUDA(cudaMalloc(&c->d_bitems, std::max<uint64_t>(1, n_keys) * sizeof(uint32_t)));
   uint32_t *d_real0 = nullptr; unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; void *d_tmp = nullptr;

@@ -90,11 +90,19 @@ class Cascade_Hashing_Matcher_Regions_B200 : public Matcher
       (*my_progress_bar) += pairs.size();
       return;
     }
-    for (size_t k = 0; k < held.size(); ++k)
+    int rc = OMVG_OK;
+    for (size_t k = 0; k < held.size() && rc == OMVG_OK; ++k)
       if (counts[k])
-        omvg_match_upload_host(ctx, static_cast<uint32_t>(k),
-                               static_cast<const uint8_t *>(held[k]->DescriptorRawData()));
-    omvg_match_prepare(ctx);
+        rc = omvg_match_upload_host(ctx, static_cast<uint32_t>(k),
+                                    static_cast<const uint8_t *>(held[k]->DescriptorRawData()));
+    if (rc == OMVG_OK) rc = omvg_match_prepare(ctx);
+    if (rc != OMVG_OK)
+    {
+      OPENMVG_LOG_ERROR << "omvg_b200: " << omvg_last_error();
+      omvg_match_destroy(ctx);
+      (*my_progress_bar) += pairs.size();
+      return;
+    }
 
     std::vector<uint32_t> pi, pj;
     std::vector<Pair> order;

@@ -78,11 +78,19 @@ class Matcher_Regions_B200 : public Matcher
       (*my_progress_bar) += pairs.size();
       return;
     }
-    for (size_t k = 0; k < held.size(); ++k)
+    int rc = OMVG_OK;
+    for (size_t k = 0; k < held.size() && rc == OMVG_OK; ++k)
       if (counts[k])
-        omvg_match_upload_host(ctx, static_cast<uint32_t>(k),
-                               static_cast<const uint8_t *>(held[k]->DescriptorRawData()));
-    omvg_match_prepare(ctx);
+        rc = omvg_match_upload_host(ctx, static_cast<uint32_t>(k),
+                                    static_cast<const uint8_t *>(held[k]->DescriptorRawData()));
+    if (rc == OMVG_OK) rc = omvg_match_prepare(ctx);
+    if (rc != OMVG_OK)
+    {
+      OPENMVG_LOG_ERROR << "omvg_b200: " << omvg_last_error();
+      omvg_match_destroy(ctx);
+      (*my_progress_bar) += pairs.size();
+      return;
+    }
 
     // Pair_Set is ordered: the CSR rows come back in the same lexicographic order the reference
     // iterates (map_Pairs by I, then J).

@@ -203,6 +203,31 @@ def descriptors(n_images: int, n_desc, seed: int = 7, inlier_frac: float = 0.3) 
     return out
 
 
+def descriptor_collection(n_images: int, n_desc: int = 5000, seed: int = 1000, block: int = 25, lo: int = 0, hi=None) -> list:
+    """The M1 / M2 collections of BASELINE.json configs[2]/[3] (200 / 1000 images x 5000): blocks of ``block``
+    images, block b drawn by :func:`descriptors` with seed ``seed + b``.  Any [lo, hi) slice can be generated
+    without the rest (each rank of a sharded run draws only its own images) and M1 is a prefix of M2."""
+    hi = n_images if hi is None else min(hi, n_images)
+    out = []
+    for b in range(lo // block, (max(hi, lo + 1) - 1) // block + 1):
+        if hi <= lo:
+            break
+        n_b = min(block, n_images - b * block)
+        blk = descriptors(n_b, n_desc, seed=seed + b)
+        a0 = max(lo, b * block) - b * block; a1 = min(hi, (b + 1) * block) - b * block
+        out.extend(blk[a0:a1])
+    return out
+
+
+def sampled_pairs(n_images: int, n_pairs: int, seed: int = 5):
+    """A seeded sample of distinct (I<J) pairs in Pair_Set (lexicographic) order."""
+    rng = np.random.default_rng(seed)
+    total = n_images * (n_images - 1) // 2
+    pick = np.sort(rng.choice(total, size=min(n_pairs, total), replace=False))
+    i, j = np.triu_indices(n_images, 1)
+    return np.ascontiguousarray(i[pick].astype(np.uint32)), np.ascontiguousarray(j[pick].astype(np.uint32))
+
+
 def exhaustive_pairs(n_images: int):
     """Pair_Builder.hpp:25-33 — all (I,J) with I<J in lexicographic order."""
     i, j = np.triu_indices(n_images, 1)

@@ -14,7 +14,7 @@
 //
 // Reference lines restated (ceres = /root/reference/src/third_party/ceres-solver):
 //   openMVG/sfm/sfm_data_BA_ceres_camera_functor.hpp:103-194,207-300,313-412,425-533,548-660
-//                                             residual functors (pinhole, K1, K3, Brown T2, fisheye)
+//                                             residual functors (pinhole, K1, K3, Brown T2, fisheye), :662-760 spherical
 //   ceres/include/ceres/rotation.h:563-622    AngleAxisRotatePoint incl. the theta^2<=eps branch
 //   ceres/include/ceres/jet.h, internal/autodiff.h:207-319   forward-mode AD (Jet below)
 //   ceres/internal/ceres/loss_function.cc:47-61   HuberLoss;  corrector.cc:41-155  Corrector
@@ -61,6 +61,9 @@ inline Jet jsqrt(const Jet &f) { Jet h; h.a = std::sqrt(f.a); const double t = 1
 inline Jet jcos(const Jet &f) { Jet h; h.a = std::cos(f.a); const double s = -std::sin(f.a); for (int i = 0; i < NJ; ++i) h.v[i] = s * f.v[i]; return h; }
 inline Jet jsin(const Jet &f) { Jet h; h.a = std::sin(f.a); const double c = std::cos(f.a); for (int i = 0; i < NJ; ++i) h.v[i] = c * f.v[i]; return h; }
 inline Jet jatan(const Jet &f) { Jet h; h.a = std::atan(f.a); const double t = 1.0 / (1.0 + f.a * f.a); for (int i = 0; i < NJ; ++i) h.v[i] = t * f.v[i]; return h; }
+// jet.h:682-695  atan2(g, f) ~= atan2(b, a) + (-b da + a db) / (a^2 + b^2)
+inline Jet jatan2(const Jet &g, const Jet &f) { Jet h; h.a = std::atan2(g.a, f.a); const double t = 1.0 / (f.a * f.a + g.a * g.a); for (int i = 0; i < NJ; ++i) h.v[i] = t * (-g.a * f.v[i] + f.a * g.v[i]); return h; }
+inline double jatan2(double y, double x) { return std::atan2(y, x); }
 inline double jsqrt(double x) { return std::sqrt(x); }
 inline double jcos(double x) { return std::cos(x); }
 inline double jsin(double x) { return std::sin(x); }
@@ -95,6 +98,16 @@ bool residual_functor(int model, const T *K, const T *ext, const T *X, const dou
   T p[3];
   angle_axis_rotate_point(ext, X, p);
   p[0] = p[0] + ext[3]; p[1] = p[1] + ext[4]; p[2] = p[2] + ext[5];
+  if (model == 7) {  // CAMERA_SPHERICAL :662-717 — no intrinsic block; K[0], K[1] carry the image size (constants)
+    const T lon = jatan2(p[0], p[2]);
+    const T lat = jatan2(-p[1], jsqrt(p[0] * p[0] + p[2] * p[2]));
+    const T c0 = lon / T(2 * M_PI), c1 = -lat / T(2 * M_PI);
+    const double w = val(K[0]), h = val(K[1]);
+    const T size(std::max(w, h));
+    res[0] = c0 * size + T(w / 2.0) - T(xy[0]);
+    res[1] = c1 * size + T(h / 2.0) - T(xy[1]);
+    return true;
+  }
   const T x = p[0] / p[2], y = p[1] / p[2];           // hnormalized()
   const T &focal = K[0]; const T &ppx = K[1]; const T &ppy = K[2];
   switch (model) {
@@ -140,7 +153,7 @@ bool residual_functor(int model, const T *K, const T *ext, const T *X, const dou
 }
 
 int model_nparams(int model) {
-  switch (model) { case 1: return 3; case 2: return 4; case 3: return 6; case 4: return 8; case 5: return 7; default: return -1; }
+  switch (model) { case 1: return 3; case 2: return 4; case 3: return 6; case 4: return 8; case 5: return 7; case 7: return 0; default: return -1; }
 }
 
 // loss_function.cc:47-61 with a = huber_a (b = a^2); use_loss == 0 -> TrivialLoss

@@ -13,6 +13,7 @@
 #include "openMVG/numeric/numeric.h"
 #include "openMVG/sfm/sfm_data.hpp"
 #include "openMVG/sfm/sfm_data_BA_ceres.hpp"
+#include "openMVG/sfm/sfm_data_filters.hpp"
 #include "openMVG/sfm/sfm_view_priors.hpp"
 
 #include "../openmvg_b200/host/Bundle_Adjustment_B200.hpp"
@@ -20,8 +21,10 @@
 #include "openMVG/matching_image_collection/Cascade_Hashing_Matcher_Regions.hpp"
 #include "../openmvg_b200/host/Matcher_Regions_B200.hpp"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <memory>
 #include <random>
 #include <set>
@@ -71,7 +74,7 @@ double huber_cost(const SfM_Data & s)
 
 // priors_and_gcp: views become ViewPriors (GPS = true centre * 3 + offset + noise; id_pose == id_view as in
 // every openMVG loader) and 6 ground control points, surveyed in the GPS frame, are observed by 4 views each.
-SfM_Data make_scene(int C, int P, int K, bool priors_and_gcp = false)
+SfM_Data make_scene(int C, int P, int K, bool priors_and_gcp = false, double outlier_frac = 0.0, int stride = 1, int short_every = 0)
 {
   std::mt19937 g(42);
   std::uniform_real_distribution<double> U(-0.6, 0.6);
@@ -101,10 +104,13 @@ SfM_Data make_scene(int C, int P, int K, bool priors_and_gcp = false)
     const Vec3 X(U(g), U(g), U(g));
     Landmark L;
     const int s0 = start(g);
-    for (int k = 0; k < K; ++k) {
-      const int i = (s0 + k) % C;
+    const int Kj = (short_every > 0 && j % short_every == 0) ? 2 : K;   // two neighbouring views: little parallax
+    for (int k = 0; k < Kj; ++k) {
+      const int i = (s0 + k * stride) % C;
       const Vec3 Xc = gt[i](X);
-      L.obs[10 + i] = Observation(Vec2(cx + f * Xc(0) / Xc(2) + 0.5 * N(g), cy + f * Xc(1) / Xc(2) + 0.5 * N(g)), j);
+      Vec2 x(cx + f * Xc(0) / Xc(2) + 0.5 * N(g), cy + f * Xc(1) / Xc(2) + 0.5 * N(g));
+      if (outlier_frac > 0 && U(g) + 0.6 < 1.2 * outlier_frac) x += Vec2(60.0 * N(g), 60.0 * N(g));     // gross outliers
+      L.obs[10 + i] = Observation(x, j);
     }
     L.X = X + Vec3(N(g), N(g), N(g)) * 0.01;
     s.structure[1000 + j] = L;
@@ -126,7 +132,7 @@ SfM_Data make_scene(int C, int P, int K, bool priors_and_gcp = false)
 
 }  // namespace
 
-int main()
+int main(int argc, char ** argv)
 {
   int failures = 0;
   // ------------------------------------------------------------------ MATCH
@@ -222,6 +228,81 @@ int main()
     std::printf("BA+GCP+priors drop-in: initial %.6f  reference %.9f  B200 %.9f  rel %.3e  max centre diff %.3e  gcp diff %.3e  ok %d/%d\n",
                 c0, ca, cb, rel, dc, dg, int(ok_ref), int(ok_b200));
     if (!ok_ref || !ok_b200 || !(rel <= 1e-6) || !(dc <= 1e-6) || !(dg <= 1e-12)) ++failures;
+  }
+  // ------------------------------------------------------------------ the BA / outlier-rejection loop (N1)
+  // reference: do { Bundle_Adjustment_Ceres::Adjust } while (RemoveOutliers_PixelResidualError(4.0, 2) +
+  // RemoveOutliers_AngleError(2.0) > 50)  (sequential_SfM.cpp:205-211, 1226-1243) vs AdjustAndReject on ONE resident problem
+  {
+    SfM_Data a = make_scene(200, 6000, 6, false, 0.04, 1, 10);      // every 10th track: two neighbouring views, ~1.8 degrees of parallax
+    SfM_Data b = a;
+    b.intrinsics[7] = std::shared_ptr<IntrinsicBase>(a.intrinsics.at(7)->clone());
+    const Optimize_Options opt(Intrinsic_Parameter_Type::ADJUST_ALL, Extrinsic_Parameter_Type::ADJUST_ALL, Structure_Parameter_Type::ADJUST_ALL);
+    size_t ref_res = 0, ref_ang = 0; int ref_rounds = 0; bool again = true;
+    while (again) {
+      Bundle_Adjustment_Ceres ba_ref(Bundle_Adjustment_Ceres::BA_Ceres_options(false, true));
+      ba_ref.Adjust(a, opt); ++ref_rounds;
+      const size_t r1 = RemoveOutliers_PixelResidualError(a, 4.0, 2), r2 = RemoveOutliers_AngleError(a, 2.0);
+      ref_res += r1; ref_ang += r2; again = r1 + r2 > 50;
+    }
+    Bundle_Adjustment_B200 ba_b200; Bundle_Adjustment_B200::RejectStats st;
+    const bool ok = ba_b200.AdjustAndReject(b, opt, 4.0, 50, 2, 2.0, &st);
+    bool same = ok && a.structure.size() == b.structure.size();
+    size_t n_obs_a = 0, n_obs_b = 0;
+    for (const auto & l : a.structure) n_obs_a += l.second.obs.size();
+    for (const auto & l : b.structure) n_obs_b += l.second.obs.size();
+    if (same) for (const auto & l : a.structure) {
+      const auto it = b.structure.find(l.first);
+      if (it == b.structure.end() || it->second.obs.size() != l.second.obs.size()) { same = false; break; }
+      for (const auto & o : l.second.obs) if (!it->second.obs.count(o.first)) { same = false; break; }
+      if (!same) break;
+    }
+    const double ca = huber_cost(a), cb = huber_cost(b), rel = std::fabs(ca - cb) / ca;
+    std::printf("BA reject loop: reference %d rounds, %zu residual outliers, %zu angle tracks -> %zu tracks / %zu obs, cost %.9f | B200 %d rounds, %zu + %zu short + %zu angle -> %zu tracks / %zu obs, cost %.9f  rel %.3e  %s\n",
+                ref_rounds, ref_res, ref_ang, a.structure.size(), n_obs_a, ca, st.rounds, st.residual_outliers, st.short_tracks, st.angle_tracks, b.structure.size(), n_obs_b, cb, rel,
+                same ? "SAME STRUCTURE" : "DIFFERENT STRUCTURE");
+    if (!same || !(rel <= 1e-6) || ref_res != st.residual_outliers || ref_ang != st.angle_tracks || ref_res == 0 || ref_ang == 0) ++failures;
+  }
+  // ------------------------------------------------------------------ Adjust() wall at config 2 through SfM_Data (--config2 [ref])
+  if (argc > 1 && std::strcmp(argv[1], "--config2") == 0)
+  {
+    const bool with_ref = argc > 2 && std::strcmp(argv[2], "ref") == 0;
+    SfM_Data a = make_scene(1000, 100000, 10, false, 0.0, 1);
+    const Optimize_Options opt(Intrinsic_Parameter_Type::ADJUST_ALL, Extrinsic_Parameter_Type::ADJUST_ALL, Structure_Parameter_Type::ADJUST_ALL);
+    double best = 1e30; Bundle_Adjustment_B200::Timing bt; double cost_b = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      SfM_Data b = a; b.intrinsics[7] = std::shared_ptr<IntrinsicBase>(a.intrinsics.at(7)->clone());
+      Bundle_Adjustment_B200 ba;
+      const auto t0 = std::chrono::steady_clock::now();
+      const bool ok = ba.Adjust(b, opt);
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (!ok) { std::printf("config2 Adjust (B200) failed after pack %.2f ms\n", ba.timing().pack_ms); ++failures; break; }
+      if (rep > 0 && ms < best) { best = ms; bt = ba.timing(); }
+      cost_b = huber_cost(b);
+      std::printf("config2 Adjust (B200) rep %d: %.2f ms  [pack %.2f, omvg_ba_solve %.2f, unpack %.2f]  device %.2f ms, %d iterations\n", rep, ms, ba.timing().pack_ms, ba.timing().solve_ms,
+                  ba.timing().unpack_ms, ba.summary().device_ms, ba.summary().iterations);
+    }
+    std::printf("CONFIG2 B200 Adjust wall best %.2f ms (pack %.2f + solve %.2f + unpack %.2f), final cost %.9f\n", best, bt.pack_ms, bt.solve_ms, bt.unpack_ms, cost_b);
+    {  // the resident loop on the same scene with 2 %% gross outliers
+      SfM_Data b = make_scene(1000, 100000, 10, false, 0.02, 1);
+      Bundle_Adjustment_B200 ba; Bundle_Adjustment_B200::RejectStats st;
+      const auto t0 = std::chrono::steady_clock::now();
+      const bool ok = ba.AdjustAndReject(b, opt, 4.0, 50, 2, 2.0, &st);
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      const auto & t = ba.timing();
+      std::printf("CONFIG2 B200 AdjustAndReject wall %.2f ms, %d rounds (pack %.2f, solves %.2f, device rejection %.2f, host angle rule %.2f, unpack+erase %.2f): %zu residual outliers, %zu short, %zu angle tracks, ok %d\n",
+                  ms, st.rounds, t.pack_ms, t.solve_ms, t.reject_ms, t.angle_ms, t.unpack_ms, st.residual_outliers, st.short_tracks, st.angle_tracks, int(ok));
+      if (!ok) ++failures;
+    }
+    if (with_ref) {
+      SfM_Data r = a; r.intrinsics[7] = std::shared_ptr<IntrinsicBase>(a.intrinsics.at(7)->clone());
+      Bundle_Adjustment_Ceres ba_ref(Bundle_Adjustment_Ceres::BA_Ceres_options(false, true));
+      const auto t0 = std::chrono::steady_clock::now();
+      const bool ok = ba_ref.Adjust(r, opt);
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      const double cr = huber_cost(r);
+      std::printf("CONFIG2 reference Adjust wall %.1f ms, final cost %.9f, rel diff %.3e, speed-up %.1fx, ok %d\n", ms, cr, std::fabs(cr - cost_b) / cr, ms / best, int(ok));
+      if (!ok || !(std::fabs(cr - cost_b) <= 1e-6 * cr)) ++failures;
+    }
   }
   std::printf(failures ? "DROPIN FAILED\n" : "DROPIN OK\n");
   return failures;

@@ -51,6 +51,7 @@ std::shared_ptr<IntrinsicBase> make_intrinsic(int model, const double * p)
     case PINHOLE_CAMERA_RADIAL3: return std::make_shared<Pinhole_Intrinsic_Radial_K3>(w, h, p[0], p[1], p[2], p[3], p[4], p[5]);
     case PINHOLE_CAMERA_BROWN:   return std::make_shared<Pinhole_Intrinsic_Brown_T2>(w, h, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]);
     case PINHOLE_CAMERA_FISHEYE: return std::make_shared<Pinhole_Intrinsic_Fisheye>(w, h, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
+    case CAMERA_SPHERICAL:       return std::make_shared<Intrinsic_Spherical>((unsigned int)p[0], (unsigned int)p[1]);   // flat layout: {w, h}
     default: return {};
   }
 }

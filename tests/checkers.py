@@ -404,3 +404,16 @@ def ref_load_matches(path, cap_pairs=100000, cap_m=10000000):
     n = ref_match().ref_load_matches(os.fsencode(path), ctypes.c_uint64(cap_pairs), _P(pI), _P(pJ), _P(off), ctypes.c_uint64(cap_m), _P(ij))
     assert n >= 0, n
     return pI[:n].copy(), pJ[:n].copy(), off[:n + 1].copy(), ij[:2 * int(off[n])].reshape(-1, 2).copy()
+
+
+def per_pair_digest(offsets, ij):
+    """(count u16, FNV-1a u64 of the (i,j) rows) per pair of a CSR result — the form the whole-M1 / sampled-M2
+    goldens are stored in (tests/golden/make_golden_m1m2.py)."""
+    off = np.asarray(offsets, np.int64); m = np.ascontiguousarray(ij, np.uint32).reshape(-1, 2)
+    n = len(off) - 1
+    counts = np.diff(off).astype(np.uint16); h = np.zeros(n, np.uint64)
+    f = oracle().oracle_fnv1a_ij
+    base = m.ctypes.data
+    for k in range(n):
+        h[k] = f(ctypes.c_void_p(base + 8 * int(off[k])), ctypes.c_int64(int(off[k + 1] - off[k])))
+    return counts, h

@@ -66,26 +66,29 @@ import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
 from openmvg_b200 import synth
+import bench
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank, world = dist.get_rank(), 2
-n_img, nd = 6, 40
-per = (n_img + world - 1) // world
-lo, hi = rank * per, min((rank + 1) * per, n_img)
-mine = synth.descriptors(hi - lo, nd, seed=1000 + rank)
+n_img, nd = 7, 40                                   # odd on purpose: the last rank's tile is short and padded
+lo, hi, per = bench.image_shard(n_img, rank, world)
+mine = synth.descriptor_collection(n_img, nd, seed=1000, block=3, lo=lo, hi=hi)      # each rank draws only ITS images
+assert len(mine) == hi - lo
 pad = torch.zeros((per * nd, 128), dtype=torch.uint8); pad[: (hi - lo) * nd] = torch.from_numpy(np.concatenate(mine))
 out = [torch.zeros_like(pad) for _ in range(world)]
 dist.all_gather(out, pad)
 allrows = torch.cat(out)[: n_img * nd]
-# every rank must hold identical descriptors, and rank r's own block must be in place
-ref = np.concatenate([np.concatenate(synth.descriptors(min((r + 1) * per, n_img) - r * per, nd, seed=1000 + r)) for r in range(world)])
+# every rank must hold the whole collection, image k at rows [k*nd, (k+1)*nd) — what upload_device_packed expects
+ref = np.concatenate(synth.descriptor_collection(n_img, nd, seed=1000, block=3))
 assert np.array_equal(allrows.numpy(), ref)
 pi, pj = synth.exhaustive_pairs(n_img)
-mine_pairs = set(zip(pi[rank::world].tolist(), pj[rank::world].tolist()))
+mpi, mpj = bench.pair_shard(pi, pj, rank, world)
+mine_pairs = set(zip(mpi.tolist(), mpj.tolist()))
 cnt = torch.tensor([len(mine_pairs)]); dist.all_reduce(cnt)
 assert int(cnt) == len(pi)                      # the shards partition the pair list
 gathered = [None, None]; dist.all_gather_object(gathered, sorted(mine_pairs))
 assert sorted(gathered[0] + gathered[1]) == sorted(zip(pi.tolist(), pj.tolist()))
 assert not (set(map(tuple, gathered[0])) & set(map(tuple, gathered[1])))
+assert abs(len(gathered[0]) - len(gathered[1])) <= 1
 dist.destroy_process_group()
 print("ok", rank)
 '''
@@ -177,7 +180,7 @@ def test_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the same metric,
     unit and workload string as our arm, impl == "reference", a cpu_baseline of kind "reference" and zero-copy e2e."""
     import json
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0", "--quick"],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
@@ -185,5 +188,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     ours = open(os.path.join(ROOT, "bench.py")).read()
-    assert ours.count(line["config"]["workload"]) == 2          # the very string our arm prints
+    assert ours.count(line["config"]["workload"]) == 1 and ours.count("BA_WORKLOAD") == 3   # one string, used by both arms
+    assert line["steps"] == len(line["cpu_baseline"]["thread_sweep"]) and line["ms_per_step"] > 0    # the steps it actually ran
+    assert set(line["config"]) == {"workload", "l2"}
     assert line["match"]["cpu_baseline"]["kind"] == "reference" and line["match"]["value"] > 0

@@ -152,6 +152,54 @@ def test_full_size_properties(matching):
     ctx.close()
 
 
+# ---- whole-collection goldens of the compiled reference (tests/golden/make_golden_m1m2.py)
+def _m1m2_gold():
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_m1_m2.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/reference_m1_m2.npz not generated")
+    return np.load(path)
+
+
+def test_whole_m1_against_reference_golden(matching):
+    """BASELINE configs[2] IN FULL: 200 images x 5000, all 19 900 pairs, per-pair match count and FNV-1a of the (i, j)
+    list identical to what the reference's Matcher_Regions(0.8, BRUTE_FORCE_L2)::Match produced for every pair."""
+    g = _m1m2_gold()
+    descs = synth.descriptor_collection(200, 5000, seed=1000)
+    pi, pj = synth.exhaustive_pairs(200)
+    ctx = matching.MatchContext(0)
+    ctx.load(descs); ctx.run(pi, pj, 0.8); off, ij = ctx.fetch(); ctx.close()
+    counts, fnv = ck.per_pair_digest(off, ij)
+    assert int(counts.sum()) == int(g["m1_counts"].sum()) > 100000
+    assert np.array_equal(counts, g["m1_counts"])
+    bad = np.flatnonzero(fnv != g["m1_fnv"])
+    assert len(bad) == 0, f"{len(bad)} of 19900 pairs differ, first {bad[:5]}"
+
+
+def test_sampled_m2_multibatch_against_reference_golden(matching, monkeypatch):
+    """BASELINE configs[3] sample: 256 seeded pairs of the 1000-image collection, run through the MULTI-BATCH path
+    (result-buffer budget cut so the pass takes several launches), bit-exact against the reference golden.
+    Only the images the sample names are uploaded (the others stay zero rows: they are never read)."""
+    g = _m1m2_gold()
+    spi, spj = g["m2_pair_i"], g["m2_pair_j"]
+    wpi, wpj = synth.sampled_pairs(1000, 256, seed=5)
+    assert np.array_equal(spi, wpi) and np.array_equal(spj, wpj)
+    used = sorted(set(spi.tolist()) | set(spj.tolist()))
+    monkeypatch.setenv("OMVG_MATCH_K12_MB", "4")        # ~100 pairs of 5000 queries per batch => 3 batches
+    ctx = matching.MatchContext(0)
+    ctx.set_images([5000] * 1000)
+    blocks = {}
+    for v in used:
+        b = v // 25
+        if b not in blocks:
+            blocks[b] = synth.descriptor_collection(1000, 5000, seed=1000, lo=25 * b, hi=25 * b + 25)
+        ctx.upload_host(v, blocks[b][v - 25 * b])
+    ctx.prepare(); ctx.run(spi, spj, 0.8); off, ij = ctx.fetch()
+    counts, fnv = ck.per_pair_digest(off, ij)
+    assert np.array_equal(counts, g["m2_counts"]) and np.array_equal(fnv, g["m2_fnv"])
+    ctx.close()
+
+
 # ---- cascade hashing on the GPU (SURVEY M9 / N2)
 def _cascade_gpu(descs, pi, pj, ratio):
     from openmvg_b200 import matching
