@@ -138,6 +138,9 @@ int omvg_matches_save(const char *path, uint64_t n_pairs, const uint32_t *pair_I
 #define OMVG_PINHOLE_CAMERA_RADIAL3  3   /* + k1 k2 k3 */
 #define OMVG_PINHOLE_CAMERA_BROWN    4   /* + k1 k2 k3 t1 t2                 (Camera_Pinhole_Brown.hpp) */
 #define OMVG_PINHOLE_CAMERA_FISHEYE  5   /* + k1 k2 k3 k4                    (Camera_Pinhole_Fisheye.hpp) */
+#define OMVG_CAMERA_SPHERICAL        7   /* no parameter block (getParams() is empty, Camera_Spherical.hpp); the two
+                                            leading doubles of the intrinsic slot carry the image size {w, h}, constants
+                                            of ResidualErrorFunctor_Intrinsic_Spherical (functor.hpp:662-760) */
 
 /* Flat scene.  Mirrors what Adjust builds at sfm_data_BA_ceres.cpp:260-396:
  *   poses[n_poses][6]            angle-axis (3) then t = -R*C (3)                  (in/out)

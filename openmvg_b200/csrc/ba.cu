@@ -25,9 +25,10 @@ namespace {
 enum Slot { S_COST = 0, S_MODEL, S_STEP2_PT, S_STEP2_POSE, S_STEP2_INTR, S_X2_PT, S_X2_POSE, S_X2_INTR,
             S_GMAX_PT, S_GMAX_CAM, S_GMAX_INTR, S_PCG_IT, S_PCG_RES, S_PCG_B, S_CAND_COST, S_COUNT = 16 };
 
-int model_nparams(int m) {
-  switch (m) { case 1: return 3; case 2: return 4; case 3: return 6; case 4: return 8; case 5: return 7; default: return -1; }
+int model_nparams(int m) {     // size of the Ceres parameter block = getParams().size()
+  switch (m) { case 1: return 3; case 2: return 4; case 3: return 6; case 4: return 8; case 5: return 7; case OMVG_CAMERA_SPHERICAL: return 0; default: return -1; }
 }
+int model_ndata(int m) { return m == OMVG_CAMERA_SPHERICAL ? 2 : model_nparams(m); }   // doubles of the slot the kernels read
 
 template <typename T> struct DevBuf {
   T *p = nullptr; size_t n = 0;
@@ -64,7 +65,7 @@ struct omvg_ba_ctx {
   DevBuf<double> Scc, Sci, Sii, rhs, Minv_c, Minv_i, work_i;
   DevBuf<double> z, res, pvec, w, zeta, pcg_part;
   DevBuf<double> gW, gAW, bX, bR, bP, bW, bZ, pcg2_part;   // two-level block-PCG workspaces
-  DevBuf<int> agg_of, agg_start, agg_cams, brow; DevBuf<double> cE, cEinv, cT, cCv, cYv, bP2; int ng = 0;
+  DevBuf<int> agg_of, agg_start, agg_cams, brow; DevBuf<double> cE, cEinv, cT, cCv, cYv, cCv2, cAW, bP2; int ng = 0;
   DevBuf<double> part, part2, part3, icol_part, scal;
   DevBuf<int> fail;
   DevBuf<unsigned long long> pcg_tim;
@@ -107,8 +108,11 @@ int validate(const omvg_ba_problem *P) {
   if (P->n_priors < 0 || (P->n_priors > 0 && (!P->prior_pose || !P->prior_center || !P->prior_weight))) return fail(OMVG_E_ARG, "bad pose-centre prior arrays");
   for (int k = 0; k < P->n_priors; ++k) if (P->prior_pose[k] < 0 || P->prior_pose[k] >= P->n_poses) return fail(OMVG_E_ARG, "prior %d: pose out of range", k);
   if (P->n_priors > 0 && !(P->prior_huber_a >= 0.0)) return fail(OMVG_E_ARG, "prior_huber_a must be >= 0");
-  if (P->n_poses > 32768) return fail(OMVG_E_UNSUPPORTED, "more than 32768 poses (camera-pair bitmap)");
-  if (P->n_intrinsics > 32) return fail(OMVG_E_UNSUPPORTED, "more than 32 intrinsic groups (dense border)");
+  // the camera-pair bitmap takes n_poses^2 / 8 bytes (+ 4x that for its prefix counts): 131072 poses = 10.7 GB of the 180
+  if (P->n_poses > 131072) return fail(OMVG_E_UNSUPPORTED, "more than 131072 poses (camera-pair bitmap)");
+  // dense border Sci [8 n_intr][6 n_poses] doubles and corner Sii [8 n_intr]^2: keep both under 16 GB
+  if ((double)P->n_intrinsics * 8.0 * ((double)P->n_poses * 6.0 + (double)P->n_intrinsics * 8.0) * 8.0 > 16e9)
+    return fail(OMVG_E_UNSUPPORTED, "%d intrinsic groups x %d poses: the dense intrinsics border would exceed 16 GB", P->n_intrinsics, P->n_poses);
   return OMVG_OK;
 }
 
@@ -315,6 +319,7 @@ int build_structure(omvg_ba_ctx *c) {
   if ((rc = c->cT.alloc(std::max(nco_max * nco_max, 3 * (size_t)GJ_B * nco_max)))) return rc;   // Cholesky route: T; Gauss-Jordan: Cold/H/Gn
   if ((rc = c->cCv.alloc((size_t)MAXRHS * nco_max))) return rc;
   if ((rc = c->cYv.alloc((size_t)MAXRHS * nco_max))) return rc;
+  if ((rc = c->cCv2.alloc((size_t)MAXRHS * nco_max + 1)) || (rc = c->cAW.alloc((size_t)MAXRHS * nco_max + 1))) return rc;
   if ((rc = c->bP2.alloc((size_t)MAXRHS * 6 * c->nc))) return rc;
   OMVG_CUDA(cudaStreamSynchronize(c->stream));
   return c->Scc.alloc((size_t)c->nnzb * 36);
@@ -373,11 +378,11 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   c->eval_grid = std::min(c->eval_blocks, c->n_sms * (getenv("OMVG_BA_EVAL_WAVES") ? atoi(getenv("OMVG_BA_EVAL_WAVES")) : 4));   // persistent grid-stride evaluation
   tm.lap("stream+events+pinned");
   c->h_intr_model.assign(P->intr_model, P->intr_model + c->ni);
-  c->kiu = 0; for (int q = 0; q < c->ni; ++q) c->kiu = std::max(c->kiu, model_nparams(P->intr_model[q]));
+  c->kiu = 3; for (int q = 0; q < c->ni; ++q) c->kiu = std::max(c->kiu, model_nparams(P->intr_model[q]));   // (>= 3: the column-sum kernels are instantiated for 3, 4, 6, 7, 8)
   const long long no = c->no;
   // intrinsics with the unused tail zeroed (so block norms only see real parameters)
   std::vector<double> h_intr((size_t)c->ni8, 0.0);
-  for (int q = 0; q < c->ni; ++q) for (int k = 0; k < model_nparams(P->intr_model[q]); ++k) h_intr[KI * q + k] = P->intrinsics[KI * q + k];
+  for (int q = 0; q < c->ni; ++q) for (int k = 0; k < model_ndata(P->intr_model[q]); ++k) h_intr[KI * q + k] = P->intrinsics[KI * q + k];
   cudaStream_t s = c->stream;
 #define UP(buf, ptr, cnt) if ((rc = upload(buf, ptr, (size_t)(cnt), s))) return rc
   UP(c->pose0, P->poses, 6 * c->nc); UP(c->intr0, h_intr.data(), c->ni8); UP(c->pt0, P->points, 3 * (size_t)c->np);
@@ -438,7 +443,7 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   AL(c->EtFi, 3 * KI * (size_t)c->np); AL(c->FtF, 36 * (size_t)c->nc); AL(c->FiFi, 64 * (size_t)c->ni);
   AL(c->EtE, 6 * (size_t)c->np); AL(c->Etb, 3 * (size_t)c->np); AL(c->Einv, 9 * (size_t)c->np); AL(c->step_pt, 3 * (size_t)c->np); AL(c->step_red, c->nred);
   AL(c->intr_mask, c->ni);
-  AL(c->Sci, (size_t)c->ni8 * 6 * c->nc); AL(c->Sii, (size_t)c->ni8 * c->ni8); AL(c->rhs, c->nred); AL(c->Minv_c, 36 * (size_t)c->nc); AL(c->Minv_i, (size_t)c->ni8 * c->ni8);
+  AL(c->Sci, (size_t)c->ni8 * 6 * c->nc); AL(c->Sii, (size_t)c->ni8 * c->ni8); AL(c->rhs, c->nred); AL(c->Minv_c, 36 * (size_t)c->nc); AL(c->Minv_i, (size_t)c->ni * KI * KI);
   AL(c->work_i, (size_t)c->ni8 * c->ni8 + c->ni8);
   AL(c->gW, (size_t)MAXW * 6 * c->nc); AL(c->gAW, (size_t)MAXW * 6 * c->nc);
   AL(c->bX, (size_t)MAXRHS * 6 * c->nc); AL(c->bR, (size_t)MAXRHS * 6 * c->nc); AL(c->bP, (size_t)MAXRHS * 6 * c->nc); AL(c->bW, (size_t)MAXRHS * 6 * c->nc); AL(c->bZ, (size_t)MAXRHS * 6 * c->nc);
@@ -519,6 +524,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   OMVG_CUDA(cudaFuncSetAttribute(eval_kernel<false, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   OMVG_CUDA(cudaFuncSetAttribute(pcg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pcg2Smem)));
   OMVG_CUDA(cudaFuncSetAttribute(pcg3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Pcg2Smem) + 4 * PCG3_NCO_MAX * sizeof(double))));
+  OMVG_CUDA(cudaFuncSetAttribute(pcg4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Pcg2Smem) + 4 * PCG3_NCO_MAX * sizeof(double))));
   if ((rc = read_scalars(c))) return rc;
   account_jac();
   double x_cost = c->h_scal[S_COST];
@@ -532,7 +538,10 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   long long pcg_total = 0;
   int coarse_age = -1; double last_pcg_its = 0, fresh_pcg_its = 1e30; bool fresh_pending = false;
   static const int coarse_every = getenv("OMVG_BA_COARSE_EVERY") ? std::max(1, atoi(getenv("OMVG_BA_COARSE_EVERY"))) : 3;
-  const int pcg_grid = c->n_sms;
+  // Small reduced systems are latency-bound on the grid-wide barriers of the PCG (4-5 us per iteration of pure
+  // synchronisation at 148 CTAs): up to `small_nc` poses ONE CTA runs the whole solve with block barriers instead.
+  static const int small_nc = getenv("OMVG_BA_PCG_SMALL") ? atoi(getenv("OMVG_BA_PCG_SMALL")) : 48;
+  const int pcg_grid = (c->nc <= small_nc && use_pcg3 && !getenv("OMVG_BA_PCG3")) ? 1 : c->n_sms;
   if (!c->gj_grid) {                                        // as many co-resident CTAs as the tile count can use
     int per_sm = 1; OMVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_invert_kernel, 256, 0));
     c->gj_grid = c->n_sms * std::max(1, std::min(per_sm, 2));
@@ -567,14 +576,14 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       OMVG_CUDA(cudaMemsetAsync(c->corner_rep.p, 0, c->corner_rep.n * sizeof(double), c->stream));
       schur_stage_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA, c->GE.p, c->corner_rep.p); LAUNCH_CHECK();
       corner_fold_kernel<<<1, 96, 0, c->stream>>>(c->corner_rep.p, c->obs_intr.p, c->nc, c->ni, c->Sii.p, c->rhs.p); LAUNCH_CHECK(); c->launches++;
-      static int occ2 = 0; if (!occ2) { OMVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, schur_pair_kernel, 256, 0)); occ2 = std::max(1, occ2); }
+      static const int occ2 = [] { int o = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, schur_pair_kernel, 256, 0); return std::max(1, o); }();   // (thread-safe: Adjust may run on several host threads)
       schur_pair_kernel<<<c->n_sms * occ2, 256, 0, c->stream>>>(SA, c->GE.p); LAUNCH_CHECK(); c->launches += 2;
       SA.skip_fast = 1;
     } else
     if (m.pts_free && !schur1) {
       static const int minb = getenv("OMVG_BA_SCHUR2_MINB") ? atoi(getenv("OMVG_BA_SCHUR2_MINB")) : 5;
       void (*kern)(SchurArgs) = minb >= 6 ? schur_point_kernel<6> : (minb >= 5 ? schur_point_kernel<5> : schur_point_kernel<3>);
-      static int occ = 0; if (!occ) { OMVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * SCHUR2_WARPS, 0)); occ = std::max(1, occ); }
+      int occ = 1; OMVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * SCHUR2_WARPS, 0)); occ = std::max(1, occ);
       kern<<<c->n_sms * occ, 32 * SCHUR2_WARPS, 0, c->stream>>>(SA); LAUNCH_CHECK(); c->launches++;   // one resident wave, grid-stride over landmarks
       SA.skip_fast = 1;
     }
@@ -587,52 +596,72 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     PcgArgs PA{}; PA.Scc = c->Scc.p; PA.rowptr = c->rowptr.p; PA.cols = c->cols.p; PA.Sci = c->Sci.p; PA.Sii = c->Sii.p; PA.rhs = c->rhs.p; PA.Minv_c = c->Minv_c.p; PA.Minv_i = c->Minv_i.p;
     PA.n_poses = c->nc; PA.ni8 = c->ni8; PA.z = c->z.p; PA.res = c->res.p; PA.p = c->pvec.p; PA.w = c->w.p; PA.zeta = c->zeta.p; PA.part = c->pcg_part.p;
     PA.tol = O->pcg_tolerance; PA.max_iter = O->pcg_max_iterations; PA.out = c->scal.p + S_PCG_IT;
+    // ---- coarse operator of the two-level preconditioner (aggregated gauge space), shared by the PCG variants.
+    // It is only a preconditioner: a slightly stale E^-1 (previous LM step, radius/3) costs a few extra PCG
+    // iterations (measured 38->40, 42->49, 43->43) but saves its O(nco^3) setup, so it is refreshed every
+    // `coarse_every` LM steps (measured at 1000 cameras, ms per solve: every step 17.9, 2: 16.0, 3: 15.2, 5: 15.9),
+    // or earlier if the last solve needed 1.5x the iterations seen right after a refresh.
+    const bool use_coarse = (use_pcg3 || !use_pcg2) && nw > 0 && c->nc >= 2;
+    const Coarse CO{c->agg_of.p, c->agg_start.p, c->agg_cams.p, c->ng, nw, use_coarse ? c->ng * nw : 0};
+    static const bool use_chol = getenv("OMVG_BA_COARSE_CHOL") != nullptr;
+    if (use_coarse) {
+      const int nco = CO.nco;
+      const bool refresh = nco > 0 && (coarse_age < 0 || coarse_age >= coarse_every || last_pcg_its > 1.5 * fresh_pcg_its + 5);
+      if (refresh) { coarse_age = 0; fresh_pending = true; }
+      ++coarse_age;
+      if (refresh) {
+        OMVG_CUDA(cudaMemsetAsync(c->cE.p, 0, (size_t)nco * nco * sizeof(double), c->stream));
+        coarse_assemble_kernel<<<(c->nnzb + 127) / 128, 128, 0, c->stream>>>(c->Scc.p, c->brow.p, c->cols.p, c->nnzb, c->gW.p, c->nc, CO, c->cE.p); LAUNCH_CHECK();
+        if (!use_chol) {                                        // blocked Gauss-Jordan, in place: cE becomes E^-1
+          double *Ep = c->cE.p, *Tp = c->cT.p; int nn = nco; int *fp = c->fail.p;
+          static const bool gj_timing = getenv("OMVG_BA_GJ_TIMING") != nullptr;
+          unsigned long long *tp = nullptr;
+          if (gj_timing) { if (!c->pcg_tim.p) { if ((rc = c->pcg_tim.alloc(8))) return rc; } OMVG_CUDA(cudaMemsetAsync(c->pcg_tim.p, 0, 64, c->stream)); tp = c->pcg_tim.p; }
+          void *cargs[] = {&Ep, &nn, &Tp, &fp, &tp};
+          const int mt = (nco + CT - 1) / CT;                   // no more CTAs than 64x64 tiles: a small coarse space pays for fewer barrier participants
+          const int gj = std::max(1, std::min(c->gj_grid, mt * mt));
+          OMVG_CUDA(cudaLaunchCooperativeKernel((void *)coarse_invert_kernel, dim3(gj), dim3(256), cargs, 0, c->stream));
+          if (gj_timing) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
+            fprintf(stderr, "[omvg_ba gj timing] us: pivot inverse %.1f slices %.1f sync %.1f tiles %.1f sync %.1f (n %d, %d CTAs)\n", h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, h[4] * 1e-3, nco, c->gj_grid); }
+        } else {
+          const size_t sm = sizeof(double) * ((size_t)CNB * CNB + 2 * CT * (CNB + 1) + 2 * CT * (CT + 1));
+          OMVG_CUDA(cudaFuncSetAttribute(coarse_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+          double *Ep = c->cE.p, *Tp = c->cT.p, *Ip = c->cEinv.p; int nn = nco; int *fp = c->fail.p;
+          void *cargs[] = {&Ep, &nn, &Tp, &Ip, &fp};
+          OMVG_CUDA(cudaLaunchCooperativeKernel((void *)coarse_setup_kernel, dim3(pcg_grid), dim3(256), cargs, sm, c->stream)); }
+        c->launches += 2;
+      }
+    }
+    const double *Einv_p = use_chol ? c->cEinv.p : c->cE.p;
     if (use_pcg2) {
       Pcg2Args P2{}; P2.Scc = c->Scc.p; P2.rowptr = c->rowptr.p; P2.cols = c->cols.p; P2.Sci = c->Sci.p; P2.Sii = c->Sii.p; P2.rhs = c->rhs.p; P2.Minv_c = c->Minv_c.p;
       P2.W = c->gW.p; P2.intr_mask = c->intr_mask.p; P2.n_poses = c->nc; P2.ni8 = c->ni8; P2.nw = nw; P2.X = c->bX.p; P2.Rv = c->bR.p; P2.Pv = c->bP.p; P2.Wv = c->bW.p; P2.Zv = c->bZ.p;
       P2.AW = c->gAW.p; P2.part = c->pcg2_part.p; P2.z = c->z.p; P2.tol = O->pcg_tolerance; P2.max_iter = O->pcg_max_iterations; P2.out = c->scal.p + S_PCG_IT;
       if (use_pcg3) {
-        Pcg3Args P3{}; P3.base = P2; P3.C = Coarse{c->agg_of.p, c->agg_start.p, c->agg_cams.p, c->ng, nw, c->ng * nw}; P3.Einv = getenv("OMVG_BA_COARSE_CHOL") ? c->cEinv.p : c->cE.p; P3.Cv = c->cCv.p; P3.Yv = c->cYv.p; P3.Pv2 = c->bP2.p;
-        const int nco = P3.C.nco;
-        // The coarse operator is only a preconditioner: a slightly stale E^-1 (previous LM step, radius/3) costs a few
-        // extra PCG iterations (measured 38->40, 42->49, 43->43) but saves its O(nco^3) setup, so it is refreshed every
-        // `coarse_every` LM steps (measured at 1000 cameras, ms per solve: every step 17.9, 2: 16.0, 3: 15.2, 5: 15.9), or earlier if the last solve needed 1.5x the iterations seen right after a refresh.
-        const bool refresh = nco > 0 && (coarse_age < 0 || coarse_age >= coarse_every || last_pcg_its > 1.5 * fresh_pcg_its + 5);
-        if (refresh) { coarse_age = 0; fresh_pending = true; }
-        ++coarse_age;
-        if (refresh) {
-          OMVG_CUDA(cudaMemsetAsync(c->cE.p, 0, (size_t)nco * nco * sizeof(double), c->stream));
-          coarse_assemble_kernel<<<(c->nnzb + 127) / 128, 128, 0, c->stream>>>(c->Scc.p, c->brow.p, c->cols.p, c->nnzb, c->gW.p, c->nc, P3.C, c->cE.p); LAUNCH_CHECK();
-          static const bool use_chol = getenv("OMVG_BA_COARSE_CHOL") != nullptr;
-          if (!use_chol) {                                        // blocked Gauss-Jordan, in place: cE becomes E^-1
-            double *Ep = c->cE.p, *Tp = c->cT.p; int nn = nco; int *fp = c->fail.p;
-            static const bool gj_timing = getenv("OMVG_BA_GJ_TIMING") != nullptr;
-            unsigned long long *tp = nullptr;
-            if (gj_timing) { if (!c->pcg_tim.p) { if ((rc = c->pcg_tim.alloc(8))) return rc; } OMVG_CUDA(cudaMemsetAsync(c->pcg_tim.p, 0, 64, c->stream)); tp = c->pcg_tim.p; }
-            void *cargs[] = {&Ep, &nn, &Tp, &fp, &tp};
-            OMVG_CUDA(cudaLaunchCooperativeKernel((void *)coarse_invert_kernel, dim3(c->gj_grid), dim3(256), cargs, 0, c->stream));
-            if (gj_timing) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
-              fprintf(stderr, "[omvg_ba gj timing] us: pivot inverse %.1f slices %.1f sync %.1f tiles %.1f sync %.1f (n %d, %d CTAs)\n", h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, h[4] * 1e-3, nco, c->gj_grid); }
-            P3.Einv = c->cE.p;
-          } else
-          { const size_t sm = sizeof(double) * ((size_t)CNB * CNB + 2 * CT * (CNB + 1) + 2 * CT * (CT + 1));
-            OMVG_CUDA(cudaFuncSetAttribute(coarse_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            double *Ep = c->cE.p, *Tp = c->cT.p, *Ip = c->cEinv.p; int nn = nco; int *fp = c->fail.p;
-            void *cargs[] = {&Ep, &nn, &Tp, &Ip, &fp};
-            OMVG_CUDA(cudaLaunchCooperativeKernel((void *)coarse_setup_kernel, dim3(pcg_grid), dim3(256), cargs, sm, c->stream)); }
-          c->launches += 2;
-        }
+        Pcg3Args P3{}; P3.base = P2; P3.C = CO; P3.C.nco = c->ng * nw; P3.Einv = Einv_p; P3.Cv = c->cCv.p; P3.Yv = c->cYv.p; P3.Pv2 = c->bP2.p;
         static const bool pcg_timing = getenv("OMVG_BA_PCG_TIMING") != nullptr;
         if (pcg_timing) { if (!c->pcg_tim.p) { if ((rc = c->pcg_tim.alloc(8))) return rc; } OMVG_CUDA(cudaMemsetAsync(c->pcg_tim.p, 0, 64, c->stream)); P3.tim = c->pcg_tim.p; }
+        static const bool force_pcg3 = getenv("OMVG_BA_PCG3") != nullptr;      // A/B: the 4-sync kernel
+        if (!force_pcg3 && P3.C.nco <= PCG3_NCO_MAX) {
+          double *cv2 = c->cCv2.p, *aw = c->cAW.p;
+          void *args[] = {&P3, &cv2, &aw};
+          OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg4_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem) + 4 * PCG3_NCO_MAX * sizeof(double), c->stream));
+          if (pcg_timing) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
+            fprintf(stderr, "[omvg_ba pcg4 timing] us: A stage %.1f y %.1f update+z %.1f reduce %.1f | B spmv %.1f reduce %.1f\n", h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, h[4] * 1e-3, h[5] * 1e-3); P3.tim = nullptr; }
+        } else {
         void *args[] = {&P3};
         OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg3_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem) + 4 * PCG3_NCO_MAX * sizeof(double), c->stream));
-        if (pcg_timing) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        if (pcg_timing && P3.tim) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
           fprintf(stderr, "[omvg_ba pcg timing] us: coarse (stage %.1f rows %.1f sync %.1f) z %.1f spmv %.1f update %.1f tail %.1f border %.1f\n", h[6] * 1e-3, h[7] * 1e-3, h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, h[4] * 1e-3, h[5] * 1e-3); }
       } else {
         void *args[] = {&P2};
         OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg2_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem), c->stream));
       }
     } else {
+      // more than 32 free intrinsic columns (e.g. one intrinsic group per image): PCG on the whole reduced system
+      // [Scc Sci'; Sci Sii] with the same aggregated coarse space on the camera rows and block-Jacobi on the intrinsics
+      if (use_coarse) { PA.W = c->gW.p; PA.C = CO; PA.Einv = Einv_p; PA.Cv = c->cCv.p; PA.Yv = c->cYv.p; }
       void *args[] = {&PA}; OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(pcg_grid), dim3(256), args, 0, c->stream));
     }
     // ---- back substitution, step = -y

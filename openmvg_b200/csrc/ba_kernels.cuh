@@ -293,9 +293,28 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
     const double *K = A.intr + KI * iq;
     const int model = A.intr_model[iq];
     double dx, dy, dd[4], dk[10];
-    distort(model, K, x, y, dx, dy, dd, dk, WANT_J);
-    const double f = K[0];
-    double r0 = K[1] + dx * f - xy.x, r1 = K[2] + dy * f - xy.y;
+    double r0, r1, f;
+    double gs[6];                                               // spherical: d(projection)/dp (2x3), unweighted
+    const bool spherical = model == OMVG_CAMERA_SPHERICAL;
+    if (spherical) {
+      // ResidualErrorFunctor_Intrinsic_Spherical (functor.hpp:662-717): lon = atan2(x, z), lat = atan2(-y, |(x, z)|),
+      // pixel = (lon, -lat) / 2pi * max(w, h) + (w, h) / 2.  K[0], K[1] carry the image size; there is no intrinsic block.
+      for (int i = 0; i < 10; ++i) dk[i] = 0.0;
+      dx = 0.0; dy = 0.0; f = 0.0; dd[0] = dd[1] = dd[2] = dd[3] = 0.0;
+      const double rho2 = safe ? 1.0 : p0 * p0 + p2 * p2, rho = sqrt(rho2), n2 = rho2 + (safe ? 0.0 : p1 * p1);
+      const double k = fmax(K[0], K[1]) / (2.0 * 3.14159265358979323846);
+      r0 = (safe ? 0.0 : atan2(p0, p2)) * k + K[0] / 2.0 - xy.x;
+      r1 = -(safe ? 0.0 : atan2(-p1, rho)) * k + K[1] / 2.0 - xy.y;
+      if (WANT_J) {
+        const double i2 = 1.0 / rho2, in2 = 1.0 / n2, ir = 1.0 / rho;
+        gs[0] = k * p2 * i2; gs[1] = 0.0; gs[2] = -k * p0 * i2;                       // k * dlon/dp
+        gs[3] = -k * p1 * p0 * ir * in2; gs[4] = k * rho * in2; gs[5] = -k * p1 * p2 * ir * in2;   // -k * dlat/dp
+      }
+    } else {
+      distort(model, K, x, y, dx, dy, dd, dk, WANT_J);
+      f = K[0];
+      r0 = K[1] + dx * f - xy.x; r1 = K[2] + dy * f - xy.y;
+    }
     if (!WANT_J && A.rnorm) A.rnorm[o] = sqrt(r0 * r0 + r1 * r1);
     if (EXT) { r0 = dead ? 0.0 : r0 * wg; r1 = dead ? 0.0 : r1 * wg; }
     const double s = r0 * r0 + r1 * r1;
@@ -314,6 +333,10 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
       double g[6];                                              // d r / d p (2x3)
       g[0] = a00 * iz; g[1] = a01 * iz; g[2] = -(a00 * x + a01 * y) * iz;
       g[3] = a10 * iz; g[4] = a11 * iz; g[5] = -(a10 * x + a11 * y) * iz;
+      if (spherical) {
+        #pragma unroll
+        for (int i = 0; i < 6; ++i) g[i] = w * gs[i];
+      }
       // point block: g * R
       #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -340,7 +363,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, MINB) eval_kernel(EvalArgs A) {
       // intrinsic block: [f, ppx, ppy, K3..K7]
       const unsigned im = A.intr_mask[iq];
       double ji0[KI], ji1[KI];
-      ji0[0] = w * dx; ji1[0] = w * dy; ji0[1] = w; ji1[1] = 0.0; ji0[2] = 0.0; ji1[2] = w;
+      ji0[0] = w * dx; ji1[0] = w * dy; ji0[1] = spherical ? 0.0 : w; ji1[1] = 0.0; ji0[2] = 0.0; ji1[2] = spherical ? 0.0 : w;
       #pragma unroll
       for (int k = 0; k < 5; ++k) { ji0[3 + k] = w * f * dk[k]; ji1[3 + k] = w * f * dk[5 + k]; }
       #pragma unroll
@@ -1083,29 +1106,34 @@ __global__ void finish_intr_kernel(double *__restrict__ Sii, const double *__res
     if (free_) Sii[(size_t)i * ni8 + i] += lmD_intr[i] * lmD_intr[i]; else Sii[(size_t)i * ni8 + i] = 1.0;
   }
   __syncthreads();
-  // the explicit inverse is only the block-Jacobi preconditioner of the single-vector PCG fallback: a single thread
-  // does the (tiny) factorisation
-  if (!need_inverse || threadIdx.x != 0) return;
-  double *L = work;
-  for (int i = 0; i < ni8 * ni8; ++i) L[i] = Sii[i];
-  for (int k = 0; k < ni8; ++k) {
-    double d = L[k * ni8 + k]; for (int q = 0; q < k; ++q) d -= L[k * ni8 + q] * L[k * ni8 + q];
-    if (!(d > 0.0) || !isfinite(d)) { atomicExch(fail, 3); return; }
-    d = sqrt(d); L[k * ni8 + k] = d;
-    for (int i = k + 1; i < ni8; ++i) { double s = L[i * ni8 + k]; for (int q = 0; q < k; ++q) s -= L[i * ni8 + q] * L[k * ni8 + q]; L[i * ni8 + k] = s / d; }
+  // the block-Jacobi preconditioner of the single-vector PCG (used when more than 32 intrinsic columns are free):
+  // Minv_i[q] = inverse of the KI x KI diagonal block of group q (constant coordinates are identity rows), one thread each
+  if (!need_inverse) return;
+  const int n_intr = ni8 / KI;
+  for (int q = threadIdx.x; q < n_intr; q += blockDim.x) {
+    double M[KI * KI];
+    for (int a = 0; a < KI; ++a) for (int b = 0; b < KI; ++b) M[a * KI + b] = Sii[(size_t)(KI * q + a) * ni8 + KI * q + b];
+    bool ok = true;
+    for (int k = 0; k < KI; ++k) {
+      double d = M[k * KI + k]; for (int p = 0; p < k; ++p) d -= M[k * KI + p] * M[k * KI + p];
+      if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }
+      d = sqrt(d); M[k * KI + k] = d;
+      for (int i = k + 1; i < KI; ++i) { double t = M[i * KI + k]; for (int p = 0; p < k; ++p) t -= M[i * KI + p] * M[k * KI + p]; M[i * KI + k] = t / d; }
+    }
+    if (!ok) { atomicExch(fail, 3); continue; }
+    for (int c = 0; c < KI; ++c) {
+      double b[KI]; for (int i = 0; i < KI; ++i) b[i] = i == c ? 1.0 : 0.0;
+      for (int i = 0; i < KI; ++i) { double t = b[i]; for (int p = 0; p < i; ++p) t -= M[i * KI + p] * b[p]; b[i] = t / M[i * KI + i]; }
+      for (int i = KI - 1; i >= 0; --i) { double t = b[i]; for (int p = i + 1; p < KI; ++p) t -= M[p * KI + i] * b[p]; b[i] = t / M[i * KI + i]; }
+      for (int i = 0; i < KI; ++i) Minv_i[(size_t)q * KI * KI + i * KI + c] = b[i];
+    }
   }
-  for (int c = 0; c < ni8; ++c) {
-    double *b = work + (size_t)ni8 * ni8 + (size_t)c * 0;   // reuse one column buffer
-    double *col = work + (size_t)ni8 * ni8;
-    for (int i = 0; i < ni8; ++i) col[i] = i == c ? 1.0 : 0.0;
-    for (int i = 0; i < ni8; ++i) { double s = col[i]; for (int q = 0; q < i; ++q) s -= L[i * ni8 + q] * col[q]; col[i] = s / L[i * ni8 + i]; }
-    for (int i = ni8 - 1; i >= 0; --i) { double s = col[i]; for (int q = i + 1; q < ni8; ++q) s -= L[q * ni8 + i] * col[q]; col[i] = s / L[i * ni8 + i]; }
-    for (int i = 0; i < ni8; ++i) Minv_i[(size_t)i * ni8 + c] = col[i];
-    (void)b;
-  }
+  (void)work;
 }
 
 // ------------------------------------------------------------------------------ PCG (cooperative)
+// aggregates of the two-level preconditioner (see PCG v3 below)
+struct Coarse { const int *agg_of, *agg_start, *agg_cams; int ng, nw, nco; };
 struct PcgArgs {
   const double *Scc; const int *rowptr, *cols; const double *Sci, *Sii, *rhs, *Minv_c, *Minv_i;
   int n_poses, ni8;
@@ -1113,6 +1141,9 @@ struct PcgArgs {
   double *part;                            // [3][gridDim.x] partial sums
   double tol; int max_iter;
   double *out;                             // [0]=iterations, [1]=final relative residual, [2]=|b|
+  // optional two-level part of the preconditioner on the camera rows (the gauge modes leave the intrinsics alone, so
+  // the coarse space of PCG v3 is the coarse space of the full system too): M^-1 = blockdiag^-1 + Wa (Wa' Scc Wa)^-1 Wa'
+  const double *W; Coarse C; const double *Einv; double *Cv, *Yv;   // W == nullptr: block-Jacobi only
 };
 
 __device__ __forceinline__ double grid_sum(cg::grid_group &grid, double v, double *part, double *sh) {
@@ -1160,18 +1191,45 @@ __device__ __forceinline__ double spmv_rows(const PcgArgs &A, const double *__re
   return dot;
 }
 
-// zeta = Minv r for this block's rows; returns partial r'zeta
-__device__ __forceinline__ double precond_rows(const PcgArgs &A, const double *__restrict__ r, double *__restrict__ zeta) {
+// zeta = Minv r for this block's rows; returns partial r'zeta.  Minv_i is block diagonal: [n_intr][KI*KI].
+// With a coarse space (A.W != nullptr) two extra grid-wide steps come first: Cv = Wa' r_c, Yv = Einv Cv.
+__device__ __forceinline__ double precond_rows(cg::grid_group &grid, const PcgArgs &A, const double *__restrict__ r, double *__restrict__ zeta) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, gwarp = tid >> 5, nwarps = nt >> 5;
   const int nc6 = 6 * A.n_poses;
+  const bool coarse = A.W != nullptr && A.C.nco > 0;
+  if (coarse) {
+    const int nw = A.C.nw, nco = A.C.nco;
+    for (int g = gwarp; g < A.C.ng; g += nwarps) {
+      const int c0 = A.C.agg_start[g], ne = 6 * (A.C.agg_start[g + 1] - c0);
+      for (int m = 0; m < nw; ++m) {
+        double v = 0;
+        for (int idx = lane; idx < ne; idx += 32) { const size_t e = 6 * (size_t)A.C.agg_cams[c0 + idx / 6] + idx % 6; v += A.W[(size_t)m * nc6 + e] * r[e]; }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) A.Cv[g * nw + m] = v;
+      }
+    }
+    grid.sync();
+    for (int row = gwarp; row < nco; row += nwarps) {
+      const double *er = A.Einv + (size_t)row * nco;
+      double v = 0; for (int k = lane; k < nco; k += 32) v += er[k] * __ldcg(A.Cv + k);
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) A.Yv[row] = v;
+    }
+    grid.sync();
+  }
   double dot = 0;
   for (int i = tid; i < nc6; i += nt) {
     const int a = i / 6, k = i % 6; const double *M = A.Minv_c + 36 * (size_t)a + 6 * k; const double *rb = r + 6 * a;
-    const double v = M[0] * rb[0] + M[1] * rb[1] + M[2] * rb[2] + M[3] * rb[3] + M[4] * rb[4] + M[5] * rb[5];
+    double v = M[0] * rb[0] + M[1] * rb[1] + M[2] * rb[2] + M[3] * rb[3] + M[4] * rb[4] + M[5] * rb[5];
+    if (coarse) { const double *y = A.Yv + A.C.agg_of[a] * A.C.nw; for (int m = 0; m < A.C.nw; ++m) v += A.W[(size_t)m * nc6 + i] * __ldcg(y + m); }
     zeta[i] = v; dot += v * r[i];
   }
   for (int q = tid; q < A.ni8; q += nt) {
-    double v = 0; for (int k = 0; k < A.ni8; ++k) v += A.Minv_i[(size_t)q * A.ni8 + k] * r[nc6 + k];
+    const double *M = A.Minv_i + (size_t)(q / KI) * KI * KI + (q % KI) * KI; const double *rb = r + nc6 + (q / KI) * KI;
+    double v = 0;
+    #pragma unroll
+    for (int k = 0; k < KI; ++k) v += M[k] * rb[k];
     zeta[nc6 + q] = v; dot += v * r[nc6 + q];
   }
   return dot;
@@ -1186,7 +1244,7 @@ __global__ void __launch_bounds__(256) pcg_kernel(PcgArgs A) {
   double bb = 0;
   for (int i = tid; i < nred; i += nt) { A.z[i] = 0.0; const double b = A.rhs[i]; A.res[i] = b; bb += b * b; }
   const double bnorm2 = grid_sum(grid, bb, P0, sh);
-  double rz = grid_sum(grid, precond_rows(A, A.res, A.zeta), P1, sh);
+  double rz = grid_sum(grid, precond_rows(grid, A, A.res, A.zeta), P1, sh);
   for (int i = tid; i < nred; i += nt) A.p[i] = A.zeta[i];
   grid.sync();
   int it = 0; double rr = bnorm2;
@@ -1198,7 +1256,7 @@ __global__ void __launch_bounds__(256) pcg_kernel(PcgArgs A) {
       for (int i = tid; i < nred; i += nt) { A.z[i] += alpha * A.p[i]; const double rn = A.res[i] - alpha * A.w[i]; A.res[i] = rn; rr_l += rn * rn; }
       rr = grid_sum(grid, rr_l, P2, sh);
       if (!(rr > A.tol * A.tol * bnorm2)) break;
-      const double rz_new = grid_sum(grid, precond_rows(A, A.res, A.zeta), P1, sh);
+      const double rz_new = grid_sum(grid, precond_rows(grid, A, A.res, A.zeta), P1, sh);
       const double beta = rz_new / rz; rz = rz_new;
       for (int i = tid; i < nred; i += nt) A.p[i] = A.zeta[i] + beta * A.p[i];
       grid.sync();
@@ -1305,6 +1363,12 @@ __device__ __forceinline__ void vsum_begin(Pcg2Smem &S, int V) {
 // fixed butterfly — the same order in every block, hence bitwise identical totals everywhere.
 __device__ __forceinline__ void vsum_end(cg::grid_group &grid, Pcg2Smem &S, int V, double *part) {
   __syncthreads();
+  if (gridDim.x == 1) {                      // single-CTA solve (small problems): a block barrier is the grid barrier
+    for (int i = threadIdx.x; i < V; i += PCG2_THREADS) { double t = 0; for (int w = 0; w < PCG2_THREADS / 32; ++w) t += S.wpart[w][i]; S.tot[i] = t; }
+    __threadfence_block();
+    __syncthreads();
+    return;
+  }
   for (int i = threadIdx.x; i < V; i += PCG2_THREADS) { double t = 0; for (int w = 0; w < PCG2_THREADS / 32; ++w) t += S.wpart[w][i]; part[(size_t)blockIdx.x * PCG2_V + i] = t; }
   grid.sync();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nb = (int)gridDim.x;
@@ -1522,7 +1586,6 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg2_kernel(Pcg2Args A) {
 // what piecewise-rigid coarse functions capture — so the iteration count stays ~30-70 from 10 to
 // 1000+ cameras where the single global gauge space needs 500-900 (measured, tools/ notes in DESIGN.md).
 //   M^-1 = blockdiag(Scc_pp)^-1 + Wa (Wa' Scc Wa)^-1 Wa',   Wa[(g,m)] = W[m] restricted to aggregate g.
-struct Coarse { const int *agg_of, *agg_start, *agg_cams; int ng, nw, nco; };
 
 // E += Wa' Scc Wa, one thread per S block (a,b): the nw x nw coupling of aggregates g(a), g(b)
 __global__ void coarse_assemble_kernel(const double *__restrict__ Scc, const int *__restrict__ brow, const int *__restrict__ cols, int nnzb,
@@ -1750,24 +1813,39 @@ __global__ void __launch_bounds__(256, 2) coarse_invert_kernel(double *__restric
   unsigned long long tlast = tim ? gtimer2() : 0ull;
   for (int k0 = 0; k0 < n; k0 += GJ_B) {
     const int nb = min(GJ_B, n - k0);
-    // ---- phase 1: B = inv(A_KK) (Gauss-Jordan in shared memory, 256 threads), identity-padded to 32
-    for (int idx = threadIdx.x; idx < GJ_B * GJ_B; idx += 256) { const int r = idx >> 5, c = idx & 31; Bs[r][c] = (r < nb && c < nb) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0); }
-    __syncthreads();
-    for (int k = 0; k < GJ_B; ++k) {
-      if (threadIdx.x < GJ_B) { s_col[threadIdx.x] = Bs[threadIdx.x][k]; s_row[threadIdx.x] = Bs[k][threadIdx.x]; }
-      __syncthreads();
-      const double piv = s_row[k];
-      if (!(piv > 0.0) || !isfinite(piv)) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(fail, 4); }
-      const double ip = 1.0 / piv;
-      for (int idx = threadIdx.x; idx < GJ_B * GJ_B; idx += 256) {
-        const int r = idx >> 5, c = idx & 31;
-        double v;
-        if (r == k) v = c == k ? ip : s_row[c] * ip;
-        else { const double f = s_col[r]; v = c == k ? -f * ip : Bs[r][c] - f * (s_row[c] * ip); }
-        Bs[r][c] = v;
+    // ---- phase 1: B = inv(A_KK), identity-padded to 32.  Gauss-Jordan by ONE warp: lane r keeps row r in registers,
+    // the pivot row goes through shared memory (one broadcast LDS per element) — no block barrier inside the 32
+    // sequential pivots (the 256-thread version paid two __syncthreads and an FP64 reciprocal per pivot: 19 us per block)
+    if (threadIdx.x < 32) {
+      const int r = threadIdx.x;
+      double b[GJ_B];
+      #pragma unroll
+      for (int c2 = 0; c2 < GJ_B; ++c2) b[c2] = (r < nb && c2 < nb) ? __ldcg(A + (size_t)(k0 + r) * n + k0 + c2) : (r == c2 ? 1.0 : 0.0);
+      #pragma unroll
+      for (int k = 0; k < GJ_B; ++k) {
+        if (r == k) {
+          #pragma unroll
+          for (int c2 = 0; c2 < GJ_B; ++c2) s_row[c2] = b[c2];
+        }
+        __syncwarp();
+        const double piv = s_row[k];
+        if (!(piv > 0.0) || !isfinite(piv)) { if (r == 0 && blockIdx.x == 0) atomicExch(fail, 4); }
+        const double ip = 1.0 / piv;
+        const double f = b[k];
+        if (r == k) {
+          #pragma unroll
+          for (int c2 = 0; c2 < GJ_B; ++c2) b[c2] = c2 == k ? ip : b[c2] * ip;
+        } else {
+          const double fi = f * ip;
+          #pragma unroll
+          for (int c2 = 0; c2 < GJ_B; ++c2) b[c2] = c2 == k ? -fi : b[c2] - fi * s_row[c2];
+        }
+        __syncwarp();
       }
-      __syncthreads();
+      #pragma unroll
+      for (int c2 = 0; c2 < GJ_B; ++c2) Bs[r][c2] = b[c2];
     }
+    __syncthreads();
     // slices of Cold / H / Gn
     GJ_LAP(0);
     // (all 32 operand loads of a slice element are issued before the first FMA: L1 is cold after a grid sync and a
@@ -2113,6 +2191,258 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg3_kernel(Pcg3Args P) {
   for (size_t i = tid; i < nc6; i += nt) { double v = A.X[i]; for (int a = 0; a < k; ++a) v -= A.X[(size_t)(1 + a) * nc6 + i] * S.zi[a]; A.z[i] = v; }
   for (int q = tid; q < A.ni8; q += nt) { double v = 0; for (int a = 0; a < k; ++a) if (S.rhs_col[1 + a] == q) v = S.zi[a]; A.z[nc6 + q] = v; }
   PCG_LAP(5);
+  if (tid == 0) { A.out[0] = (double)it; A.out[1] = sqrt(S.worst); A.out[2] = sqrt(S.bb[0]); }
+}
+
+// ------------------------------------------------------------------------------ PCG v4 (aggregate-owned, 2 grid syncs per iteration)
+// Same mathematics as v3 (block elimination of the intrinsics border, M^-1 = blockdiag^-1 + Wa (Wa' Scc Wa)^-1 Wa'),
+// different ownership: CTA g owns aggregate g — its camera rows of the SpMV, its slices of every vector, its nw rows of
+// the coarse solve.  That removes two of the four grid-wide steps of an iteration:
+//   * the coarse solve needs no step of its own: every CTA stages the (tiny) coarse residual and computes only the
+//     nw rows y_g = Einv[g rows, :] c it needs itself (one L2 round trip: the row loads are all in flight together);
+//   * the coarse residual of the NEW r needs no step either: c_new = c - alpha Wa' w, and Wa' w of an aggregate is
+//     formed inside its CTA during the SpMV and published with the same grid sync that publishes p'w.
+// Per iteration:  [A] alpha; x += alpha p, r -= alpha w, |r|^2; c_new; y_g; z = Minv r + Wa y; r'z      -> sync
+//                 [B] beta, convergence test; w = Scc (z + beta p) on the fly, p'w, Wa' w of the aggregate -> sync
+// (v3: coarse solve -> sync, z -> sync, SpMV -> sync, update -> sync.)  Reductions are fixed-order.
+constexpr int PCG4_MAXCAM = 32;        // cameras per aggregate handled in place (aggregation keeps them <= ~16)
+__global__ void __launch_bounds__(PCG2_THREADS) pcg4_kernel(Pcg3Args P, double *__restrict__ Cv2, double *__restrict__ AW) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ unsigned char pcg2_smem_raw[];
+  Pcg2Smem &S = *reinterpret_cast<Pcg2Smem *>(pcg2_smem_raw);
+  double *sCv = reinterpret_cast<double *>(pcg2_smem_raw + sizeof(Pcg2Smem));     // [4][PCG3_NCO_MAX] coarse residual chunk
+  __shared__ double s_y[MAXW][MAXRHS];                                            // y_g of the aggregate being processed
+  __shared__ double s_aw[PCG2_THREADS / 32][4][MAXW];                             // per-warp Wa' w partials (one chunk of 4 rhs)
+  const Pcg2Args &A = P.base; const Coarse &C = P.C;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  constexpr int NWARP = PCG2_THREADS / 32;
+  const size_t nc6 = 6 * (size_t)A.n_poses;
+  const int nw = C.nw, nco = C.nco;
+  if (threadIdx.x == 0) {
+    int n = 1; S.rhs_col[0] = -1;
+    for (int q = 0; q < A.ni8; ++q) if ((A.intr_mask[q / KI] >> (q % KI)) & 1) { if (n < MAXRHS) S.rhs_col[n++] = q; }
+    S.nrhs = n;
+  }
+  __syncthreads();
+  const int nrhs = S.nrhs;
+  double *Pcur = A.Pv, *Pnext = P.Pv2;
+  double *Ccur = P.Cv, *Cnext = Cv2;               // coarse residual, ping-pong: [nrhs][nco]
+  // ---- init (own aggregates): X = 0, P = 0, W = 0, R = B, |b|^2, c = Wa' b, AW = 0
+  vsum_begin(S, nrhs);
+  for (int g = blockIdx.x; g < C.ng; g += gridDim.x) {
+    const int c0 = C.agg_start[g], ne = 6 * (C.agg_start[g + 1] - c0);
+    for (int j = wib; j < nrhs; j += NWARP) {
+      const double *src = j == 0 ? A.rhs : A.Sci + (size_t)S.rhs_col[j] * nc6;
+      double v = 0, cm[MAXW];
+      #pragma unroll
+      for (int m = 0; m < MAXW; ++m) cm[m] = 0.0;
+      for (int idx = lane; idx < ne; idx += 32) {
+        const size_t e = 6 * (size_t)C.agg_cams[c0 + idx / 6] + idx % 6; const double b = src[e];
+        A.X[j * nc6 + e] = 0.0; Pcur[j * nc6 + e] = 0.0; A.Wv[j * nc6 + e] = 0.0; A.Rv[j * nc6 + e] = b; v += b * b;
+        #pragma unroll
+        for (int m = 0; m < MAXW; ++m) if (m < nw) cm[m] += A.W[m * nc6 + e] * b;
+      }
+      warp_acc(S, v, j);
+      #pragma unroll
+      for (int m = 0; m < MAXW; ++m) if (m < nw) {
+        double cv = cm[m]; for (int o = 16; o > 0; o >>= 1) cv += __shfl_xor_sync(0xffffffffu, cv, o);
+        if (lane == 0) { Ccur[(size_t)j * nco + g * nw + m] = cv; AW[(size_t)j * nco + g * nw + m] = 0.0; }
+      }
+    }
+  }
+  vsum_end(grid, S, nrhs, A.part);
+  if (threadIdx.x < nrhs) { const int j = threadIdx.x; S.bb[j] = S.tot[j]; S.done[j] = !(S.tot[j] > 0.0); S.alpha[j] = 0; S.beta[j] = 0; S.rz[j] = 0; }
+  if (threadIdx.x == 0) { S.worst = 0; S.all_done = 0; }
+  __syncthreads();
+  int it = 0;
+  unsigned long long tlast = P.tim ? gtimer() : 0ull;
+  for (;;) {
+    // ================================================================= [A]
+    vsum_begin(S, 2 * nrhs);
+    for (int j0 = 0; j0 < nrhs; j0 += 4) {
+      const int nj = min(4, nrhs - j0);
+      // coarse residual of the new r for ALL aggregates: c_new = c - alpha Wa'w  (every CTA forms the whole (tiny) vector;
+      // the owner of an aggregate also stores its entries for the next iteration)
+      if (nco > 0) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < nco; k += PCG2_THREADS) {
+          const int g = k / nw; const bool mine = (g % (int)gridDim.x) == (int)blockIdx.x;
+          #pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nj) {
+            const size_t o = (size_t)(j0 + j) * nco + k;
+            const double cn = __ldcg(Ccur + o) - S.alpha[j0 + j] * __ldcg(AW + o);
+            sCv[j * PCG3_NCO_MAX + k] = cn;
+            if (mine) Cnext[o] = cn;
+          }
+        }
+        __syncthreads();
+      }
+      PCG_LAP(0);
+      for (int g = blockIdx.x; g < C.ng; g += gridDim.x) {
+        const int c0 = C.agg_start[g], ne = 6 * (C.agg_start[g + 1] - c0);
+        // y_g[m][j] = Einv[g nw + m, :] . c_new[j, :]   (warp m)
+        if (nco > 0) {
+          for (int m = wib; m < nw; m += NWARP) {
+            const double *er = P.Einv + (size_t)(g * nw + m) * nco;
+            double ev[PCG3_NCO_MAX / 32];
+            #pragma unroll
+            for (int q = 0; q < PCG3_NCO_MAX / 32; ++q) { const int k = lane + 32 * q; ev[q] = k < nco ? __ldcg(er + k) : 0.0; }
+            double acc[4] = {0, 0, 0, 0};
+            #pragma unroll
+            for (int q = 0; q < PCG3_NCO_MAX / 32; ++q) { const int k = lane + 32 * q;
+              if (k < nco) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < nj) acc[j] += ev[q] * sCv[j * PCG3_NCO_MAX + k]; } }
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              double v = acc[j]; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              if (lane == 0 && j < nj) s_y[m][j0 + j] = v;
+            }
+          }
+          __syncthreads();
+          PCG_LAP(1);
+        }
+        // own slices: x += alpha p ; r -= alpha w ; |r|^2 ; z = Minv r + Wa y ; r'z       (warp per right-hand side)
+        for (int j = j0 + wib; j < j0 + nj; j += NWARP) {
+          if (S.done[j]) continue;
+          const double al = S.alpha[j];
+          double y[MAXW];
+          #pragma unroll
+          for (int m = 0; m < MAXW; ++m) y[m] = (m < nw && nco > 0) ? s_y[m][j] : 0.0;
+          double rr = 0, rz = 0;
+          // (r of a camera is needed whole for Minv r: update it first, then form z)
+          for (int idx = lane; idx < ne; idx += 32) {
+            const size_t e = 6 * (size_t)C.agg_cams[c0 + idx / 6] + idx % 6;
+            A.X[j * nc6 + e] += al * Pcur[j * nc6 + e];
+            const double rn = A.Rv[j * nc6 + e] - al * A.Wv[j * nc6 + e]; A.Rv[j * nc6 + e] = rn; rr += rn * rn;
+          }
+          __syncwarp();
+          for (int idx = lane; idx < ne; idx += 32) {
+            const size_t cam = C.agg_cams[c0 + idx / 6]; const int k = idx % 6; const size_t e = 6 * cam + k;
+            const double *rb = A.Rv + j * nc6 + 6 * cam;
+            const double2 *M2 = reinterpret_cast<const double2 *>(A.Minv_c + 36 * cam + 6 * k), *r2 = reinterpret_cast<const double2 *>(rb);
+            const double2 m0 = M2[0], m1 = M2[1], m2 = M2[2], b0 = r2[0], b1 = r2[1], b2 = r2[2];
+            double zz = m0.x * b0.x + m0.y * b0.y + m1.x * b1.x + m1.y * b1.y + m2.x * b2.x + m2.y * b2.y;
+            #pragma unroll
+            for (int m = 0; m < MAXW; ++m) if (m < nw) zz += A.W[m * nc6 + e] * y[m];
+            A.Zv[j * nc6 + e] = zz; rz += zz * rb[k];
+          }
+          warp_acc(S, rz, j); warp_acc(S, rr, nrhs + j);
+        }
+        __syncthreads();                                   // s_y is reused by the next aggregate / chunk
+      }
+    }
+    PCG_LAP(2);
+    vsum_end(grid, S, 2 * nrhs, A.part);
+    PCG_LAP(3);
+    { double *t2 = Ccur; Ccur = Cnext; Cnext = t2; }
+    if (threadIdx.x < nrhs) { const int j = threadIdx.x; if (!S.done[j]) { const double rzn = S.tot[j]; S.beta[j] = it == 0 ? 0.0 : rzn / S.rz[j]; S.rz[j] = rzn; } }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int ad = 1; double wmax = 0;
+      for (int j = 0; j < nrhs; ++j) if (!S.done[j]) { const double rel2 = S.tot[nrhs + j] / S.bb[j]; wmax = fmax(wmax, rel2); if (!(rel2 > A.tol * A.tol)) S.done[j] = 1; else ad = 0; }
+      S.all_done = ad; if (it > 0) S.worst = wmax;
+    }
+    __syncthreads();
+    if (S.all_done || it >= A.max_iter) break;
+    // ================================================================= [B]  w = Scc (z + beta p) ; p'w ; Wa' w
+    vsum_begin(S, nrhs);
+    for (int j0 = 0; j0 < nrhs; j0 += 4) {
+      const int nj = min(4, nrhs - j0);
+      for (int g = blockIdx.x; g < C.ng; g += gridDim.x) {
+        const int c0 = C.agg_start[g], ncam = C.agg_start[g + 1] - c0;
+        for (int i = threadIdx.x; i < NWARP * 4 * MAXW; i += PCG2_THREADS) (&s_aw[0][0][0])[i] = 0.0;
+        __syncthreads();
+        for (int ci = wib; ci < ncam; ci += NWARP) {
+          const int a = C.agg_cams[c0 + ci];
+          double acc[4][6];
+          #pragma unroll
+          for (int j = 0; j < 4; ++j)
+            #pragma unroll
+            for (int i = 0; i < 6; ++i) acc[j][i] = 0.0;
+          for (int e = A.rowptr[a] + lane; e < A.rowptr[a + 1]; e += 32) {
+            const double *blk = A.Scc + 36 * (size_t)e; const int cb = 6 * A.cols[e];
+            double b[36];
+            #pragma unroll
+            for (int i = 0; i < 9; ++i) ldg256(blk + 4 * i, b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]);
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < nj && !S.done[j0 + j]) {
+                const size_t off = (size_t)(j0 + j) * nc6 + cb; const double bt = S.beta[j0 + j];
+                const double2 *zp = reinterpret_cast<const double2 *>(A.Zv + off), *pp = reinterpret_cast<const double2 *>(Pcur + off);
+                const double2 z0 = zp[0], z1 = zp[1], z2 = zp[2], q0 = pp[0], q1 = pp[1], q2 = pp[2];
+                const double xv[6] = {z0.x + bt * q0.x, z0.y + bt * q0.y, z1.x + bt * q1.x, z1.y + bt * q1.y, z2.x + bt * q2.x, z2.y + bt * q2.y};
+                #pragma unroll
+                for (int i = 0; i < 6; ++i)
+                  #pragma unroll
+                  for (int k = 0; k < 6; ++k) acc[j][i] += b[i * 6 + k] * xv[k];
+              }
+            }
+          }
+          #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < nj && !S.done[j0 + j]) {
+              #pragma unroll
+              for (int i = 0; i < 6; ++i) { double v = acc[j][i]; for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o); acc[j][i] = v; }
+              if (lane == 0) {
+                const size_t off = (size_t)(j0 + j) * nc6 + 6 * (size_t)a; const double bt = S.beta[j0 + j];
+                double d = 0;
+                for (int i = 0; i < 6; ++i) { const double pv = A.Zv[off + i] + bt * Pcur[off + i]; Pnext[off + i] = pv; A.Wv[off + i] = acc[j][i]; d += acc[j][i] * pv; }
+                S.wpart[wib][j0 + j] += d;
+                for (int m = 0; m < nw; ++m) { double t = 0; for (int i = 0; i < 6; ++i) t += A.W[m * nc6 + 6 * (size_t)a + i] * acc[j][i]; s_aw[wib][j][m] += t; }
+              }
+            }
+          }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nj * nw; i += PCG2_THREADS) {
+          const int j = i / nw, m = i % nw;
+          if (!S.done[j0 + j]) { double t = 0; for (int w = 0; w < NWARP; ++w) t += s_aw[w][j][m]; AW[(size_t)(j0 + j) * nco + g * nw + m] = t; }
+        }
+        __syncthreads();
+      }
+    }
+    PCG_LAP(4);
+    vsum_end(grid, S, nrhs, A.part);              // its grid.sync also publishes Wv, Pnext and AW
+    PCG_LAP(5);
+    { double *t2 = Pcur; Pcur = Pnext; Pnext = t2; }
+    if (threadIdx.x < nrhs) { const int j = threadIdx.x; S.alpha[j] = S.done[j] ? 0.0 : S.rz[j] / S.tot[j]; }
+    __syncthreads();
+    ++it;
+  }
+  // ---- border: (Sii - Sci Y2) zi = bi - Sci y1 ; zc = y1 - Y2 zi      (as v3)
+  const int k = nrhs - 1;
+  if (k > 0) {
+    for (int a = 0; a < k; ++a) {
+      vsum_begin(S, k + 1);
+      const double *row = A.Sci + (size_t)S.rhs_col[1 + a] * nc6;
+      for (int b = 0; b <= k; ++b) {
+        const double *x = A.X + (size_t)(b == k ? 0 : 1 + b) * nc6;
+        double v = 0; for (size_t i = tid; i < nc6; i += nt) v += row[i] * x[i];
+        warp_acc(S, v, b);
+      }
+      vsum_end(grid, S, k + 1, A.part);
+      if (threadIdx.x <= k) {
+        const int b = threadIdx.x;
+        if (b < k) S.T[a][b] = A.Sii[(size_t)S.rhs_col[1 + a] * A.ni8 + S.rhs_col[1 + b]] - S.tot[b];
+        else S.T[a][k] = A.rhs[nc6 + S.rhs_col[1 + a]] - S.tot[k];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      for (int a = 0; a < k; ++a) for (int b = a + 1; b < k; ++b) { const double m = 0.5 * (S.T[a][b] + S.T[b][a]); S.T[a][b] = m; S.T[b][a] = m; }
+      for (int c = 0; c < k; ++c) {
+        int piv = c; for (int r2 = c + 1; r2 < k; ++r2) if (fabs(S.T[r2][c]) > fabs(S.T[piv][c])) piv = r2;
+        if (piv != c) for (int q = 0; q <= k; ++q) { const double t2 = S.T[c][q]; S.T[c][q] = S.T[piv][q]; S.T[piv][q] = t2; }
+        for (int r2 = c + 1; r2 < k; ++r2) { const double f = S.T[r2][c] / S.T[c][c]; for (int q = c; q <= k; ++q) S.T[r2][q] -= f * S.T[c][q]; }
+      }
+      for (int c = k - 1; c >= 0; --c) { double sacc = S.T[c][k]; for (int q = c + 1; q < k; ++q) sacc -= S.T[c][q] * S.zi[q]; S.zi[c] = sacc / S.T[c][c]; }
+    }
+    __syncthreads();
+  }
+  for (size_t i = tid; i < nc6; i += nt) { double v = A.X[i]; for (int a = 0; a < k; ++a) v -= A.X[(size_t)(1 + a) * nc6 + i] * S.zi[a]; A.z[i] = v; }
+  for (int q = tid; q < A.ni8; q += nt) { double v = 0; for (int a = 0; a < k; ++a) if (S.rhs_col[1 + a] == q) v = S.zi[a]; A.z[nc6 + q] = v; }
   if (tid == 0) { A.out[0] = (double)it; A.out[1] = sqrt(S.worst); A.out[2] = sqrt(S.bb[0]); }
 }
 

@@ -71,7 +71,7 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
     int device_;
   };
   // wall-clock of the last Adjust / AdjustAndReject, milliseconds (where the end-to-end time goes)
-  struct Timing { double pack_ms = 0, solve_ms = 0, reject_ms = 0, angle_ms = 0, unpack_ms = 0; int rounds = 0; };
+  struct Timing { double pack_ms = 0, solve_ms = 0, reject_ms = 0, angle_ms = 0, unpack_ms = 0, erase_ms = 0, destroy_ms = 0; int rounds = 0; };
   struct RejectStats { size_t residual_outliers = 0, short_tracks = 0, angle_tracks = 0; int rounds = 0; };
 
   Bundle_Adjustment_B200() {}
@@ -142,6 +142,8 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
     const size_t n_obs = f.obs_view.size(), n_reg = f.lm.size();
     std::vector<uint32_t> bits((n_obs + 31) / 32);
     std::vector<uint8_t> obs_alive(n_obs, 1), pt_alive(f.points.size() / 3, 1), pt_now(f.points.size() / 3, 0), kill(f.points.size() / 3, 0);
+    AngleWork angle_work;
+    PrepareAngleWork(f, angle_work);
     bool ok = true, again = true;
     while (again)
     {
@@ -164,7 +166,7 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
       // ---- angle rule on the host (poses / intrinsics of this round, flat arrays, openMVG's own ray geometry)
       const auto t3 = now();
       UnpackCameras(sfm_data, options, f);
-      const size_t n_angle = AngleRule(sfm_data, f, obs_alive, pt_alive, min_angle_deg, kill);
+      const size_t n_angle = AngleRule(f, angle_work, obs_alive, pt_alive, min_angle_deg, kill);
       if (n_angle)
       {
         int64_t nt = 0;
@@ -184,15 +186,19 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
       if (ok)
       {
         Unpack(sfm_data, options, f, true);
+        timing_.unpack_ms = ms_since(t4);
+        const auto t5 = now();
         // the rejected observations / tracks leave SfM_Data exactly as the reference's filters erase them
         for (size_t o = 0; o < f.n_regular_obs; ++o)
           if (!obs_alive[o] && pt_alive[f.obs_point[o]]) f.lm[f.obs_point[o]]->obs.erase(f.obs_view_id[o]);
         for (size_t j = 0; j < n_reg; ++j)
           if (!pt_alive[j]) sfm_data.structure.erase(f.lm_id[j]);
+        timing_.erase_ms = ms_since(t5);
       }
     }
+    const auto t6 = now();
     omvg_ba_destroy(ctx);
-    timing_.unpack_ms = ms_since(t4);
+    timing_.destroy_ms = ms_since(t6);
     timing_.rounds = st.rounds;
     if (stats) *stats = st;
     return ok;
@@ -470,39 +476,63 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
 
   // RemoveOutliers_AngleError (sfm_data_filters.cpp:77-122) on the flat arrays: a track whose largest angle between
   // any two of its (live) bearing rays is below min_angle is removed.  The rays are what AngleBetweenRay
-  // (cameras/Camera_Intrinsics.hpp:263-280) forms, computed once per observation instead of once per pair.
-  size_t AngleRule(const SfM_Data & sfm_data, const Flat & f, const std::vector<uint8_t> & obs_alive, const std::vector<uint8_t> & pt_alive,
+  // (cameras/Camera_Intrinsics.hpp:263-280) forms — (R' * intrinsic(ud_pixel)).normalized() — computed once per
+  // observation instead of once per pair, through the intrinsic's own batch operator() (one call per block of
+  // observations of one intrinsic group: the per-point overload allocates a dynamic matrix per call).
+  struct AngleWork { std::vector<uint32_t> order; std::vector<size_t> seg; std::vector<Vec3> rays; };
+  static void PrepareAngleWork(const Flat & f, AngleWork & w)
+  {
+    const size_t n = f.n_regular_obs, ni = f.intr_ptr.size();
+    w.seg.assign(ni + 1, 0);
+    for (size_t o = 0; o < n; ++o) ++w.seg[f.view_intr[f.obs_view[o]] + 1];
+    for (size_t q = 0; q < ni; ++q) w.seg[q + 1] += w.seg[q];
+    w.order.resize(n);
+    std::vector<size_t> cur(w.seg.begin(), w.seg.end() - 1);
+    for (size_t o = 0; o < n; ++o) w.order[cur[f.view_intr[f.obs_view[o]]]++] = static_cast<uint32_t>(o);
+    w.rays.resize(n);
+  }
+  size_t AngleRule(const Flat & f, AngleWork & w, const std::vector<uint8_t> & obs_alive, const std::vector<uint8_t> & pt_alive,
                    double min_angle_deg, std::vector<uint8_t> & kill) const
   {
-    (void)sfm_data;
     const int64_t n_reg = static_cast<int64_t>(f.lm.size());
     std::vector<Mat3> Rt(f.pose_ptr.size());
     for (size_t p = 0; p < f.pose_ptr.size(); ++p) Rt[p] = f.pose_ptr[p]->rotation().transpose();
+    // ---- bearing rays, blocks of one intrinsic group
+    constexpr size_t BLK = 4096;
+    std::vector<std::pair<size_t, size_t>> blocks;              // [begin, end) into w.order, one intrinsic each
+    for (size_t q = 0; q + 1 < w.seg.size(); ++q)
+      for (size_t b = w.seg[q]; b < w.seg[q + 1]; b += BLK) blocks.emplace_back(b, std::min(b + BLK, w.seg[q + 1]));
+    const int64_t nb = static_cast<int64_t>(blocks.size());
+#ifdef OPENMVG_USE_OPENMP
+    #pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int64_t bi = 0; bi < nb; ++bi)
+    {
+      const size_t b0 = blocks[bi].first, b1 = blocks[bi].second, m = b1 - b0;
+      const cameras::IntrinsicBase * intr = f.intr_ptr[f.view_intr[f.obs_view[w.order[b0]]]];
+      Mat2X pts(2, m);
+      for (size_t i = 0; i < m; ++i) { const size_t o = w.order[b0 + i]; pts.col(i) = intr->get_ud_pixel(Vec2(f.obs_xy[2 * o], f.obs_xy[2 * o + 1])); }
+      const Mat3X bearing = (*intr)(pts);
+      for (size_t i = 0; i < m; ++i) { const size_t o = w.order[b0 + i]; w.rays[o] = (Rt[f.view_pose[f.obs_view[o]]] * bearing.col(i)).normalized(); }
+    }
+    // ---- per track: the largest pairwise angle of the live observations
     std::fill(kill.begin(), kill.end(), 0);
     size_t removed = 0;
 #ifdef OPENMVG_USE_OPENMP
-    #pragma omp parallel for schedule(dynamic, 256) reduction(+:removed)
+    #pragma omp parallel for schedule(dynamic, 512) reduction(+:removed)
 #endif
     for (int64_t j = 0; j < n_reg; ++j)
     {
       if (!pt_alive[j]) continue;
-      Vec3 rays[64]; std::vector<Vec3> more;
-      size_t n = 0;
       const size_t lo = f.lm_first[j], hi = f.lm_first[j + 1];
-      Vec3 * r = rays;
-      if (hi - lo > 64) { more.resize(hi - lo); r = more.data(); }
-      for (size_t o = lo; o < hi; ++o)
-      {
-        if (!obs_alive[o]) continue;
-        const int32_t v = f.obs_view[o];
-        const cameras::IntrinsicBase * intr = f.intr_ptr[f.view_intr[v]];
-        const Vec2 x(f.obs_xy[2 * o], f.obs_xy[2 * o + 1]);
-        r[n++] = (Rt[f.view_pose[v]] * (*intr)(intr->get_ud_pixel(x))).normalized();
-      }
       double max_angle = 0.0;
-      for (size_t a = 0; a < n; ++a)
-        for (size_t b = a + 1; b < n; ++b)
-          max_angle = std::max(max_angle, R2D(acos(clamp(r[a].dot(r[b]), -1.0 + 1.e-8, 1.0 - 1.e-8))));
+      for (size_t a = lo; a < hi; ++a)
+      {
+        if (!obs_alive[a]) continue;
+        for (size_t b = a + 1; b < hi; ++b)
+          if (obs_alive[b])
+            max_angle = std::max(max_angle, R2D(acos(clamp(w.rays[a].dot(w.rays[b]), -1.0 + 1.e-8, 1.0 - 1.e-8))));
+      }
       if (max_angle < min_angle_deg) { kill[j] = 1; ++removed; }
     }
     return removed;

@@ -22,7 +22,8 @@ PINHOLE_CAMERA_RADIAL1 = 2
 PINHOLE_CAMERA_RADIAL3 = 3
 PINHOLE_CAMERA_BROWN = 4
 PINHOLE_CAMERA_FISHEYE = 5
-INTR_NPARAMS = {1: 3, 2: 4, 3: 6, 4: 8, 5: 7}
+CAMERA_SPHERICAL = 7          # no parameter block; the intrinsic slot carries the image size {w, h}
+INTR_NPARAMS = {1: 3, 2: 4, 3: 6, 4: 8, 5: 7, 7: 0}
 INTR_STRIDE = 8
 
 
@@ -100,9 +101,17 @@ def ba_scene(n_cams: int, n_points: int, obs_per_point: int, seed: int = 42,
     obs_point = np.repeat(np.arange(n_points, dtype=np.int32), obs_per_point)
     obs_view = cam.reshape(-1).astype(np.int32)
     Xc = np.einsum('oij,oj->oi', gtR[obs_view], X[obs_point] - gtC[obs_view])
-    u = Xc[:, :2] / Xc[:, 2:3]
-    u = _distort(u, model, gt_dist)
-    xy = np.stack([cx + f * u[:, 0], cy + f * u[:, 1]], 1) + rng.normal(0, noise_px, (len(obs_view), 2))
+    if model == CAMERA_SPHERICAL:
+        # Camera_Spherical.hpp / functor.hpp:700-712: lon = atan2(x, z), lat = atan2(-y, |(x, z)|), pixel = (lon, -lat) / 2pi * max(w, h) + (w, h) / 2
+        w_img, h_img = 4000.0, 2000.0
+        intr[:, 0], intr[:, 1], intr[:, 2] = w_img, h_img, 0.0
+        lon = np.arctan2(Xc[:, 0], Xc[:, 2]); lat = np.arctan2(-Xc[:, 1], np.hypot(Xc[:, 0], Xc[:, 2]))
+        size = max(w_img, h_img)
+        xy = np.stack([lon / (2 * np.pi) * size + w_img / 2, -lat / (2 * np.pi) * size + h_img / 2], 1) + rng.normal(0, noise_px, (len(obs_view), 2))
+    else:
+        u = Xc[:, :2] / Xc[:, 2:3]
+        u = _distort(u, model, gt_dist)
+        xy = np.stack([cx + f * u[:, 0], cy + f * u[:, 1]], 1) + rng.normal(0, noise_px, (len(obs_view), 2))
     if outlier_frac > 0:
         bad = rng.random(len(obs_view)) < outlier_frac
         xy[bad] += rng.normal(0, 60.0, (int(bad.sum()), 2))

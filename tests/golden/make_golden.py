@@ -120,6 +120,32 @@ def main_io():
     ck.ref_save_descs(os.path.join(HERE, "desc_fixture.desc"), synth.descriptors(1, [37], seed=3)[0])
 
 
+# Added after the first golden run (round 2): the sixth camera model and scenes with many intrinsic groups.  `more`
+# appends / replaces these in reference_outputs.json without touching the rest.
+BA_MORE_CASES = [
+    dict(name="spherical", scene=dict(n_cams=14, n_points=700, obs_per_point=6, seed=8, model=7), opts={}),
+    dict(name="spherical_rotation_only", scene=dict(n_cams=14, n_points=700, obs_per_point=6, seed=8, model=7), opts=dict(extrinsics_opt=2)),
+    dict(name="intr40", scene=dict(n_cams=40, n_points=2000, obs_per_point=6, seed=3, n_intrinsics=40), opts={}),
+    dict(name="intr200_radial3", scene=dict(n_cams=200, n_points=6000, obs_per_point=8, seed=3, n_intrinsics=200, model=3), opts={}),
+    dict(name="intr5_brown", scene=dict(n_cams=30, n_points=1500, obs_per_point=8, seed=3, n_intrinsics=5, model=4), opts={}),
+]
+
+
+def main_more():
+    path = os.path.join(HERE, "reference_outputs.json")
+    out = json.load(open(path))
+    names = {c["name"] for c in BA_MORE_CASES}
+    out["ba"] = [c for c in out["ba"] if c["name"] not in names]
+    for c in BA_MORE_CASES:
+        s = synth.ba_scene(**c["scene"])
+        ref_opts = {k: v for k, v in c["opts"].items() if k in ("intrinsics_opt", "extrinsics_opt", "structure_opt", "use_loss")}
+        r = ck.ref_ba_adjust(s, threads=8, **ref_opts)
+        out["ba"].append(dict(name=c["name"], scene=c["scene"], opts=c["opts"], ok=r["ok"], initial_cost=r["initial_cost"], final_cost=r["final_cost"],
+                              iterations=r["iterations"], successful=r["successful"], unsuccessful=r["unsuccessful"], termination=r["termination"]))
+        print("ba", c["name"], r["initial_cost"], r["final_cost"], r["iterations"], r["termination"])
+    json.dump(out, open(path, "w"), indent=1)
+
+
 def main():
     out = {"match": [], "ba": []}
     arrays = {}
@@ -151,6 +177,8 @@ if __name__ == "__main__":
         main_cascade()
     elif len(sys.argv) > 1 and sys.argv[1] == "io":
         main_io()
+    elif len(sys.argv) > 1 and sys.argv[1] == "more":
+        main_more()
     else:
         main()
         main_ext()
