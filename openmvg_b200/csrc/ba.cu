@@ -540,8 +540,9 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   static const int coarse_every = getenv("OMVG_BA_COARSE_EVERY") ? std::max(1, atoi(getenv("OMVG_BA_COARSE_EVERY"))) : 3;
   // Small reduced systems are latency-bound on the grid-wide barriers of the PCG (4-5 us per iteration of pure
   // synchronisation at 148 CTAs): up to `small_nc` poses ONE CTA runs the whole solve with block barriers instead.
-  static const int small_nc = getenv("OMVG_BA_PCG_SMALL") ? atoi(getenv("OMVG_BA_PCG_SMALL")) : 48;
-  const int pcg_grid = (c->nc <= small_nc && use_pcg3 && !getenv("OMVG_BA_PCG3")) ? 1 : c->n_sms;
+  // (measured: 0.70 vs 0.74 ms per LM iteration at 10 poses, but 0.99 vs 0.84 at 20: one CTA serialises the SpMV)
+  static const int small_nc = getenv("OMVG_BA_PCG_SMALL") ? atoi(getenv("OMVG_BA_PCG_SMALL")) : 12;
+  const int pcg_grid = (c->nc <= small_nc && use_pcg3) ? 1 : c->n_sms;
   if (!c->gj_grid) {                                        // as many co-resident CTAs as the tile count can use
     int per_sm = 1; OMVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_invert_kernel, 256, 0));
     c->gj_grid = c->n_sms * std::max(1, std::min(per_sm, 2));
@@ -641,8 +642,11 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
         Pcg3Args P3{}; P3.base = P2; P3.C = CO; P3.C.nco = c->ng * nw; P3.Einv = Einv_p; P3.Cv = c->cCv.p; P3.Yv = c->cYv.p; P3.Pv2 = c->bP2.p;
         static const bool pcg_timing = getenv("OMVG_BA_PCG_TIMING") != nullptr;
         if (pcg_timing) { if (!c->pcg_tim.p) { if ((rc = c->pcg_tim.alloc(8))) return rc; } OMVG_CUDA(cudaMemsetAsync(c->pcg_tim.p, 0, 64, c->stream)); P3.tim = c->pcg_tim.p; }
-        static const bool force_pcg3 = getenv("OMVG_BA_PCG3") != nullptr;      // A/B: the 4-sync kernel
-        if (!force_pcg3 && P3.C.nco <= PCG3_NCO_MAX) {
+        // pcg4 (2 grid syncs per iteration instead of 4) is kept for A/B and for the single-CTA mode: at 148 CTAs it is
+        // NOT faster (measured, config 2: 14.7 vs 14.2 ms per solve) — every CTA re-stages the whole coarse residual
+        // (6 us per iteration) where v3 pays its two extra barriers (2 x 3.5 us).  See DESIGN.md §4.3.
+        static const bool want_pcg4 = getenv("OMVG_BA_PCG4") != nullptr;
+        if ((want_pcg4 || pcg_grid == 1) && P3.C.nco <= PCG3_NCO_MAX) {
           double *cv2 = c->cCv2.p, *aw = c->cAW.p;
           void *args[] = {&P3, &cv2, &aw};
           OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg4_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem) + 4 * PCG3_NCO_MAX * sizeof(double), c->stream));
