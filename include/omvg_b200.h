@@ -129,6 +129,24 @@ int omvg_match_load_desc_files(omvg_match_ctx *ctx, uint32_t n_images, const cha
 int omvg_matches_save(const char *path, uint64_t n_pairs, const uint32_t *pair_I, const uint32_t *pair_J,
                       const uint64_t *offsets, const uint32_t *ij);
 
+/* ===================================================================== GEOMETRIC FILTER ==== */
+/* Per-pair a-contrario RANSAC with the fundamental-matrix model: what GeometricFilter_FMatrix_AC::Robust_estimation
+ * (matching_image_collection/F_ACRobust.hpp:45-106) runs for every pair of ImageCollectionGeometricFilter::
+ * Robust_model_estimation (GeometricFilter.hpp:66-128) — ACKernelAdaptor<SevenPointSolver, EpipolarDistanceError,
+ * UnnormalizerT> + ACRANSAC (robust_estimation/robust_estimator_ACRansac.hpp:303-490) with std::mt19937(default_seed).
+ * One CTA per pair; same sample sequence, same NFA scoring, same inlier lists as the reference.
+ *   offsets[n_pairs+1]        CSR over the putative matches of the pairs (omvg_match_fetch layout)
+ *   xI, xJ [n_matches][2]     pixel positions of the matched features in image I / J (MatchesPairToMat)
+ *   image_size[n_pairs][4]    wI hI wJ hJ (View::ui_width / ui_height)
+ *   precision                 upper bound in pixels (main_GeometricFilter.cpp:304 passes 4.0); must be finite
+ *   max_iterations            2048 in main_GeometricFilter.cpp:82
+ * out: inliers[n_matches] (pair p: the first n_inliers[p] entries of its segment, ascending match index; the reference
+ * keeps the pair iff n_inliers[p] > 2.5 * 7), F[n_pairs][9] row-major un-normalised, stats[n_pairs][2] = {errorMax
+ * (pixels), minNFA}. */
+int omvg_geom_fundamental_acransac(int device, uint64_t n_pairs, const uint64_t *offsets, const double *xI, const double *xJ,
+                                   const int32_t *image_size, double precision, uint32_t max_iterations,
+                                   uint32_t *inliers, uint32_t *n_inliers, double *F, double *stats);
+
 /* ===================================================================== BA ================= */
 #define OMVG_BA_INTR_STRIDE 8   /* doubles reserved per intrinsic block */
 

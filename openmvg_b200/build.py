@@ -8,7 +8,9 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libomvg_b200.so")
-SOURCES = ["match.cu", "ba.cu", "io.cu"]
+SOURCES = ["match.cu", "ba.cu", "io.cu", "geom.cu"]
+# geom.cu mirrors a CPU control flow whose comparisons must see the same roundings: no FMA contraction there
+EXTRA_FLAGS = {"geom.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp", "--use_fast_math=false"]
 
@@ -38,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             continue
         o = os.path.join(CSRC, src[:-3] + ".o")
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-c", s, "-o", o]
+            cmd = [nvcc] + [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + EXTRA_FLAGS.get(src, []) + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
             jobs.append(cmd)

@@ -65,7 +65,7 @@ struct omvg_ba_ctx {
   DevBuf<double> Scc, Sci, Sii, rhs, Minv_c, Minv_i, work_i;
   DevBuf<double> z, res, pvec, w, zeta, pcg_part;
   DevBuf<double> gW, gAW, bX, bR, bP, bW, bZ, pcg2_part;   // two-level block-PCG workspaces
-  DevBuf<int> agg_of, agg_start, agg_cams, brow; DevBuf<double> cE, cEinv, cT, cCv, cYv, cCv2, cAW, bP2; int ng = 0;
+  DevBuf<int> agg_of, agg_start, agg_cams, brow; DevBuf<double> cE, cEinv, cT, cCv, cYv, cCv2, cAW, bP2; int ng = 0, agg_maxsize = 0;
   DevBuf<double> part, part2, part3, icol_part, scal;
   DevBuf<int> fail;
   DevBuf<unsigned long long> pcg_tim;
@@ -309,6 +309,7 @@ int build_structure(omvg_ba_ctx *c) {
   for (int g = 0; g < ng; ++g) agg_start[g + 1] += agg_start[g];
   { std::vector<int> cur(agg_start.begin(), agg_start.end() - 1); for (int a = 0; a < c->nc; ++a) agg_cams[cur[agg_of[a]]++] = a; }
   c->ng = ng;
+  c->agg_maxsize = 0; for (int gq = 0; gq < ng; ++gq) c->agg_maxsize = std::max(c->agg_maxsize, agg_start[gq + 1] - agg_start[gq]);
   if ((rc = upload(c->agg_of, agg_of.data(), c->nc, c->stream))) return rc;
   if ((rc = upload(c->agg_start, agg_start.data(), ng + 1, c->stream))) return rc;
   if ((rc = upload(c->agg_cams, agg_cams.data(), c->nc, c->stream))) return rc;
@@ -645,6 +646,23 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
         // pcg4 (2 grid syncs per iteration instead of 4) is kept for A/B and for the single-CTA mode: at 148 CTAs it is
         // NOT faster (measured, config 2: 14.7 vs 14.2 ms per solve) — every CTA re-stages the whole coarse residual
         // (6 us per iteration) where v3 pays its two extra barriers (2 x 3.5 us).  See DESIGN.md §4.3.
+        // v5: shared-memory resident, aggregate-owned (2 barriers + 2 L2 round trips per iteration).  Needs one CTA per
+        // aggregate, <= 4 right-hand sides (1 + free intrinsic columns) and aggregates of <= 16 cameras; else v3.
+        static const bool no_pcg5 = getenv("OMVG_BA_PCG3") != nullptr || getenv("OMVG_BA_PCG4") != nullptr;
+        const int nrhs_host = 1 + n_free_intr;
+        if (!no_pcg5 && pcg_grid > 1 && nrhs_host <= PCG5_NR && c->ng <= pcg_grid && c->agg_maxsize <= PCG5_MC && P3.C.nco <= PCG3_NCO_MAX) {
+          const size_t fixed = sizeof(Pcg2Smem) + sizeof(Pcg5Smem) + (size_t)PCG5_NR * PCG3_NCO_MAX * sizeof(double);
+          static const int smem_max = [] { int v = 0, dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); return v; }();
+          const int nb_cache = (int)std::max<long long>(0, ((long long)smem_max - (long long)fixed - 2048) /   /* (static shared memory of the kernel + slack) */ (long long)(PCG5_BS * sizeof(double) + sizeof(int)));
+          const size_t smem = fixed + (size_t)nb_cache * (PCG5_BS * sizeof(double) + sizeof(int)) + 16;
+          OMVG_CUDA(cudaFuncSetAttribute(pcg5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          double *cg2 = c->cCv2.p, *aw = c->cAW.p; int nbc = nb_cache;
+          void *args[] = {&P3, &cg2, &aw, &nbc};
+          // one CTA per aggregate and no more: idle CTAs would only add participants to the two barriers of every iteration
+          OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg5_kernel, dim3(std::max(1, c->ng)), dim3(PCG2_THREADS), args, smem, c->stream));
+          if (pcg_timing) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
+            fprintf(stderr, "[omvg_ba pcg5 timing] us: A wait-AW %.1f y %.1f local %.1f reduce %.1f | B spmv %.1f reduce %.1f (cache %d blocks)\n", h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, h[4] * 1e-3, h[5] * 1e-3, nb_cache); P3.tim = nullptr; }
+        } else {
         static const bool want_pcg4 = getenv("OMVG_BA_PCG4") != nullptr;
         if ((want_pcg4 || pcg_grid == 1) && P3.C.nco <= PCG3_NCO_MAX) {
           double *cv2 = c->cCv2.p, *aw = c->cAW.p;
@@ -655,6 +673,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
         } else {
         void *args[] = {&P3};
         OMVG_CUDA(cudaLaunchCooperativeKernel((void *)pcg3_kernel, dim3(pcg_grid), dim3(PCG2_THREADS), args, sizeof(Pcg2Smem) + 4 * PCG3_NCO_MAX * sizeof(double), c->stream));
+        }
         }
         if (pcg_timing && P3.tim) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
           fprintf(stderr, "[omvg_ba pcg timing] us: coarse (stage %.1f rows %.1f sync %.1f) z %.1f spmv %.1f update %.1f tail %.1f border %.1f\n", h[6] * 1e-3, h[7] * 1e-3, h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, h[4] * 1e-3, h[5] * 1e-3); }

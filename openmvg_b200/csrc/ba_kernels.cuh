@@ -2446,6 +2446,271 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg4_kernel(Pcg3Args P, double *
   if (tid == 0) { A.out[0] = (double)it; A.out[1] = sqrt(S.worst); A.out[2] = sqrt(S.bb[0]); }
 }
 
+// ------------------------------------------------------------------------------ PCG v5 (shared-memory resident)
+// The v3 iteration is four grid-wide phases of three or four DEPENDENT L2 round trips each (every vector element a
+// CTA touches was last written by another SM): ~26 us per iteration at 1000 cameras for ~0.3 us of arithmetic.
+// Here CTA g owns aggregate g for the whole solve and keeps everything it owns in shared memory: its slices of
+// x, r, p, z, w for up to 4 right-hand sides, its block-Jacobi inverses, its gauge vectors, the coarse residual and
+// (as far as they fit: ~110 KB) the S blocks of its camera rows.  Per iteration only this crosses the chip:
+//   [A] read  alpha-partials + Wa'w of all aggregates (one L2 trip)   write  z of its cameras, r'z / |r|^2 partials
+//   [B] read  beta-partials + z, p of the neighbour cameras (one trip) write  p of its cameras, p'w partials, Wa'w
+// i.e. two grid barriers and two L2 round trips; the coarse solve (its nw rows of Einv, fetched into registers in the
+// shadow of the Wa'w read), the block-Jacobi step, the vector updates and the SpMV arithmetic are local.
+// Same recurrences as v4 (c_new = c - alpha Wa'w), same stopping rule and iteration count as v3.
+constexpr int PCG5_NR = 4;            // right-hand sides held in shared memory (1 + free intrinsic columns)
+constexpr int PCG5_MC = 21;           // cameras per aggregate (aggregation keeps them <= ~16; 2000-camera scenes reach 17-20)
+constexpr int PCG5_ST = ((PCG5_MC * 6 + 31) / 32) * 32;   // per-rhs thread stride: a warp never straddles two right-hand sides
+constexpr int PCG5_BS = 37;           // padded block stride (doubles): lane-per-block reads without 4-way bank conflicts
+struct Pcg5Smem {
+  double x[PCG5_NR][PCG5_MC * 6], r[PCG5_NR][PCG5_MC * 6], p[PCG5_NR][PCG5_MC * 6], z[PCG5_NR][PCG5_MC * 6], w[PCG5_NR][PCG5_MC * 6];
+  double minv[PCG5_MC][36], wg[MAXW][PCG5_MC * 6];
+  double y[MAXW][PCG5_NR], aw[PCG2_THREADS / 32][PCG5_NR][MAXW];
+  int cams[PCG5_MC], rowstart[PCG5_MC + 1], rowptr0[PCG5_MC];
+  int ncam, nb_cached;
+};
+__global__ void __launch_bounds__(PCG2_THREADS) pcg5_kernel(Pcg3Args P, double *__restrict__ Cg, double *__restrict__ AW, int nb_cache) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ unsigned char pcg2_smem_raw[];
+  Pcg2Smem &S = *reinterpret_cast<Pcg2Smem *>(pcg2_smem_raw);
+  Pcg5Smem &L = *reinterpret_cast<Pcg5Smem *>(pcg2_smem_raw + sizeof(Pcg2Smem));
+  double *sCv = reinterpret_cast<double *>(pcg2_smem_raw + sizeof(Pcg2Smem) + sizeof(Pcg5Smem));      // [PCG5_NR][PCG3_NCO_MAX]
+  double *sS = sCv + PCG5_NR * PCG3_NCO_MAX;                                                          // [nb_cache][PCG5_BS]
+  int *sCol = reinterpret_cast<int *>(sS + (size_t)nb_cache * PCG5_BS);                               // [nb_cache]
+  const Pcg2Args &A = P.base; const Coarse &C = P.C;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  constexpr int NWARP = PCG2_THREADS / 32;
+  const size_t nc6 = 6 * (size_t)A.n_poses;
+  const int nw = C.nw, nco = C.nco;
+  const int g = blockIdx.x;                       // the aggregate this CTA owns (CTAs beyond ng only take part in the barriers)
+  const bool own = g < C.ng;
+  if (threadIdx.x == 0) {
+    int n = 1; S.rhs_col[0] = -1;
+    for (int q = 0; q < A.ni8; ++q) if ((A.intr_mask[q / KI] >> (q % KI)) & 1) { if (n < MAXRHS) S.rhs_col[n++] = q; }
+    S.nrhs = n;
+    const int c0 = own ? C.agg_start[g] : 0; L.ncam = own ? C.agg_start[g + 1] - c0 : 0;
+    int nb = 0;
+    for (int ci = 0; ci < L.ncam; ++ci) { const int a = C.agg_cams[c0 + ci]; L.cams[ci] = a; L.rowstart[ci] = nb; L.rowptr0[ci] = A.rowptr[a]; nb += A.rowptr[a + 1] - A.rowptr[a]; }
+    L.rowstart[L.ncam] = nb; L.nb_cached = min(nb, nb_cache);
+  }
+  __syncthreads();
+  const int nrhs = S.nrhs, ncam = L.ncam, ne = 6 * ncam;
+  double *Pcur = A.Pv, *Pnext = P.Pv2;
+  // ---- load what this CTA owns: block-Jacobi inverses, gauge vectors, S blocks of its rows
+  for (int i = threadIdx.x; i < ncam * 36; i += PCG2_THREADS) L.minv[i / 36][i % 36] = A.Minv_c[36 * (size_t)L.cams[i / 36] + i % 36];
+  for (int i = threadIdx.x; i < nw * ne; i += PCG2_THREADS) { const int m = i / ne, idx = i % ne; L.wg[m][idx] = A.W[m * nc6 + 6 * (size_t)L.cams[idx / 6] + idx % 6]; }
+  for (int ci = 0; ci < ncam; ++ci) {
+    const int nbr = L.rowstart[ci + 1] - L.rowstart[ci];
+    for (int i = threadIdx.x; i < nbr * 36; i += PCG2_THREADS) {
+      const int lb = L.rowstart[ci] + i / 36;
+      if (lb < nb_cache) sS[(size_t)lb * PCG5_BS + i % 36] = A.Scc[36 * (size_t)(L.rowptr0[ci] + i / 36) + i % 36];
+    }
+    for (int i = threadIdx.x; i < nbr; i += PCG2_THREADS) { const int lb = L.rowstart[ci] + i; if (lb < nb_cache) sCol[lb] = A.cols[L.rowptr0[ci] + i]; }
+  }
+  // ---- init: x = 0, p = 0, w = 0, r = b, |b|^2, coarse residual of this aggregate -> Cg, p (global) = 0
+  vsum_begin(S, nrhs);
+  for (int t = threadIdx.x; t < nrhs * PCG5_ST; t += PCG2_THREADS) {
+    const int j = t / PCG5_ST, idx = t % PCG5_ST;                       // (PCG5_ST is a multiple of 32: a warp never straddles two right-hand sides)
+    double v = 0;
+    if (idx < ne) {
+      const size_t e = 6 * (size_t)L.cams[idx / 6] + idx % 6;
+      const double b = (j == 0 ? A.rhs : A.Sci + (size_t)S.rhs_col[j] * nc6)[e];
+      L.x[j][idx] = 0.0; L.p[j][idx] = 0.0; L.w[j][idx] = 0.0; L.r[j][idx] = b; v = b * b;
+      Pcur[j * nc6 + e] = 0.0;
+    }
+    warp_acc(S, v, j);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nrhs * nw; i += PCG2_THREADS) {
+    const int j = i / nw, m = i % nw;
+    double cv = 0; for (int idx = 0; idx < ne; ++idx) cv += L.wg[m][idx] * L.r[j][idx];
+    if (own) { Cg[(size_t)j * nco + g * nw + m] = cv; AW[(size_t)j * nco + g * nw + m] = 0.0; }
+  }
+  vsum_end(grid, S, nrhs, A.part);
+  if (threadIdx.x < nrhs) { const int j = threadIdx.x; S.bb[j] = S.tot[j]; S.done[j] = !(S.tot[j] > 0.0); S.alpha[j] = 0; S.beta[j] = 0; S.rz[j] = 0; }
+  if (threadIdx.x == 0) { S.worst = 0; S.all_done = 0; }
+  for (int i = threadIdx.x; i < nrhs * nco; i += PCG2_THREADS) sCv[(i / nco) * PCG3_NCO_MAX + i % nco] = __ldcg(Cg + (size_t)(i / nco) * nco + i % nco);
+  __syncthreads();
+  int it = 0;
+  unsigned long long tlast = P.tim ? gtimer() : 0ull;
+  for (;;) {
+    // ================================================================= [A]
+    vsum_begin(S, 2 * nrhs);
+    { // coarse step: this aggregate's rows of Einv go to registers while Wa'w of all aggregates arrives
+      double ev[PCG3_NCO_MAX / 32];
+      const bool yrow = own && wib < nw && nco > 0;
+      if (yrow) {
+        const double *er = P.Einv + (size_t)(g * nw + wib) * nco;
+        #pragma unroll
+        for (int q = 0; q < PCG3_NCO_MAX / 32; ++q) { const int k = lane + 32 * q; ev[q] = k < nco ? __ldcg(er + k) : 0.0; }
+      }
+      if (it > 0)
+        for (int i = threadIdx.x; i < nrhs * nco; i += PCG2_THREADS) { const int j = i / nco, k = i % nco; sCv[j * PCG3_NCO_MAX + k] -= S.alpha[j] * __ldcg(AW + (size_t)j * nco + k); }
+      __syncthreads();
+      PCG_LAP(0);
+      if (yrow) {
+        double acc[PCG5_NR] = {0, 0, 0, 0};
+        #pragma unroll
+        for (int q = 0; q < PCG3_NCO_MAX / 32; ++q) { const int k = lane + 32 * q;
+          if (k < nco) {
+            #pragma unroll
+            for (int j = 0; j < PCG5_NR; ++j) if (j < nrhs) acc[j] += ev[q] * sCv[j * PCG3_NCO_MAX + k]; } }
+        #pragma unroll
+        for (int j = 0; j < PCG5_NR; ++j) {
+          double v = acc[j]; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && j < nrhs) L.y[wib][j] = v;
+        }
+      }
+      __syncthreads();
+      PCG_LAP(1);
+    }
+    // local: x += alpha p ; r -= alpha w ; |r|^2
+    for (int t = threadIdx.x; t < nrhs * PCG5_ST; t += PCG2_THREADS) {
+      const int j = t / PCG5_ST, idx = t % PCG5_ST;
+      double rr = 0;
+      if (idx < ne && !S.done[j]) {
+        const double al = S.alpha[j];
+        L.x[j][idx] += al * L.p[j][idx];
+        const double rn = L.r[j][idx] - al * L.w[j][idx]; L.r[j][idx] = rn; rr = rn * rn;
+      }
+      warp_acc(S, rr, nrhs + j);
+    }
+    __syncthreads();
+    // local: z = Minv r + Wa y ; r'z ; z of the own cameras is published for the neighbours' SpMV
+    for (int t = threadIdx.x; t < nrhs * PCG5_ST; t += PCG2_THREADS) {
+      const int j = t / PCG5_ST, idx = t % PCG5_ST;
+      double rz = 0;
+      if (idx < ne && !S.done[j]) {
+        const int ci = idx / 6, k = idx % 6;
+        const double *M = L.minv[ci] + 6 * k, *rb = L.r[j] + 6 * ci;
+        double zz = M[0] * rb[0] + M[1] * rb[1] + M[2] * rb[2] + M[3] * rb[3] + M[4] * rb[4] + M[5] * rb[5];
+        if (nco > 0) for (int m = 0; m < nw; ++m) zz += L.wg[m][idx] * L.y[m][j];
+        L.z[j][idx] = zz; rz = zz * rb[k];
+        A.Zv[j * nc6 + 6 * (size_t)L.cams[ci] + k] = zz;
+      }
+      warp_acc(S, rz, j);
+    }
+    PCG_LAP(2);
+    vsum_end(grid, S, 2 * nrhs, A.part);
+    PCG_LAP(3);
+    if (threadIdx.x < nrhs) { const int j = threadIdx.x; if (!S.done[j]) { const double rzn = S.tot[j]; S.beta[j] = it == 0 ? 0.0 : rzn / S.rz[j]; S.rz[j] = rzn; } }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int ad = 1; double wmax = 0;
+      for (int j = 0; j < nrhs; ++j) if (!S.done[j]) { const double rel2 = S.tot[nrhs + j] / S.bb[j]; wmax = fmax(wmax, rel2); if (!(rel2 > A.tol * A.tol)) S.done[j] = 1; else ad = 0; }
+      S.all_done = ad; if (it > 0) S.worst = wmax;
+    }
+    __syncthreads();
+    if (S.all_done || it >= A.max_iter) break;
+    // ================================================================= [B]  w = Scc (z + beta p) ; p'w ; Wa' w
+    vsum_begin(S, nrhs);
+    for (int i = threadIdx.x; i < NWARP * PCG5_NR * MAXW; i += PCG2_THREADS) (&L.aw[0][0][0])[i] = 0.0;
+    __syncthreads();
+    for (int ci = wib; ci < ncam; ci += NWARP) {
+      const int a = L.cams[ci];
+      double acc[PCG5_NR][6];
+      #pragma unroll
+      for (int j = 0; j < PCG5_NR; ++j)
+        #pragma unroll
+        for (int i = 0; i < 6; ++i) acc[j][i] = 0.0;
+      const int nbr = L.rowstart[ci + 1] - L.rowstart[ci];
+      for (int e = lane; e < nbr; e += 32) {
+        const int lb = L.rowstart[ci] + e;
+        double b[36]; int cb;
+        if (lb < nb_cache) {
+          const double *blk = sS + (size_t)lb * PCG5_BS;
+          #pragma unroll
+          for (int i = 0; i < 36; ++i) b[i] = blk[i];
+          cb = 6 * sCol[lb];
+        } else {
+          const double *blk = A.Scc + 36 * (size_t)(L.rowptr0[ci] + e);
+          #pragma unroll
+          for (int i = 0; i < 9; ++i) ldg256(blk + 4 * i, b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]);
+          cb = 6 * A.cols[L.rowptr0[ci] + e];
+        }
+        #pragma unroll
+        for (int j = 0; j < PCG5_NR; ++j) {
+          if (j < nrhs && !S.done[j]) {
+            const size_t off = (size_t)j * nc6 + cb; const double bt = S.beta[j];
+            const double2 *zp = reinterpret_cast<const double2 *>(A.Zv + off), *pp = reinterpret_cast<const double2 *>(Pcur + off);
+            const double2 z0 = __ldcg(zp), z1 = __ldcg(zp + 1), z2 = __ldcg(zp + 2), q0 = __ldcg(pp), q1 = __ldcg(pp + 1), q2 = __ldcg(pp + 2);
+            const double xv[6] = {z0.x + bt * q0.x, z0.y + bt * q0.y, z1.x + bt * q1.x, z1.y + bt * q1.y, z2.x + bt * q2.x, z2.y + bt * q2.y};
+            #pragma unroll
+            for (int i = 0; i < 6; ++i)
+              #pragma unroll
+              for (int k = 0; k < 6; ++k) acc[j][i] += b[i * 6 + k] * xv[k];
+          }
+        }
+      }
+      #pragma unroll
+      for (int j = 0; j < PCG5_NR; ++j) {
+        if (j < nrhs && !S.done[j]) {
+          #pragma unroll
+          for (int i = 0; i < 6; ++i) { double v = acc[j][i]; for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o); acc[j][i] = v; }
+          if (lane == 0) {
+            const double bt = S.beta[j]; double d = 0;
+            for (int i = 0; i < 6; ++i) {
+              const double pv = L.z[j][6 * ci + i] + bt * L.p[j][6 * ci + i];
+              L.p[j][6 * ci + i] = pv; L.w[j][6 * ci + i] = acc[j][i]; d += acc[j][i] * pv;
+              Pnext[(size_t)j * nc6 + 6 * (size_t)a + i] = pv;
+            }
+            S.wpart[wib][j] += d;
+            for (int m = 0; m < nw; ++m) { double t2 = 0; for (int i = 0; i < 6; ++i) t2 += L.wg[m][6 * ci + i] * acc[j][i]; L.aw[wib][j][m] += t2; }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (own)
+      for (int i = threadIdx.x; i < nrhs * nw; i += PCG2_THREADS) {
+        const int j = i / nw, m = i % nw;
+        if (!S.done[j]) { double t2 = 0; for (int w2 = 0; w2 < NWARP; ++w2) t2 += L.aw[w2][j][m]; AW[(size_t)j * nco + g * nw + m] = t2; }
+      }
+    PCG_LAP(4);
+    vsum_end(grid, S, nrhs, A.part);              // its grid.sync also publishes p of the own cameras and Wa'w
+    PCG_LAP(5);
+    { double *t2 = Pcur; Pcur = Pnext; Pnext = t2; }
+    if (threadIdx.x < nrhs) { const int j = threadIdx.x; S.alpha[j] = S.done[j] ? 0.0 : S.rz[j] / S.tot[j]; }
+    __syncthreads();
+    ++it;
+  }
+  // ---- the solutions leave shared memory; then the border as in v3
+  for (int t = threadIdx.x; t < nrhs * PCG5_ST; t += PCG2_THREADS) { const int j = t / PCG5_ST, idx = t % PCG5_ST; if (idx < ne) A.X[j * nc6 + 6 * (size_t)L.cams[idx / 6] + idx % 6] = L.x[j][idx]; }
+  grid.sync();
+  const int k = nrhs - 1;
+  if (k > 0) {
+    for (int a = 0; a < k; ++a) {
+      vsum_begin(S, k + 1);
+      const double *row = A.Sci + (size_t)S.rhs_col[1 + a] * nc6;
+      for (int b = 0; b <= k; ++b) {
+        const double *x = A.X + (size_t)(b == k ? 0 : 1 + b) * nc6;
+        double v = 0; for (size_t i = tid; i < nc6; i += nt) v += row[i] * __ldcg(x + i);
+        warp_acc(S, v, b);
+      }
+      vsum_end(grid, S, k + 1, A.part);
+      if (threadIdx.x <= k) {
+        const int b = threadIdx.x;
+        if (b < k) S.T[a][b] = A.Sii[(size_t)S.rhs_col[1 + a] * A.ni8 + S.rhs_col[1 + b]] - S.tot[b];
+        else S.T[a][k] = A.rhs[nc6 + S.rhs_col[1 + a]] - S.tot[k];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      for (int a = 0; a < k; ++a) for (int b = a + 1; b < k; ++b) { const double m = 0.5 * (S.T[a][b] + S.T[b][a]); S.T[a][b] = m; S.T[b][a] = m; }
+      for (int c = 0; c < k; ++c) {
+        int piv = c; for (int r2 = c + 1; r2 < k; ++r2) if (fabs(S.T[r2][c]) > fabs(S.T[piv][c])) piv = r2;
+        if (piv != c) for (int q = 0; q <= k; ++q) { const double t2 = S.T[c][q]; S.T[c][q] = S.T[piv][q]; S.T[piv][q] = t2; }
+        for (int r2 = c + 1; r2 < k; ++r2) { const double f = S.T[r2][c] / S.T[c][c]; for (int q = c; q <= k; ++q) S.T[r2][q] -= f * S.T[c][q]; }
+      }
+      for (int c = k - 1; c >= 0; --c) { double sacc = S.T[c][k]; for (int q = c + 1; q < k; ++q) sacc -= S.T[c][q] * S.zi[q]; S.zi[c] = sacc / S.T[c][c]; }
+    }
+    __syncthreads();
+  }
+  for (size_t i = tid; i < nc6; i += nt) { double v = __ldcg(A.X + i); for (int a = 0; a < k; ++a) v -= __ldcg(A.X + (size_t)(1 + a) * nc6 + i) * S.zi[a]; A.z[i] = v; }
+  for (int q = tid; q < A.ni8; q += nt) { double v = 0; for (int a = 0; a < k; ++a) if (S.rhs_col[1 + a] == q) v = S.zi[a]; A.z[nc6 + q] = v; }
+  if (tid == 0) { A.out[0] = (double)it; A.out[1] = sqrt(S.worst); A.out[2] = sqrt(S.bb[0]); }
+}
+
 // ------------------------------------------------------------------------------ back substitution
 // y_pt = Einv (Etb - sum_obs EtFc z_c + EtFi z_i) ; step = -y  (levenberg_marquardt_strategy.cc:120)
 __global__ void backsub_kernel(const double *__restrict__ Jp, const double *__restrict__ Jc, const double *__restrict__ Ji,

@@ -241,3 +241,24 @@ def exhaustive_pairs(n_images: int):
     """Pair_Builder.hpp:25-33 — all (I,J) with I<J in lexicographic order."""
     i, j = np.triu_indices(n_images, 1)
     return np.ascontiguousarray(i.astype(np.uint32)), np.ascontiguousarray(j.astype(np.uint32))
+
+
+def two_view_matches(n: int, outlier_frac: float = 0.3, noise_px: float = 0.5, seed: int = 3, wh=(1000, 1000)):
+    """Putative matches of one image pair for the geometric filter: n correspondences, a fraction
+    of them gross outliers, the rest projections of a 3-D point cloud in two pinhole views + pixel noise.
+    Positions are rounded to float32 as openMVG features store them (features/feature.hpp: PointFeature x, y are float).
+    -> (xI [n,2], xJ [n,2]) float64, inlier mask [n]"""
+    rng = np.random.default_rng(seed)
+    w, h = wh
+    f = 1.1 * max(w, h)
+    X = np.stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1.2, 1.2, n), rng.uniform(4.0, 9.0, n)], 1)
+    R2 = _rodrigues(np.array([0.03, -0.25, 0.02])); C2 = np.array([1.2, 0.05, 0.3])
+
+    def proj(R, C):
+        Xc = (X - C) @ R.T
+        return np.stack([w / 2 + f * Xc[:, 0] / Xc[:, 2], h / 2 + f * Xc[:, 1] / Xc[:, 2]], 1)
+    xI = proj(np.eye(3), np.zeros(3)) + rng.normal(0, noise_px, (n, 2))
+    xJ = proj(R2, C2) + rng.normal(0, noise_px, (n, 2))
+    out = rng.random(n) < outlier_frac
+    xJ[out] = np.stack([rng.uniform(0, w, int(out.sum())), rng.uniform(0, h, int(out.sum()))], 1)
+    return xI.astype(np.float32).astype(np.float64), xJ.astype(np.float32).astype(np.float64), ~out

@@ -20,6 +20,9 @@
 #include "../openmvg_b200/host/Cascade_Hashing_Matcher_Regions_B200.hpp"
 #include "openMVG/matching_image_collection/Cascade_Hashing_Matcher_Regions.hpp"
 #include "../openmvg_b200/host/Matcher_Regions_B200.hpp"
+#include "../openmvg_b200/host/GeometricFilter_B200.hpp"
+#include "openMVG/matching_image_collection/GeometricFilter.hpp"
+#include "openMVG/matching_image_collection/F_ACRobust.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -228,6 +231,59 @@ int main(int argc, char ** argv)
     std::printf("BA+GCP+priors drop-in: initial %.6f  reference %.9f  B200 %.9f  rel %.3e  max centre diff %.3e  gcp diff %.3e  ok %d/%d\n",
                 c0, ca, cb, rel, dc, dg, int(ok_ref), int(ok_b200));
     if (!ok_ref || !ok_b200 || !(rel <= 1e-6) || !(dc <= 1e-6) || !(dg <= 1e-12)) ++failures;
+  }
+  // ------------------------------------------------------------------ geometric filtering, F model (N4)
+  // reference: ImageCollectionGeometricFilter::Robust_model_estimation(GeometricFilter_FMatrix_AC(4.0, 2048), putative)
+  {
+    std::mt19937 g(11);
+    std::uniform_real_distribution<double> U(-1.0, 1.0), Upx(0.0, 1000.0), U01(0.0, 1.0);
+    std::normal_distribution<double> N(0, 1);
+    SfM_Data s;
+    s.intrinsics[0] = std::make_shared<Pinhole_Intrinsic_Radial_K1>(1000, 1000, 1100, 500, 500, 0.03);      // positions get un-distorted
+    const int V = 4, P = 900;
+    std::vector<Pose3> poses;
+    for (int v = 0; v < V; ++v) {
+      const Vec3 c(0.6 * v, 0.05 * v, 0.1 * v);
+      const Vec3 aa(0.01 * v, -0.08 * v, 0.005 * v);
+      const Mat3 R = aa.norm() > 0 ? Eigen::AngleAxisd(aa.norm(), aa.normalized()).toRotationMatrix() : Mat3(Mat3::Identity());
+      poses.emplace_back(R, c);
+      s.views[v] = std::make_shared<View>("", v, v == 3 ? UndefinedIndexT : 0, v, 1000, 1000);   // view 3 has no intrinsic: raw positions
+    }
+    auto provider = std::make_shared<InMemory_Regions_Provider>();
+    provider->set_type(new features::SIFT_Regions);
+    std::vector<Vec3> X(P);
+    for (auto & x : X) x = Vec3(1.5 * U(g), 1.2 * U(g), 6.5 + 2.5 * U(g));
+    for (int v = 0; v < V; ++v) {
+      auto r = std::make_shared<features::SIFT_Regions>();
+      r->Features().resize(P); r->Descriptors().resize(P);
+      for (int j = 0; j < P; ++j) {
+        const Vec2 x = s.intrinsics.at(0)->project(poses[v](X[j])) + Vec2(0.4 * N(g), 0.4 * N(g));
+        r->Features()[j] = features::SIOPointFeature(float(x(0)), float(x(1)), 1.f, 0.f);
+      }
+      provider->set(v, r);
+    }
+    matching::PairWiseMatches putative;
+    for (int a = 0; a < V; ++a) for (int b = a + 1; b < V; ++b) {
+      matching::IndMatches m;
+      const int n = (a == 0 && b == 1) ? P : (a == 1 && b == 2) ? 12 : 300 + 100 * a;      // one pair with too few matches
+      for (int j = 0; j < n; ++j) m.emplace_back(j, U01(g) < 0.35 ? int(U01(g) * (P - 1)) : j);   // 35 % wrong correspondences
+      putative.insert({{a, b}, m});
+    }
+    matching_image_collection::ImageCollectionGeometricFilter ref_filter(&s, provider);
+    ref_filter.Robust_model_estimation(matching_image_collection::GeometricFilter_FMatrix_AC(4.0, 2048), putative);
+    matching_image_collection::ImageCollectionGeometricFilter_B200 gpu_filter(&s, provider);
+    const bool ok = gpu_filter.Robust_model_estimation_F(putative, 4.0, 2048);
+    const auto & A = ref_filter.Get_geometric_matches(); const auto & B = gpu_filter.Get_geometric_matches();
+    bool same = ok && A.size() == B.size();
+    size_t total = 0;
+    for (const auto & kv : A) {
+      const auto it = B.find(kv.first);
+      if (it == B.end() || it->second.size() != kv.second.size()) { same = false; break; }
+      for (size_t i = 0; i < kv.second.size(); ++i) if (kv.second[i].i_ != it->second[i].i_ || kv.second[i].j_ != it->second[i].j_) { same = false; break; }
+      total += kv.second.size();
+    }
+    std::printf("GEOMETRIC FILTER (F, AC-RANSAC) drop-in: %zu of %zu pairs kept, %zu geometric matches, %s\n", A.size(), putative.size(), total, same ? "IDENTICAL" : "DIFFERENT");
+    if (!same || total == 0 || A.size() == putative.size()) ++failures;
   }
   // ------------------------------------------------------------------ the BA / outlier-rejection loop (N1)
   // reference: do { Bundle_Adjustment_Ceres::Adjust } while (RemoveOutliers_PixelResidualError(4.0, 2) +

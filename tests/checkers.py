@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 REF_MATCH_SO = os.path.join(ROOT, "oracle", "_ref", "libref_match.so")
 REF_BA_SO = os.path.join(ROOT, "oracle", "_ref", "libref_ba.so")
+REF_GEOM_SO = os.path.join(ROOT, "oracle", "_ref", "libref_geom.so")
 
 _P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
 
@@ -417,3 +418,34 @@ def per_pair_digest(offsets, ij):
     for k in range(n):
         h[k] = f(ctypes.c_void_p(base + 8 * int(off[k])), ctypes.c_int64(int(off[k + 1] - off[k])))
     return counts, h
+
+
+# ----------------------------------------------------------------------------- geometric filtering (N4)
+def have_ref_geom():
+    return os.path.exists(REF_GEOM_SO)
+
+
+def ref_geom():
+    if "rg" not in _cache:
+        _cache["rg"] = ctypes.CDLL(REF_GEOM_SO)
+    return _cache["rg"]
+
+
+def _acransac(fn, xI, xJ, wh, precision, iterations, with_trace):
+    xI = np.ascontiguousarray(xI, np.float64); xJ = np.ascontiguousarray(xJ, np.float64)
+    n = len(xI)
+    inl = np.zeros(max(n, 1), np.uint32); F = np.zeros(9); stats = np.zeros(2); trace = np.zeros(3, np.int32)
+    args = [_P(xI), _P(xJ), n, int(wh[0]), int(wh[1]), int(wh[2]), int(wh[3]), ctypes.c_double(precision), ctypes.c_uint(iterations), _P(inl), _P(F), _P(stats)]
+    if with_trace:
+        args.append(_P(trace))
+    k = fn(*args)
+    return dict(inliers=inl[:k].copy(), F=F.reshape(3, 3), error_max=float(stats[0]), min_nfa=float(stats[1]), trace=trace)
+
+
+def ref_acransac_fundamental(xI, xJ, wh=(1000, 1000, 1000, 1000), precision=4.0, iterations=2048):
+    """The reference's ACRANSAC + ACKernelAdaptor<SevenPointSolver, EpipolarDistanceError, UnnormalizerT> (F_ACRobust.hpp:66-83)."""
+    return _acransac(ref_geom().ref_acransac_fundamental, xI, xJ, wh, precision, iterations, False)
+
+
+def oracle_acransac_fundamental(xI, xJ, wh=(1000, 1000, 1000, 1000), precision=4.0, iterations=2048):
+    return _acransac(oracle().oracle_acransac_fundamental, xI, xJ, wh, precision, iterations, True)

@@ -146,6 +146,39 @@ def main_more():
     json.dump(out, open(path, "w"), indent=1)
 
 
+# Geometric filter: the reference's ACRANSAC with the fundamental-matrix kernel on seeded putative
+# matches of one pair (synth.two_view_matches).  `geom` appends the section without touching the rest.
+GEOM_CASES = [
+    dict(name="p300", n=300, outlier_frac=0.3, seed=3), dict(name="p1500_half_outliers", n=1500, outlier_frac=0.5, seed=4),
+    dict(name="p60", n=60, outlier_frac=0.2, seed=5), dict(name="p200_no_model", n=200, outlier_frac=0.9, seed=6),
+    dict(name="p8", n=8, outlier_frac=0.0, seed=7), dict(name="p7", n=7, outlier_frac=0.0, seed=8),
+    dict(name="p500", n=500, outlier_frac=0.3, seed=9), dict(name="p2500_wide", n=2500, outlier_frac=0.4, seed=10, wh=(4000, 3000)),
+    dict(name="p30_clean", n=30, outlier_frac=0.0, seed=11), dict(name="p18", n=18, outlier_frac=0.1, seed=12),
+]
+
+
+def geom_case_inputs(c):
+    wh = tuple(c.get("wh", (1000, 1000)))
+    xI, xJ, _ = synth.two_view_matches(c["n"], c["outlier_frac"], seed=c["seed"], wh=wh)
+    return xI, xJ, (wh[0], wh[1], wh[0], wh[1])
+
+
+def main_geom():
+    path = os.path.join(HERE, "reference_outputs.json")
+    out = json.load(open(path))
+    out["geom_F"] = []
+    for c in GEOM_CASES:
+        xI, xJ, wh = geom_case_inputs(c)
+        r = ck.ref_acransac_fundamental(xI, xJ, wh, 4.0, 2048)
+        inl = np.ascontiguousarray(np.stack([r["inliers"], r["inliers"]], 1).astype(np.uint32))
+        fnv = int(ck.oracle().oracle_fnv1a_ij(inl.ctypes.data_as(ck.ctypes.c_void_p), ck.ctypes.c_int64(len(inl))))
+        Fn = r["F"] / np.linalg.norm(r["F"]) if len(r["inliers"]) else r["F"]
+        out["geom_F"].append(dict(c, n_inliers=int(len(r["inliers"])), inliers_fnv1a=str(fnv), error_max=repr(r["error_max"]), min_nfa=repr(r["min_nfa"]),
+                                  F_unit=[float(v) for v in Fn.reshape(-1)]))
+        print("geom", c["name"], len(r["inliers"]), r["error_max"], r["min_nfa"])
+    json.dump(out, open(path, "w"), indent=1)
+
+
 def main():
     out = {"match": [], "ba": []}
     arrays = {}
@@ -179,6 +212,8 @@ if __name__ == "__main__":
         main_io()
     elif len(sys.argv) > 1 and sys.argv[1] == "more":
         main_more()
+    elif len(sys.argv) > 1 and sys.argv[1] == "geom":
+        main_geom()
     else:
         main()
         main_ext()
