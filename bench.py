@@ -49,6 +49,7 @@ M2_IMAGES = 1000
 OPS_PER_DESC_PAIR = 256               # 128 MAC
 SWEEP_CAMS = (50, 100, 200, 500, 2000)
 CPU_MATCH_IMAGES = 26                 # 325 pairs of 5000 x 5000: ~3 s of the reference on a 128-thread host
+GEOM_PAIRS, GEOM_MATCHES = 2000, 800  # geometric-filter leg: pairs x putative matches per pair
 
 
 def peaks():
@@ -204,6 +205,22 @@ def run_ours(args):
                               ms_per_lm_iter=best["device_ms"] / best["iterations"], pcg_iterations=int(best["pcg_iterations"]),
                               kernel_launches=int(best["kernel_launches"]), final_cost=best["final_cost"]))
 
+    # ------------------------------------------------------------------ geometric filter, rank 0 at N = 1
+    geom = None
+    if world == 1 and not args.no_sweep:
+        from openmvg_b200 import geometry
+        pairs = [synth.two_view_matches(GEOM_MATCHES, 0.35, seed=500 + k, wh=(1600, 1200))[:2] for k in range(GEOM_PAIRS)]
+        goff = np.concatenate([[0], np.cumsum([len(p_[0]) for p_ in pairs])]).astype(np.uint64)
+        gI = np.concatenate([p_[0] for p_ in pairs]); gJ = np.concatenate([p_[1] for p_ in pairs])
+        gsz = np.tile(np.array([1600, 1200, 1600, 1200], np.int32), (GEOM_PAIRS, 1))
+        geometry.fundamental_acransac(goff, gI, gJ, gsz, 4.0, 2048, device=local)
+        t0 = time.perf_counter(); gres = geometry.fundamental_acransac(goff, gI, gJ, gsz, 4.0, 2048, device=local); g_wall = time.perf_counter() - t0
+        geom = {"metric": "pairs/sec", "value": GEOM_PAIRS / g_wall, "unit": "pairs/s", "ms_per_step": g_wall * 1e3,
+                "config": {"workload": f"AC-RANSAC fundamental-matrix filter (GeometricFilter_FMatrix_AC(4.0, 2048)), {GEOM_PAIRS} pairs x {GEOM_MATCHES} putative matches, 35 % outliers"},
+                "pairs_kept": int(sum(len(r_["inliers"]) > 17 for r_ in gres)), "inliers": int(sum(len(r_["inliers"]) for r_ in gres)),
+                "note": "host arrays in, host arrays out (one omvg_geom_fundamental_acransac call: H2D, one CTA per pair, D2H)"}
+        launches += 1
+
     # ------------------------------------------------------------------ MATCH (pairs sharded over ranks)
     def match_leg(n_img, steps, warm, e2e_steps, with_cascade):
         nonlocal launches
@@ -323,6 +340,8 @@ def run_ours(args):
             line["m2"] = m2; line["m2_value"] = m2["value"]; line["m2_e2e"] = m2["e2e"]["value"]
         if sweep is not None:
             line["ba_sweep"] = sweep
+        if geom is not None:
+            line["geom"] = geom
         if not args.no_cpu and world == 1:
             cb, mb, _ = cpu_baselines(scene, full=False)
             line["cpu_baseline"], line["match"]["cpu_baseline"] = cb, mb
@@ -380,6 +399,14 @@ def cpu_baselines(scene, full, quick=False):
             t0 = time.perf_counter(); ck.ref_cascade_collection(descs, pi, pj, 0.8); dtc = time.perf_counter() - t0
             extra["cascade_hashing"] = dict(cpu_baseline=dict(value=len(pi) / dtc, unit="pairs/s", cores=cores, kind="reference", seconds=dtc,
                                                               sample=f"Cascade_Hashing_Matcher_Regions::Match on the same {len(pi)} pairs (hashing included)"))
+        if ck.have_ref_geom():
+            gp = [synth.two_view_matches(GEOM_MATCHES, 0.35, seed=500 + k, wh=(1600, 1200))[:2] for k in range(200)]
+            t0 = time.perf_counter()
+            for a_, b_ in gp:
+                ck.ref_acransac_fundamental(a_, b_, (1600, 1200, 1600, 1200), 4.0, 2048)
+            dtg = time.perf_counter() - t0
+            extra["geom"] = dict(cpu_baseline=dict(value=200 / dtg, unit="pairs/s", cores=1, kind="reference", seconds=dtg,
+                                                   sample="ACRANSAC + ACKernelAdaptor<SevenPointSolver, EpipolarDistanceError> on the first 200 pairs, ONE host thread (the reference runs one pair per OpenMP thread: multiply by the cores for its collection rate)"))
         if ck.have_ref_ba():
             sw = []
             for C in SWEEP_CAMS:
@@ -418,6 +445,8 @@ def run_reference(args):
         line["match"]["cascade_hashing"] = extra["cascade_hashing"]
     if "ba_sweep" in extra:
         line["ba_sweep"] = extra["ba_sweep"]
+    if "geom" in extra:
+        line["geom"] = extra["geom"]
     print(json.dumps(line))
 
 

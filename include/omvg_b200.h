@@ -146,6 +146,15 @@ int omvg_matches_save(const char *path, uint64_t n_pairs, const uint32_t *pair_I
 int omvg_geom_fundamental_acransac(int device, uint64_t n_pairs, const uint64_t *offsets, const double *xI, const double *xJ,
                                    const int32_t *image_size, double precision, uint32_t max_iterations,
                                    uint32_t *inliers, uint32_t *n_inliers, double *F, double *stats);
+/* The same with the model as an argument: OMVG_GEOM_FUNDAMENTAL (above) or OMVG_GEOM_HOMOGRAPHY =
+ * GeometricFilter_HMatrix_AC (matching_image_collection/H_ACRobust.hpp:46-112: ACKernelAdaptor<FourPointSolver,
+ * AsymmetricError, UnnormalizerI>, point-to-point error model, one model per 4-point sample; the reference keeps the
+ * pair iff n_inliers > 2.5 * 4).  F then holds the homography. */
+#define OMVG_GEOM_FUNDAMENTAL 0
+#define OMVG_GEOM_HOMOGRAPHY  1
+int omvg_geom_acransac(int device, int32_t model, uint64_t n_pairs, const uint64_t *offsets, const double *xI, const double *xJ,
+                       const int32_t *image_size, double precision, uint32_t max_iterations,
+                       uint32_t *inliers, uint32_t *n_inliers, double *F, double *stats);
 
 /* ===================================================================== BA ================= */
 #define OMVG_BA_INTR_STRIDE 8   /* doubles reserved per intrinsic block */

@@ -1349,19 +1349,19 @@ struct Pcg2Smem {
 };
 
 // warp-reduce v; lane 0 ADDS it into this warp's slot idx (slots are zeroed by vsum_begin)
-__device__ __forceinline__ void warp_acc(Pcg2Smem &S, double v, int idx) {
+template <class SM> __device__ __forceinline__ void warp_acc(SM &S, double v, int idx) {
   #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0) S.wpart[threadIdx.x >> 5][idx] += v;
 }
-__device__ __forceinline__ void vsum_begin(Pcg2Smem &S, int V) {
+template <class SM> __device__ __forceinline__ void vsum_begin(SM &S, int V) {
   for (int i = threadIdx.x; i < V * (PCG2_THREADS / 32); i += PCG2_THREADS) S.wpart[i / V][i % V] = 0.0;
   __syncthreads();
 }
 // block partials -> global -> grid.sync -> fixed-order totals in S.tot[0..V) (identical in every block).
 // Cross-block sum: one warp per value, lanes stride over the blocks (5 loads each at 148 blocks), then a
 // fixed butterfly — the same order in every block, hence bitwise identical totals everywhere.
-__device__ __forceinline__ void vsum_end(cg::grid_group &grid, Pcg2Smem &S, int V, double *part) {
+template <class SM> __device__ __forceinline__ void vsum_end(cg::grid_group &grid, SM &S, int V, double *part) {
   __syncthreads();
   if (gridDim.x == 1) {                      // single-CTA solve (small problems): a block barrier is the grid barrier
     for (int i = threadIdx.x; i < V; i += PCG2_THREADS) { double t = 0; for (int w = 0; w < PCG2_THREADS / 32; ++w) t += S.wpart[w][i]; S.tot[i] = t; }
@@ -2461,21 +2461,36 @@ constexpr int PCG5_NR = 4;            // right-hand sides held in shared memory 
 constexpr int PCG5_MC = 21;           // cameras per aggregate (aggregation keeps them <= ~16; 2000-camera scenes reach 17-20)
 constexpr int PCG5_ST = ((PCG5_MC * 6 + 31) / 32) * 32;   // per-rhs thread stride: a warp never straddles two right-hand sides
 constexpr int PCG5_BS = 37;           // padded block stride (doubles): lane-per-block reads without 4-way bank conflicts
+constexpr int PCG5_NB = 112;          // neighbour cameras of an aggregate (union of the columns of its rows) staged per iteration
+constexpr int PCG5_PS = PCG5_NR * 6 + 1;   // doubles per staged neighbour (4 rhs x 6, +1 pad: lanes hit different banks)
+// reduction / control block of pcg5: at most 2 * PCG5_NR values per reduction (Pcg2Smem is sized for 33 right-hand sides
+// x 8 generators and would cost 36 KB of the shared memory the S-block cache wants)
+struct Pcg5Red {
+  double wpart[PCG2_THREADS / 32][2 * PCG5_NR + 8];
+  double tot[2 * PCG5_NR + 8];
+  double alpha[PCG5_NR + 1], beta[PCG5_NR + 1], rz[PCG5_NR + 1], bb[PCG5_NR + 1], zi[PCG5_NR + 1];
+  double T[PCG5_NR + 1][PCG5_NR + 2];
+  int rhs_col[PCG5_NR + 1];
+  unsigned char done[PCG5_NR + 4];
+  int nrhs, all_done; double worst;
+};
 struct Pcg5Smem {
   double x[PCG5_NR][PCG5_MC * 6], r[PCG5_NR][PCG5_MC * 6], p[PCG5_NR][PCG5_MC * 6], z[PCG5_NR][PCG5_MC * 6], w[PCG5_NR][PCG5_MC * 6];
   double minv[PCG5_MC][36], wg[MAXW][PCG5_MC * 6];
-  double y[MAXW][PCG5_NR], aw[PCG2_THREADS / 32][PCG5_NR][MAXW];
-  int cams[PCG5_MC], rowstart[PCG5_MC + 1], rowptr0[PCG5_MC];
-  int ncam, nb_cached;
+  double y[MAXW][PCG5_NR], aw[PCG2_THREADS / 32][PCG5_NR][MAXW], wrow[PCG2_THREADS / 32][PCG5_NR][6], drow[PCG2_THREADS / 32][PCG5_NR * 6];
+  int cams[PCG5_MC], rowstart[PCG5_MC + 1], rowptr0[PCG5_MC], nbl[PCG5_NB];
+  int ncam, nb_cached, nnb;
 };
-__global__ void __launch_bounds__(PCG2_THREADS) pcg5_kernel(Pcg3Args P, double *__restrict__ Cg, double *__restrict__ AW, int nb_cache) {
+__global__ void __launch_bounds__(PCG2_THREADS) pcg5_kernel(Pcg3Args P, double *__restrict__ Cg, double *__restrict__ AW, int nb_cache,
+                                                                const int *__restrict__ nb_start, const int *__restrict__ nb_list, const unsigned short *__restrict__ blk_lcol) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ unsigned char pcg2_smem_raw[];
-  Pcg2Smem &S = *reinterpret_cast<Pcg2Smem *>(pcg2_smem_raw);
-  Pcg5Smem &L = *reinterpret_cast<Pcg5Smem *>(pcg2_smem_raw + sizeof(Pcg2Smem));
-  double *sCv = reinterpret_cast<double *>(pcg2_smem_raw + sizeof(Pcg2Smem) + sizeof(Pcg5Smem));      // [PCG5_NR][PCG3_NCO_MAX]
-  double *sS = sCv + PCG5_NR * PCG3_NCO_MAX;                                                          // [nb_cache][PCG5_BS]
-  int *sCol = reinterpret_cast<int *>(sS + (size_t)nb_cache * PCG5_BS);                               // [nb_cache]
+  Pcg5Red &S = *reinterpret_cast<Pcg5Red *>(pcg2_smem_raw);
+  Pcg5Smem &L = *reinterpret_cast<Pcg5Smem *>(pcg2_smem_raw + sizeof(Pcg5Red));
+  double *sCv = reinterpret_cast<double *>(pcg2_smem_raw + sizeof(Pcg5Red) + sizeof(Pcg5Smem));      // [PCG5_NR][PCG3_NCO_MAX]
+  double *sPN = sCv + PCG5_NR * PCG3_NCO_MAX;                                                         // [PCG5_NB][PCG5_PS] p = z + beta p of the neighbours
+  double *sS = sPN + PCG5_NB * PCG5_PS;                                                               // [nb_cache][PCG5_BS]
+  unsigned short *sCol = reinterpret_cast<unsigned short *>(sS + (size_t)nb_cache * PCG5_BS);         // [nb_cache] position of the block's column in the neighbour list
   const Pcg2Args &A = P.base; const Coarse &C = P.C;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -2486,7 +2501,7 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg5_kernel(Pcg3Args P, double *
   const bool own = g < C.ng;
   if (threadIdx.x == 0) {
     int n = 1; S.rhs_col[0] = -1;
-    for (int q = 0; q < A.ni8; ++q) if ((A.intr_mask[q / KI] >> (q % KI)) & 1) { if (n < MAXRHS) S.rhs_col[n++] = q; }
+    for (int q = 0; q < A.ni8; ++q) if ((A.intr_mask[q / KI] >> (q % KI)) & 1) { if (n < PCG5_NR) S.rhs_col[n++] = q; }
     S.nrhs = n;
     const int c0 = own ? C.agg_start[g] : 0; L.ncam = own ? C.agg_start[g + 1] - c0 : 0;
     int nb = 0;
@@ -2496,6 +2511,10 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg5_kernel(Pcg3Args P, double *
   __syncthreads();
   const int nrhs = S.nrhs, ncam = L.ncam, ne = 6 * ncam;
   double *Pcur = A.Pv, *Pnext = P.Pv2;
+  { const int nb0 = own ? nb_start[g] : 0; const int nnb = own ? nb_start[g + 1] - nb0 : 0;
+    if (threadIdx.x == 0) L.nnb = nnb;
+    for (int i = threadIdx.x; i < nnb; i += PCG2_THREADS) L.nbl[i] = nb_list[nb0 + i]; }
+  __syncthreads();
   // ---- load what this CTA owns: block-Jacobi inverses, gauge vectors, S blocks of its rows
   for (int i = threadIdx.x; i < ncam * 36; i += PCG2_THREADS) L.minv[i / 36][i % 36] = A.Minv_c[36 * (size_t)L.cams[i / 36] + i % 36];
   for (int i = threadIdx.x; i < nw * ne; i += PCG2_THREADS) { const int m = i / ne, idx = i % ne; L.wg[m][idx] = A.W[m * nc6 + 6 * (size_t)L.cams[idx / 6] + idx % 6]; }
@@ -2505,7 +2524,7 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg5_kernel(Pcg3Args P, double *
       const int lb = L.rowstart[ci] + i / 36;
       if (lb < nb_cache) sS[(size_t)lb * PCG5_BS + i % 36] = A.Scc[36 * (size_t)(L.rowptr0[ci] + i / 36) + i % 36];
     }
-    for (int i = threadIdx.x; i < nbr; i += PCG2_THREADS) { const int lb = L.rowstart[ci] + i; if (lb < nb_cache) sCol[lb] = A.cols[L.rowptr0[ci] + i]; }
+    for (int i = threadIdx.x; i < nbr; i += PCG2_THREADS) { const int lb = L.rowstart[ci] + i; if (lb < nb_cache) sCol[lb] = blk_lcol[L.rowptr0[ci] + i]; }
   }
   // ---- init: x = 0, p = 0, w = 0, r = b, |b|^2, coarse residual of this aggregate -> Cg, p (global) = 0
   vsum_begin(S, nrhs);
@@ -2544,8 +2563,17 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg5_kernel(Pcg3Args P, double *
         #pragma unroll
         for (int q = 0; q < PCG3_NCO_MAX / 32; ++q) { const int k = lane + 32 * q; ev[q] = k < nco ? __ldcg(er + k) : 0.0; }
       }
-      if (it > 0)
-        for (int i = threadIdx.x; i < nrhs * nco; i += PCG2_THREADS) { const int j = i / nco, k = i % nco; sCv[j * PCG3_NCO_MAX + k] -= S.alpha[j] * __ldcg(AW + (size_t)j * nco + k); }
+      if (it > 0) {                                              // all loads in flight before the first use: ONE L2 round trip
+        double awv[PCG5_NR][PCG3_NCO_MAX / PCG2_THREADS];
+        #pragma unroll
+        for (int j = 0; j < PCG5_NR; ++j)
+          #pragma unroll
+          for (int q = 0; q < PCG3_NCO_MAX / PCG2_THREADS; ++q) { const int k2 = threadIdx.x + PCG2_THREADS * q; awv[j][q] = (j < nrhs && k2 < nco) ? __ldcg(AW + (size_t)j * nco + k2) : 0.0; }
+        #pragma unroll
+        for (int j = 0; j < PCG5_NR; ++j)
+          #pragma unroll
+          for (int q = 0; q < PCG3_NCO_MAX / PCG2_THREADS; ++q) { const int k2 = threadIdx.x + PCG2_THREADS * q; if (j < nrhs && k2 < nco) sCv[j * PCG3_NCO_MAX + k2] -= S.alpha[j] * awv[j][q]; }
+      }
       __syncthreads();
       PCG_LAP(0);
       if (yrow) {
@@ -2605,6 +2633,31 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg5_kernel(Pcg3Args P, double *
     // ================================================================= [B]  w = Scc (z + beta p) ; p'w ; Wa' w
     vsum_begin(S, nrhs);
     for (int i = threadIdx.x; i < NWARP * PCG5_NR * MAXW; i += PCG2_THREADS) (&L.aw[0][0][0])[i] = 0.0;
+    // p = z + beta p of every neighbour camera, gathered ONCE per iteration (each is used by up to ncam rows)
+    { constexpr int NQ = (PCG5_NB * PCG5_NR * 3 + PCG2_THREADS - 1) / PCG2_THREADS;
+      const int total = L.nnb * nrhs * 3, per = nrhs * 3;
+      double2 zz[NQ], pp[NQ];
+      #pragma unroll
+      for (int q = 0; q < NQ; ++q) {                              // every load issued before the first use: ONE L2 round trip
+        const int t = threadIdx.x + PCG2_THREADS * q;
+        zz[q] = make_double2(0.0, 0.0); pp[q] = zz[q];
+        if (t < total) {
+          const int u = t / per, rj = t - u * per, j = rj / 3, h = rj - 3 * j;
+          if (!S.done[j]) {
+            const size_t off = (size_t)j * nc6 + 6 * (size_t)L.nbl[u] + 2 * h;
+            zz[q] = __ldcg(reinterpret_cast<const double2 *>(A.Zv + off)); pp[q] = __ldcg(reinterpret_cast<const double2 *>(Pcur + off));
+          }
+        }
+      }
+      #pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int t = threadIdx.x + PCG2_THREADS * q;
+        if (t < total) {
+          const int u = t / per, rj = t - u * per, j = rj / 3, h = rj - 3 * j;
+          if (!S.done[j]) { const double bt = S.beta[j]; sPN[u * PCG5_PS + j * 6 + 2 * h] = zz[q].x + bt * pp[q].x; sPN[u * PCG5_PS + j * 6 + 2 * h + 1] = zz[q].y + bt * pp[q].y; }
+        }
+      } }
+    PCG_LAP(6);
     __syncthreads();
     for (int ci = wib; ci < ncam; ci += NWARP) {
       const int a = L.cams[ci];
@@ -2616,50 +2669,61 @@ __global__ void __launch_bounds__(PCG2_THREADS) pcg5_kernel(Pcg3Args P, double *
       const int nbr = L.rowstart[ci + 1] - L.rowstart[ci];
       for (int e = lane; e < nbr; e += 32) {
         const int lb = L.rowstart[ci] + e;
-        double b[36]; int cb;
+        double b[36]; int lc;
         if (lb < nb_cache) {
           const double *blk = sS + (size_t)lb * PCG5_BS;
           #pragma unroll
           for (int i = 0; i < 36; ++i) b[i] = blk[i];
-          cb = 6 * sCol[lb];
+          lc = sCol[lb];
         } else {
           const double *blk = A.Scc + 36 * (size_t)(L.rowptr0[ci] + e);
           #pragma unroll
           for (int i = 0; i < 9; ++i) ldg256(blk + 4 * i, b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]);
-          cb = 6 * A.cols[L.rowptr0[ci] + e];
+          lc = blk_lcol[L.rowptr0[ci] + e];
         }
+        const double *pn = sPN + lc * PCG5_PS;
         #pragma unroll
         for (int j = 0; j < PCG5_NR; ++j) {
           if (j < nrhs && !S.done[j]) {
-            const size_t off = (size_t)j * nc6 + cb; const double bt = S.beta[j];
-            const double2 *zp = reinterpret_cast<const double2 *>(A.Zv + off), *pp = reinterpret_cast<const double2 *>(Pcur + off);
-            const double2 z0 = __ldcg(zp), z1 = __ldcg(zp + 1), z2 = __ldcg(zp + 2), q0 = __ldcg(pp), q1 = __ldcg(pp + 1), q2 = __ldcg(pp + 2);
-            const double xv[6] = {z0.x + bt * q0.x, z0.y + bt * q0.y, z1.x + bt * q1.x, z1.y + bt * q1.y, z2.x + bt * q2.x, z2.y + bt * q2.y};
+            double xv[6];
+            #pragma unroll
+            for (int k2 = 0; k2 < 6; ++k2) xv[k2] = pn[j * 6 + k2];
             #pragma unroll
             for (int i = 0; i < 6; ++i)
               #pragma unroll
-              for (int k = 0; k < 6; ++k) acc[j][i] += b[i * 6 + k] * xv[k];
+              for (int k2 = 0; k2 < 6; ++k2) acc[j][i] += b[i * 6 + k2] * xv[k2];
           }
         }
       }
+      // row totals -> lane 0 -> shared memory, then the per-element tail runs on 24 / 28 lanes instead of one
       #pragma unroll
       for (int j = 0; j < PCG5_NR; ++j) {
         if (j < nrhs && !S.done[j]) {
           #pragma unroll
-          for (int i = 0; i < 6; ++i) { double v = acc[j][i]; for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o); acc[j][i] = v; }
-          if (lane == 0) {
-            const double bt = S.beta[j]; double d = 0;
-            for (int i = 0; i < 6; ++i) {
-              const double pv = L.z[j][6 * ci + i] + bt * L.p[j][6 * ci + i];
-              L.p[j][6 * ci + i] = pv; L.w[j][6 * ci + i] = acc[j][i]; d += acc[j][i] * pv;
-              Pnext[(size_t)j * nc6 + 6 * (size_t)a + i] = pv;
-            }
-            S.wpart[wib][j] += d;
-            for (int m = 0; m < nw; ++m) { double t2 = 0; for (int i = 0; i < 6; ++i) t2 += L.wg[m][6 * ci + i] * acc[j][i]; L.aw[wib][j][m] += t2; }
-          }
+          for (int i = 0; i < 6; ++i) { double v = acc[j][i]; for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o); if (lane == 0) L.wrow[wib][j][i] = v; }
         }
       }
+      __syncwarp();
+      if (lane < PCG5_NR * 6) {                                   // lane = (j, i): p = z + beta p, w, p'w partial
+        const int j = lane / 6, i = lane - 6 * j;
+        double d = 0.0;
+        if (j < nrhs && !S.done[j]) {
+          const double bt = S.beta[j], wv = L.wrow[wib][j][i];
+          const double pv = L.z[j][6 * ci + i] + bt * L.p[j][6 * ci + i];
+          L.p[j][6 * ci + i] = pv; L.w[j][6 * ci + i] = wv; d = wv * pv;
+          Pnext[(size_t)j * nc6 + 6 * (size_t)a + i] = pv;
+        }
+        L.drow[wib][lane] = d;
+      }
+      __syncwarp();
+      if (lane < PCG5_NR) { const int j = lane; if (j < nrhs && !S.done[j]) { double d = 0; for (int i = 0; i < 6; ++i) d += L.drow[wib][6 * j + i]; S.wpart[wib][j] += d; } }
+      if (lane < PCG5_NR * MAXW) {                                // lane = (j, m): Wa' w of this row
+        const int j = lane / MAXW, m = lane - MAXW * j;
+        if (j < nrhs && m < nw && !S.done[j]) { double t2 = 0; for (int i = 0; i < 6; ++i) t2 += L.wg[m][6 * ci + i] * L.wrow[wib][j][i]; L.aw[wib][j][m] += t2; }
+      }
+      __syncwarp();
     }
+    PCG_LAP(7);
     __syncthreads();
     if (own)
       for (int i = threadIdx.x; i < nrhs * nw; i += PCG2_THREADS) {

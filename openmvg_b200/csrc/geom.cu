@@ -13,7 +13,7 @@
 // std::mt19937 stream is consumed in order), so the parallelism is ACROSS pairs — one CTA per pair, thousands of
 // pairs per launch — and, inside a pair, across the matches (residuals, the 20-bin NFA histogram, the ordered
 // inlier compaction).  The control flow, the generator (MT19937 + libstdc++'s Lemire down-scaling) and every
-// floating-point expression that feeds a comparison follow oracle/acransac_oracle.cpp line by line; this file is
+// floating-point expression that feeds a comparison follow the CPU restatement used by the tests (acransac_oracle.cpp) line by line; this file is
 // compiled with -fmad=false so those expressions round exactly as the CPU evaluates them.
 #include "common.cuh"
 
@@ -108,11 +108,21 @@ __device__ __forceinline__ double epipolar_error(const double *F, double x, doub
   return dt * dt / (fx0 * fx0 + fx1 * fx1);
 }
 
+// solver_homography_kernel.hpp:59-63
+__device__ __forceinline__ double transfer_error(const double *H, double x, double y, double u, double v) {
+  const double p0 = H[0] * x + H[1] * y + H[2], p1 = H[3] * x + H[4] * y + H[5], p2 = H[6] * x + H[7] * y + H[8];
+  const double dx = u - p0 / p2, dy = v - p1 / p2;
+  return dx * dx + dy * dy;
+}
+__device__ __forceinline__ double model_error(int model, const double *M, double x, double y, double u, double v) {
+  return model == 0 ? epipolar_error(M, x, y, u, v) : transfer_error(M, x, y, u, v);
+}
+
 struct Args {
   const unsigned long long *offsets;       // [n_pairs + 1] into the match arrays
   const double *xI, *xJ;                   // [n_matches][2] pixels
   const int *image_size;                   // [n_pairs][4] wI hI wJ hJ
-  double precision; unsigned int iterations;
+  double precision; unsigned int iterations; int model;   // model 0: fundamental (7 points, <= 3 models), 1: homography (4 points, 1 model)
   double *x1, *x2;                         // scratch [n_matches][2]: normalised points
   float *logc_n, *logc_k, *l10;            // scratch [n_matches + n_pairs] each (n + 1 entries per pair)
   uint32_t *vec_index;                     // scratch [n_matches]
@@ -132,23 +142,23 @@ struct Smem {
 };
 
 // rand_sampling.hpp:35-58 / 71-95 (thread 0)
-__device__ void sample_reject(Rng &g, uint32_t total, uint32_t *s) {
+__device__ void sample_reject(Rng &g, int ms, uint32_t total, uint32_t *s) {
   int cnt = 0;
-  while (cnt < 7) {
+  while (cnt < ms) {
     const uint32_t v = lemire(g, total);
     bool found = false;
     for (int j = 0; j < cnt && !found; ++j) found = s[j] == v;
     if (!found) s[cnt++] = v;
   }
 }
-__device__ void sample_shuffle(Rng &g, uint32_t *vec_index, uint32_t size, uint32_t *s) {
-  if (7 > size) return;                                        // UniformSample returns false and leaves the sample as it was
+__device__ void sample_shuffle(Rng &g, int ms, uint32_t *vec_index, uint32_t size, uint32_t *s) {
+  if ((uint32_t)ms > size) return;                             // UniformSample returns false and leaves the sample as it was
   const uint32_t last = size - 1;
-  for (uint32_t i = 0; i < 7; ++i) {
+  for (uint32_t i = 0; i < (uint32_t)ms; ++i) {
     const uint32_t k = i + lemire(g, last - i + 1);
     const uint32_t a = vec_index[i], b = vec_index[k]; vec_index[i] = b; vec_index[k] = a;
   }
-  for (int i = 0; i < 7; ++i) s[i] = vec_index[i];
+  for (int i = 0; i < ms; ++i) s[i] = vec_index[i];
 }
 
 __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
@@ -166,7 +176,8 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
       A.n_inliers[pair] = 0; A.stats[2 * pair] = 0.0; A.stats[2 * pair + 1] = 0.0;
       for (int i = 0; i < 9; ++i) A.F[9 * (size_t)pair + i] = (i % 4 == 0) ? 1.0 : 0.0;
     }
-    if (nData <= 7) continue;                                     // ACRANSAC: nData <= sizeSample -> {0, 0}
+    const int ms = A.model == 0 ? 7 : 4;                          // MINIMUM_SAMPLES; MAX_MODELS = 3 / 1
+    if (nData <= (unsigned int)ms) continue;                      // ACRANSAC: nData <= sizeSample -> {0, 0}
     // ---- kernel adaptor: normalisation (conditioning.cpp:54-77), logalpha0
     const int wI = A.image_size[4 * pair], hI = A.image_size[4 * pair + 1], wJ = A.image_size[4 * pair + 2], hJ = A.image_size[4 * pair + 3];
     if (threadIdx.x == 0) {
@@ -181,7 +192,9 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
       x2[2 * i] = (S.N2[0] * xJ[2 * i] + S.N2[2]) / 1.0; x2[2 * i + 1] = (S.N2[4] * xJ[2 * i + 1] + S.N2[5]) / 1.0;
       vec_index[i] = i;
     }
-    const double logalpha0 = log10(2. * hypot((double)wJ, (double)hJ) / (wJ * (double)hJ) / S.N2[0]);
+    const double logalpha0 = A.model == 0 ? log10(2. * hypot((double)wJ, (double)hJ) / (wJ * (double)hJ) / S.N2[0])       // point to line
+                                          : log10(3.14159265358979323846 / (wJ * (double)hJ) / (S.N2[0] * S.N2[0]));   // point to point
+    const double mult_error = A.model == 0 ? 0.5 : 1.0;
     const double maxThreshold = A.precision * A.precision * S.N2[0] * S.N2[0];
     // ---- NFA tables (robust_estimator_ACRansac.hpp:57-119), float arithmetic in the reference's order
     for (unsigned int i = threadIdx.x; i <= nData; i += THREADS) l10[i] = (float)log10((double)(float)i);
@@ -190,11 +203,11 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
       { unsigned int kk = k; float r = 0.f;                         // logcombi(k, n)
         if (kk < nData) { if (nData - kk < kk) kk = nData - kk; for (unsigned int i = 1; i <= kk; ++i) r += l10[nData - i + 1] - l10[i]; }
         logc_n[k] = r; }
-      { unsigned int kk = 7; const unsigned int m = k; float r = 0.f;   // logcombi(7, m)
+      { unsigned int kk = (unsigned int)ms; const unsigned int m = k; float r = 0.f;   // logcombi(MINIMUM_SAMPLES, m)
         if (kk < m) { if (m - kk < kk) kk = m - kk; for (unsigned int i = 1; i <= kk; ++i) r += l10[m - i + 1] - l10[i]; }
         logc_k[k] = r; }
     }
-    const double loge0 = log10((double)3 * (double)(nData - 7));
+    const double loge0 = log10((double)(A.model == 0 ? 3 : 1) * (double)(nData - ms));
     __syncthreads();
     // ---- ACRANSAC main loop (robust_estimator_ACRansac.hpp:330-480); the scalars live in every thread (uniform)
     Rng g{S.mt, 624};
@@ -207,24 +220,32 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
     for (unsigned int iter = 0; iter < nIter && iter < A.iterations; ++iter) {
       __syncthreads();
       if (threadIdx.x == 0) {
-        if (bACRansacMode) sample_shuffle(g, vec_index, index_size, S.sample); else sample_reject(g, nData, S.sample);
+        if (bACRansacMode) sample_shuffle(g, ms, vec_index, index_size, S.sample); else sample_reject(g, ms, nData, S.sample);
       }
       __syncthreads();
       // A'A of the 7 epipolar constraints, summed in sample order
       if (threadIdx.x < 81) {
         const int i = threadIdx.x / 9, j = threadIdx.x % 9;
         double acc = 0;
-        for (int t = 0; t < 7; ++t) {
+        for (int t = 0; t < ms; ++t) {
           const unsigned int s = S.sample[t];
           const double x = x1[2 * s], y = x1[2 * s + 1], u = x2[2 * s], v = x2[2 * s + 1];
-          const double r[9] = {u * x, u * y, u, v * x, v * y, v, x, y, 1.0};
-          acc += r[i] * r[j];
+          if (A.model == 0) {                                     // EncodeEpipolarEquation (solver_fundamental_kernel.hpp:83-93)
+            const double r[9] = {u * x, u * y, u, v * x, v * y, v, x, y, 1.0};
+            acc += r[i] * r[j];
+          } else {                                                // BuildActionMatrix (solver_homography_kernel.cpp:38-58): two rows per point
+            const double r0[9] = {x, y, 1.0, 0, 0, 0, -u * x, -u * y, -u * 1.0};
+            const double r1[9] = {0, 0, 0, x, y, 1.0, -v * x, -v * y, -v * 1.0};
+            acc += r0[i] * r0[j] + r1[i] * r1[j];
+          }
         }
         S.AtA[i][j] = acc;
       }
       __syncthreads();
       if (threadIdx.x == 0) {
         smallest_two_eigvecs(S.AtA, S.V, S.f1, S.f2);
+        if (A.model != 0) { for (int t = 0; t < 9; ++t) S.models[0][t] = S.f1[t]; S.n_models = 1; }
+        else {
         const double a = S.f1[0], j = S.f2[0], b = S.f1[1], k = S.f2[1], c = S.f1[2], l = S.f2[2], d = S.f1[3], m = S.f2[3], e = S.f1[4], n = S.f2[4],
                      f = S.f1[5], o = S.f2[5], gg = S.f1[6], p = S.f2[6], h = S.f1[7], q = S.f2[7], i = S.f1[8], r = S.f2[8];
         const double P[4] = {
@@ -238,6 +259,7 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
         if (P[0] != 0.0) nr = solve_cubic(P[2] / P[3], P[1] / P[3], P[0] / P[3], roots);
         for (int kk = 0; kk < nr; ++kk) for (int t = 0; t < 9; ++t) S.models[kk][t] = S.f1[t] + roots[kk] * S.f2[t];
         S.n_models = nr;
+        }
       }
       __syncthreads();
       const int n_models = S.n_models;
@@ -250,13 +272,13 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
         const double by_interval = NBINS / (maxThreshold - 0.0);
         int le = 0;
         for (unsigned int i = threadIdx.x; i < nData; i += THREADS) {
-          const double e = epipolar_error(S.models[mi], x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1]);
+          const double e = model_error(A.model, S.models[mi], x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1]);
           if (e <= maxThreshold) ++le;
           if (e >= 0.0) { const unsigned long long b = (unsigned long long)((e - 0.0) * by_interval); if (b < (unsigned long long)NBINS) atomicAdd(&S.hist[(int)b], 1); }
         }
         if (!bACRansacMode) { for (int o = 16; o > 0; o >>= 1) le += __shfl_xor_sync(0xffffffffu, le, o); if ((threadIdx.x & 31) == 0) atomicAdd(&S.n_le, le); }
         __syncthreads();
-        if (!bACRansacMode && (double)S.n_le > 2.5 * 7) bACRansacMode = true;       // (uniform: every thread reads the same count)
+        if (!bACRansacMode && (double)S.n_le > 2.5 * ms) bACRansacMode = true;       // (uniform: every thread reads the same count)
         if (bACRansacMode) {
           if (threadIdx.x == 0) {
             const double feps = (double)FLT_EPSILON;
@@ -266,9 +288,9 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
             for (int bin = 0; bin < NBINS; ++bin) {
               cum += (unsigned int)S.hist[bin];
               const double rv = val * (double)bin + 0.0;
-              if (cum > 7 && rv > feps) {
-                const double logalpha = logalpha0 + 0.5 * log10(rv + feps);
-                const double cur = loge0 + logalpha * (double)(cum - 7) + logc_n[cum] + logc_k[cum];
+              if (cum > (unsigned int)ms && rv > feps) {
+                const double logalpha = logalpha0 + mult_error * log10(rv + feps);
+                const double cur = loge0 + logalpha * (double)(cum - ms) + logc_n[cum] + logc_k[cum];
                 if (cur < best_nfa && cur < 0) { best_nfa = cur; best_thr = rv; }
               }
             }
@@ -282,7 +304,7 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
             for (unsigned int i0 = 0; i0 < nData; i0 += THREADS) {
               const unsigned int i = i0 + threadIdx.x;
               bool in = false;
-              if (i < nData) in = epipolar_error(S.models[mi], x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1]) <= thr;
+              if (i < nData) in = model_error(A.model, S.models[mi], x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1]) <= thr;
               const unsigned int bal = __ballot_sync(0xffffffffu, in);
               if ((threadIdx.x & 31) == 0) S.warp_cnt[threadIdx.x >> 5] = __popc(bal);
               __syncthreads();
@@ -296,7 +318,7 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
             n_inl = base;
             // (the inlier list is overwritten even when the support is too small: ComputeNFA_and_inliers returns false
             //  then and the score is NOT updated, robust_estimator_ACRansac.hpp:243-256)
-            if (n_inl > 7) {
+            if (n_inl > (unsigned int)ms) {
               better = true; minNFA = S.nfa_val; errorMax = thr;
               if (threadIdx.x < 9) A.F[9 * (size_t)pair + threadIdx.x] = S.models[mi][threadIdx.x];
             }
@@ -321,7 +343,13 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
       if (n_inl > 0) {
         double M[9], T[9], U[9];
         for (int i = 0; i < 9; ++i) M[i] = A.F[9 * (size_t)pair + i];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += S.N2[3 * k + r] * M[3 * k + c]; T[3 * r + c] = v; }
+        if (A.model == 0) {      // UnnormalizerT: N2' * F * N1
+          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += S.N2[3 * k + r] * M[3 * k + c]; T[3 * r + c] = v; }
+        } else {                 // UnnormalizerI: N2^-1 * H * N1
+          const double d = S.N2[0], a2 = S.N2[2], b2 = S.N2[5];
+          const double I2[9] = {1.0 / d, 0, -a2 / d, 0, 1.0 / d, -b2 / d, 0, 0, 1.0};
+          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += I2[3 * r + k] * M[3 * k + c]; T[3 * r + c] = v; }
+        }
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += T[3 * r + k] * S.N1[3 * k + c]; U[3 * r + c] = v; }
         for (int i = 0; i < 9; ++i) A.F[9 * (size_t)pair + i] = U[i];
         errorMax = sqrt(errorMax) / S.N2[0];
@@ -333,10 +361,11 @@ __global__ void __launch_bounds__(THREADS) acransac_f_kernel(Args A) {
 
 }}  // namespace omvg::geom
 
-extern "C" int omvg_geom_fundamental_acransac(int device, uint64_t n_pairs, const uint64_t *offsets, const double *xI, const double *xJ,
-                                              const int32_t *image_size, double precision, uint32_t max_iterations,
-                                              uint32_t *inliers, uint32_t *n_inliers, double *F, double *stats) {
+extern "C" int omvg_geom_acransac(int device, int32_t model, uint64_t n_pairs, const uint64_t *offsets, const double *xI, const double *xJ,
+                                  const int32_t *image_size, double precision, uint32_t max_iterations,
+                                  uint32_t *inliers, uint32_t *n_inliers, double *F, double *stats) {
   using namespace omvg;
+  if (model != OMVG_GEOM_FUNDAMENTAL && model != OMVG_GEOM_HOMOGRAPHY) return fail(OMVG_E_UNSUPPORTED, "geometric model %d is not implemented on the GPU path (0 = fundamental, 1 = homography)", model);
   if (n_pairs && (!offsets || !image_size || !n_inliers || !F || !stats)) return fail(OMVG_E_ARG, "null argument");
   if (!(precision > 0.0) || !std::isfinite(precision)) return fail(OMVG_E_UNSUPPORTED, "the GPU filter needs a finite upper bound of the precision (main_GeometricFilter uses 4.0)");
   if (max_iterations < 1) return fail(OMVG_E_ARG, "max_iterations must be >= 1");
@@ -369,6 +398,7 @@ extern "C" int omvg_geom_fundamental_acransac(int device, uint64_t n_pairs, cons
   OMVG_CUDA(cudaMemcpyAsync(d_off, offsets, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
   OMVG_CUDA(cudaMemcpyAsync(d_sz, image_size, n_pairs * 16, cudaMemcpyHostToDevice, st));
   if (nm) { OMVG_CUDA(cudaMemcpyAsync(d_xI, xI, nm * 16, cudaMemcpyHostToDevice, st)); OMVG_CUDA(cudaMemcpyAsync(d_xJ, xJ, nm * 16, cudaMemcpyHostToDevice, st)); }
+  A.model = model;
   A.offsets = d_off; A.xI = d_xI; A.xJ = d_xJ; A.image_size = d_sz; A.precision = precision; A.iterations = max_iterations;
   A.x1 = d_x1; A.x2 = d_x2; A.logc_n = d_ln; A.logc_k = d_lk; A.l10 = d_l10; A.vec_index = d_idx; A.inliers = d_inl; A.n_inliers = d_ninl; A.F = d_F; A.stats = d_stats;
   A.n_pairs = (unsigned int)n_pairs;
@@ -382,4 +412,10 @@ extern "C" int omvg_geom_fundamental_acransac(int device, uint64_t n_pairs, cons
   OMVG_CUDA(cudaMemcpyAsync(stats, d_stats, n_pairs * 16, cudaMemcpyDeviceToHost, st));
   OMVG_CUDA(cudaStreamSynchronize(st));
   return OMVG_OK;
+}
+
+extern "C" int omvg_geom_fundamental_acransac(int device, uint64_t n_pairs, const uint64_t *offsets, const double *xI, const double *xJ,
+                                              const int32_t *image_size, double precision, uint32_t max_iterations,
+                                              uint32_t *inliers, uint32_t *n_inliers, double *F, double *stats) {
+  return omvg_geom_acransac(device, OMVG_GEOM_FUNDAMENTAL, n_pairs, offsets, xI, xJ, image_size, precision, max_iterations, inliers, n_inliers, F, stats);
 }

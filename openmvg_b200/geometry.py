@@ -13,7 +13,19 @@ from ._lib import check, lib
 _vp = ctypes.c_void_p
 
 
+FUNDAMENTAL, HOMOGRAPHY = 0, 1
+
+
 def fundamental_acransac(offsets, xI, xJ, image_size, precision: float = 4.0, max_iterations: int = 2048, device: int = 0):
+    return acransac(FUNDAMENTAL, offsets, xI, xJ, image_size, precision, max_iterations, device)
+
+
+def homography_acransac(offsets, xI, xJ, image_size, precision: float = 4.0, max_iterations: int = 2048, device: int = 0):
+    """GeometricFilter_HMatrix_AC::Robust_estimation per pair (H_ACRobust.hpp:46-112); `F` of the result holds H."""
+    return acransac(HOMOGRAPHY, offsets, xI, xJ, image_size, precision, max_iterations, device)
+
+
+def acransac(model, offsets, xI, xJ, image_size, precision: float = 4.0, max_iterations: int = 2048, device: int = 0):
     """offsets[n_pairs+1]; xI, xJ [n_matches, 2] float64; image_size [n_pairs, 4] (wI, hI, wJ, hJ).
     -> list of dicts per pair: inliers (uint32 indices into the pair's matches), F [3,3], error_max, min_nfa"""
     off = np.ascontiguousarray(offsets, np.uint64); n_pairs = len(off) - 1
@@ -22,7 +34,7 @@ def fundamental_acransac(offsets, xI, xJ, image_size, precision: float = 4.0, ma
     nm = int(off[-1]); assert len(xI) == nm == len(xJ) and len(sz) == n_pairs
     inl = np.zeros(max(nm, 1), np.uint32); ninl = np.zeros(max(n_pairs, 1), np.uint32); F = np.zeros((max(n_pairs, 1), 9)); st = np.zeros((max(n_pairs, 1), 2))
     p = lambda a: a.ctypes.data_as(_vp)   # noqa: E731
-    check(lib().omvg_geom_fundamental_acransac(int(device), ctypes.c_uint64(n_pairs), p(off), p(xI), p(xJ), p(sz), ctypes.c_double(precision),
+    check(lib().omvg_geom_acransac(int(device), int(model), ctypes.c_uint64(n_pairs), p(off), p(xI), p(xJ), p(sz), ctypes.c_double(precision),
                                                ctypes.c_uint32(max_iterations), p(inl), p(ninl), p(F), p(st)))
     out = []
     for k in range(n_pairs):

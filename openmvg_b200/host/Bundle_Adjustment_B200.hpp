@@ -46,6 +46,10 @@
 
 #include "omvg_b200.h"
 
+#ifdef OPENMVG_USE_OPENMP
+#include <omp.h>
+#endif
+
 #include <algorithm>
 #include <chrono>
 #include <limits>
@@ -205,6 +209,16 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
   }
 
   private:
+  // Short host loops: a handful of threads, not all 128 of a shared host (measured on a busy box: the write-back of
+  // 100k points took 54 ms under a 128-thread OpenMP team and 4 ms otherwise; one slow core stalls the whole team)
+  static int HostThreads()
+  {
+#ifdef OPENMVG_USE_OPENMP
+    return std::max(1, std::min(16, omp_get_max_threads()));
+#else
+    return 1;
+#endif
+  }
   using clock_t_ = std::chrono::steady_clock;
   static clock_t_::time_point now() { return clock_t_::now(); }
   static double ms_since(clock_t_::time_point t) { return std::chrono::duration<double, std::milli>(clock_t_::now() - t).count(); }
@@ -330,7 +344,7 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
     f.points.resize(3 * (n_reg + n_gcp)); f.obs_view.resize(n_all); f.obs_point.resize(n_all); f.obs_xy.resize(2 * n_all); f.obs_view_id.resize(n_all);
     int bad = 0;
 #ifdef OPENMVG_USE_OPENMP
-    #pragma omp parallel for schedule(static) reduction(+:bad)
+    #pragma omp parallel for schedule(static) reduction(+:bad) num_threads(HostThreads())
 #endif
     for (int64_t j = 0; j < static_cast<int64_t>(n_reg); ++j)
     {
@@ -457,10 +471,7 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
     if (with_points && options.structure_opt == Structure_Parameter_Type::ADJUST_ALL)
     {
       const int64_t n = static_cast<int64_t>(f.lm.size());
-#ifdef OPENMVG_USE_OPENMP
-      #pragma omp parallel for schedule(static)
-#endif
-      for (int64_t j = 0; j < n; ++j)
+      for (int64_t j = 0; j < n; ++j)                         // (serial: 100k stores are ~1 ms, a thread team costs more)
         f.lm[j]->X = Vec3(f.points[3 * j], f.points[3 * j + 1], f.points[3 * j + 2]);
     }
   }
@@ -504,7 +515,7 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
       for (size_t b = w.seg[q]; b < w.seg[q + 1]; b += BLK) blocks.emplace_back(b, std::min(b + BLK, w.seg[q + 1]));
     const int64_t nb = static_cast<int64_t>(blocks.size());
 #ifdef OPENMVG_USE_OPENMP
-    #pragma omp parallel for schedule(dynamic, 1)
+    #pragma omp parallel for schedule(dynamic, 1) num_threads(HostThreads())
 #endif
     for (int64_t bi = 0; bi < nb; ++bi)
     {
@@ -519,7 +530,7 @@ class Bundle_Adjustment_B200 : public Bundle_Adjustment
     std::fill(kill.begin(), kill.end(), 0);
     size_t removed = 0;
 #ifdef OPENMVG_USE_OPENMP
-    #pragma omp parallel for schedule(dynamic, 512) reduction(+:removed)
+    #pragma omp parallel for schedule(dynamic, 512) reduction(+:removed) num_threads(HostThreads())
 #endif
     for (int64_t j = 0; j < n_reg; ++j)
     {

@@ -8,6 +8,7 @@
 // omvg_geom_fundamental_acransac (one CTA per pair; same MT19937 sample sequence and NFA decisions as ACRANSAC), and a
 // pair is kept iff it has more than 2.5 * 7 inliers (F_ACRobust.hpp:85).  Guided matching is not part of this path.
 //
+// Robust_model_estimation_H is the same for GeometricFilter_HMatrix_AC (H_ACRobust.hpp: 4-point homography).
 // Header-only; compile inside an openMVG build and link libomvg_b200.so.
 #ifndef OPENMVG_B200_GEOMETRIC_FILTER_B200_HPP
 #define OPENMVG_B200_GEOMETRIC_FILTER_B200_HPP
@@ -35,6 +36,14 @@ struct ImageCollectionGeometricFilter_B200
   // F model, a-contrario (GeometricFilter_FMatrix_AC(dPrecision, iteration)); returns false on a device error
   bool Robust_model_estimation_F(const matching::PairWiseMatches & putative_matches, double dPrecision = 4.0, uint32_t iteration = 2048,
                                  system::ProgressInterface * my_progress_bar = nullptr)
+  { return Robust_model_estimation(OMVG_GEOM_FUNDAMENTAL, putative_matches, dPrecision, iteration, my_progress_bar); }
+  // H model (GeometricFilter_HMatrix_AC(dPrecision, iteration), H_ACRobust.hpp:46-112): kept iff more than 2.5 * 4 inliers
+  bool Robust_model_estimation_H(const matching::PairWiseMatches & putative_matches, double dPrecision = 4.0, uint32_t iteration = 2048,
+                                 system::ProgressInterface * my_progress_bar = nullptr)
+  { return Robust_model_estimation(OMVG_GEOM_HOMOGRAPHY, putative_matches, dPrecision, iteration, my_progress_bar); }
+
+  bool Robust_model_estimation(int32_t model, const matching::PairWiseMatches & putative_matches, double dPrecision, uint32_t iteration,
+                               system::ProgressInterface * my_progress_bar = nullptr)
   {
     if (!my_progress_bar) my_progress_bar = &system::ProgressInterface::dummy();
     my_progress_bar->Restart(putative_matches.size(), "- Geometric filtering (B200) -");
@@ -55,7 +64,9 @@ struct ImageCollectionGeometricFilter_B200
     const size_t n_pairs = order.size();
     std::vector<uint32_t> inliers(xI.size() / 2 + 1), n_inliers(n_pairs + 1);
     F_.assign(9 * n_pairs, 0.0); stats_.assign(2 * n_pairs, 0.0);
-    if (omvg_geom_fundamental_acransac(device_, n_pairs, offsets.data(), xI.data(), xJ.data(), size.data(), dPrecision, iteration,
+    _map_GeometricMatches.clear();
+    const double min_samples = model == OMVG_GEOM_FUNDAMENTAL ? 7.0 : 4.0;
+    if (omvg_geom_acransac(device_, model, n_pairs, offsets.data(), xI.data(), xJ.data(), size.data(), dPrecision, iteration,
                                        inliers.data(), n_inliers.data(), F_.data(), stats_.data()) != OMVG_OK)
     {
       OPENMVG_LOG_ERROR << "omvg_b200: " << omvg_last_error();
@@ -63,7 +74,7 @@ struct ImageCollectionGeometricFilter_B200
     }
     for (size_t p = 0; p < n_pairs; ++p)
     {
-      if (n_inliers[p] > 7 * 2.5)                               // F_ACRobust.hpp:85
+      if (n_inliers[p] > min_samples * 2.5)                      // F_ACRobust.hpp:85, H_ACRobust.hpp:97
       {
         matching::IndMatches geometric_inliers;
         geometric_inliers.reserve(n_inliers[p]);
@@ -78,7 +89,7 @@ struct ImageCollectionGeometricFilter_B200
   const matching::PairWiseMatches & Get_geometric_matches() const { return _map_GeometricMatches; }
 
   const sfm::SfM_Data * sfm_data_;
-  const std::shared_ptr<sfm::Regions_Provider> & regions_provider_;
+  const std::shared_ptr<sfm::Regions_Provider> regions_provider_;   // (a copy: the reference keeps a reference, which dangles when bound to a converted temporary)
   int device_;
   matching::PairWiseMatches _map_GeometricMatches;
   std::vector<double> F_, stats_;                               // per pair (map order): un-normalised F, {errorMax, minNFA}

@@ -243,15 +243,18 @@ def exhaustive_pairs(n_images: int):
     return np.ascontiguousarray(i.astype(np.uint32)), np.ascontiguousarray(j.astype(np.uint32))
 
 
-def two_view_matches(n: int, outlier_frac: float = 0.3, noise_px: float = 0.5, seed: int = 3, wh=(1000, 1000)):
+def two_view_matches(n: int, outlier_frac: float = 0.3, noise_px: float = 0.5, seed: int = 3, wh=(1000, 1000), planar: bool = False):
     """Putative matches of one image pair for the geometric filter: n correspondences, a fraction
     of them gross outliers, the rest projections of a 3-D point cloud in two pinhole views + pixel noise.
     Positions are rounded to float32 as openMVG features store them (features/feature.hpp: PointFeature x, y are float).
+    planar=True puts the points on a plane (homography model).
     -> (xI [n,2], xJ [n,2]) float64, inlier mask [n]"""
     rng = np.random.default_rng(seed)
     w, h = wh
     f = 1.1 * max(w, h)
     X = np.stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1.2, 1.2, n), rng.uniform(4.0, 9.0, n)], 1)
+    if planar:                                                 # a plane: the two views are related by a homography
+        X[:, 2] = 6.0 + 0.3 * X[:, 0] - 0.2 * X[:, 1]
     R2 = _rodrigues(np.array([0.03, -0.25, 0.02])); C2 = np.array([1.2, 0.05, 0.3])
 
     def proj(R, C):

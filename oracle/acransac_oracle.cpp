@@ -142,14 +142,18 @@ void smallest_two_eigvecs(double A[9][9], double f1[9], double f2[9]) {
   for (int k = 0; k < 9; ++k) { f1[k] = V[k][i1]; f2[k] = V[k][i2]; }
 }
 
+// model 0: fundamental matrix (7-point solver, point-to-line error, up to 3 models per sample; F_ACRobust.hpp:66-83)
+// model 1: homography (4-point DLT, asymmetric transfer error, point-to-point; H_ACRobust.hpp:78-89)
 struct Kernel {
   int n; std::vector<double> x1, x2;           // normalised points, interleaved
-  double N1[9], N2[9], logalpha0;
+  double N1[9], N2[9], logalpha0, mult_error;
+  int model, min_samples, max_models;
 };
 
 // conditioning.cpp:54-77 ; ACKernelAdaptator.hpp:120-140
-void make_kernel(const double *xI, const double *xJ, int n, int wI, int hI, int wJ, int hJ, Kernel &K) {
+void make_kernel(const double *xI, const double *xJ, int n, int wI, int hI, int wJ, int hJ, int model, Kernel &K) {
   K.n = n; K.x1.resize(2 * n); K.x2.resize(2 * n);
+  K.model = model; K.min_samples = model == 0 ? 7 : 4; K.max_models = model == 0 ? 3 : 1; K.mult_error = model == 0 ? 0.5 : 1.0;
   auto norm = [](int w, int h, double T[9]) {
     const double d = 1.0 / std::sqrt((double)(w * h));
     for (int i = 0; i < 9; ++i) T[i] = 0; T[0] = T[4] = d; T[8] = 1.0;
@@ -161,7 +165,31 @@ void make_kernel(const double *xI, const double *xJ, int n, int wI, int hI, int 
     K.x2[2 * i] = (K.N2[0] * xJ[2 * i] + K.N2[2]) / 1.0; K.x2[2 * i + 1] = (K.N2[4] * xJ[2 * i + 1] + K.N2[5]) / 1.0;
   }
   const double D = std::hypot((double)wJ, (double)hJ), A = wJ * (double)hJ;
-  K.logalpha0 = std::log10(2. * D / A / K.N2[0]);
+  K.logalpha0 = model == 0 ? std::log10(2. * D / A / K.N2[0])                      // point to line (ACKernelAdaptator.hpp:47-56)
+                           : std::log10(M_PI / (wJ * (double)hJ) / (K.N2[0] * K.N2[0]));   // point to point (:64-74)
+}
+
+// solver_homography_kernel.cpp:36-84: the right singular vector of the 8 x 9 DLT matrix for the smallest singular
+// value = the eigenvector of L'L for the smallest eigenvalue (sign / scale are immaterial to the transfer error)
+int four_point(const Kernel &K, const std::vector<uint32_t> &s, double H[3][9]) {
+  double LtL[9][9];
+  for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) LtL[i][j] = 0;
+  for (int t = 0; t < 4; ++t) {
+    const double x = K.x1[2 * s[t]], y = K.x1[2 * s[t] + 1], u = K.x2[2 * s[t]], v = K.x2[2 * s[t] + 1];
+    const double r0[9] = {x, y, 1.0, 0, 0, 0, -u * x, -u * y, -u * 1.0};
+    const double r1[9] = {0, 0, 0, x, y, 1.0, -v * x, -v * y, -v * 1.0};
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) LtL[i][j] += r0[i] * r0[j] + r1[i] * r1[j];
+  }
+  double f1[9], f2[9];
+  smallest_two_eigvecs(LtL, f1, f2);
+  for (int t = 0; t < 9; ++t) H[0][t] = f1[t];
+  return 1;
+}
+// solver_homography_kernel.hpp:59-63
+inline double transfer_error(const double H[9], double x, double y, double u, double v) {
+  const double p0 = H[0] * x + H[1] * y + H[2], p1 = H[3] * x + H[4] * y + H[5], p2 = H[6] * x + H[7] * y + H[8];
+  const double dx = u - p0 / p2, dy = v - p1 / p2;
+  return dx * dx + dy * dy;
 }
 
 // solver_fundamental_kernel.cpp:38-95: up to 3 models (row-major 3x3)
@@ -209,12 +237,12 @@ struct NFA {
   }
   NFA(const Kernel &k_, double maxthr, bool q) : K(k_), residuals(k_.n), max_threshold(maxthr), quantified(q) {
     const uint32_t n = (uint32_t)K.n;
-    loge0 = std::log10((double)3 * (double)(K.n - 7));               // MAX_MODELS * (NumSamples - MINIMUM_SAMPLES)
+    loge0 = std::log10((double)K.max_models * (double)(K.n - K.min_samples));   // MAX_MODELS * (NumSamples - MINIMUM_SAMPLES)
     std::vector<float> l10(n + 1);
     for (uint32_t i = 0; i <= n; ++i) l10[i] = (float)std::log10((double)(float)i);
     logc_n.resize(n + 1); logc_k.resize(n + 1);
     for (uint32_t k = 0; k <= n; ++k) logc_n[k] = logcombi(k, n, l10);
-    for (uint32_t m = 0; m <= n; ++m) logc_k[m] = logcombi(7, m, l10);
+    for (uint32_t m = 0; m <= n; ++m) logc_k[m] = logcombi((uint32_t)K.min_samples, m, l10);
   }
   bool compute(std::vector<uint32_t> &inliers, std::pair<double, double> &nfa_threshold) {
     const double feps = std::numeric_limits<float>::epsilon();
@@ -234,9 +262,9 @@ struct NFA {
       for (int bin = 0; bin < nBins; ++bin) {
         cum += (unsigned int)freq[bin];
         const double rv = val * (double)bin + 0.0;
-        if (cum > 7 && rv > feps) {
-          const double logalpha = K.logalpha0 + 0.5 * std::log10(rv + feps);
-          const std::pair<double, double> cur(loge0 + logalpha * (double)(cum - 7) + logc_n[cum] + logc_k[cum], rv);
+        if (cum > (unsigned int)K.min_samples && rv > feps) {
+          const double logalpha = K.logalpha0 + K.mult_error * std::log10(rv + feps);
+          const std::pair<double, double> cur(loge0 + logalpha * (double)(cum - K.min_samples) + logc_n[cum] + logc_k[cum], rv);
           if (cur.first < best.first && cur.first < 0) best = cur;
         }
       }
@@ -244,17 +272,17 @@ struct NFA {
         nfa_threshold = best;
         inliers.clear();
         for (uint32_t i = 0; i < (uint32_t)K.n; ++i) if (residuals[i] <= nfa_threshold.second) inliers.push_back(i);
-        return inliers.size() > 7;
+        return inliers.size() > (size_t)K.min_samples;
       }
     } else {
       sorted.clear();
       for (uint32_t i = 0; i < (uint32_t)K.n; ++i) sorted.emplace_back(residuals[i], i);
       std::sort(sorted.begin(), sorted.end());
-      std::pair<double, uint32_t> best(std::numeric_limits<double>::infinity(), 7);
+      std::pair<double, uint32_t> best(std::numeric_limits<double>::infinity(), (uint32_t)K.min_samples);
       const size_t n = K.n;
-      for (size_t k = 8; k <= n && sorted[k - 1].first <= max_threshold; ++k) {
-        const double logalpha = K.logalpha0 + 0.5 * std::log10(sorted[k - 1].first + feps);
-        const std::pair<double, uint32_t> cur(loge0 + logalpha * (double)(k - 7) + logc_n[k] + logc_k[k], (uint32_t)k);
+      for (size_t k = K.min_samples + 1; k <= n && sorted[k - 1].first <= max_threshold; ++k) {
+        const double logalpha = K.logalpha0 + K.mult_error * std::log10(sorted[k - 1].first + feps);
+        const std::pair<double, uint32_t> cur(loge0 + logalpha * (double)(k - K.min_samples) + logc_n[k] + logc_k[k], (uint32_t)k);
         if (cur.first < best.first) best = cur;
       }
       if (best.first < nfa_threshold.first) {
@@ -272,18 +300,18 @@ struct NFA {
 
 extern "C" {
 
-// Same contract as ref_acransac_fundamental (oracle/ref_geom_driver.cpp).  trace (optional, may be null):
+// Same contract as ref_acransac_fundamental / ref_acransac_homography (oracle/ref_geom_driver.cpp).  trace (optional):
 // {iterations run, models evaluated, iteration at which AC-RANSAC mode was entered or -1}.
-int oracle_acransac_fundamental(const double *xI, const double *xJ, int n, int wI, int hI, int wJ, int hJ, double precision, unsigned int iterations,
-                                uint32_t *inliers_out, double *F_out, double *stats, int *trace) {
+static int acransac(int model, const double *xI, const double *xJ, int n, int wI, int hI, int wJ, int hJ, double precision, unsigned int iterations,
+                    uint32_t *inliers_out, double *F_out, double *stats, int *trace) {
   std::vector<uint32_t> vec_inliers;
-  double model[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double best_model[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   stats[0] = 0.0; stats[1] = 0.0;
-  for (int i = 0; i < 9; ++i) F_out[i] = model[i];
+  for (int i = 0; i < 9; ++i) F_out[i] = best_model[i];
   if (trace) { trace[0] = trace[1] = 0; trace[2] = -1; }
-  const unsigned int sizeSample = 7, nData = (unsigned int)n;
+  Kernel K; make_kernel(xI, xJ, n, wI, hI, wJ, hJ, model, K);
+  const unsigned int sizeSample = (unsigned int)K.min_samples, nData = (unsigned int)n;
   if (nData <= sizeSample) return 0;
-  Kernel K; make_kernel(xI, xJ, n, wI, hI, wJ, hJ, K);
   const double inf = std::numeric_limits<double>::infinity();
   const double prec2 = precision > 0 ? precision * precision : inf;
   std::vector<uint32_t> vec_index(nData); for (unsigned int i = 0; i < nData; ++i) vec_index[i] = i;
@@ -300,11 +328,13 @@ int oracle_acransac_fundamental(const double *xI, const double *xJ, int n, int w
     if (bACRansacMode) uniform_sample_shuffle(sizeSample, rng, vec_index, vec_sample);
     else uniform_sample_reject(sizeSample, nData, rng, vec_sample);
     double Fs[3][9];
-    const int nm = seven_point(K, vec_sample, Fs);
+    const int nm = model == 0 ? seven_point(K, vec_sample, Fs) : four_point(K, vec_sample, Fs);
     bool better = false;
     for (int mi = 0; mi < nm; ++mi) {
       ++n_models;
-      for (unsigned int i = 0; i < nData; ++i) nfa.residuals[i] = epipolar_error(Fs[mi], K.x1[2 * i], K.x1[2 * i + 1], K.x2[2 * i], K.x2[2 * i + 1]);
+      for (unsigned int i = 0; i < nData; ++i)
+        nfa.residuals[i] = model == 0 ? epipolar_error(Fs[mi], K.x1[2 * i], K.x1[2 * i + 1], K.x2[2 * i], K.x2[2 * i + 1])
+                                      : transfer_error(Fs[mi], K.x1[2 * i], K.x1[2 * i + 1], K.x2[2 * i], K.x2[2 * i + 1]);
       if (!bACRansacMode) {
         unsigned int nInlier = 0;
         for (unsigned int i = 0; i < nData; ++i) if (nfa.residuals[i] <= maxThreshold) ++nInlier;
@@ -314,7 +344,7 @@ int oracle_acransac_fundamental(const double *xI, const double *xJ, int n, int w
         std::pair<double, double> nfa_threshold(minNFA, 0.0);
         if (nfa.compute(vec_inliers, nfa_threshold)) {
           better = true; minNFA = nfa_threshold.first; errorMax = nfa_threshold.second;
-          std::memcpy(model, Fs[mi], sizeof model);
+          std::memcpy(best_model, Fs[mi], sizeof best_model);
         }
       }
     }
@@ -330,17 +360,31 @@ int oracle_acransac_fundamental(const double *xI, const double *xJ, int n, int w
   if (trace) { trace[0] = (int)iter; trace[1] = n_models; }
   if (minNFA >= 0) vec_inliers.clear();
   if (!vec_inliers.empty()) {
-    // UnnormalizerT: F = N2' * F * N1 ; unormalizeError
     double T[9], U[9];
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += K.N2[3 * k + r] * model[3 * k + c]; T[3 * r + c] = v; }
+    if (model == 0) {      // UnnormalizerT: F = N2' * F * N1
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += K.N2[3 * k + r] * best_model[3 * k + c]; T[3 * r + c] = v; }
+    } else {               // UnnormalizerI: H = N2^-1 * H * N1 ; N2 = [[d,0,a],[0,d,b],[0,0,1]] -> N2^-1 = [[1/d,0,-a/d],[0,1/d,-b/d],[0,0,1]]
+      const double d = K.N2[0], a2 = K.N2[2], b2 = K.N2[5];
+      const double I2[9] = {1.0 / d, 0, -a2 / d, 0, 1.0 / d, -b2 / d, 0, 0, 1.0};
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += I2[3 * r + k] * best_model[3 * k + c]; T[3 * r + c] = v; }
+    }
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += T[3 * r + k] * K.N1[3 * k + c]; U[3 * r + c] = v; }
-    std::memcpy(model, U, sizeof model);
+    std::memcpy(best_model, U, sizeof best_model);
     errorMax = std::sqrt(errorMax) / K.N2[0];
   }
   for (size_t i = 0; i < vec_inliers.size(); ++i) inliers_out[i] = vec_inliers[i];
-  for (int i = 0; i < 9; ++i) F_out[i] = model[i];
+  for (int i = 0; i < 9; ++i) F_out[i] = best_model[i];
   stats[0] = errorMax; stats[1] = minNFA;
   return (int)vec_inliers.size();
+}
+
+int oracle_acransac_fundamental(const double *xI, const double *xJ, int n, int wI, int hI, int wJ, int hJ, double precision, unsigned int iterations,
+                                uint32_t *inliers_out, double *F_out, double *stats, int *trace) {
+  return acransac(0, xI, xJ, n, wI, hI, wJ, hJ, precision, iterations, inliers_out, F_out, stats, trace);
+}
+int oracle_acransac_homography(const double *xI, const double *xJ, int n, int wI, int hI, int wJ, int hJ, double precision, unsigned int iterations,
+                               uint32_t *inliers_out, double *H_out, double *stats, int *trace) {
+  return acransac(1, xI, xJ, n, wI, hI, wJ, hJ, precision, iterations, inliers_out, H_out, stats, trace);
 }
 
 }  // extern "C"

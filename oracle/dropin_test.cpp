@@ -23,6 +23,7 @@
 #include "../openmvg_b200/host/GeometricFilter_B200.hpp"
 #include "openMVG/matching_image_collection/GeometricFilter.hpp"
 #include "openMVG/matching_image_collection/F_ACRobust.hpp"
+#include "openMVG/matching_image_collection/H_ACRobust.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -137,6 +138,7 @@ SfM_Data make_scene(int C, int P, int K, bool priors_and_gcp = false, double out
 
 int main(int argc, char ** argv)
 {
+  std::setvbuf(stdout, nullptr, _IOLBF, 0);          // line-buffered even into a pipe: a crash must not swallow earlier results
   int failures = 0;
   // ------------------------------------------------------------------ MATCH
   {
@@ -269,9 +271,11 @@ int main(int argc, char ** argv)
       for (int j = 0; j < n; ++j) m.emplace_back(j, U01(g) < 0.35 ? int(U01(g) * (P - 1)) : j);   // 35 % wrong correspondences
       putative.insert({{a, b}, m});
     }
-    matching_image_collection::ImageCollectionGeometricFilter ref_filter(&s, provider);
+    // (both filters keep a REFERENCE to the shared_ptr<Regions_Provider>: hand them an lvalue of exactly that type)
+    const std::shared_ptr<sfm::Regions_Provider> base_provider = provider;
+    matching_image_collection::ImageCollectionGeometricFilter ref_filter(&s, base_provider);
     ref_filter.Robust_model_estimation(matching_image_collection::GeometricFilter_FMatrix_AC(4.0, 2048), putative);
-    matching_image_collection::ImageCollectionGeometricFilter_B200 gpu_filter(&s, provider);
+    matching_image_collection::ImageCollectionGeometricFilter_B200 gpu_filter(&s, base_provider);
     const bool ok = gpu_filter.Robust_model_estimation_F(putative, 4.0, 2048);
     const auto & A = ref_filter.Get_geometric_matches(); const auto & B = gpu_filter.Get_geometric_matches();
     bool same = ok && A.size() == B.size();
@@ -284,6 +288,21 @@ int main(int argc, char ** argv)
     }
     std::printf("GEOMETRIC FILTER (F, AC-RANSAC) drop-in: %zu of %zu pairs kept, %zu geometric matches, %s\n", A.size(), putative.size(), total, same ? "IDENTICAL" : "DIFFERENT");
     if (!same || total == 0 || A.size() == putative.size()) ++failures;
+    // the homography model on the same putative matches (a general scene: few pairs survive, which is the point of the test)
+    matching_image_collection::ImageCollectionGeometricFilter ref_h(&s, base_provider);
+    ref_h.Robust_model_estimation(matching_image_collection::GeometricFilter_HMatrix_AC(4.0, 2048), putative);
+    matching_image_collection::ImageCollectionGeometricFilter_B200 gpu_h(&s, base_provider);
+    const bool okh = gpu_h.Robust_model_estimation_H(putative, 4.0, 2048);
+    const auto & AH = ref_h.Get_geometric_matches(); const auto & BH = gpu_h.Get_geometric_matches();
+    bool sameh = okh && AH.size() == BH.size(); size_t totalh = 0;
+    for (const auto & kv : AH) {
+      const auto it = BH.find(kv.first);
+      if (it == BH.end() || it->second.size() != kv.second.size()) { sameh = false; break; }
+      for (size_t i = 0; i < kv.second.size(); ++i) if (kv.second[i].i_ != it->second[i].i_ || kv.second[i].j_ != it->second[i].j_) { sameh = false; break; }
+      totalh += kv.second.size();
+    }
+    std::printf("GEOMETRIC FILTER (H, AC-RANSAC) drop-in: %zu of %zu pairs kept, %zu geometric matches, %s\n", AH.size(), putative.size(), totalh, sameh ? "IDENTICAL" : "DIFFERENT");
+    if (!sameh) ++failures;
   }
   // ------------------------------------------------------------------ the BA / outlier-rejection loop (N1)
   // reference: do { Bundle_Adjustment_Ceres::Adjust } while (RemoveOutliers_PixelResidualError(4.0, 2) +

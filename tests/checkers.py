@@ -449,3 +449,12 @@ def ref_acransac_fundamental(xI, xJ, wh=(1000, 1000, 1000, 1000), precision=4.0,
 
 def oracle_acransac_fundamental(xI, xJ, wh=(1000, 1000, 1000, 1000), precision=4.0, iterations=2048):
     return _acransac(oracle().oracle_acransac_fundamental, xI, xJ, wh, precision, iterations, True)
+
+
+def ref_acransac_homography(xI, xJ, wh=(1000, 1000, 1000, 1000), precision=4.0, iterations=2048):
+    """The reference's ACRANSAC + ACKernelAdaptor<FourPointSolver, AsymmetricError, UnnormalizerI> (H_ACRobust.hpp:78-95)."""
+    return _acransac(ref_geom().ref_acransac_homography, xI, xJ, wh, precision, iterations, False)
+
+
+def oracle_acransac_homography(xI, xJ, wh=(1000, 1000, 1000, 1000), precision=4.0, iterations=2048):
+    return _acransac(oracle().oracle_acransac_homography, xI, xJ, wh, precision, iterations, True)

@@ -163,10 +163,28 @@ def geom_case_inputs(c):
     return xI, xJ, (wh[0], wh[1], wh[0], wh[1])
 
 
+GEOM_H_CASES = [
+    dict(name="h300", n=300, outlier_frac=0.3, seed=3), dict(name="h1500_half_outliers", n=1500, outlier_frac=0.5, seed=4),
+    dict(name="h60", n=60, outlier_frac=0.2, seed=5), dict(name="h200_no_model", n=200, outlier_frac=0.9, seed=6),
+    dict(name="h5", n=5, outlier_frac=0.0, seed=7), dict(name="h4", n=4, outlier_frac=0.0, seed=8),
+    dict(name="h2500_wide", n=2500, outlier_frac=0.4, seed=10, wh=(4000, 3000)), dict(name="h12", n=12, outlier_frac=0.1, seed=10),
+]
+
+
 def main_geom():
     path = os.path.join(HERE, "reference_outputs.json")
     out = json.load(open(path))
-    out["geom_F"] = []
+    out["geom_F"] = []; out["geom_H"] = []
+    for c in GEOM_H_CASES:
+        wh = tuple(c.get("wh", (1000, 1000)))
+        xI, xJ, _ = synth.two_view_matches(c["n"], c["outlier_frac"], seed=c["seed"], wh=wh, planar=True)
+        r = ck.ref_acransac_homography(xI, xJ, (wh[0], wh[1], wh[0], wh[1]), 4.0, 2048)
+        inl = np.ascontiguousarray(np.stack([r["inliers"], r["inliers"]], 1).astype(np.uint32))
+        fnv = int(ck.oracle().oracle_fnv1a_ij(inl.ctypes.data_as(ck.ctypes.c_void_p), ck.ctypes.c_int64(len(inl))))
+        Hn = r["F"] / np.linalg.norm(r["F"]) if len(r["inliers"]) else r["F"]
+        out["geom_H"].append(dict(c, n_inliers=int(len(r["inliers"])), inliers_fnv1a=str(fnv), error_max=repr(r["error_max"]), min_nfa=repr(r["min_nfa"]),
+                                  F_unit=[float(v) for v in Hn.reshape(-1)]))
+        print("geom H", c["name"], len(r["inliers"]), r["error_max"], r["min_nfa"])
     for c in GEOM_CASES:
         xI, xJ, wh = geom_case_inputs(c)
         r = ck.ref_acransac_fundamental(xI, xJ, wh, 4.0, 2048)

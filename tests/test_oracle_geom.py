@@ -12,12 +12,20 @@ import checkers as ck
 from openmvg_b200 import synth
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.json"))).get("geom_F", [])
+_ALL = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.json")))
+GOLD = _ALL.get("geom_F", [])
+GOLD_H = _ALL.get("geom_H", [])
 
 
 def case_inputs(c):
     wh = tuple(c.get("wh", (1000, 1000)))
     xI, xJ, _ = synth.two_view_matches(c["n"], c["outlier_frac"], seed=c["seed"], wh=wh)
+    return xI, xJ, (wh[0], wh[1], wh[0], wh[1])
+
+
+def case_inputs_h(c):
+    wh = tuple(c.get("wh", (1000, 1000)))
+    xI, xJ, _ = synth.two_view_matches(c["n"], c["outlier_frac"], seed=c["seed"], wh=wh, planar=True)
     return xI, xJ, (wh[0], wh[1], wh[0], wh[1])
 
 
@@ -62,4 +70,23 @@ def test_oracle_against_compiled_reference(seed):
     r = ck.ref_acransac_fundamental(xI, xJ, wh, 4.0, it); o = ck.oracle_acransac_fundamental(xI, xJ, wh, 4.0, it)
     assert np.array_equal(r["inliers"], o["inliers"]), (n, of, it)
     assert r["error_max"] == o["error_max"] or abs(r["error_max"] - o["error_max"]) <= 1e-9 * abs(r["error_max"])
+    assert r["min_nfa"] == o["min_nfa"] or abs(r["min_nfa"] - o["min_nfa"]) <= 1e-9 * abs(r["min_nfa"])
+
+
+@pytest.mark.parametrize("c", GOLD_H, ids=lambda c: c["name"])
+def test_homography_oracle_against_reference_golden(c):
+    """The homography model (GeometricFilter_HMatrix_AC: 4-point DLT, asymmetric transfer error, point-to-point NFA)."""
+    xI, xJ, wh = case_inputs_h(c)
+    check_against_gold(ck.oracle_acransac_homography(xI, xJ, wh, 4.0, 2048), c)
+
+
+@pytest.mark.skipif(not ck.have_ref_geom(), reason="oracle/_ref/libref_geom.so not built (no /root/reference here)")
+@pytest.mark.parametrize("seed", range(40, 48))
+def test_homography_oracle_against_compiled_reference(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(5, 900)); of = float(rng.uniform(0.0, 0.7)); it = int(rng.choice([64, 2048]))
+    xI, xJ, _ = synth.two_view_matches(n, of, seed=seed, wh=(1600, 1200), planar=True)
+    wh = (1600, 1200, 1600, 1200)
+    r = ck.ref_acransac_homography(xI, xJ, wh, 4.0, it); o = ck.oracle_acransac_homography(xI, xJ, wh, 4.0, it)
+    assert np.array_equal(r["inliers"], o["inliers"]), (n, of, it)
     assert r["min_nfa"] == o["min_nfa"] or abs(r["min_nfa"] - o["min_nfa"]) <= 1e-9 * abs(r["min_nfa"])
