@@ -279,7 +279,7 @@ def run_ours(args):
         int8_peak = 2.0 * pk["bf16_sustained"]                          # dense INT8 = 2x bf16 rate; bf16 is the measured figure
         # one pass may take several launches (pair batches sized by the result-buffer budget): rate over all of them
         roof = dict(bound="tensor", achieved=OPS_PER_DESC_PAIR * desc_pairs_rank * steps / max(tc_ms / 1e3, 1e-12) / 1e12, peak=int8_peak, unit="TOP/s", traffic=None,
-                    kernel="match_tc_kernel (tcgen05 kind::i8 + fused top-2)", launches=tc_n, avg_ms=tc_s * 1e3,
+                    kernel="match_dig2_kernel (tcgen05 kind::i8, 4 descriptor K-slices + 1 digit slice, fused top-2; 256 algorithmic op per descriptor pair, the fifth slice is not counted)", launches=tc_n, avg_ms=tc_s * 1e3,
                     peak_source=f"2 x {pk['src']} bf16 sustained (INT8 dense rate = 2 x bf16)")
         roof["frac"] = roof["achieved"] / roof["peak"]
         gather_bytes = (world - 1) * per * MATCH_DESC * 128 if world > 1 else 0

@@ -91,6 +91,11 @@ uint64_t omvg_match_launch_count(const omvg_match_ctx *ctx);
 /* Device time (ms, CUDA events on the context's stream) and launch count of the dominant
  * kernel (the tcgen05 distance/top-2 kernel) accumulated since the last call with reset!=0. */
 int omvg_match_kernel_time(omvg_match_ctx *ctx, double *ms, uint64_t *launches, int reset);
+/* Which distance/top-2 kernel omvg_match_run will use for the prepared collection: 5 = fifth-K-slice kernel (the
+ * per-column constant rides in the MMA; needs max|b|^2 - min|b|^2 <= 3.9e6 inside every image), 4 = the kernel with
+ * the per-accumulator key arithmetic (any uint8 descriptors; also forced by OMVG_MATCH_TC4=1), 0 = not prepared.
+ * Both give bit-identical matches. */
+int omvg_match_kernel_variant(const omvg_match_ctx *ctx);
 
 /* ---- cascade hashing: openMVG's default matcher for scalar descriptors ("FASTCASCADEHASHINGL2",
  * matching/cascade_hasher.hpp, matching_image_collection/Cascade_Hashing_Matcher_Regions.cpp:38-226).

@@ -26,6 +26,8 @@ def lib() -> ctypes.CDLL:
         L.omvg_last_error.restype = ctypes.c_char_p
         L.omvg_match_launch_count.restype = ctypes.c_uint64
         L.omvg_match_launch_count.argtypes = [ctypes.c_void_p]
+        L.omvg_match_kernel_variant.restype = ctypes.c_int
+        L.omvg_match_kernel_variant.argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
 

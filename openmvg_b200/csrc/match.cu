@@ -41,8 +41,10 @@ constexpr int B_STAGE_BYTES = B_BYTES + CK_BYTES;
 constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*align slack*/ + 2048 /*merge*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2-5 / 6-9 epilogue for even / odd tiles
 constexpr int KEY_MIN = INT_MIN;
+constexpr int MATCH_NSPLIT_DEFAULT = 2;
 
-struct Unit { uint32_t q_row, db_row, n_db_tiles, out_off; };   // one (pair, 128-query tile)
+struct Unit { uint32_t q_row, db_row, n_db_tiles, out_off; };   // one (pair, 128-query tile); n_db_tiles = tiles | (rows per group / 32) << 20
+constexpr uint32_t UNIT_TILES_MASK = 0xFFFFFu;
 
 // --------------------------------------------------------------------------------- prep kernel
 // norm[r] = |row r|^2 ; ckey[r] = -256*norm + (local_row / G) for real rows, INT_MIN for padding.
@@ -99,7 +101,7 @@ __device__ __forceinline__ void chunk_update(const int32_t (&r)[32], uint32_t ck
   k1 = max(k1, gm);
 }
 
-template <bool DRAIN_ONLY>
+template <int DRAIN_ONLY>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ ckey,
                 const Unit *__restrict__ units, uint32_t n_units, int2 *__restrict__ k12) {
@@ -138,7 +140,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
         mbar_wait(&empty_a[as], ((ul >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&full_a[as], A_BYTES);
         tma_load_2d(a_smem + as * A_BYTES, &tmap, 0, (int)un.q_row, &full_a[as]);
-        for (uint32_t t = 0; t < un.n_db_tiles; ++t, ++g) {
+        for (uint32_t t = 0; t < (un.n_db_tiles & UNIT_TILES_MASK); ++t, ++g) {
           const uint32_t st = g % B_STAGES;
           mbar_wait(&empty_b[st], ((g / B_STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&full_b[st], B_STAGE_BYTES);
@@ -156,7 +158,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
       constexpr uint32_t idesc = make_idesc_u8(TILE_Q, TILE_DB);
       uint32_t g = 0, ul = 0;
       for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
-        const uint32_t n_tiles = units[u].n_db_tiles;
+        const uint32_t n_tiles = units[u].n_db_tiles & UNIT_TILES_MASK;
         const uint32_t as = ul & 1;
         mbar_wait(&full_a[as], (ul >> 1) & 1);
         const uint32_t a_addr = smem_u32(a_smem + as * A_BYTES);
@@ -185,7 +187,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
     for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
       const Unit un = units[u];
       int k1 = KEY_MIN, k2 = KEY_MIN;
-      for (uint32_t t = 0; t < un.n_db_tiles; ++t, ++g) {
+      for (uint32_t t = 0; t < (un.n_db_tiles & UNIT_TILES_MASK); ++t, ++g) {
         if ((g & 1) != wg) continue;
         const uint32_t st = g % B_STAGES, acc = wg;
         mbar_wait(&full_b[st], (g / B_STAGES) & 1);      // packed keys of this tile are in smem
@@ -226,15 +228,417 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restr
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+
+// --------------------------------------------------------------------------------- tcgen05 kernel, fifth K-slice
+// The shipped kernel.  match_tc_kernel above spends 1 IMAD per accumulator on key = 512*dot + ckey[column]; here the
+// per-column constant rides in the MMA instead: a fifth K=32 slice multiplies a CONSTANT A tile (weights
+// 1, 255 x 15, 1, 255 x 15 in every row) with 32 signed "digits" per database row (u8 x s8, its own instruction
+// descriptor) so that the accumulator is   acc = q.b - h(b) + c0(image),  h = ceil(|b|^2 / 2).
+// The epilogue is then a pure running max (VIMNMX3: half an instruction per accumulator) and ONE key per 32-column
+// chunk, key = 256 * max + group.  What is lost is the parity of |b|^2:  2 q.b - |b|^2 = 2 acc - 2 c0 + p, p in
+// {0, 1}; the finalize kernel works with the two-sided bound and falls back to an exact scan of the whole database
+// image in the (rare) cases where the one unit matters — see match_finalize_kernel<true>.  Padding rows carry the
+// most negative digit vector (DIG_PAD), strictly below every real column, and zero descriptors.
+// Digit range: v = c0 - h must lie in [DIG_VMIN, DIG_VMAX]; omvg_match_prepare picks c0 per image and uses this
+// kernel only if every image fits (|b|^2 spread <= 3.9 M inside an image: always true for SIFT, whose |b|^2 is
+// ~2.6e5); otherwise match_tc_kernel runs.  NSPLIT = epilogue warps per TMEM lane quarter and accumulator.
+constexpr int DIG_LEN = 32;
+constexpr int DG_BYTES = TILE_DB * DIG_LEN;                      //  8 KB of digits per database tile
+constexpr int B5_STAGE_BYTES = B_BYTES + DG_BYTES;               // 40 KB
+constexpr int ACONST_BYTES = TILE_Q * DIG_LEN;                   //  4 KB
+constexpr int DIG_PAD = -128 * 2 - 128 * 255 * 30;               // -979456: all 32 digits = -128
+constexpr int DIG_VMIN = -979328, DIG_VMAX = 971676;             // v = d0 + 255 M, d0 in [-128, 126], M in [-3840, 3810]
+constexpr int DIG_SPREAD_MAX = DIG_VMAX - DIG_VMIN;              // 1 951 004 (in units of h)
+template <int NSPLIT> constexpr int smem5_bytes() {
+  return A_STAGES * A_BYTES + B_STAGES * B5_STAGE_BYTES + ACONST_BYTES + 1024 /*align slack*/ + 2 * (2 * NSPLIT - 1) * TILE_Q * 8 /*merge*/ + 256 /*barriers*/;
+}
+
+// per-image min / max of h = ceil(|row|^2 / 2) over the real rows (one block per image)
+__global__ void prep_minmax_kernel(const int32_t *__restrict__ norm, const uint32_t *__restrict__ img_row0,
+                                   const uint32_t *__restrict__ img_count, int2 *__restrict__ out) {
+  __shared__ int smin[8], smax[8];
+  const uint32_t img = blockIdx.x, r0 = img_row0[img], n = img_count[img];
+  int lo = INT_MAX, hi = INT_MIN;
+  for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) { const int h = (norm[r0 + r] + 1) >> 1; lo = min(lo, h); hi = max(hi, h); }
+  #pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = min(lo, smin[w]); hi = max(hi, smax[w]); } out[img] = make_int2(lo, hi); }
+}
+
+// digits of v = c0 - h for real rows, all -128 for padding rows.  Byte 0 and byte 16 have weight 1, the others 255.
+__global__ void prep_digits_kernel(const int32_t *__restrict__ norm, const uint32_t *__restrict__ img_row0,
+                                   const uint32_t *__restrict__ img_count, const uint32_t *__restrict__ row_img,
+                                   const int32_t *__restrict__ img_c0, uint4 *__restrict__ dig, uint32_t total_rows) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= total_rows) return;
+  const uint32_t img = row_img[r >> 8], local = r - img_row0[img];
+  uint32_t w[8];
+  if (local < img_count[img]) {
+    const int v = img_c0[img] - ((norm[r] + 1) >> 1);
+    int M = (v + 128) / 255; if ((v + 128) - M * 255 < 0) --M;                // floor division
+    const int d0 = v - 255 * M;                                               // [-128, 126]
+    int qd = M / 30; if (M - qd * 30 < 0) --qd;
+    const int rem = M - qd * 30;                                              // [0, 29]
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t word = 0;
+      #pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int pos = 4 * i + b;
+        int d;
+        if (pos == 0) d = d0; else if (pos == 16) d = 0;
+        else { const int k = pos < 16 ? pos - 1 : pos - 2; d = qd + (k < rem ? 1 : 0); }
+        word |= (uint32_t)(d & 255) << (8 * b);
+      }
+      w[i] = word;
+    }
+  } else {
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = 0x80808080u;
+  }
+  dig[2 * (size_t)r] = make_uint4(w[0], w[1], w[2], w[3]);
+  dig[2 * (size_t)r + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+__device__ __forceinline__ void chunk_max(const int32_t (&r)[32], int gid, int &k1, int &k2) {
+  int g0 = max(max(r[0], r[1]), r[2]), g1 = max(max(r[8], r[9]), r[10]), g2 = max(max(r[16], r[17]), r[18]), g3 = max(max(r[24], r[25]), r[26]);
+  g0 = max(max(g0, r[3]), r[4]); g1 = max(max(g1, r[11]), r[12]); g2 = max(max(g2, r[19]), r[20]); g3 = max(max(g3, r[27]), r[28]);
+  g0 = max(max(g0, r[5]), r[6]); g1 = max(max(g1, r[13]), r[14]); g2 = max(max(g2, r[21]), r[22]); g3 = max(max(g3, r[29]), r[30]);
+  const int gm = max(max(max(g0, r[7]), max(g1, r[15])), max(max(g2, r[23]), max(g3, r[31])));
+  const int key = gm * 256 + gid;
+  k2 = max(k2, min(k1, key));
+  k1 = max(k1, key);
+}
+
+// K-major operand tile of 32-byte rows under the 32-byte swizzle (TMA SWIZZLE_32B): 8-row x 32-B atoms, SBO 256 B.
+__device__ __forceinline__ uint64_t make_kmajor_sw32_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(256 >> 4) << 32;                     // SBO
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)6 << 61;                              // SWIZZLE_32B
+  return d;
+}
+
+template <int NSPLIT, bool DRAIN_ONLY>
+__global__ void __launch_bounds__(64 + 256 * NSPLIT, 1)
+match_dig_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_dig,
+                 const Unit *__restrict__ units, uint32_t n_units, int2 *__restrict__ k12) {
+  constexpr int NMERGE = 2 * NSPLIT - 1;               // partial top-2 lists merged by the first warps of a row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *a_smem = smem;                                        // [A_STAGES][16 KB]
+  uint8_t *b_smem = smem + A_STAGES * A_BYTES;                   // [B_STAGES][32 KB descriptors + 8 KB digits]
+  uint8_t *aconst = b_smem + B_STAGES * B5_STAGE_BYTES;          // [128][32 B] constant weights
+  int2 *merge = reinterpret_cast<int2 *>(aconst + ACONST_BYTES); // [2][NMERGE][128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(merge + 2 * NMERGE * TILE_Q);
+  uint64_t *full_a = bars, *empty_a = bars + 2, *full_b = bars + 4, *empty_b = bars + 8;
+  uint64_t *tmem_full = bars + 12, *tmem_empty = bars + 14;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap); prefetch_tmap(&tmap_dig);
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * NSPLIT); }
+    fence_barrier_init();
+  }
+  // weights of the fifth slice: both 16-byte halves of every row are {1, 255 x 15}, so the swizzle cannot matter
+  for (int i = threadIdx.x; i < ACONST_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *>(aconst)[i] = make_uint4(0xFFFFFF01u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  fence_proxy_async();
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t g = 0, ul = 0;
+      for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+        const Unit un = units[u];
+        const uint32_t as = ul & 1, n_tiles = un.n_db_tiles & UNIT_TILES_MASK;
+        mbar_wait(&empty_a[as], ((ul >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full_a[as], A_BYTES);
+        tma_load_2d(a_smem + as * A_BYTES, &tmap, 0, (int)un.q_row, &full_a[as]);
+        for (uint32_t t = 0; t < n_tiles; ++t, ++g) {
+          const uint32_t st = g % B_STAGES;
+          mbar_wait(&empty_b[st], ((g / B_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_b[st], B5_STAGE_BYTES);
+          uint8_t *dst = b_smem + st * B5_STAGE_BYTES;
+          const uint32_t row = un.db_row + t * TILE_DB;
+          tma_load_2d(dst, &tmap, 0, (int)row, &full_b[st]);
+          tma_load_2d(dst + A_BYTES, &tmap, 0, (int)(row + 128), &full_b[st]);
+          tma_load_2d(dst + B_BYTES, &tmap_dig, 0, (int)row, &full_b[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_u8(TILE_Q, TILE_DB);
+      constexpr uint32_t idesc5 = idesc | (1u << 10);             // B operand signed: u8 weights x s8 digits
+      const uint64_t ac_desc = make_kmajor_sw32_desc(smem_u32(aconst));
+      uint32_t g = 0, ul = 0;
+      for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+        const uint32_t n_tiles = units[u].n_db_tiles & UNIT_TILES_MASK;
+        const uint32_t as = ul & 1;
+        mbar_wait(&full_a[as], (ul >> 1) & 1);
+        const uint32_t a_addr = smem_u32(a_smem + as * A_BYTES);
+        for (uint32_t t = 0; t < n_tiles; ++t, ++g) {
+          const uint32_t st = g % B_STAGES, acc = g & 1;
+          mbar_wait(&full_b[st], (g / B_STAGES) & 1);
+          mbar_wait(&tmem_empty[acc], ((g >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(b_smem + st * B5_STAGE_BYTES);
+          const uint32_t d = tmem_base + acc * TILE_DB;
+          #pragma unroll
+          for (int k = 0; k < OMVG_DESC_LEN / 32; ++k)
+            umma_i8(d, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32), idesc, k > 0);
+          umma_i8(d, ac_desc, make_kmajor_sw32_desc(b_addr + B_BYTES), idesc5, 1);
+          tc_commit(&empty_b[st]);
+          tc_commit(&tmem_full[acc]);
+        }
+        tc_commit(&empty_a[as]);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (8 * NSPLIT warps)
+    const uint32_t e = warp - 2;
+    const uint32_t wg = e / (4 * NSPLIT);                 // accumulator / tile parity served by this warp
+    const uint32_t part = (e % (4 * NSPLIT)) >> 2;        // which 256/NSPLIT-column part of the accumulator
+    const uint32_t quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    constexpr uint32_t NCH = 8 / NSPLIT;                  // 32-column chunks per warp and tile
+    const uint32_t c0 = part * NCH;
+    uint32_t g = 0, ul = 0;
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+      const Unit un = units[u];
+      const uint32_t n_tiles = un.n_db_tiles & UNIT_TILES_MASK, gdiv = (un.n_db_tiles >> 20) & 0x7FFu;
+      int k1 = KEY_MIN, k2 = KEY_MIN;
+      for (uint32_t t = 0; t < n_tiles; ++t, ++g) {
+        if ((g & 1) != wg) continue;
+        const uint32_t acc = wg;
+        mbar_wait(&tmem_full[acc], (g >> 1) & 1);        // accumulator complete
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + acc * TILE_DB + c0 * 32;
+        const uint32_t chunk0 = t * 8 + c0;
+        int32_t ra[32], rb[32];
+        tmem_ld_32x32(taddr, ra);
+        #pragma unroll
+        for (uint32_t c = 0; c < NCH; c += 2) {
+          tmem_ld_wait_dep(ra);
+          tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+          if (!DRAIN_ONLY) chunk_max(ra, (int)(gdiv <= 1 ? chunk0 + c : (chunk0 + c) / gdiv), k1, k2);
+          tmem_ld_wait_dep(rb);
+          if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+          if (!DRAIN_ONLY) chunk_max(rb, (int)(gdiv <= 1 ? chunk0 + c + 1 : (chunk0 + c + 1) / gdiv), k1, k2);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+      // merge the partial top-2 lists of the 2 * NSPLIT warps of a row (disjoint chunks) and store
+      int2 *mb = merge + (ul & 1) * NMERGE * TILE_Q;
+      const uint32_t slot = wg * NSPLIT + part;            // slot 0 merges
+      if (slot) mb[(slot - 1) * TILE_Q + row_in_tile] = make_int2(k1, k2);
+      asm volatile("bar.sync 1, %0;" :: "n"(256 * NSPLIT) : "memory");
+      if (slot == 0) {
+        #pragma unroll
+        for (int sI = 0; sI < NMERGE; ++sI) {
+          const int2 o = mb[sI * TILE_Q + row_in_tile];
+          const int lo = min(k1, o.x);
+          k1 = max(k1, o.x);
+          k2 = max(lo, max(k2, o.y));
+        }
+        k12[(size_t)un.out_off + row_in_tile] = make_int2(k1, k2);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+
+// --------------------------------------------------------------------------------- two query tiles per database tile
+// match_dig_kernel streams the whole database image through every CTA once per 128 queries: 40 KB per 640 tensor
+// cycles and SM = 18 TB/s of L2 -> SM traffic at full rate, which the L2 does not deliver (the TMA + MMA skeleton
+// WITHOUT any epilogue runs at 61-69 % tensor pipe).  Here one CTA keeps TWO query tiles (256 queries) resident and
+// multiplies both with every database tile it loads: accumulator 0 = queries 0-127, accumulator 1 = queries
+// 128-255, which are at the same time the two halves of the TMEM double buffer (the epilogue of accumulator 0 runs
+// under the MMAs of accumulator 1 and vice versa).  L2 -> SM bytes per MMA halve.  Same keys, same finalize pass.
+constexpr int A2_BYTES = 2 * A_BYTES;                            // 32 KB: two query tiles
+constexpr int B2_STAGES = 3;
+constexpr uint32_t UNIT_TWO = 0x80000000u;                       // Unit.n_db_tiles bit 31: the super-tile has a second query tile
+template <int NSPLIT> constexpr int smem6_bytes() {
+  return A_STAGES * A2_BYTES + B2_STAGES * B5_STAGE_BYTES + ACONST_BYTES + 1024 /*align slack*/ + 2 * 2 * TILE_Q * 8 /*merge*/ + 256 /*barriers*/;
+}
+
+template <int NSPLIT, bool DRAIN_ONLY>
+__global__ void __launch_bounds__(64 + 256 * NSPLIT, 1)
+match_dig2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_dig,
+                  const Unit *__restrict__ units, uint32_t n_units, int2 *__restrict__ k12) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *a_smem = smem;                                        // [A_STAGES][2 x 16 KB]
+  uint8_t *b_smem = smem + A_STAGES * A2_BYTES;                  // [B2_STAGES][32 KB descriptors + 8 KB digits]
+  uint8_t *aconst = b_smem + B2_STAGES * B5_STAGE_BYTES;         // [128][32 B] constant weights
+  int2 *merge = reinterpret_cast<int2 *>(aconst + ACONST_BYTES); // [2 accumulators][2][128] (NSPLIT == 2 only)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(merge + 2 * 2 * TILE_Q);
+  uint64_t *full_a = bars, *empty_a = bars + 2, *full_b = bars + 4, *empty_b = bars + 8;
+  uint64_t *tmem_full = bars + 12, *tmem_empty = bars + 14;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap); prefetch_tmap(&tmap_dig);
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < B2_STAGES; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * NSPLIT); }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < ACONST_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *>(aconst)[i] = make_uint4(0xFFFFFF01u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  fence_proxy_async();
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t g = 0, ul = 0;
+      for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+        const Unit un = units[u];
+        const uint32_t as = ul & 1, n_tiles = un.n_db_tiles & UNIT_TILES_MASK;
+        const bool two = (un.n_db_tiles & UNIT_TWO) != 0;
+        mbar_wait(&empty_a[as], ((ul >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full_a[as], two ? A2_BYTES : A_BYTES);
+        tma_load_2d(a_smem + as * A2_BYTES, &tmap, 0, (int)un.q_row, &full_a[as]);
+        if (two) tma_load_2d(a_smem + as * A2_BYTES + A_BYTES, &tmap, 0, (int)(un.q_row + TILE_Q), &full_a[as]);
+        for (uint32_t t = 0; t < n_tiles; ++t, ++g) {
+          const uint32_t st = g % B2_STAGES;
+          mbar_wait(&empty_b[st], ((g / B2_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_b[st], B5_STAGE_BYTES);
+          uint8_t *dst = b_smem + st * B5_STAGE_BYTES;
+          const uint32_t row = un.db_row + t * TILE_DB;
+          tma_load_2d(dst, &tmap, 0, (int)row, &full_b[st]);
+          tma_load_2d(dst + A_BYTES, &tmap, 0, (int)(row + 128), &full_b[st]);
+          tma_load_2d(dst + B_BYTES, &tmap_dig, 0, (int)row, &full_b[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_u8(TILE_Q, TILE_DB);
+      constexpr uint32_t idesc5 = idesc | (1u << 10);             // B operand signed: u8 weights x s8 digits
+      const uint64_t ac_desc = make_kmajor_sw32_desc(smem_u32(aconst));
+      uint32_t g = 0, ul = 0, cnt[2] = {0, 0};                    // cnt[h]: accumulations issued into accumulator h
+      for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ul) {
+        const uint32_t ndt = units[u].n_db_tiles;
+        const uint32_t n_tiles = ndt & UNIT_TILES_MASK, nh = (ndt & UNIT_TWO) ? 2u : 1u;
+        const uint32_t as = ul & 1;
+        mbar_wait(&full_a[as], (ul >> 1) & 1);
+        const uint32_t a_addr = smem_u32(a_smem + as * A2_BYTES);
+        for (uint32_t t = 0; t < n_tiles; ++t, ++g) {
+          const uint32_t st = g % B2_STAGES;
+          mbar_wait(&full_b[st], (g / B2_STAGES) & 1);
+          const uint32_t b_addr = smem_u32(b_smem + st * B5_STAGE_BYTES);
+          const uint64_t dg_desc = make_kmajor_sw32_desc(b_addr + B_BYTES);
+          for (uint32_t h = 0; h < nh; ++h) {
+            mbar_wait(&tmem_empty[h], (cnt[h] & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + h * TILE_DB;
+            #pragma unroll
+            for (int k = 0; k < OMVG_DESC_LEN / 32; ++k)
+              umma_i8(d, make_kmajor_sw128_desc(a_addr + h * A_BYTES + k * 32), make_kmajor_sw128_desc(b_addr + k * 32), idesc, k > 0);
+            umma_i8(d, ac_desc, dg_desc, idesc5, 1);
+            tc_commit(&tmem_full[h]);
+            ++cnt[h];
+          }
+          tc_commit(&empty_b[st]);
+        }
+        tc_commit(&empty_a[as]);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (8 * NSPLIT warps)
+    const uint32_t e = warp - 2;
+    const uint32_t wg = e / (4 * NSPLIT);                 // accumulator = query tile (0: rows 0-127, 1: rows 128-255)
+    const uint32_t part = (e % (4 * NSPLIT)) >> 2;        // which 256/NSPLIT-column part of the accumulator
+    const uint32_t quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    constexpr uint32_t NCH = 8 / NSPLIT;                  // 32-column chunks per warp and tile
+    const uint32_t c0 = part * NCH;
+    uint32_t cnt = 0, um = 0;                             // accumulations consumed from this accumulator; units merged
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const Unit un = units[u];
+      if (wg == 1 && !(un.n_db_tiles & UNIT_TWO)) continue;
+      const uint32_t n_tiles = un.n_db_tiles & UNIT_TILES_MASK, gdiv = (un.n_db_tiles >> 20) & 0x7FFu;
+      int k1 = KEY_MIN, k2 = KEY_MIN;
+      for (uint32_t t = 0; t < n_tiles; ++t, ++cnt) {
+        mbar_wait(&tmem_full[wg], cnt & 1);               // accumulator complete
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + wg * TILE_DB + c0 * 32;
+        const uint32_t chunk0 = t * 8 + c0;
+        int32_t ra[32], rb[32];
+        tmem_ld_32x32(taddr, ra);
+        #pragma unroll
+        for (uint32_t c = 0; c < NCH; c += 2) {
+          tmem_ld_wait_dep(ra);
+          tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+          if (!DRAIN_ONLY) chunk_max(ra, (int)(gdiv <= 1 ? chunk0 + c : (chunk0 + c) / gdiv), k1, k2);
+          tmem_ld_wait_dep(rb);
+          if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+          else {                                             // every column of the accumulator is in registers: hand it back
+            tc_fence_before();                               // to the MMA warp before the arithmetic of the last chunk
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[wg]);
+          }
+          if (!DRAIN_ONLY) chunk_max(rb, (int)(gdiv <= 1 ? chunk0 + c + 1 : (chunk0 + c + 1) / gdiv), k1, k2);
+        }
+      }
+      if (NSPLIT == 2) {                                   // merge the two column parts of this accumulator
+        int2 *mb = merge + (wg * 2 + (um & 1)) * TILE_Q; ++um;
+        if (part) mb[row_in_tile] = make_int2(k1, k2);
+        if (wg == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (part == 0) { const int2 o = mb[row_in_tile]; const int lo = min(k1, o.x); k1 = max(k1, o.x); k2 = max(lo, max(k2, o.y)); }
+      }
+      if (part == 0) k12[(size_t)un.out_off + wg * TILE_Q + row_in_tile] = make_int2(k1, k2);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // --------------------------------------------------------------------------------- finalize
-struct PairInfo { uint32_t db_row0, db_count, db_group, q_row0, q_count; uint32_t unit0; uint64_t out_off; };
+struct PairInfo { uint32_t db_row0, db_count, db_group, q_row0, q_count; uint32_t unit0; uint64_t out_off; int32_t db_c0; int32_t pad_; };
 
 // expand the per-pair table into the (pair, 128-query tile) work units on the device (one block per pair)
-__global__ void expand_units_kernel(const PairInfo *__restrict__ pairs, Unit *__restrict__ units) {
+// q_tiles = 1: one unit per 128 queries; q_tiles = 2 (match_dig2_kernel): one unit per 256 queries, UNIT_TWO set when the
+// second query tile holds real rows
+__global__ void expand_units_kernel(const PairInfo *__restrict__ pairs, Unit *__restrict__ units, uint32_t q_tiles) {
   const PairInfo P = pairs[blockIdx.x];
-  const uint32_t qt = (P.q_count + TILE_Q - 1) / TILE_Q, dt = (P.db_count + TILE_DB - 1) / TILE_DB;
-  for (uint32_t t = threadIdx.x; t < qt; t += blockDim.x)
-    units[P.unit0 + t] = Unit{P.q_row0 + t * TILE_Q, P.db_row0, dt, (uint32_t)(P.out_off + t * TILE_Q)};
+  const uint32_t rows = TILE_Q * q_tiles;
+  const uint32_t qt = (P.q_count + rows - 1) / rows, dt = (P.db_count + TILE_DB - 1) / TILE_DB;
+  for (uint32_t t = threadIdx.x; t < qt; t += blockDim.x) {
+    const uint32_t two = (q_tiles == 2 && P.q_count - t * rows > TILE_Q) ? UNIT_TWO : 0u;
+    units[P.unit0 + t] = Unit{P.q_row0 + t * rows, P.db_row0, dt | ((P.db_group / 32) << 20) | two, (uint32_t)(P.out_off + t * rows)};
+  }
 }
 
 // exact top-2 of one query inside rows [r0, r1) of the database; whole warp cooperates.
@@ -273,6 +677,18 @@ __device__ __forceinline__ void warp_rescan(const uint8_t *__restrict__ desc, co
 }
 
 constexpr int FIN_THREADS = 256;
+// DIG = false: keys of match_tc_kernel (exact d1, exact bound ub2).
+// DIG = true : keys of match_dig_kernel.  A = key >> 8 is the chunk maximum of acc = q.b - h + c0, so the best column
+// of that chunk has distance  D - 1 or D,  D = |q|^2 - 2 A + 2 c0  (parity of |b|^2 unknown).  Then
+//   * A1 > A2: the nearest neighbour lies in the chunk (group) of A1 — every other column has acc <= A2 <= A1 - 1, i.e.
+//     distance >= D1 + 1; its exact distance and index come from the group re-scan as before.
+//   * A1 == A2: two chunks tie to within the parity -> exact scan of the whole database image for this query.
+//   * the best column outside the group bounds d2 from above by D2 and the truth is D2 - 1 or D2; if the ratio test
+//     gives the same answer for both, that is the answer, otherwise -> exact scan of the whole image.
+//   * candidates are pre-filtered with the weakest case (d1 >= D1 - 1, d2 <= D2); float() and the multiplication by a
+//     non-negative constant are monotone, so nothing that could pass is dropped.
+// Chunks that hold only padding have A == DIG_PAD (never reached by a real column): "no second chunk".
+template <bool DIG>
 __global__ void __launch_bounds__(FIN_THREADS)
 match_finalize_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ norm,
                       const PairInfo *__restrict__ pairs, int2 *__restrict__ k12, uint32_t *__restrict__ counts,
@@ -287,17 +703,28 @@ match_finalize_kernel(const uint8_t *__restrict__ desc, const int32_t *__restric
   for (uint32_t q0 = 0; q0 < P.q_count; q0 += FIN_THREADS) {
     const uint32_t q = q0 + threadIdx.x;
     const bool valid = q < P.q_count;
-    int d1 = 0, ub2 = 0; uint32_t g1 = 0; bool cand = false;
+    int ub2 = 0, lo2 = 0; uint32_t g1 = 0; bool cand = false, full = false;
     if (valid) {
       const int2 K = io[q];
       const int qn = norm[P.q_row0 + q];
-      d1 = qn - (K.x >> 8);
       g1 = (uint32_t)(K.x & 255);
-      ub2 = (K.y == KEY_MIN) ? INT_MAX : qn - (K.y >> 8);
-      cand = __int2float_rn(d1) < __fmul_rn(fratio, __int2float_rn(ub2));
+      if (!DIG) {
+        const int d1 = qn - (K.x >> 8);
+        ub2 = (K.y == KEY_MIN) ? INT_MAX : qn - (K.y >> 8);
+        lo2 = ub2;
+        cand = __int2float_rn(d1) < __fmul_rn(fratio, __int2float_rn(ub2));
+      } else {
+        const int A1 = K.x >> 8, A2 = K.y >> 8;
+        const int D1 = qn - 2 * A1 + 2 * P.db_c0;
+        const bool none2 = A2 <= DIG_PAD;
+        ub2 = none2 ? INT_MAX : qn - 2 * A2 + 2 * P.db_c0;
+        lo2 = none2 ? INT_MAX : ub2 - 1;
+        cand = __int2float_rn(max(D1 - 1, 0)) < __fmul_rn(fratio, __int2float_rn(ub2));
+        full = cand && !none2 && A1 == A2;
+      }
     }
     bool keep = false; uint32_t idx = 0;
-    uint32_t m = __ballot_sync(0xffffffffu, cand);
+    uint32_t m = __ballot_sync(0xffffffffu, cand && !full);
     while (m) {
       const int src = __ffs(m) - 1; m &= m - 1;
       const uint32_t qq = __shfl_sync(0xffffffffu, q, src);
@@ -307,9 +734,20 @@ match_finalize_kernel(const uint8_t *__restrict__ desc, const int32_t *__restric
       int bd1, bd2; uint32_t bi1;
       warp_rescan(desc, norm, P.q_row0 + qq, r0, r1, P.db_row0, lane, bd1, bi1, bd2);
       if (lane == src) {
-        const int d2 = min(ub2, bd2);
-        keep = __int2float_rn(bd1) < __fmul_rn(fratio, __int2float_rn(d2));   // matching_filters.hpp:57
+        const bool k_hi = __int2float_rn(bd1) < __fmul_rn(fratio, __int2float_rn(min(ub2, bd2)));   // matching_filters.hpp:57
+        const bool k_lo = __int2float_rn(bd1) < __fmul_rn(fratio, __int2float_rn(min(lo2, bd2)));
+        if (k_hi == k_lo) keep = k_hi; else full = true;
         idx = bi1;
+      }
+    }
+    if (DIG) {                                          // exact scan of the whole database image (rare)
+      m = __ballot_sync(0xffffffffu, full);
+      while (m) {
+        const int src = __ffs(m) - 1; m &= m - 1;
+        const uint32_t qq = __shfl_sync(0xffffffffu, q, src);
+        int bd1, bd2; uint32_t bi1;
+        warp_rescan(desc, norm, P.q_row0 + qq, P.db_row0, P.db_row0 + P.db_count, P.db_row0, lane, bd1, bi1, bd2);
+        if (lane == src) { keep = __int2float_rn(bd1) < __fmul_rn(fratio, __int2float_rn(bd2)); idx = bi1; }
       }
     }
     // ordered compaction (ascending q): block exclusive scan of keep
@@ -641,7 +1079,9 @@ struct omvg_match_ctx {
   uint8_t *d_desc = nullptr; int32_t *d_norm = nullptr, *d_ckey = nullptr;
   uint32_t *d_img_row0 = nullptr, *d_img_count = nullptr, *d_img_group = nullptr, *d_row_img = nullptr;
   bool uploaded = false, prepared = false;
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_dig;
+  // fifth-slice kernel (match_dig_kernel): 32 signed digits per arena row, per-image offset c0, eligibility
+  uint4 *d_dig = nullptr; int32_t *d_img_c0 = nullptr; int2 *d_hmm = nullptr; std::vector<int32_t> c0; bool use_dig = false;
   // run state
   int2 *d_k12 = nullptr; size_t k12_cap = 0;           // in int2 elements
   Unit *d_units = nullptr; size_t units_cap = 0;
@@ -678,6 +1118,13 @@ int make_tmap(omvg_match_ctx *c) {
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(OMVG_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  const cuuint64_t ddims[2] = {DIG_LEN, c->total_rows};
+  const cuuint64_t dstrides[1] = {DIG_LEN};
+  const cuuint32_t dbox[2] = {DIG_LEN, TILE_DB};
+  const CUresult r2 = ((encode_tiled_fn)fn)(&c->tmap_dig, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_dig, ddims, dstrides, dbox, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r2 != CUDA_SUCCESS) return fail(OMVG_E_CUDA, "cuTensorMapEncodeTiled (digits) failed (%d)", (int)r2);
   return OMVG_OK;
 }
 
@@ -685,7 +1132,8 @@ void free_images(omvg_match_ctx *c) {
   cudaFree(c->d_code); cudaFree(c->d_bid); cudaFree(c->d_bstart); cudaFree(c->d_bitems); cudaFree(c->d_proj); cudaFree(c->d_zm);
   c->d_code = c->d_bid = nullptr; c->d_bstart = c->d_bitems = nullptr; c->d_proj = c->d_zm = nullptr; c->cascade_ready = false;
   cudaFree(c->d_desc); cudaFree(c->d_norm); cudaFree(c->d_ckey); cudaFree(c->d_img_row0); cudaFree(c->d_img_count);
-  cudaFree(c->d_img_group); cudaFree(c->d_row_img);
+  cudaFree(c->d_img_group); cudaFree(c->d_row_img); cudaFree(c->d_dig); cudaFree(c->d_img_c0); cudaFree(c->d_hmm);
+  c->d_dig = nullptr; c->d_img_c0 = nullptr; c->d_hmm = nullptr; c->use_dig = false;
   c->d_desc = nullptr; c->d_norm = c->d_ckey = nullptr; c->d_img_row0 = c->d_img_count = c->d_img_group = c->d_row_img = nullptr;
 }
 
@@ -714,18 +1162,18 @@ int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_
               std::vector<Unit> &units, std::vector<PairInfo> &pinfo) {
   units.clear(); pinfo.clear();
   size_t out = 0, n_units = 0;
+  const bool use_dig2 = c->use_dig && !getenv("OMVG_MATCH_M128");   // A/B: one query tile per CTA pass (match_dig_kernel)
   for (uint64_t p = p0; p < p1; ++p) {
     const uint32_t I = pi[p], J = pj[p];
-    PairInfo P{}; P.db_row0 = c->row0[I]; P.db_count = c->counts[I]; P.db_group = c->group[I];
+    PairInfo P{}; P.db_row0 = c->row0[I]; P.db_count = c->counts[I]; P.db_group = c->group[I]; P.db_c0 = c->c0.empty() ? 0 : c->c0[I];
     P.q_row0 = c->row0[J]; P.q_count = c->counts[J]; P.out_off = out;
     // Matcher_Regions.cpp:65-69,85-90 (empty regions) and matcher_brute_force.hpp:108-113 (NN > rows)
     const bool active = P.db_count >= 2 && P.q_count >= 1;
     if (!active) P.q_count = 0;
     pinfo.push_back(P);
     if (!active) continue;
-    const uint32_t qt = (P.q_count + TILE_Q - 1) / TILE_Q, dt = (P.db_count + TILE_DB - 1) / TILE_DB;
-    (void)dt;
-    pinfo.back().unit0 = (uint32_t)n_units; n_units += qt;
+    const uint32_t qt = (P.q_count + TILE_Q - 1) / TILE_Q;
+    pinfo.back().unit0 = (uint32_t)n_units; n_units += use_dig2 ? (qt + 1) / 2 : qt;
     out += size_t(qt) * TILE_Q;
   }
   if (out > 0xffffffffull) return fail(OMVG_E_ARG, "batch too large");
@@ -741,19 +1189,33 @@ int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_
   }
   OMVG_CUDA(cudaMemcpyAsync(c->d_pairs, pinfo.data(), nb * sizeof(PairInfo), cudaMemcpyHostToDevice, c->stream));
   if (n_units) {
-    expand_units_kernel<<<nb, 64, 0, c->stream>>>(c->d_pairs, c->d_units); OMVG_CUDA(cudaGetLastError()); c->launches++;
+    expand_units_kernel<<<nb, 64, 0, c->stream>>>(c->d_pairs, c->d_units, use_dig2 ? 2u : 1u); OMVG_CUDA(cudaGetLastError()); c->launches++;
     const uint32_t grid = (uint32_t)std::min<size_t>(n_units, (size_t)c->n_sms);
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     OMVG_CUDA(cudaEventRecord(e0, c->stream));
     // OMVG_MATCH_DRAIN_ONLY=1 (measurement aid, results are garbage): epilogue reads TMEM but does no arithmetic
     static const bool drain_only = getenv("OMVG_MATCH_DRAIN_ONLY") != nullptr;
-    if (drain_only) match_tc_kernel<true><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)n_units, c->d_k12);
-    else match_tc_kernel<false><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)n_units, c->d_k12);
+    const int nsplit = getenv("OMVG_MATCH_NSPLIT") ? atoi(getenv("OMVG_MATCH_NSPLIT")) : MATCH_NSPLIT_DEFAULT;   // epilogue warps per lane quarter and accumulator
+    if (use_dig2) {
+      if (nsplit == 2) { if (drain_only) match_dig2_kernel<2, true><<<grid, 64 + 512, smem6_bytes<2>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12);
+                         else match_dig2_kernel<2, false><<<grid, 64 + 512, smem6_bytes<2>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12); }
+      else             { if (drain_only) match_dig2_kernel<1, true><<<grid, 64 + 256, smem6_bytes<1>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12);
+                         else match_dig2_kernel<1, false><<<grid, 64 + 256, smem6_bytes<1>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12); }
+    }
+    else if (c->use_dig) {
+      if (nsplit == 2) { if (drain_only) match_dig_kernel<2, true><<<grid, 64 + 512, smem5_bytes<2>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12);
+                         else match_dig_kernel<2, false><<<grid, 64 + 512, smem5_bytes<2>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12); }
+      else             { if (drain_only) match_dig_kernel<1, true><<<grid, 64 + 256, smem5_bytes<1>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12);
+                         else match_dig_kernel<1, false><<<grid, 64 + 256, smem5_bytes<1>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12); }
+    }
+    else if (drain_only) match_tc_kernel<1><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)n_units, c->d_k12);
+    else match_tc_kernel<0><<<grid, TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, (uint32_t)n_units, c->d_k12);
     OMVG_CUDA(cudaGetLastError());
     OMVG_CUDA(cudaEventRecord(e1, c->stream));
     c->pending.emplace_back(e0, e1); c->tc_launches++; c->launches++;
   }
-  match_finalize_kernel<<<nb, FIN_THREADS, 0, c->stream>>>(c->d_desc, c->d_norm, c->d_pairs, c->d_k12, c->d_counts, fratio);
+  if (c->use_dig) match_finalize_kernel<true><<<nb, FIN_THREADS, 0, c->stream>>>(c->d_desc, c->d_norm, c->d_pairs, c->d_k12, c->d_counts, fratio);
+  else match_finalize_kernel<false><<<nb, FIN_THREADS, 0, c->stream>>>(c->d_desc, c->d_norm, c->d_pairs, c->d_k12, c->d_counts, fratio);
   OMVG_CUDA(cudaGetLastError());
   scan_counts_kernel<<<1, 1024, 0, c->stream>>>(c->d_counts, nb, c->d_offsets + p0, c->d_total);
   OMVG_CUDA(cudaGetLastError());
@@ -801,8 +1263,16 @@ int omvg_match_create(omvg_match_ctx **out, int device) {
   OMVG_CUDA(cudaSetDevice(device));
   omvg_match_ctx *c = new omvg_match_ctx; c->device = device; c->n_sms = n_sms;
   OMVG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6_bytes<1>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6_bytes<1>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6_bytes<2>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6_bytes<2>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5_bytes<1>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5_bytes<1>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5_bytes<2>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5_bytes<2>()));
   OMVG_CUDA(cudaMalloc(&c->d_total, sizeof(uint64_t)));
   if (const char *e = getenv("OMVG_MATCH_K12_MB")) c->k12_budget_bytes = size_t(atol(e)) << 20;
   *out = c; return OMVG_OK;
@@ -841,6 +1311,7 @@ int omvg_match_set_images(omvg_match_ctx *c, uint32_t n_images, const uint32_t *
   OMVG_CUDA(cudaMalloc(&c->d_desc, rows * OMVG_DESC_LEN));
   OMVG_CUDA(cudaMemsetAsync(c->d_desc, 0, rows * OMVG_DESC_LEN, c->stream));
   OMVG_CUDA(cudaMalloc(&c->d_norm, rows * 4)); OMVG_CUDA(cudaMalloc(&c->d_ckey, rows * 4));
+  OMVG_CUDA(cudaMalloc(&c->d_dig, rows * DIG_LEN)); OMVG_CUDA(cudaMalloc(&c->d_img_c0, std::max(1u, n_images) * 4)); OMVG_CUDA(cudaMalloc(&c->d_hmm, std::max(1u, n_images) * sizeof(int2)));
   OMVG_CUDA(cudaMalloc(&c->d_img_row0, std::max(1u, n_images) * 4)); OMVG_CUDA(cudaMalloc(&c->d_img_count, std::max(1u, n_images) * 4));
   OMVG_CUDA(cudaMalloc(&c->d_img_group, std::max(1u, n_images) * 4)); OMVG_CUDA(cudaMalloc(&c->d_row_img, row_img.size() * 4));
   if (n_images) {
@@ -890,7 +1361,30 @@ int omvg_match_prepare(omvg_match_ctx *c) {
   prep_rows_kernel<<<(c->total_rows + rows_per_block - 1) / rows_per_block, threads, 0, c->stream>>>(
       c->d_desc, c->d_img_row0, c->d_img_count, c->d_img_group, c->d_row_img, c->d_norm, c->d_ckey, c->total_rows);
   OMVG_CUDA(cudaGetLastError());
-  c->launches++; c->prepared = true; c->cascade_ready = false; return OMVG_OK;
+  c->launches++;
+  // fifth-slice kernel: per-image range of h = ceil(|b|^2 / 2) -> offset c0 and eligibility (one small read-back)
+  c->c0.assign(c->n_images, 0); c->use_dig = false;
+  const bool force_tc4 = getenv("OMVG_MATCH_TC4") != nullptr;         // A/B: the round-1 kernel (IMAD epilogue)
+  if (c->n_images && !force_tc4) {
+    prep_minmax_kernel<<<c->n_images, 256, 0, c->stream>>>(c->d_norm, c->d_img_row0, c->d_img_count, c->d_hmm); OMVG_CUDA(cudaGetLastError());
+    std::vector<int2> hmm(c->n_images);
+    OMVG_CUDA(cudaMemcpyAsync(hmm.data(), c->d_hmm, c->n_images * sizeof(int2), cudaMemcpyDeviceToHost, c->stream));
+    OMVG_CUDA(cudaStreamSynchronize(c->stream));
+    bool ok = true;
+    for (uint32_t k = 0; k < c->n_images; ++k) {
+      if (!c->counts[k]) continue;
+      if ((long long)hmm[k].y - hmm[k].x > DIG_SPREAD_MAX || c->group[k] / 32 >= 2048) { ok = false; break; }
+      c->c0[k] = std::max(0, hmm[k].y + DIG_VMIN);                           // v = c0 - h in [DIG_VMIN, DIG_VMAX]
+    }
+    if (ok) {
+      OMVG_CUDA(cudaMemcpyAsync(c->d_img_c0, c->c0.data(), c->n_images * 4, cudaMemcpyHostToDevice, c->stream));
+      prep_digits_kernel<<<(c->total_rows + 255) / 256, 256, 0, c->stream>>>(c->d_norm, c->d_img_row0, c->d_img_count, c->d_row_img, c->d_img_c0, c->d_dig, c->total_rows);
+      OMVG_CUDA(cudaGetLastError());
+      OMVG_CUDA(cudaStreamSynchronize(c->stream));                            // c->c0 (host vector) is read by the copy above
+      c->launches += 2; c->use_dig = true;
+    }
+  }
+  c->prepared = true; c->cascade_ready = false; return OMVG_OK;
 }
 
 int omvg_match_run(omvg_match_ctx *c, const uint32_t *pair_i, const uint32_t *pair_j, uint64_t n_pairs, float dist_ratio) {
@@ -952,6 +1446,7 @@ int omvg_match_fetch(omvg_match_ctx *c, const uint64_t **offsets, const uint32_t
 }
 
 uint64_t omvg_match_launch_count(const omvg_match_ctx *c) { return c ? c->launches : 0; }
+int omvg_match_kernel_variant(const omvg_match_ctx *c) { return (!c || !c->prepared) ? 0 : (c->use_dig ? 5 : 4); }
 
 int omvg_match_kernel_time(omvg_match_ctx *c, double *ms, uint64_t *launches, int reset) {
   if (!c) return fail(OMVG_E_ARG, "null ctx");
@@ -1138,7 +1633,7 @@ int omvg_match_debug_top2_tc(omvg_match_ctx *c, uint32_t I, uint32_t J, int32_t 
   if ((rc = ensure(c->d_k12, c->k12_cap, size_t(qt) * TILE_Q))) return rc;
   if ((rc = ensure(c->d_units, c->units_cap, units.size()))) return rc;
   OMVG_CUDA(cudaMemcpyAsync(c->d_units, units.data(), units.size() * sizeof(Unit), cudaMemcpyHostToDevice, c->stream));
-  match_tc_kernel<false><<<std::min<uint32_t>(qt, c->n_sms), TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, qt, c->d_k12);
+  match_tc_kernel<0><<<std::min<uint32_t>(qt, c->n_sms), TC_THREADS, SMEM_BYTES, c->stream>>>(c->tmap, c->d_ckey, c->d_units, qt, c->d_k12);
   OMVG_CUDA(cudaGetLastError()); c->launches++;
   int32_t *dd1, *dd2; uint32_t *dg1;
   OMVG_CUDA(cudaMalloc(&dd1, nq * 4)); OMVG_CUDA(cudaMalloc(&dd2, nq * 4)); OMVG_CUDA(cudaMalloc(&dg1, nq * 4));

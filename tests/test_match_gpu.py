@@ -316,3 +316,82 @@ def test_load_desc_files_equals_in_memory_upload(tmp_path):
         assert (key in seen) == (len(m) > 0)
         if len(m):
             assert np.array_equal(seen[key], m)
+
+
+# ---- the fifth-K-slice kernel (match_dig_kernel) against the key-arithmetic kernel and the oracle
+def _near_tie_collection(seed):
+    """Rows that differ from each other by +-1 in a few elements: distances of 0, 1, 2, ... with both parities of |b|^2,
+    so the chunk maxima tie to within the parity and the exact-scan fallbacks of the finalize pass run."""
+    rng = np.random.default_rng(seed)
+    base = synth.descriptors(1, 40, seed=seed + 1)[0].astype(np.int64)
+    rows = []
+    for b in base:
+        for _ in range(12):
+            v = b.copy()
+            k = rng.integers(0, 4)
+            idx = rng.choice(128, size=k, replace=False)
+            v[idx] += rng.choice([-1, 1], size=k)
+            rows.append(np.clip(v, 0, 255))
+    rows = np.array(rows, np.uint8)
+    a = rows[rng.permutation(len(rows))]
+    b = rows[rng.permutation(len(rows))][:300]
+    c = np.clip(rows.astype(np.int64) + rng.integers(-1, 2, rows.shape), 0, 255).astype(np.uint8)
+    return [a, b, c]
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_fifth_slice_near_ties(matching, seed):
+    descs = _near_tie_collection(seed)
+    n = len(descs)
+    pi, pj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    pi = pi.reshape(-1).astype(np.uint32); pj = pj.reshape(-1).astype(np.uint32)
+    ctx = matching.MatchContext(0)
+    ctx.load(descs)
+    assert ctx.kernel_variant() == 5
+    for ratio in (0.8, 0.95, 0.999, 1.0):
+        ctx.run(pi, pj, ratio)
+        off, ij = ctx.fetch()
+        ooff, oij = ck.oracle_match_collection(descs, pi, pj, ratio)
+        _csr_equal(off, ij, ooff, oij)
+    ctx.close()
+
+
+def test_kernel_variants_agree(matching, monkeypatch):
+    """Default (fifth slice, two query tiles per database tile) = two epilogue warps per lane quarter = one query tile per
+    database tile = the key-arithmetic kernel."""
+    rng = np.random.default_rng(8)
+    descs = synth.descriptors(5, [1500, 700, 2300, 33, 900], seed=31)
+    descs.append(rng.integers(0, 256, (800, 128), dtype=np.int64).astype(np.uint8))       # |b|^2 ~ 2.8e6: c0 > 0
+    descs.append(rng.integers(0, 256, (600, 128), dtype=np.int64).astype(np.uint8))
+    pi, pj = synth.exhaustive_pairs(len(descs))
+    pi = np.concatenate([pi, pj]); pj = np.concatenate([pj, pi[:len(pj)]])
+    ooff, oij = ck.oracle_match_collection(descs, pi, pj, 0.8)
+    results = []
+    for env in ({}, {"OMVG_MATCH_NSPLIT": "2"}, {"OMVG_MATCH_M128": "1"}, {"OMVG_MATCH_M128": "1", "OMVG_MATCH_NSPLIT": "2"}, {"OMVG_MATCH_TC4": "1"}):
+        for k in ("OMVG_MATCH_NSPLIT", "OMVG_MATCH_TC4", "OMVG_MATCH_M128"): monkeypatch.delenv(k, raising=False)
+        for k, v in env.items(): monkeypatch.setenv(k, v)
+        ctx = matching.MatchContext(0)
+        ctx.load(descs)
+        assert ctx.kernel_variant() == (4 if "OMVG_MATCH_TC4" in env else 5)
+        ctx.run(pi, pj, 0.8)
+        off, ij = ctx.fetch()
+        _csr_equal(off, ij, ooff, oij)
+        ctx.close()
+
+
+def test_wide_norm_spread_takes_the_key_arithmetic_kernel(matching):
+    """All-zero and all-255 descriptors in ONE image: |b|^2 spans 8.3e6, more than 32 signed digits can carry."""
+    rng = np.random.default_rng(3)
+    mixed = np.concatenate([np.zeros((40, 128), np.uint8), np.full((40, 128), 255, np.uint8),
+                            rng.integers(0, 256, (300, 128), dtype=np.int64).astype(np.uint8)])
+    descs = [mixed, synth.descriptors(1, 500, seed=77)[0], mixed[::-1].copy()]
+    pi, pj = synth.exhaustive_pairs(3)
+    pi = np.concatenate([pi, pj]); pj = np.concatenate([pj, pi[:len(pj)]])
+    ctx = matching.MatchContext(0)
+    ctx.load(descs)
+    assert ctx.kernel_variant() == 4
+    ctx.run(pi, pj, 0.8)
+    off, ij = ctx.fetch()
+    ooff, oij = ck.oracle_match_collection(descs, pi, pj, 0.8)
+    _csr_equal(off, ij, ooff, oij)
+    ctx.close()

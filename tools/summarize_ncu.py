@@ -13,6 +13,9 @@ FULL_KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size"
              "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.per_cycle_active",
              "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
              "sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+             "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+             "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.per_cycle_elapsed",
+             "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.peak_sustained",
              "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
              "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
              "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second",
