@@ -625,19 +625,220 @@ match_dig2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+
+// --------------------------------------------------------------------------------- CTA pair (tcgen05 cta_group::2)
+// match_dig2_kernel is bound by shared-memory bandwidth: every SS-mode MMA re-reads A (4 KB) and B (8 KB) from shared
+// memory per 128 tensor cycles, next to the TMA writes.  Here two CTAs of a cluster (one TPC) run ONE M256 N256 K32 MMA
+// per K-slice: CTA r holds query rows [256 r, 256 r + 256) of a 512-query super-tile (two A tiles, as before) and HALF of
+// every database tile (128 of its 256 rows + their digits); the tensor cores exchange the B halves over the pair link,
+// so each SM reads 4 KB + 4 KB per MMA and receives half the TMA bytes.  Only CTA 0 issues MMAs; both load, both drain
+// their own TMEM.  Barrier ownership: full_a / full_b / tmem_empty live in CTA 0 (TMA of CTA 1 completes on them through
+// the peer-masked address, epilogue warps of both CTAs arrive remotely); empty_a / empty_b / tmem_full exist in both
+// CTAs and are signalled by tcgen05.commit ... multicast.
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                       // shared::cluster address of the same offset in CTA 0 of the pair
+constexpr int B3_STAGES = 6;
+constexpr int B3_STAGE_BYTES = A_BYTES + TILE_Q * DIG_LEN;       // 16 KB descriptors + 4 KB digits: half a database tile
+template <int NSPLIT> constexpr int smem7_bytes() {
+  return A_STAGES * A2_BYTES + B3_STAGES * B3_STAGE_BYTES + ACONST_BYTES + 1024 /*align slack*/ + 2 * 2 * TILE_Q * 8 /*merge*/ + 512 /*barriers*/;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// data into this CTA's shared memory, completion bytes on CTA 0's barrier at the same offset
+__device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const void *tmap, int x, int y, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & PEER_MASK), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(cols) : "memory");
+}
+// one arrival on the barrier at this offset in BOTH CTAs when all MMAs issued so far have finished
+__device__ __forceinline__ void tc_commit2(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p; }"
+               :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
+// Unit.n_db_tiles for this kernel: tiles | (rows per group / 32) << 20 (9 bits) | valid 128-query tiles (1..4) << 29
+template <int NSPLIT, bool DRAIN_ONLY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NSPLIT, 1)
+match_dig3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_dig,
+                  const Unit *__restrict__ units, uint32_t n_units, int2 *__restrict__ k12) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *a_smem = smem;                                        // [A_STAGES][2 x 16 KB]
+  uint8_t *b_smem = smem + A_STAGES * A2_BYTES;                  // [B3_STAGES][16 KB descriptors + 4 KB digits]
+  uint8_t *aconst = b_smem + B3_STAGES * B3_STAGE_BYTES;         // [128][32 B] constant weights
+  int2 *merge = reinterpret_cast<int2 *>(aconst + ACONST_BYTES); // [2 accumulators][2][128] (NSPLIT == 2 only)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(merge + 2 * 2 * TILE_Q);
+  uint64_t *full_a = bars, *empty_a = bars + 2, *full_b = bars + 4, *empty_b = bars + 4 + B3_STAGES;
+  uint64_t *tmem_full = bars + 4 + 2 * B3_STAGES, *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap); prefetch_tmap(&tmap_dig);
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < B3_STAGES; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 4 * NSPLIT); }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < ACONST_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *>(aconst)[i] = make_uint4(0xFFFFFF01u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  fence_proxy_async();
+  if (warp == 2) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();                                            // barriers of both CTAs initialised before any remote arrival
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t g = 0, ul = 0;
+      for (uint32_t u = cluster_id; u < n_units; u += n_clusters, ++ul) {
+        const Unit un = units[u];
+        const uint32_t as = ul & 1, n_tiles = un.n_db_tiles & UNIT_TILES_MASK;
+        mbar_wait(&empty_a[as], ((ul >> 1) & 1) ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full_a[as], 2 * A2_BYTES);
+        const uint32_t qr = un.q_row + rank * 2 * TILE_Q;
+        tma_load_2d_2sm(a_smem + as * A2_BYTES, &tmap, 0, (int)qr, &full_a[as]);
+        tma_load_2d_2sm(a_smem + as * A2_BYTES + A_BYTES, &tmap, 0, (int)(qr + TILE_Q), &full_a[as]);
+        for (uint32_t t = 0; t < n_tiles; ++t, ++g) {
+          const uint32_t st = g % B3_STAGES;
+          mbar_wait(&empty_b[st], ((g / B3_STAGES) & 1) ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_b[st], 2 * B3_STAGE_BYTES);
+          uint8_t *dst = b_smem + st * B3_STAGE_BYTES;
+          const uint32_t row = un.db_row + t * TILE_DB + rank * TILE_Q;     // this CTA's half of the database tile
+          tma_load_2d_2sm(dst, &tmap, 0, (int)row, &full_b[st]);
+          tma_load_2d_2sm(dst + A_BYTES, &tmap_dig, 0, (int)row, &full_b[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (CTA 0 only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_u8(2 * TILE_Q, TILE_DB);
+      constexpr uint32_t idesc5 = idesc | (1u << 10);             // B operand signed: u8 weights x s8 digits
+      const uint64_t ac_desc = make_kmajor_sw32_desc(smem_u32(aconst));
+      uint32_t g = 0, ul = 0, cnt[2] = {0, 0};
+      for (uint32_t u = cluster_id; u < n_units; u += n_clusters, ++ul) {
+        const uint32_t ndt = units[u].n_db_tiles;
+        const uint32_t n_tiles = ndt & UNIT_TILES_MASK, nh = (ndt >> 29) >= 2 ? 2u : 1u;
+        const uint32_t as = ul & 1;
+        mbar_wait(&full_a[as], (ul >> 1) & 1);
+        const uint32_t a_addr = smem_u32(a_smem + as * A2_BYTES);
+        for (uint32_t t = 0; t < n_tiles; ++t, ++g) {
+          const uint32_t st = g % B3_STAGES;
+          mbar_wait(&full_b[st], (g / B3_STAGES) & 1);
+          const uint32_t b_addr = smem_u32(b_smem + st * B3_STAGE_BYTES);
+          const uint64_t dg_desc = make_kmajor_sw32_desc(b_addr + A_BYTES);
+          for (uint32_t h = 0; h < nh; ++h) {
+            mbar_wait(&tmem_empty[h], (cnt[h] & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + h * TILE_DB;
+            #pragma unroll
+            for (int k = 0; k < OMVG_DESC_LEN / 32; ++k)
+              umma_i8_2sm(d, make_kmajor_sw128_desc(a_addr + h * A_BYTES + k * 32), make_kmajor_sw128_desc(b_addr + k * 32), idesc, k > 0);
+            umma_i8_2sm(d, ac_desc, dg_desc, idesc5, 1);
+            tc_commit2(&tmem_full[h]);
+            ++cnt[h];
+          }
+          tc_commit2(&empty_b[st]);
+        }
+        tc_commit2(&empty_a[as]);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (8 * NSPLIT warps, both CTAs)
+    const uint32_t e = warp - 2;
+    const uint32_t wg = e / (4 * NSPLIT);                 // accumulator = query tile 2 * rank + wg of the super-tile
+    const uint32_t part = (e % (4 * NSPLIT)) >> 2;
+    const uint32_t quarter = warp & 3;
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    constexpr uint32_t NCH = 8 / NSPLIT;
+    const uint32_t c0 = part * NCH;
+    uint32_t cnt = 0, um = 0;
+    for (uint32_t u = cluster_id; u < n_units; u += n_clusters) {
+      const Unit un = units[u];
+      const uint32_t nvt = un.n_db_tiles >> 29;
+      if (wg == 1 && nvt < 2) continue;                   // accumulator 1 is not used by this super-tile (in either CTA)
+      const bool valid = 2 * rank + wg < nvt;             // this query tile holds real rows
+      const uint32_t n_tiles = un.n_db_tiles & UNIT_TILES_MASK, gdiv = (un.n_db_tiles >> 20) & 0x1FFu;
+      int k1 = KEY_MIN, k2 = KEY_MIN;
+      for (uint32_t t = 0; t < n_tiles; ++t, ++cnt) {
+        mbar_wait(&tmem_full[wg], cnt & 1);
+        tc_fence_after();
+        if (!valid) {                                     // padding tile: just hand the accumulator back
+          tc_fence_before(); __syncwarp();
+          if (lane == 0) mbar_arrive_cta0(&tmem_empty[wg]);
+          continue;
+        }
+        const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + wg * TILE_DB + c0 * 32;
+        const uint32_t chunk0 = t * 8 + c0;
+        int32_t ra[32], rb[32];
+        tmem_ld_32x32(taddr, ra);
+        #pragma unroll
+        for (uint32_t c = 0; c < NCH; c += 2) {
+          tmem_ld_wait_dep(ra);
+          tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+          if (!DRAIN_ONLY) chunk_max(ra, (int)(gdiv <= 1 ? chunk0 + c : (chunk0 + c) / gdiv), k1, k2);
+          tmem_ld_wait_dep(rb);
+          if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+          else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta0(&tmem_empty[wg]);
+          }
+          if (!DRAIN_ONLY) chunk_max(rb, (int)(gdiv <= 1 ? chunk0 + c + 1 : (chunk0 + c + 1) / gdiv), k1, k2);
+        }
+      }
+      if (!valid) continue;                               // (uniform over the warps of this accumulator)
+      if (NSPLIT == 2) {
+        int2 *mb = merge + (wg * 2 + (um & 1)) * TILE_Q; ++um;
+        if (part) mb[row_in_tile] = make_int2(k1, k2);
+        if (wg == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (part == 0) { const int2 o = mb[row_in_tile]; const int lo = min(k1, o.x); k1 = max(k1, o.x); k2 = max(lo, max(k2, o.y)); }
+      }
+      if (part == 0) k12[(size_t)un.out_off + (2 * rank + wg) * TILE_Q + row_in_tile] = make_int2(k1, k2);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                     // the peer may still be reading this CTA's shared memory / TMEM
+  if (warp == 2) tmem_dealloc2(tmem_base, 512);
+}
+
 // --------------------------------------------------------------------------------- finalize
 struct PairInfo { uint32_t db_row0, db_count, db_group, q_row0, q_count; uint32_t unit0; uint64_t out_off; int32_t db_c0; int32_t pad_; };
 
 // expand the per-pair table into the (pair, 128-query tile) work units on the device (one block per pair)
 // q_tiles = 1: one unit per 128 queries; q_tiles = 2 (match_dig2_kernel): one unit per 256 queries, UNIT_TWO set when the
 // second query tile holds real rows
+// q_tiles = 4 (match_dig3_kernel): one unit per 512 queries, the number of query tiles with real rows in bits 29-31
 __global__ void expand_units_kernel(const PairInfo *__restrict__ pairs, Unit *__restrict__ units, uint32_t q_tiles) {
   const PairInfo P = pairs[blockIdx.x];
   const uint32_t rows = TILE_Q * q_tiles;
   const uint32_t qt = (P.q_count + rows - 1) / rows, dt = (P.db_count + TILE_DB - 1) / TILE_DB;
   for (uint32_t t = threadIdx.x; t < qt; t += blockDim.x) {
-    const uint32_t two = (q_tiles == 2 && P.q_count - t * rows > TILE_Q) ? UNIT_TWO : 0u;
-    units[P.unit0 + t] = Unit{P.q_row0 + t * rows, P.db_row0, dt | ((P.db_group / 32) << 20) | two, (uint32_t)(P.out_off + t * rows)};
+    uint32_t flags = 0;
+    if (q_tiles == 2 && P.q_count - t * rows > TILE_Q) flags = UNIT_TWO;
+    if (q_tiles == 4) flags = min(4u, (P.q_count - t * rows + TILE_Q - 1) / TILE_Q) << 29;
+    units[P.unit0 + t] = Unit{P.q_row0 + t * rows, P.db_row0, dt | ((P.db_group / 32) << 20) | flags, (uint32_t)(P.out_off + t * rows)};
   }
 }
 
@@ -1079,7 +1280,8 @@ struct omvg_match_ctx {
   uint8_t *d_desc = nullptr; int32_t *d_norm = nullptr, *d_ckey = nullptr;
   uint32_t *d_img_row0 = nullptr, *d_img_count = nullptr, *d_img_group = nullptr, *d_row_img = nullptr;
   bool uploaded = false, prepared = false;
-  CUtensorMap tmap, tmap_dig;
+  CUtensorMap tmap, tmap_dig, tmap_dig128;   // digits: 256-row boxes (one CTA per tile) and 128-row boxes (CTA pair)
+  int max_clusters = 0;
   // fifth-slice kernel (match_dig_kernel): 32 signed digits per arena row, per-image offset c0, eligibility
   uint4 *d_dig = nullptr; int32_t *d_img_c0 = nullptr; int2 *d_hmm = nullptr; std::vector<int32_t> c0; bool use_dig = false;
   // run state
@@ -1125,6 +1327,11 @@ int make_tmap(omvg_match_ctx *c) {
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r2 != CUDA_SUCCESS) return fail(OMVG_E_CUDA, "cuTensorMapEncodeTiled (digits) failed (%d)", (int)r2);
+  const cuuint32_t dbox2[2] = {DIG_LEN, TILE_Q};
+  const CUresult r3 = ((encode_tiled_fn)fn)(&c->tmap_dig128, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_dig, ddims, dstrides, dbox2, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r3 != CUDA_SUCCESS) return fail(OMVG_E_CUDA, "cuTensorMapEncodeTiled (digits, 128 rows) failed (%d)", (int)r3);
   return OMVG_OK;
 }
 
@@ -1163,6 +1370,8 @@ int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_
   units.clear(); pinfo.clear();
   size_t out = 0, n_units = 0;
   const bool use_dig2 = c->use_dig && !getenv("OMVG_MATCH_M128");   // A/B: one query tile per CTA pass (match_dig_kernel)
+  bool use_dig3 = use_dig2 && c->max_clusters > 0 && getenv("OMVG_MATCH_2SM") != nullptr;   // CTA pair, tcgen05 cta_group::2
+  if (use_dig3) for (uint64_t p = p0; p < p1; ++p) if (c->group[pi[p]] / 32 >= 512) { use_dig3 = false; break; }
   for (uint64_t p = p0; p < p1; ++p) {
     const uint32_t I = pi[p], J = pj[p];
     PairInfo P{}; P.db_row0 = c->row0[I]; P.db_count = c->counts[I]; P.db_group = c->group[I]; P.db_c0 = c->c0.empty() ? 0 : c->c0[I];
@@ -1173,7 +1382,7 @@ int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_
     pinfo.push_back(P);
     if (!active) continue;
     const uint32_t qt = (P.q_count + TILE_Q - 1) / TILE_Q;
-    pinfo.back().unit0 = (uint32_t)n_units; n_units += use_dig2 ? (qt + 1) / 2 : qt;
+    pinfo.back().unit0 = (uint32_t)n_units; n_units += use_dig3 ? (qt + 3) / 4 : (use_dig2 ? (qt + 1) / 2 : qt);
     out += size_t(qt) * TILE_Q;
   }
   if (out > 0xffffffffull) return fail(OMVG_E_ARG, "batch too large");
@@ -1189,14 +1398,21 @@ int run_batch(omvg_match_ctx *c, const uint32_t *pi, const uint32_t *pj, uint64_
   }
   OMVG_CUDA(cudaMemcpyAsync(c->d_pairs, pinfo.data(), nb * sizeof(PairInfo), cudaMemcpyHostToDevice, c->stream));
   if (n_units) {
-    expand_units_kernel<<<nb, 64, 0, c->stream>>>(c->d_pairs, c->d_units, use_dig2 ? 2u : 1u); OMVG_CUDA(cudaGetLastError()); c->launches++;
+    expand_units_kernel<<<nb, 64, 0, c->stream>>>(c->d_pairs, c->d_units, use_dig3 ? 4u : (use_dig2 ? 2u : 1u)); OMVG_CUDA(cudaGetLastError()); c->launches++;
     const uint32_t grid = (uint32_t)std::min<size_t>(n_units, (size_t)c->n_sms);
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     OMVG_CUDA(cudaEventRecord(e0, c->stream));
     // OMVG_MATCH_DRAIN_ONLY=1 (measurement aid, results are garbage): epilogue reads TMEM but does no arithmetic
     static const bool drain_only = getenv("OMVG_MATCH_DRAIN_ONLY") != nullptr;
     const int nsplit = getenv("OMVG_MATCH_NSPLIT") ? atoi(getenv("OMVG_MATCH_NSPLIT")) : MATCH_NSPLIT_DEFAULT;   // epilogue warps per lane quarter and accumulator
-    if (use_dig2) {
+    if (use_dig3) {
+      const uint32_t grid3 = 2 * (uint32_t)std::min<size_t>(n_units, (size_t)c->max_clusters);
+      if (nsplit == 2) { if (drain_only) match_dig3_kernel<2, true><<<grid3, 64 + 512, smem7_bytes<2>(), c->stream>>>(c->tmap, c->tmap_dig128, c->d_units, (uint32_t)n_units, c->d_k12);
+                         else match_dig3_kernel<2, false><<<grid3, 64 + 512, smem7_bytes<2>(), c->stream>>>(c->tmap, c->tmap_dig128, c->d_units, (uint32_t)n_units, c->d_k12); }
+      else             { if (drain_only) match_dig3_kernel<1, true><<<grid3, 64 + 256, smem7_bytes<1>(), c->stream>>>(c->tmap, c->tmap_dig128, c->d_units, (uint32_t)n_units, c->d_k12);
+                         else match_dig3_kernel<1, false><<<grid3, 64 + 256, smem7_bytes<1>(), c->stream>>>(c->tmap, c->tmap_dig128, c->d_units, (uint32_t)n_units, c->d_k12); }
+    }
+    else if (use_dig2) {
       if (nsplit == 2) { if (drain_only) match_dig2_kernel<2, true><<<grid, 64 + 512, smem6_bytes<2>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12);
                          else match_dig2_kernel<2, false><<<grid, 64 + 512, smem6_bytes<2>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12); }
       else             { if (drain_only) match_dig2_kernel<1, true><<<grid, 64 + 256, smem6_bytes<1>(), c->stream>>>(c->tmap, c->tmap_dig, c->d_units, (uint32_t)n_units, c->d_k12);
@@ -1265,6 +1481,18 @@ int omvg_match_create(omvg_match_ctx **out, int device) {
   OMVG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   OMVG_CUDA(cudaFuncSetAttribute(match_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem7_bytes<1>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem7_bytes<1>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem7_bytes<2>()));
+  OMVG_CUDA(cudaFuncSetAttribute(match_dig3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem7_bytes<2>()));
+  { // how many CTA pairs can be resident at once (a GPC with an odd number of usable SMs leaves one SM without a partner)
+    cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(2 * n_sms); cfg.blockDim = dim3(64 + 512); cfg.dynamicSmemBytes = smem7_bytes<2>();
+    cudaLaunchAttribute at{}; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, match_dig3_kernel<2, false>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+    c->max_clusters = ncl;
+  }
   OMVG_CUDA(cudaFuncSetAttribute(match_dig2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6_bytes<1>()));
   OMVG_CUDA(cudaFuncSetAttribute(match_dig2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6_bytes<1>()));
   OMVG_CUDA(cudaFuncSetAttribute(match_dig2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6_bytes<2>()));
@@ -1447,6 +1675,7 @@ int omvg_match_fetch(omvg_match_ctx *c, const uint64_t **offsets, const uint32_t
 
 uint64_t omvg_match_launch_count(const omvg_match_ctx *c) { return c ? c->launches : 0; }
 int omvg_match_kernel_variant(const omvg_match_ctx *c) { return (!c || !c->prepared) ? 0 : (c->use_dig ? 5 : 4); }
+int omvg_match_max_clusters(const omvg_match_ctx *c) { return c ? c->max_clusters : 0; }
 
 int omvg_match_kernel_time(omvg_match_ctx *c, double *ms, uint64_t *launches, int reset) {
   if (!c) return fail(OMVG_E_ARG, "null ctx");

@@ -367,8 +367,9 @@ def test_kernel_variants_agree(matching, monkeypatch):
     pi = np.concatenate([pi, pj]); pj = np.concatenate([pj, pi[:len(pj)]])
     ooff, oij = ck.oracle_match_collection(descs, pi, pj, 0.8)
     results = []
-    for env in ({}, {"OMVG_MATCH_NSPLIT": "2"}, {"OMVG_MATCH_M128": "1"}, {"OMVG_MATCH_M128": "1", "OMVG_MATCH_NSPLIT": "2"}, {"OMVG_MATCH_TC4": "1"}):
-        for k in ("OMVG_MATCH_NSPLIT", "OMVG_MATCH_TC4", "OMVG_MATCH_M128"): monkeypatch.delenv(k, raising=False)
+    for env in ({}, {"OMVG_MATCH_NSPLIT": "1"}, {"OMVG_MATCH_2SM": "1"}, {"OMVG_MATCH_2SM": "1", "OMVG_MATCH_NSPLIT": "1"}, {"OMVG_MATCH_M128": "1"},
+                {"OMVG_MATCH_M128": "1", "OMVG_MATCH_NSPLIT": "1"}, {"OMVG_MATCH_TC4": "1"}):
+        for k in ("OMVG_MATCH_NSPLIT", "OMVG_MATCH_TC4", "OMVG_MATCH_M128", "OMVG_MATCH_2SM"): monkeypatch.delenv(k, raising=False)
         for k, v in env.items(): monkeypatch.setenv(k, v)
         ctx = matching.MatchContext(0)
         ctx.load(descs)
