@@ -171,9 +171,8 @@ int eval_cost(omvg_ba_ctx *c, const omvg_ba_options *o, int which, int slot) {
 }
 
 int colsums(omvg_ba_ctx *c) {
-  point_accum_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Ji.p, c->r.p, c->pt_start.p, c->pt_single.p, c->np, c->no, c->kiu, c->EtE.p, c->Etb.p, c->EtFi.p); LAUNCH_CHECK();
-  point_diag_from_EtE_kernel<<<(c->np + 255) / 256, 256, 0, c->stream>>>(c->EtE.p, c->np, c->diag_pt.p); LAUNCH_CHECK();
-  cam_colsum_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Jc.p, c->r.p, c->cam_start.p, c->cam_obs.p, c->nc, c->no, c->diag_cam.p, c->g_cam.p, c->FtF.p); LAUNCH_CHECK();
+  point_accum_kernel<<<(c->np + 127) / 128, 128, 0, c->stream>>>(c->Jp.p, c->Ji.p, c->r.p, c->pt_start.p, c->pt_single.p, c->np, c->no, c->kiu, c->EtE.p, c->Etb.p, c->EtFi.p, c->diag_pt.p); LAUNCH_CHECK();
+  cam_colsum_kernel<<<c->nc, CCS_THREADS, 0, c->stream>>>(c->Jc.p, c->r.p, c->cam_start.p, c->cam_obs.p, c->nc, c->no, c->diag_cam.p, c->g_cam.p, c->FtF.p); LAUNCH_CHECK();
   if (c->npri) { prior_accum_kernel<<<(c->npri + 127) / 128, 128, 0, c->stream>>>(c->JP.p, c->rP.p, c->prior_pose.p, c->npri, c->diag_cam.p, c->g_cam.p, c->FtF.p); LAUNCH_CHECK(); c->launches++; }
   const int chunks = c->ics_chunks;
   { const dim3 g(chunks, c->ni);
@@ -186,7 +185,7 @@ int colsums(omvg_ba_ctx *c) {
     } }
   LAUNCH_CHECK();
   intr_colsum_final_kernel<<<c->ni * 72, 128, 0, c->stream>>>(c->icol_part.p, chunks, c->ni, c->diag_intr.p, c->g_intr.p, c->FiFi.p); LAUNCH_CHECK();
-  c->launches += 5; return OMVG_OK;
+  c->launches += 4; return OMVG_OK;
 }
 
 // full evaluation at parameter set `which`: cost, corrected r and J (scaled), column sums, gradient max
@@ -226,10 +225,9 @@ int eval_jac(omvg_ba_ctx *c, const omvg_ba_options *o, const Masks &m, int which
   if ((rc = colsums(c))) return rc;
   // gradient max norm (unscaled): g = J_scaled' r / scale
   const int gb = 64;
-  grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->Etb.p, c->sc_pt.p, m.pts_free ? 3 * c->np : 0, c->part2.p); LAUNCH_CHECK();
-  grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->g_cam.p, c->sc_cam.p, 6 * c->nc, c->part2.p + gb); LAUNCH_CHECK();
-  grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->g_intr.p, c->sc_intr.p, c->ni8, c->part2.p + 2 * gb); LAUNCH_CHECK();
-  c->launches += 3;
+  Vec3 GV{}; GV.s[0] = Vec3Seg{c->Etb.p, c->sc_pt.p, m.pts_free ? 3 * c->np : 0}; GV.s[1] = Vec3Seg{c->g_cam.p, c->sc_cam.p, 6 * c->nc}; GV.s[2] = Vec3Seg{c->g_intr.p, c->sc_intr.p, c->ni8};
+  grad_max3_kernel<<<dim3(gb, 3), 256, 0, c->stream>>>(GV, c->part2.p); LAUNCH_CHECK();     // part2[3][64], read back by read_scalars
+  c->launches += 1;
   return OMVG_OK;
 }
 
@@ -554,8 +552,11 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   auto account_jac = [&]() { float ms = 0; cudaEventSynchronize(c->evj1); cudaEventElapsedTime(&ms, c->evj0, c->evj1); jac_ms += ms; ++jac_launches; };
 
   if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
+  // small reduced systems are solved directly by one CTA (dense_solve_kernel): no gauge / coarse space / PCG
+  const int dense_max = getenv("OMVG_BA_DENSE_MAX") ? std::min(DENSE_MAX, atoi(getenv("OMVG_BA_DENSE_MAX"))) : DENSE_MAX;
+  const bool use_dense = 6 * c->nc + c->ni8 <= dense_max;
   int nw = 0;
-  if ((rc = make_gauge(c, m, nw))) return rc;
+  if (!use_dense && (rc = make_gauge(c, m, nw))) return rc;
   int n_free_intr = 0; for (unsigned mm : m.intr_mask) n_free_intr += __builtin_popcount(mm);
   const bool use_pcg2 = n_free_intr <= MAXRHS - 1 && !getenv("OMVG_BA_PCG1");
   const bool use_pcg3 = use_pcg2 && !getenv("OMVG_BA_PCG2") && c->nc >= 2;
@@ -599,14 +600,16 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     if (radius <= O->min_radius) { termination = 4; break; }
     ++iteration;
     // ---- LM diagonal (levenberg_marquardt_strategy.cc:75-87); diag_* always belong to the current J
-    lm_diag_kernel<<<(3 * c->np + 255) / 256, 256, 0, c->stream>>>(c->diag_pt.p, 3 * c->np, O->min_lm_diagonal, O->max_lm_diagonal, radius, c->lmD_pt.p); LAUNCH_CHECK();
-    lm_diag_kernel<<<(6 * c->nc + 255) / 256, 256, 0, c->stream>>>(c->diag_cam.p, 6 * c->nc, O->min_lm_diagonal, O->max_lm_diagonal, radius, c->lmD_cam.p); LAUNCH_CHECK();
-    lm_diag_kernel<<<(c->ni8 + 255) / 256, 256, 0, c->stream>>>(c->diag_intr.p, c->ni8, O->min_lm_diagonal, O->max_lm_diagonal, radius, c->lmD_intr.p); LAUNCH_CHECK();
+    { Diag3 DG{}; DG.s[0] = Diag3Seg{c->diag_pt.p, c->lmD_pt.p, 3 * c->np}; DG.s[1] = Diag3Seg{c->diag_cam.p, c->lmD_cam.p, 6 * c->nc}; DG.s[2] = Diag3Seg{c->diag_intr.p, c->lmD_intr.p, c->ni8};
+      const int nb = std::max(1, std::min(2 * c->n_sms, (3 * c->np + 255) / 256));
+      lm_diag3_kernel<<<dim3(nb, 3), 256, 0, c->stream>>>(DG, O->min_lm_diagonal, O->max_lm_diagonal, radius); LAUNCH_CHECK(); }
     // ---- reduced camera system
-    OMVG_CUDA(cudaMemsetAsync(c->Scc.p, 0, (size_t)c->nnzb * 36 * sizeof(double), c->stream));
-    OMVG_CUDA(cudaMemsetAsync(c->Sci.p, 0, c->Sci.n * sizeof(double), c->stream));
-    OMVG_CUDA(cudaMemsetAsync(c->Sii.p, 0, c->Sii.n * sizeof(double), c->stream));
-    OMVG_CUDA(cudaMemsetAsync(c->rhs.p, 0, c->nred * sizeof(double), c->stream));
+    const bool split_schur = m.pts_free && !getenv("OMVG_BA_SCHUR1") && !getenv("OMVG_BA_SCHUR2");
+    if (split_schur && !c->corner_rep.p) { if ((rc = c->corner_rep.alloc((size_t)CORNER_REPS * (KI * KI + KI)))) return rc; }
+    { Zero4 Z{}; Z.p[0] = c->Scc.p; Z.n[0] = (long long)c->nnzb * 36; Z.p[1] = c->Sci.p; Z.n[1] = (long long)c->Sci.n; Z.p[2] = c->Sii.p; Z.n[2] = (long long)c->Sii.n;
+      Z.p[3] = split_schur ? c->corner_rep.p : c->rhs.p; Z.n[3] = split_schur ? (long long)c->corner_rep.n : 0;     // (rhs is fully written by s_init_kernel)
+      const int nb = (int)std::max<long long>(1, std::min<long long>(4 * c->n_sms, (Z.n[0] + 255) / 256));
+      zero4_kernel<<<dim3(nb, 4), 256, 0, c->stream>>>(Z); LAUNCH_CHECK(); }
     SchurArgs SA{}; SA.r = c->r.p; SA.Jp = c->Jp.p; SA.Jc = c->Jc.p; SA.Ji = c->Ji.p; SA.EtE = c->EtE.p; SA.Etb = c->Etb.p; SA.EtFi = c->EtFi.p; SA.lmD_pt = c->lmD_pt.p; SA.pt_single = c->pt_single.p; SA.FtF = c->FtF.p; SA.FiFi = c->FiFi.p; SA.g_cam = c->g_cam.p; SA.g_intr = c->g_intr.p;
     SA.obs_pose = c->obs_pose.p; SA.obs_intr = c->obs_intr.p; SA.obs_pt = c->obs_pt.p; SA.pt_start = c->pt_start.p; SA.n = c->no; SA.n_poses = c->nc; SA.n_intr = c->ni;
     SA.pts_free = m.pts_free; SA.kiu = c->kiu; SA.bsr = Bsr{c->bitmap.p, c->wprefix.p, c->rowptr.p, c->words}; SA.Scc = c->Scc.p; SA.Sci = c->Sci.p; SA.Sii = c->Sii.p; SA.rhs = c->rhs.p;
@@ -617,8 +620,6 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     static const bool schur2 = getenv("OMVG_BA_SCHUR2") != nullptr;      // fused warp-per-landmark kernel (A/B)
     if (m.pts_free && !schur1 && !schur2) {
       if (!c->GE.p) { if ((rc = c->GE.alloc(36 * (size_t)c->no))) return rc; }
-      if (!c->corner_rep.p) { if ((rc = c->corner_rep.alloc((size_t)CORNER_REPS * (KI * KI + KI)))) return rc; }
-      OMVG_CUDA(cudaMemsetAsync(c->corner_rep.p, 0, c->corner_rep.n * sizeof(double), c->stream));
       schur_stage_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA, c->GE.p, c->corner_rep.p); LAUNCH_CHECK();
       corner_fold_kernel<<<1, 96, 0, c->stream>>>(c->corner_rep.p, c->obs_intr.p, c->nc, c->ni, c->Sii.p, c->rhs.p); LAUNCH_CHECK(); c->launches++;
       static const int occ2 = [] { int o = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, schur_pair_kernel, 256, 0); return std::max(1, o); }();   // (thread-safe: Adjust may run on several host threads)
@@ -635,8 +636,8 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     if (!m.pts_free || schur1 || c->n_slow > 0) { schur_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA); LAUNCH_CHECK(); }
     mirror_kernel<<<(c->nc * 32 + 255) / 256, 256, 0, c->stream>>>(c->Scc.p, SA.bsr, c->cols.p, c->nc); LAUNCH_CHECK();
     c->launches += 2;
-    finish_cam_kernel<<<(c->nc + 63) / 64, 64, 0, c->stream>>>(c->Scc.p, SA.bsr, c->lmD_cam.p, m.pose_mask, c->nc, c->Minv_c.p, c->fail.p); LAUNCH_CHECK();
-    finish_intr_kernel<<<1, 256, 0, c->stream>>>(c->Sii.p, c->lmD_intr.p, c->intr_mask.p, c->ni8, c->Minv_i.p, c->work_i.p, c->fail.p, use_pcg2 ? 0 : 1); LAUNCH_CHECK();
+    finish_cam_kernel<<<(c->nc + 63) / 64, 64, 0, c->stream>>>(c->Scc.p, SA.bsr, c->lmD_cam.p, m.pose_mask, c->nc, c->Minv_c.p, c->fail.p, use_dense ? 0 : 1); LAUNCH_CHECK();
+    finish_intr_kernel<<<1, 256, 0, c->stream>>>(c->Sii.p, c->lmD_intr.p, c->intr_mask.p, c->ni8, c->Minv_i.p, c->work_i.p, c->fail.p, (use_pcg2 || use_dense) ? 0 : 1); LAUNCH_CHECK();
     // ---- PCG on S z = rhs
     PcgArgs PA{}; PA.Scc = c->Scc.p; PA.rowptr = c->rowptr.p; PA.cols = c->cols.p; PA.Sci = c->Sci.p; PA.Sii = c->Sii.p; PA.rhs = c->rhs.p; PA.Minv_c = c->Minv_c.p; PA.Minv_i = c->Minv_i.p;
     PA.n_poses = c->nc; PA.ni8 = c->ni8; PA.z = c->z.p; PA.res = c->res.p; PA.p = c->pvec.p; PA.w = c->w.p; PA.zeta = c->zeta.p; PA.part = c->pcg_part.p;
@@ -646,7 +647,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     // iterations (measured 38->40, 42->49, 43->43) but saves its O(nco^3) setup, so it is refreshed every
     // `coarse_every` LM steps (measured at 1000 cameras, ms per solve: every step 17.9, 2: 16.0, 3: 15.2, 5: 15.9),
     // or earlier if the last solve needed 1.5x the iterations seen right after a refresh.
-    const bool use_coarse = (use_pcg3 || !use_pcg2) && nw > 0 && c->nc >= 2;
+    const bool use_coarse = !use_dense && (use_pcg3 || !use_pcg2) && nw > 0 && c->nc >= 2;
     const Coarse CO{c->agg_of.p, c->agg_start.p, c->agg_cams.p, c->ng, nw, use_coarse ? c->ng * nw : 0};
     static const bool use_chol = getenv("OMVG_BA_COARSE_CHOL") != nullptr;
     if (use_coarse) {
@@ -678,6 +679,17 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       }
     }
     const double *Einv_p = use_chol ? c->cEinv.p : c->cE.p;
+    if (use_dense) {
+      const int nd = 6 * c->nc + c->ni8;
+      const size_t dsm = ((size_t)nd * (nd + 1) / 2 + (3 + DENSE_NB) * (size_t)nd) * sizeof(double);
+      OMVG_CUDA(cudaFuncSetAttribute(dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      static const bool dense_timing = getenv("OMVG_BA_DENSE_TIMING") != nullptr;
+      unsigned long long *tp = nullptr;
+      if (dense_timing) { if (!c->pcg_tim.p) { if ((rc = c->pcg_tim.alloc(8))) return rc; } OMVG_CUDA(cudaMemsetAsync(c->pcg_tim.p, 0, 64, c->stream)); tp = c->pcg_tim.p; }
+      dense_solve_kernel<<<1, 1024, dsm, c->stream>>>(c->Scc.p, c->rowptr.p, c->cols.p, c->Sci.p, c->Sii.p, c->rhs.p, c->nc, c->ni8, c->z.p, c->fail.p, c->scal.p + S_PCG_IT, tp); LAUNCH_CHECK();
+      if (dense_timing) { unsigned long long h[8]; OMVG_CUDA(cudaMemcpyAsync(h, c->pcg_tim.p, 64, cudaMemcpyDeviceToHost, c->stream)); OMVG_CUDA(cudaStreamSynchronize(c->stream));
+        fprintf(stderr, "[omvg_ba dense timing] n %d us: assemble %.1f factor %.1f backward %.1f\n", nd, h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3); }
+    } else
     if (use_pcg2) {
       Pcg2Args P2{}; P2.Scc = c->Scc.p; P2.rowptr = c->rowptr.p; P2.cols = c->cols.p; P2.Sci = c->Sci.p; P2.Sii = c->Sii.p; P2.rhs = c->rhs.p; P2.Minv_c = c->Minv_c.p;
       P2.W = c->gW.p; P2.intr_mask = c->intr_mask.p; P2.n_poses = c->nc; P2.ni8 = c->ni8; P2.nw = nw; P2.X = c->bX.p; P2.Rv = c->bR.p; P2.Pv = c->bP.p; P2.Wv = c->bW.p; P2.Zv = c->bZ.p;
@@ -744,18 +756,22 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     negate_kernel<<<(c->nred + 255) / 256, 256, 0, c->stream>>>(c->z.p, c->nred, c->step_red.p); LAUNCH_CHECK();
     // ---- model cost change
     model_kernel<<<c->eval_blocks, MODEL_THREADS, 0, c->stream>>>(c->r.p, c->Jp.p, c->Jc.p, c->Ji.p, c->obs_pose.p, c->obs_intr.p, c->obs_pt.p, c->no, c->nc, c->kiu, c->step_pt.p, c->step_red.p, c->part.p); LAUNCH_CHECK();
-    c->launches += 10;
+    c->launches += 9;
     if (c->npri) { prior_model_kernel<<<1, PRIOR_THREADS, 0, c->stream>>>(c->JP.p, c->rP.p, c->prior_pose.p, c->npri, c->step_red.p, c->part.p + c->eval_blocks); LAUNCH_CHECK(); c->launches++; }
     if ((rc = reduce_to(c, c->part.p, c->eval_blocks + (c->npri ? 1 : 0), S_MODEL))) return rc;
     // ---- candidate = Plus(x, step * scale)
     const int ub = 64;
-    update_kernel<<<ub, 256, 0, c->stream>>>(c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, m.pts_free ? c->pt_mask.p : nullptr, 0, c->pt[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
-    if ((rc = reduce_to(c, c->part2.p, ub, S_STEP2_PT))) return rc; if ((rc = reduce_to(c, c->part3.p, ub, S_X2_PT))) return rc;
-    update_kernel<<<ub, 256, 0, c->stream>>>(c->pose[0].p, c->step_red.p, c->sc_cam.p, 6 * c->nc, 6, m.pose_mask, nullptr, 0, c->pose[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
-    if ((rc = reduce_to(c, c->part2.p, ub, S_STEP2_POSE))) return rc; if ((rc = reduce_to(c, c->part3.p, ub, S_X2_POSE))) return rc;
-    update_kernel<<<ub, 256, 0, c->stream>>>(c->intr[0].p, c->step_red.p + 6 * c->nc, c->sc_intr.p, c->ni8, KI, 0u, c->intr_mask.p, 0, c->intr[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
-    if ((rc = reduce_to(c, c->part2.p, ub, S_STEP2_INTR))) return rc; if ((rc = reduce_to(c, c->part3.p, ub, S_X2_INTR))) return rc;
-    c->launches += 3;
+    auto update_all = [&]() -> int {       // candidate = Plus(x, step * scale) for the three parameter blocks; |step|^2 and |x|^2 into S_STEP2_* / S_X2_*
+      Upd3 U{};
+      U.s[0] = UpdSeg{c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, m.pts_free ? c->pt_mask.p : nullptr, c->pt[1].p};
+      U.s[1] = UpdSeg{c->pose[0].p, c->step_red.p, c->sc_cam.p, 6 * c->nc, 6, m.pose_mask, nullptr, c->pose[1].p};
+      U.s[2] = UpdSeg{c->intr[0].p, c->step_red.p + 6 * c->nc, c->sc_intr.p, c->ni8, KI, 0u, c->intr_mask.p, c->intr[1].p};
+      update3_kernel<<<dim3(ub, 3), 256, 0, c->stream>>>(U, c->part3.p); LAUNCH_CHECK();
+      static_assert(S_STEP2_POSE == S_STEP2_PT + 1 && S_STEP2_INTR == S_STEP2_PT + 2 && S_X2_PT == S_STEP2_PT + 3 && S_X2_POSE == S_STEP2_PT + 4 && S_X2_INTR == S_STEP2_PT + 5, "slot order");
+      reduce_multi_kernel<<<6, 1024, 0, c->stream>>>(c->part3.p, ub, c->scal.p + S_STEP2_PT); LAUNCH_CHECK();
+      c->launches += 2; return OMVG_OK;
+    };
+    if ((rc = update_all())) return rc;
     if ((rc = eval_cost(c, O, 1, S_CAND_COST))) return rc;
     if ((rc = read_scalars(c))) return rc;
     const double *h = c->h_scal;
@@ -785,21 +801,9 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       std::swap(c->pose[0].p, c->pose[1].p); std::swap(c->intr[0].p, c->intr[1].p); std::swap(c->pt[0].p, c->pt[1].p); std::swap(c->camR[0].p, c->camR[1].p); std::swap(c->camrec[0].p, c->camrec[1].p);
       // |x| of the accepted iterate = sqrt(|x_old|^2 ...) is not reusable: recompute from the candidate norms
       if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
-      if ((rc = make_gauge(c, m, nw))) return rc;
+      if (!use_dense && (rc = make_gauge(c, m, nw))) return rc;
       // x_norm of the new x: update_kernel measures |x| of its input; run the three norm passes on the new x
-      update_kernel<<<ub, 256, 0, c->stream>>>(c->pt[0].p, c->step_pt.p, c->sc_pt.p, 3 * c->np, 3, m.pts_free ? 7u : 0u, m.pts_free ? c->pt_mask.p : nullptr, 0, c->pt[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
-      if ((rc = reduce_to(c, c->part3.p, ub, S_X2_PT))) return rc;
-      update_kernel<<<ub, 256, 0, c->stream>>>(c->pose[0].p, c->step_red.p, c->sc_cam.p, 6 * c->nc, 6, m.pose_mask, nullptr, 0, c->pose[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
-      if ((rc = reduce_to(c, c->part3.p, ub, S_X2_POSE))) return rc;
-      update_kernel<<<ub, 256, 0, c->stream>>>(c->intr[0].p, c->step_red.p + 6 * c->nc, c->sc_intr.p, c->ni8, KI, 0u, c->intr_mask.p, 0, c->intr[1].p, c->part2.p, c->part3.p); LAUNCH_CHECK();
-      if ((rc = reduce_to(c, c->part3.p, ub, S_X2_INTR))) return rc;
-      c->launches += 3;
-      // gradient partials were written to part2 by eval_jac before the norm passes reused it: re-run them last
-      const int gb = 64;
-      grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->Etb.p, c->sc_pt.p, m.pts_free ? 3 * c->np : 0, c->part2.p); LAUNCH_CHECK();
-      grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->g_cam.p, c->sc_cam.p, 6 * c->nc, c->part2.p + gb); LAUNCH_CHECK();
-      grad_max_kernel<<<gb, 256, 0, c->stream>>>(c->g_intr.p, c->sc_intr.p, c->ni8, c->part2.p + 2 * gb); LAUNCH_CHECK();
-      c->launches += 3;
+      if ((rc = update_all())) return rc;     // (the gradient maxima of eval_jac sit in part2, the norm partials in part3)
       if ((rc = read_scalars(c))) return rc;
       account_jac();
       x_cost = c->h_scal[S_COST]; gmax = host_gmax(c);

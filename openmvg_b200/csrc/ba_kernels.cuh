@@ -466,7 +466,7 @@ __global__ void reduce_partials_kernel(const double *__restrict__ part, int n, d
 // intrinsic group (pt_single), EtFi = sum_obs Jp' Ji (3 x KI) from the (scaled) blocks.
 __global__ void point_accum_kernel(const double *__restrict__ Jp, const double *__restrict__ Ji, const double *__restrict__ r, const int *__restrict__ pt_start,
                                    const unsigned char *__restrict__ pt_single, int n_points, long long n, int kiu, double *__restrict__ EtE, double *__restrict__ Etb,
-                                   double *__restrict__ EtFi) {
+                                   double *__restrict__ EtFi, double *__restrict__ diag_pt) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_points) return;
   double e00 = 0, e10 = 0, e11 = 0, e20 = 0, e21 = 0, e22 = 0, b0 = 0, b1 = 0, b2 = 0;
@@ -487,22 +487,26 @@ __global__ void point_accum_kernel(const double *__restrict__ Jp, const double *
     }
   }
   double *E = EtE + 6 * (size_t)j; E[0] = e00; E[1] = e10; E[2] = e11; E[3] = e20; E[4] = e21; E[5] = e22;
+  diag_pt[3 * (size_t)j] = e00; diag_pt[3 * (size_t)j + 1] = e11; diag_pt[3 * (size_t)j + 2] = e22;       // squared column norms
   Etb[3 * (size_t)j] = b0; Etb[3 * (size_t)j + 1] = b1; Etb[3 * (size_t)j + 2] = b2;
   #pragma unroll
   for (int k = 0; k < 3 * KI; ++k) EtFi[(size_t)j * 3 * KI + k] = fi[k];
 }
 
-// per pose (one warp): Fc'Fc (6x6, full), squared column norms (its diagonal) and gradient Fc'r over the
-// pose's observation list — fixed order, no atomics.
-__global__ void cam_colsum_kernel(const double *__restrict__ Jc, const double *__restrict__ r, const int *__restrict__ cam_start,
+// per pose (one CTA of CCS_THREADS): Fc'Fc (6x6, full), squared column norms (its diagonal) and gradient Fc'r over the
+// pose's observation list — fixed order (lane, then warp), no atomics.  One warp per pose left 7 warps per SM at 1000
+// poses and a 16-deep chain of dependent gathers: 82 us at 1000 cameras, 43 us at 10.
+constexpr int CCS_THREADS = 128;
+__global__ void __launch_bounds__(CCS_THREADS) cam_colsum_kernel(const double *__restrict__ Jc, const double *__restrict__ r, const int *__restrict__ cam_start,
                                   const int *__restrict__ cam_obs, int n_poses, long long n, double *__restrict__ diag_cam,
                                   double *__restrict__ g_cam, double *__restrict__ FtF) {
-  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  __shared__ double sh[CCS_THREADS / 32][27];
+  const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (p >= n_poses) return;
   double m[21], g[6] = {0, 0, 0, 0, 0, 0};
   #pragma unroll
   for (int k = 0; k < 21; ++k) m[k] = 0.0;
-  for (int t = cam_start[p] + lane; t < cam_start[p + 1]; t += 32) {
+  for (int t = cam_start[p] + threadIdx.x; t < cam_start[p + 1]; t += CCS_THREADS) {
     const long long o = cam_obs[t];
     const double r0 = r[o], r1 = r[n + o];
     double a[6], b[6];
@@ -519,9 +523,23 @@ __global__ void cam_colsum_kernel(const double *__restrict__ Jc, const double *_
   #pragma unroll
   for (int k = 0; k < 6; ++k) { for (int o = 16; o > 0; o >>= 1) g[k] += __shfl_down_sync(0xffffffffu, g[k], o); }
   if (lane == 0) {
+    #pragma unroll
+    for (int k = 0; k < 21; ++k) sh[warp][k] = m[k];
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) sh[warp][21 + k] = g[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double v = 0.0;
+    #pragma unroll
+    for (int w = 0; w < CCS_THREADS / 32; ++w) v += sh[w][threadIdx.x];
+    sh[0][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     int q = 0;
-    for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) { FtF[36 * (size_t)p + i * 6 + k] = m[q]; FtF[36 * (size_t)p + k * 6 + i] = m[q]; ++q; }
-    for (int k = 0; k < 6; ++k) { diag_cam[6 * p + k] = FtF[36 * (size_t)p + k * 6 + k]; g_cam[6 * p + k] = g[k]; }
+    for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) { FtF[36 * (size_t)p + i * 6 + k] = sh[0][q]; FtF[36 * (size_t)p + k * 6 + i] = sh[0][q]; ++q; }
+    for (int k = 0; k < 6; ++k) { diag_cam[6 * p + k] = FtF[36 * (size_t)p + k * 6 + k]; g_cam[6 * p + k] = sh[0][21 + k]; }
   }
 }
 
@@ -1072,11 +1090,12 @@ __global__ void mirror_kernel(double *__restrict__ Scc, Bsr B, const int *__rest
 
 // S diag += D^2 (free columns) / = 1 (masked columns); block-Jacobi preconditioner Minv_c = inv(diag block)
 __global__ void finish_cam_kernel(double *__restrict__ Scc, Bsr B, const double *__restrict__ lmD_cam, unsigned pose_mask, int n_poses,
-                                  double *__restrict__ Minv, int *__restrict__ fail) {
+                                  double *__restrict__ Minv, int *__restrict__ fail, int need_inverse) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x; if (p >= n_poses) return;
   double *blk = Scc + 36 * (size_t)bsr_find(B, p, p);
   double M[36];
   for (int k = 0; k < 6; ++k) { if ((pose_mask >> k) & 1) blk[k * 6 + k] += lmD_cam[6 * p + k] * lmD_cam[6 * p + k]; else blk[k * 6 + k] = 1.0; }
+  if (!need_inverse) return;                          // direct solve (dense_solve_kernel): no preconditioner
   for (int k = 0; k < 36; ++k) M[k] = blk[k];
   // Cholesky 6x6 in place (lower), then inverse via forward/back substitution of unit vectors
   for (int k = 0; k < 6; ++k) {
@@ -1129,6 +1148,127 @@ __global__ void finish_intr_kernel(double *__restrict__ Sii, const double *__res
     }
   }
   (void)work;
+}
+
+
+// ------------------------------------------------------------------------------ small reduced systems: direct solve
+// Up to DENSE_MAX unknowns (37 cameras with one shared intrinsic group) the reduced system  [Scc Sci'; Sci Sii] z = rhs
+// is solved exactly, as Ceres does (schur_complement_solver.cc: dense / sparse Cholesky), by ONE CTA: the lower triangle
+// is assembled packed in shared memory, factored as L D L' (right-looking, columns kept unscaled so that a step needs
+// one barrier and no square root) and solved by one warp with shuffles.  An iterative solve is pure latency at this
+// size: the single-CTA PCG took 254 us per solve at 10 cameras and 420 us at 50, this takes a few tens of us.
+// A non-positive pivot raises `fail` (the LM loop treats the step as invalid, like a failed Cholesky in Ceres).
+constexpr int DENSE_MAX = 220;                      // (n (n + 1) / 2 + (3 + DENSE_NB) n) doubles <= 227 KB of shared memory
+constexpr int DENSE_NB = 8;                         // panel width of the blocked factorisation
+__global__ void __launch_bounds__(1024) dense_solve_kernel(const double *__restrict__ Scc, const int *__restrict__ rowptr, const int *__restrict__ cols,
+                                                          const double *__restrict__ Sci, const double *__restrict__ Sii, const double *__restrict__ rhs,
+                                                          int n_poses, int ni8, double *__restrict__ z, int *__restrict__ fail, double *__restrict__ out,
+                                                          unsigned long long *__restrict__ tim) {
+  extern __shared__ double dsm[];
+  unsigned long long tlast = 0; if (tim && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast));
+#define DENSE_LAP(k) do { if (tim && threadIdx.x == 0) { unsigned long long now_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)); tim[k] += now_ - tlast; tlast = now_; } } while (0)
+  const int nc6 = 6 * n_poses, n = nc6 + ni8;
+  double *L = dsm;                                   // packed lower triangle, row i at i (i + 1) / 2
+  double *y = L + n * (n + 1) / 2;                   // right-hand side / solution
+  double *invd = y + n;                              // 1 / d_k
+  double *acc = invd + n;                            // backward substitution: sum_{k>i} c_ki x_k
+  double *Lp = acc + n;                              // [n][DENSE_NB] multipliers l_ic = c_ic / d_c of the current panel
+  __shared__ int bad;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  if (tid == 0) bad = 0;
+  for (int i = tid; i < n * (n + 1) / 2; i += nt) L[i] = 0.0;
+  for (int i = tid; i < n; i += nt) { y[i] = rhs[i]; acc[i] = 0.0; }
+  for (int i = tid; i < n * DENSE_NB; i += nt) Lp[i] = 0.0;
+  __syncthreads();
+  // camera-camera blocks (both triangles are stored; take b <= a), one warp per block row
+  for (int a = warp; a < n_poses; a += nwarps)
+    for (int e = rowptr[a]; e < rowptr[a + 1]; ++e) {
+      const int b = cols[e]; if (b > a) break;
+      const double *blk = Scc + 36 * (size_t)e;
+      for (int k = lane; k < 36; k += 32) { const int i = 6 * a + k / 6, j = 6 * b + k % 6; if (j <= i) L[i * (i + 1) / 2 + j] = blk[k]; }
+    }
+  for (int q = warp; q < ni8; q += nwarps) {
+    double *row = L + (nc6 + q) * (nc6 + q + 1) / 2;
+    for (int k = lane; k < nc6; k += 32) row[k] = Sci[(size_t)q * nc6 + k];
+    for (int k = lane; k <= q; k += 32) row[nc6 + k] = Sii[(size_t)q * ni8 + k];
+  }
+  __syncthreads();
+  DENSE_LAP(0);
+  // L D L', right-looking, DENSE_NB columns per panel.  Column k of L keeps the UNSCALED c_ik = l_ik d_k, the diagonal d_k.
+  // Panel: one barrier per column, a handful of elements per thread (the columns of the panel right of it, the multiplier
+  // l_ic into Lp, the right-hand side: y is eliminated along with the columns).  Trailing matrix: ONE pass per panel,
+  // L[i][j] -= sum_c Lp[i][c] c_jc with the eight c_jc of a column in registers — a rank-1 update per column moved
+  // 24 bytes of shared memory per element and column and ran at the shared-memory bandwidth (291 us at n = 188).
+  const int ty = warp, tx = lane;                    // requires 1024 threads
+  bool ok = true;
+  for (int k0 = 0; k0 < n && ok; k0 += DENSE_NB) {
+    const int nb = n - k0 < DENSE_NB ? n - k0 : DENSE_NB;
+    for (int c = 0; c < nb; ++c) {
+      const int kc = k0 + c;
+      const double dk = L[kc * (kc + 1) / 2 + kc];
+      if (!(dk > 0.0) || !isfinite(dk)) { ok = false; break; }            // (uniform: every thread reads the same dk)
+      const double inv = __drcp_rn(dk);
+      if (tid == 0) invd[kc] = inv;
+      const double yk = y[kc];
+      const int nrows = n - kc - 1, ncols = nb - c;
+      for (int p = tid; p < nrows * ncols; p += nt) {
+        const int r = p / ncols, sl = c + p % ncols, i = kc + 1 + r;
+        const double li = L[i * (i + 1) / 2 + kc] * inv;
+        if (sl == c) { Lp[i * DENSE_NB + c] = li; y[i] -= li * yk; }
+        else { const int j = k0 + sl; if (j <= i) L[i * (i + 1) / 2 + j] -= li * L[j * (j + 1) / 2 + kc]; }
+      }
+      __syncthreads();
+    }
+    const int t0 = k0 + nb;
+    if (ok && t0 < n) {
+      for (int j = t0 + ((tx - t0) & 31); j < n; j += 32) {
+        double cj[DENSE_NB];
+        #pragma unroll
+        for (int c = 0; c < DENSE_NB; ++c) cj[c] = c < nb ? L[j * (j + 1) / 2 + k0 + c] : 0.0;
+        for (int i = j + ((ty - j) & 31); i < n; i += 32) {
+          const double *__restrict__ lp = Lp + i * DENSE_NB;
+          double a = L[i * (i + 1) / 2 + j];
+          #pragma unroll
+          for (int c = 0; c < DENSE_NB; ++c) a -= lp[c] * cj[c];
+          L[i * (i + 1) / 2 + j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!ok) { if (tid == 0) { atomicExch(fail, 4); out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; } for (int i = tid; i < n; i += nt) z[i] = 0.0; return; }
+  DENSE_LAP(1);
+  // y now holds w = L^-1 b.  Backward: x_i = (w_i - sum_{k>i} c_ki x_k) / d_i, 32 unknowns at a time from the bottom: one
+  // warp solves the 32 x 32 triangle (lane = unknown, one shuffle per step, row k of L is contiguous), then every thread
+  // adds the block's contribution to the accumulators of the rows above it.
+  for (int b1 = n; b1 > 0; b1 -= 32) {
+    const int b0 = b1 > 32 ? b1 - 32 : 0, mrows = b1 - b0;
+    if (warp == 0) {
+      const int i = b0 + lane;
+      const bool mine = lane < mrows;
+      double a = mine ? acc[i] : 0.0; const double w = mine ? y[i] : 0.0, idv = mine ? invd[i] : 0.0;
+      for (int kk = mrows - 1; kk >= 0; --kk) {
+        const double xc = (w - a) * idv;                                   // final for lane kk at this step
+        const double xk = __shfl_sync(0xffffffffu, xc, kk);
+        if (lane == kk) y[i] = xk;
+        if (lane < kk) a += L[(b0 + kk) * (b0 + kk + 1) / 2 + i] * xk;
+      }
+    }
+    __syncthreads();
+    if (tid < b0) {
+      double a0 = 0.0, a1 = 0.0;
+      int k = b0;
+      for (; k + 1 < b1; k += 2) { a0 += L[k * (k + 1) / 2 + tid] * y[k]; a1 += L[(k + 1) * (k + 2) / 2 + tid] * y[k + 1]; }
+      if (k < b1) a0 += L[k * (k + 1) / 2 + tid] * y[k];
+      acc[tid] += a0 + a1;
+    }
+    __syncthreads();
+  }
+  DENSE_LAP(2);
+  for (int i = tid; i < n; i += nt) z[i] = y[i];
+  if (tid == 0) { out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; }
+#undef DENSE_LAP
+  (void)bad;
 }
 
 // ------------------------------------------------------------------------------ PCG (cooperative)
@@ -2883,6 +3023,63 @@ __global__ void update_kernel(const double *__restrict__ x, const double *__rest
   }
   const double a = block_sum<256>(ds, sh); const double b = block_sum<256>(xs, sh);
   if (threadIdx.x == 0) { part_step[blockIdx.x] = a; part_x[blockIdx.x] = b; }
+}
+
+
+// ------------------------------------------------------------------------------ merged small launches
+// The LM loop used to issue ~50 launches per iteration, half of them a few microseconds of work on one vector each
+// (three parameter blocks x {update, two reductions}, three gradient maxima, three LM diagonals, four memsets).  One
+// launch per group, blockIdx.y selecting the parameter block; the arithmetic and the reduction orders are unchanged.
+struct UpdSeg { const double *x, *step, *scale; int n, stride; unsigned uniform_mask; const unsigned *block_mask; double *cand; };
+struct Upd3 { UpdSeg s[3]; };
+// part[seg][gridDim.x] = |step * scale|^2 partials, part[3 + seg][gridDim.x] = |x|^2 partials (seg: points, poses, intrinsics)
+__global__ void update3_kernel(Upd3 U, double *__restrict__ part) {
+  __shared__ double sh[8];
+  const UpdSeg &S = U.s[blockIdx.y];
+  double ds = 0, xs = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < S.n; i += gridDim.x * 256) {
+    const int blk = i / S.stride, k = i % S.stride;
+    const unsigned m = S.block_mask ? S.block_mask[blk] : S.uniform_mask;
+    const double xv = S.x[i];
+    double d = 0;
+    if ((m >> k) & 1) d = S.step[i] * S.scale[i];
+    S.cand[i] = xv + d;
+    ds += d * d;
+    if (m != 0) xs += xv * xv;                                // constant blocks are not part of the reduced program
+  }
+  const double a = block_sum<256>(ds, sh); const double b = block_sum<256>(xs, sh);
+  if (threadIdx.x == 0) { part[blockIdx.y * gridDim.x + blockIdx.x] = a; part[(3 + blockIdx.y) * gridDim.x + blockIdx.x] = b; }
+}
+// out[b] = sum of part[b][0..n) (block b; same order as reduce_partials_kernel)
+__global__ void reduce_multi_kernel(const double *__restrict__ part, int n, double *__restrict__ out) {
+  __shared__ double sh[32];
+  const double *p = part + (size_t)blockIdx.x * n;
+  double v = 0; for (int i = threadIdx.x; i < n; i += 1024) v += p[i];
+  const double t = block_sum<1024>(v, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+struct Vec3Seg { const double *a, *b; int n; };
+struct Vec3 { Vec3Seg s[3]; };
+__global__ void grad_max3_kernel(Vec3 V, double *__restrict__ part) {          // a = gradient, b = scale
+  __shared__ double sh[8];
+  const Vec3Seg &S = V.s[blockIdx.y];
+  double m = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < S.n; i += gridDim.x * 256) m = fmax(m, fabs(S.a[i] / S.b[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int i = 1; i < 8; ++i) m = fmax(m, sh[i]); part[blockIdx.y * gridDim.x + blockIdx.x] = m; }
+}
+struct Diag3Seg { const double *diag; double *lmD; int n; };
+struct Diag3 { Diag3Seg s[3]; };
+__global__ void lm_diag3_kernel(Diag3 D, double lo, double hi, double radius) {
+  const Diag3Seg &S = D.s[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += gridDim.x * blockDim.x) S.lmD[i] = sqrt(fmin(fmax(S.diag[i], lo), hi) / radius);
+}
+struct Zero4 { double *p[4]; long long n[4]; };
+__global__ void zero4_kernel(Zero4 Z) {
+  double *p = Z.p[blockIdx.y]; const long long n = Z.n[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.0;
 }
 
 }}  // namespace omvg::ba
