@@ -1970,7 +1970,7 @@ __global__ void __launch_bounds__(256, 2) coarse_invert_kernel(double *__restric
         __syncwarp();
         const double piv = s_row[k];
         if (!(piv > 0.0) || !isfinite(piv)) { if (r == 0 && blockIdx.x == 0) atomicExch(fail, 4); }
-        const double ip = 1.0 / piv;
+        const double ip = __drcp_rn(piv);                  // (1.0 / piv compiles to the same reciprocal plus a slow-path division)
         const double f = b[k];
         if (r == k) {
           #pragma unroll
