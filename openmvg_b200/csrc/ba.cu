@@ -41,13 +41,14 @@ template <typename T> struct DevBuf {
 
 // stream / events / pinned scalars of a context: creating and destroying them costs ~2.5 ms per Adjust, so
 // released sets are kept per device and reused (omvg_trim_cache() frees them)
-struct CtxRes { cudaStream_t stream = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; double *h_scal = nullptr; };
+struct CtxRes { cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; double *h_scal = nullptr; };
 struct ResPool { std::mutex mu; std::vector<CtxRes> free_[16]; };
 static ResPool &res_pool() { static ResPool p; return p; }
 
 struct omvg_ba_ctx {
   int device = 0, n_sms = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: payload upload under the structure build (omvg_ba_create)
+  cudaEvent_t ev_up = nullptr;
   int nc = 0, ni = 0, np = 0, nv = 0; long long no = 0;
   int ni8 = 0, nred = 0, words = 0, nnzb = 0, eval_blocks = 0, eval_grid = 0, kiu = KI, gj_grid = 0, ics_chunks = 64;
   std::vector<int> perm;                    // sorted position -> caller's observation index (fetched on first use)
@@ -376,7 +377,7 @@ void omvg_trim_cache(void) {
   ResPool &rp = res_pool(); std::lock_guard<std::mutex> g(rp.mu);
   int cur = 0; cudaGetDevice(&cur);
   for (int d = 0; d < 16; ++d) { if (rp.free_[d].empty()) continue; cudaSetDevice(d);
-    for (CtxRes &r : rp.free_[d]) { cudaFreeHost(r.h_scal); for (cudaEvent_t e : r.ev) cudaEventDestroy(e); cudaStreamDestroy(r.stream); }
+    for (CtxRes &r : rp.free_[d]) { cudaFreeHost(r.h_scal); for (cudaEvent_t e : r.ev) cudaEventDestroy(e); cudaStreamDestroy(r.stream); cudaStreamDestroy(r.stream2); }
     rp.free_[d].clear(); }
   cudaSetDevice(cur);
 }
@@ -411,10 +412,12 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
     { ResPool &rp = res_pool(); std::lock_guard<std::mutex> g(rp.mu); auto &v = rp.free_[device & 15]; if (!v.empty()) { r = v.back(); v.pop_back(); have = true; } }
     if (!have) {
       OMVG_CUDA(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+      OMVG_CUDA(cudaStreamCreateWithFlags(&r.stream2, cudaStreamNonBlocking));
       for (int i = 0; i < 4; ++i) OMVG_CUDA(cudaEventCreate(&r.ev[i]));
+      OMVG_CUDA(cudaEventCreateWithFlags(&r.ev[4], cudaEventDisableTiming));
       OMVG_CUDA(cudaMallocHost(&r.h_scal, (S_COUNT + 192 + 2) * sizeof(double)));
     }
-    c->stream = r.stream; c->ev0 = r.ev[0]; c->ev1 = r.ev[1]; c->evj0 = r.ev[2]; c->evj1 = r.ev[3]; c->h_scal = r.h_scal; }
+    c->stream = r.stream; c->stream2 = r.stream2; c->ev0 = r.ev[0]; c->ev1 = r.ev[1]; c->evj0 = r.ev[2]; c->evj1 = r.ev[3]; c->ev_up = r.ev[4]; c->h_scal = r.h_scal; }
   c->nc = P->n_poses; c->ni = P->n_intrinsics; c->np = P->n_points; c->nv = P->n_views; c->no = P->n_obs;
   c->ni8 = KI * c->ni; c->nred = 6 * c->nc + c->ni8; c->eval_blocks = (int)std::max<long long>(1, (c->no + EVAL_THREADS - 1) / EVAL_THREADS);
   c->eval_grid = std::min(c->eval_blocks, c->n_sms * (getenv("OMVG_BA_EVAL_WAVES") ? atoi(getenv("OMVG_BA_EVAL_WAVES")) : 4));   // persistent grid-stride evaluation
@@ -430,12 +433,17 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   UP(c->pose0, P->poses, 6 * c->nc); UP(c->intr0, h_intr.data(), c->ni8); UP(c->pt0, P->points, 3 * (size_t)c->np);
   UP(c->intr_model, P->intr_model, c->ni);
   // ---- observations: upload as given, then sort by landmark / build the per-pose lists on the device
-  { DevBuf<int> raw_view, raw_point, d_view_pose, d_view_intr, keys, iota, keys2, bad; DevBuf<double> raw_xy, raw_w; DevBuf<unsigned char> raw_fl, cubtmp;
-    UP(raw_view, P->obs_view, no); UP(raw_point, P->obs_point, no); UP(raw_xy, P->obs_xy, 2 * no);
+  // the image positions / weights / flags (16-25 B per observation) are only needed by the last gather: their upload runs on
+  // a second stream under the sorts and the structure build (pinned host buffers; pageable ones are staged synchronously)
+  DevBuf<double> raw_xy, raw_w; DevBuf<unsigned char> raw_fl;
+  { DevBuf<int> raw_view, raw_point, d_view_pose, d_view_intr, keys, iota, keys2, bad; DevBuf<unsigned char> cubtmp;
+    UP(raw_view, P->obs_view, no); UP(raw_point, P->obs_point, no);
     UP(d_view_pose, P->view_pose, c->nv); UP(d_view_intr, P->view_intr, c->nv);
-    if (P->obs_weight) { UP(raw_w, P->obs_weight, no); if ((rc = c->obs_w.alloc(no))) return rc; }
-    if (P->obs_no_loss) { UP(raw_fl, P->obs_no_loss, no); if ((rc = c->obs_flags.alloc(no))) return rc; }
-    if (tm.on) cudaStreamSynchronize(s);
+    if ((rc = upload(raw_xy, P->obs_xy, (size_t)(2 * no), c->stream2))) return rc;
+    if (P->obs_weight) { if ((rc = upload(raw_w, P->obs_weight, (size_t)no, c->stream2))) return rc; if ((rc = c->obs_w.alloc(no))) return rc; }
+    if (P->obs_no_loss) { if ((rc = upload(raw_fl, P->obs_no_loss, (size_t)no, c->stream2))) return rc; if ((rc = c->obs_flags.alloc(no))) return rc; }
+    OMVG_CUDA(cudaEventRecord(c->ev_up, c->stream2));
+    if (tm.on) { cudaStreamSynchronize(s); cudaStreamSynchronize(c->stream2); }
     tm.lap("uploads");
     if ((rc = keys.alloc(no)) || (rc = iota.alloc(no)) || (rc = keys2.alloc(no)) || (rc = bad.alloc(1))) return rc;
     if ((rc = c->d_perm.alloc(no)) || (rc = c->obs_pose.alloc(no)) || (rc = c->obs_intr.alloc(no)) || (rc = c->obs_pt.alloc(no)) || (rc = c->obs_xy.alloc(2 * no))) return rc;
@@ -451,8 +459,8 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
     if ((rc = cubtmp.alloc(std::max(tb1, tb2)))) return rc;
     size_t tb = cubtmp.n;
     OMVG_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, keys.p, c->obs_pt.p, iota.p, c->d_perm.p, (int)no, 0, pbits, s));
-    setup_gather_kernel<<<gb, 256, 0, s>>>(c->d_perm.p, raw_view.p, d_view_pose.p, d_view_intr.p, reinterpret_cast<const double2 *>(raw_xy.p), raw_w.p, raw_fl.p, no, c->nv,
-                                           c->obs_pose.p, c->obs_intr.p, reinterpret_cast<double2 *>(c->obs_xy.p), c->obs_w.p, c->obs_flags.p, iota.p); LAUNCH_CHECK();
+    setup_gather_kernel<<<gb, 256, 0, s>>>(c->d_perm.p, raw_view.p, d_view_pose.p, d_view_intr.p, nullptr, nullptr, nullptr, no, c->nv,
+                                           c->obs_pose.p, c->obs_intr.p, nullptr, nullptr, nullptr, iota.p); LAUNCH_CHECK();
     setup_starts_kernel<<<(unsigned)((no + 256) / 256), 256, 0, s>>>(c->obs_pt.p, no, c->np, c->pt_start.p); LAUNCH_CHECK();
     tb = cubtmp.n;
     OMVG_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, c->obs_pose.p, keys2.p, iota.p, c->cam_obs.p, (int)no, 0, cbits, s));
@@ -499,6 +507,10 @@ int omvg_ba_create(omvg_ba_ctx **out, int device, const omvg_ba_problem *P) {
   tm.lap("allocations");
   if ((rc = build_structure(c))) return rc;
   tm.lap("structure");
+  OMVG_CUDA(cudaStreamWaitEvent(s, c->ev_up, 0));
+  setup_gather_xy_kernel<<<(unsigned)((no + 255) / 256), 256, 0, s>>>(c->d_perm.p, reinterpret_cast<const double2 *>(raw_xy.p), raw_w.p, raw_fl.p, no,
+                                                                  reinterpret_cast<double2 *>(c->obs_xy.p), c->obs_w.p, c->obs_flags.p); LAUNCH_CHECK();
+  c->launches++;
   if ((rc = omvg_ba_reset(c))) return rc;
   OMVG_CUDA(cudaStreamSynchronize(s));
   guard.release();
@@ -518,10 +530,11 @@ int omvg_ba_destroy(omvg_ba_ctx *c) {
   if (!c) return OMVG_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  CtxRes r; r.stream = c->stream; r.ev[0] = c->ev0; r.ev[1] = c->ev1; r.ev[2] = c->evj0; r.ev[3] = c->evj1; r.h_scal = c->h_scal;
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
+  CtxRes r; r.stream = c->stream; r.stream2 = c->stream2; r.ev[0] = c->ev0; r.ev[1] = c->ev1; r.ev[2] = c->evj0; r.ev[3] = c->evj1; r.ev[4] = c->ev_up; r.h_scal = c->h_scal;
   const int dev = c->device & 15;
   delete c;                                   // DevBuf destructors hand device memory back to the pool
-  if (r.stream && r.ev[3] && r.h_scal) { ResPool &rp = res_pool(); std::lock_guard<std::mutex> g(rp.mu); rp.free_[dev].push_back(r); }
+  if (r.stream && r.stream2 && r.ev[4] && r.h_scal) { ResPool &rp = res_pool(); std::lock_guard<std::mutex> g(rp.mu); rp.free_[dev].push_back(r); }
   else { if (r.h_scal) cudaFreeHost(r.h_scal); for (cudaEvent_t e : r.ev) if (e) cudaEventDestroy(e); if (r.stream) cudaStreamDestroy(r.stream); }
   return OMVG_OK;
 }

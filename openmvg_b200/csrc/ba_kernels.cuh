@@ -127,10 +127,20 @@ __global__ void setup_gather_kernel(const int *__restrict__ perm, const int *__r
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int o = perm[t]; int v = obs_view[o]; v = min(max(v, 0), n_views - 1);
-  s_pose[t] = view_pose[v]; s_intr[t] = view_intr[v]; s_xy[t] = xy[o];
+  s_pose[t] = view_pose[v]; s_intr[t] = view_intr[v];
+  if (xy) { s_xy[t] = xy[o]; if (s_w) s_w[t] = w_in[o]; if (s_fl) s_fl[t] = fl_in[o] ? 1 : 0; }
+  iota[t] = (int)t;
+}
+// the per-observation payload (image positions, weights, flags) into landmark order; runs last in omvg_ba_create so that
+// its 16 B/observation upload (a second stream) overlaps the sorts and the structure build
+__global__ void setup_gather_xy_kernel(const int *__restrict__ perm, const double2 *__restrict__ xy, const double *__restrict__ w_in, const unsigned char *__restrict__ fl_in,
+                                       long long n, double2 *__restrict__ s_xy, double *__restrict__ s_w, unsigned char *__restrict__ s_fl) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int o = perm[t];
+  s_xy[t] = xy[o];
   if (s_w) s_w[t] = w_in[o];
   if (s_fl) s_fl[t] = fl_in[o] ? 1 : 0;
-  iota[t] = (int)t;
 }
 // segment starts of a sorted key array: start[k] = first t with key[t] >= k, start[n_keys] = n (empty keys included)
 __global__ void setup_starts_kernel(const int *__restrict__ key, long long n, int n_keys, int *__restrict__ start) {
