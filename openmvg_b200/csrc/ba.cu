@@ -68,6 +68,7 @@ struct omvg_ba_ctx {
   DevBuf<double> gW, gAW, bX, bR, bP, bW, bZ, pcg2_part;   // two-level block-PCG workspaces
   DevBuf<int> agg_of, agg_start, agg_cams, brow, nb_start, nb_list; DevBuf<unsigned short> blk_lcol; int nb_max = 0;   // neighbour lists of the aggregates (pcg5)
   DevBuf<double> cE, cEinv, cT, cCv, cYv, cCv2, cAW, bP2; int ng = 0, agg_maxsize = 0;
+  DevBuf<double> dA, dT;                             // dense reduced system / scratch of its in-place inverse (mid-size scenes)
   DevBuf<double> part, part2, part3, icol_part, scal;
   DevBuf<int> fail;
   DevBuf<unsigned long long> pcg_tim;
@@ -567,7 +568,10 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
   if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
   // small reduced systems are solved directly by one CTA (dense_solve_kernel): no gauge / coarse space / PCG
   const int dense_max = getenv("OMVG_BA_DENSE_MAX") ? std::min(DENSE_MAX, atoi(getenv("OMVG_BA_DENSE_MAX"))) : DENSE_MAX;
-  const bool use_dense = 6 * c->nc + c->ni8 <= dense_max;
+  const bool use_dense1 = 6 * c->nc + c->ni8 <= dense_max;                      // one CTA, shared memory
+  const int dense2_max = getenv("OMVG_BA_DENSE2_MAX") ? std::min(1024, atoi(getenv("OMVG_BA_DENSE2_MAX"))) : 640;
+  const bool use_dense2 = !use_dense1 && 6 * c->nc + c->ni8 <= dense2_max;      // explicit inverse by the blocked Gauss-Jordan kernel
+  const bool use_dense = use_dense1 || use_dense2;
   int nw = 0;
   if (!use_dense && (rc = make_gauge(c, m, nw))) return rc;
   int n_free_intr = 0; for (unsigned mm : m.intr_mask) n_free_intr += __builtin_popcount(mm);
@@ -692,7 +696,19 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       }
     }
     const double *Einv_p = use_chol ? c->cEinv.p : c->cE.p;
-    if (use_dense) {
+    if (use_dense2) {
+      int nd = 6 * c->nc + c->ni8;
+      if (!c->dA.p) { if ((rc = c->dA.alloc((size_t)nd * nd)) || (rc = c->dT.alloc(3 * (size_t)GJ_B * nd))) return rc; }
+      OMVG_CUDA(cudaMemsetAsync(c->dA.p, 0, (size_t)nd * nd * sizeof(double), c->stream));
+      dense_assemble_kernel<<<std::max(1, std::min(4 * c->n_sms, (36 * c->nnzb + 255) / 256)), 256, 0, c->stream>>>(c->Scc.p, c->brow.p, c->cols.p, c->nnzb, c->Sci.p, c->Sii.p, c->nc, c->ni8, c->dA.p); LAUNCH_CHECK();
+      double *Ap = c->dA.p, *Tp = c->dT.p; int *fp = c->fail.p; unsigned long long *tp = nullptr;
+      void *cargs[] = {&Ap, &nd, &Tp, &fp, &tp};
+      const int mt = (nd + CT - 1) / CT;
+      OMVG_CUDA(cudaLaunchCooperativeKernel((void *)coarse_invert_kernel, dim3(std::max(1, std::min(c->gj_grid, mt * mt))), dim3(256), cargs, 0, c->stream));
+      dense_apply_kernel<<<(nd * 32 + 255) / 256, 256, 0, c->stream>>>(c->dA.p, c->rhs.p, nd, c->z.p, c->scal.p + S_PCG_IT); LAUNCH_CHECK();
+      c->launches += 3;
+    } else
+    if (use_dense1) {
       const int nd = 6 * c->nc + c->ni8;
       const size_t dsm = ((size_t)nd * (nd + 1) / 2 + (3 + DENSE_NB) * (size_t)nd) * sizeof(double);
       OMVG_CUDA(cudaFuncSetAttribute(dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));

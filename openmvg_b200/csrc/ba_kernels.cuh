@@ -3036,6 +3036,38 @@ __global__ void update_kernel(const double *__restrict__ x, const double *__rest
 }
 
 
+// ------------------------------------------------------------------------------ mid-size reduced systems: explicit inverse
+// Between DENSE_MAX and DENSE2_MAX = 640 unknowns (36 .. ~105 cameras) the reduced system is still too small for the PCG to be
+// anything but latency (21 iterations of 20 us at 50 cameras) and too large for one CTA's shared memory: it is assembled
+// dense in global memory, inverted in place by the blocked Gauss-Jordan kernel that already inverts the coarse operator
+// (coarse_invert_kernel: all SMs, one rank-32 update of every tile per pivot block) and applied to the right-hand side.
+__global__ void dense_assemble_kernel(const double *__restrict__ Scc, const int *__restrict__ brow, const int *__restrict__ cols, int nnzb,
+                                      const double *__restrict__ Sci, const double *__restrict__ Sii, int n_poses, int ni8, double *__restrict__ A) {
+  const int nc6 = 6 * n_poses, n = nc6 + ni8;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  for (long long t = tid; t < 36ll * nnzb; t += nt) {                 // camera-camera blocks (both triangles are stored)
+    const int e = (int)(t / 36), k = (int)(t % 36);
+    A[(size_t)(6 * brow[e] + k / 6) * n + 6 * cols[e] + k % 6] = Scc[t];
+  }
+  for (long long t = tid; t < (long long)ni8 * nc6; t += nt) {        // border and its transpose
+    const int q = (int)(t / nc6), k = (int)(t % nc6);
+    const double v = Sci[t];
+    A[(size_t)(nc6 + q) * n + k] = v; A[(size_t)k * n + nc6 + q] = v;
+  }
+  for (long long t = tid; t < (long long)ni8 * ni8; t += nt) A[(size_t)(nc6 + t / ni8) * n + nc6 + t % ni8] = Sii[t];
+}
+// z = Ainv rhs (one warp per row)
+__global__ void dense_apply_kernel(const double *__restrict__ Ainv, const double *__restrict__ rhs, int n, double *__restrict__ z, double *__restrict__ out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row == 0 && lane == 0) { out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; }
+  if (row >= n) return;
+  const double *a = Ainv + (size_t)row * n;
+  double v = 0.0;
+  for (int k = lane; k < n; k += 32) v += a[k] * rhs[k];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) z[row] = v;
+}
+
 // ------------------------------------------------------------------------------ merged small launches
 // The LM loop used to issue ~50 launches per iteration, half of them a few microseconds of work on one vector each
 // (three parameter blocks x {update, two reductions}, three gradient maxima, three LM diagonals, four memsets).  One

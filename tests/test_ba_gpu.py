@@ -85,6 +85,7 @@ def test_multiple_intrinsic_groups(ba, n_intr, model):
 
 def test_pcg_variants_agree(ba, monkeypatch):
     """Two-level block-PCG (default) and plain block-Jacobi PCG with the border inside the iteration."""
+    monkeypatch.setenv("OMVG_BA_DENSE_MAX", "0"); monkeypatch.setenv("OMVG_BA_DENSE2_MAX", "0")     # (40 cameras would be solved directly)
     s = synth.ba_scene(40, 2000, 8, seed=12)
     a = ba.solve(s)
     monkeypatch.setenv("OMVG_BA_PCG1", "1")
@@ -318,13 +319,14 @@ def test_remove_points_on_resident_scene(ba):
 
 
 def test_direct_and_iterative_reduced_solves_agree(ba, monkeypatch):
-    """Up to 220 reduced unknowns one CTA solves the reduced camera system directly (dense L D L', as Ceres' Cholesky does);
-    above, and with OMVG_BA_DENSE_MAX=0, the two-level PCG runs.  Same LM trajectory either way."""
-    for cams, model in ((12, 1), (30, 3), (35, 1)):       # 6 * 35 + 8 = 218 unknowns <= 220
+    """Up to 220 reduced unknowns one CTA solves the reduced camera system directly (dense L D L', as Ceres' Cholesky does),
+    up to 640 it is inverted explicitly (blocked Gauss-Jordan over all SMs); above, and with OMVG_BA_DENSE_MAX=0 /
+    OMVG_BA_DENSE2_MAX=0, the two-level PCG runs.  Same LM trajectory either way."""
+    for cams, model in ((12, 1), (30, 3), (35, 1), (50, 1), (80, 2)):   # 6 * 35 + 8 = 218 unknowns <= 220: one CTA; up to 640: explicit inverse
         s = synth.ba_scene(cams, 60 * cams, 8, seed=5 + cams, model=model)
-        monkeypatch.delenv("OMVG_BA_DENSE_MAX", raising=False)
+        monkeypatch.delenv("OMVG_BA_DENSE_MAX", raising=False); monkeypatch.delenv("OMVG_BA_DENSE2_MAX", raising=False)
         a = ba.solve(s)
-        monkeypatch.setenv("OMVG_BA_DENSE_MAX", "0")
+        monkeypatch.setenv("OMVG_BA_DENSE_MAX", "0"); monkeypatch.setenv("OMVG_BA_DENSE2_MAX", "0")
         b = ba.solve(s)
         assert a["pcg_iterations"] == 0 and b["pcg_iterations"] > 0, (cams, a["pcg_iterations"], b["pcg_iterations"])
         assert a["iterations"] == b["iterations"]
@@ -337,7 +339,7 @@ def test_tight_pcg_reproduces_oracle_to_rounding(ba, monkeypatch):
     """The only approximation in the iterative path is the inner PCG tolerance (default 1e-8, final cost within
     ~3e-9 of the exact-solve reference over all golden cases; north_star allows 1e-6).  Tightened to 1e-12
     the result agrees with the exact (dense Cholesky) oracle to rounding."""
-    monkeypatch.setenv("OMVG_BA_DENSE_MAX", "0")
+    monkeypatch.setenv("OMVG_BA_DENSE_MAX", "0"); monkeypatch.setenv("OMVG_BA_DENSE2_MAX", "0")
     s = synth.ba_scene(30, 1500, 8)
     g = ba.solve(s, pcg_tolerance=1e-12)
     o = ck.oracle_ba_solve(s)
