@@ -831,7 +831,7 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
       // |x| of the accepted iterate = sqrt(|x_old|^2 ...) is not reusable: recompute from the candidate norms
       if ((rc = eval_jac(c, O, m, 0, have_scale, true))) return rc;
       if (!use_dense && (rc = make_gauge(c, m, nw))) return rc;
-      // x_norm of the new x: update_kernel measures |x| of its input; run the three norm passes on the new x
+      // x_norm of the new x: update3_kernel measures |x| of its input: one more pass over the new x
       if ((rc = update_all())) return rc;     // (the gradient maxima of eval_jac sit in part2, the norm partials in part3)
       if ((rc = read_scalars(c))) return rc;
       account_jac();

@@ -13,9 +13,11 @@
 //   schur_kernel        SchurEliminator::Eliminate (schur_eliminator_impl.h:176-298, :374-410, :499-548)
 //   pcg_kernel          ConjugateGradientsSolver::Solve (conjugate_gradients_solver.cc:66-245) with a
 //                       block-Jacobi preconditioner, standing in for SimplicialLDLT (eigensparse.cc:45-143)
+//   dense_solve_kernel  the same solve done directly (dense L D L' in one CTA) for <= 220 reduced unknowns;
+//                       dense_assemble / coarse_invert / dense_apply: explicit inverse up to 640
 //   backsub_kernel      SchurEliminator::BackSubstitute (schur_eliminator_impl.h:303-366)
 //   model_kernel        model_cost_change (trust_region_minimizer.cc:402-405)
-//   update_kernel       Program::Plus + SubsetParameterization::Plus (program.cc:115-127)
+//   update3_kernel      Program::Plus + SubsetParameterization::Plus (program.cc:115-127)
 #pragma once
 #include "common.cuh"
 #include <cooperative_groups.h>
@@ -615,10 +617,6 @@ __global__ void __launch_bounds__(128) intr_colsum_final_kernel(const double *__
 __global__ void make_scale_kernel(const double *__restrict__ n2, int n, double *__restrict__ scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) scale[i] = 1.0 / (1.0 + sqrt(n2[i]));
 }
-__global__ void point_diag_from_EtE_kernel(const double *__restrict__ EtE, int n_points, double *__restrict__ diag_pt) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= n_points) return;
-  diag_pt[3 * j] = EtE[6 * (size_t)j]; diag_pt[3 * j + 1] = EtE[6 * (size_t)j + 2]; diag_pt[3 * j + 2] = EtE[6 * (size_t)j + 5];
-}
 // apply the just-computed column scaling to the unscaled J of iteration 0 (ScaleColumns, :253)
 __global__ void scale_J_kernel(double *__restrict__ Jp, double *__restrict__ Jc, double *__restrict__ Ji, const int *__restrict__ obs_pose,
                                const int *__restrict__ obs_intr, const int *__restrict__ obs_pt, long long n, int kiu,
@@ -632,20 +630,7 @@ __global__ void scale_J_kernel(double *__restrict__ Jp, double *__restrict__ Jc,
   }
 }
 // g_unscaled = g_scaled / scale ; then max |g| over free columns (gradient_max_norm)
-__global__ void grad_max_kernel(const double *__restrict__ g, const double *__restrict__ scale, int n, double *__restrict__ part) {
-  __shared__ double sh[8];
-  double m = 0;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) m = fmax(m, fabs(g[i] / scale[i]));
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) { for (int i = 1; i < 8; ++i) m = fmax(m, sh[i]); part[blockIdx.x] = m; }
-}
 
-// lmD = sqrt(clamp(diag, lo, hi) / radius)   (levenberg_marquardt_strategy.cc:75-87)
-__global__ void lm_diag_kernel(const double *__restrict__ diag, int n, double lo, double hi, double radius, double *__restrict__ lmD) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) lmD[i] = sqrt(fmin(fmax(diag[i], lo), hi) / radius);
-}
 
 // ------------------------------------------------------------------------------ reduced system
 // Camera-pair structure: bitmap[nc][words] (bit b of row a set <=> S block (a,b) exists),
@@ -3016,24 +3001,6 @@ __global__ void __launch_bounds__(MODEL_THREADS) model_kernel(const double *__re
 }
 
 // candidate = x + step * scale on free coordinates; partials of |delta|^2 (ambient) and |x|^2
-__global__ void update_kernel(const double *__restrict__ x, const double *__restrict__ step, const double *__restrict__ scale, int n, int stride,
-                              unsigned uniform_mask, const unsigned *__restrict__ block_mask, int count_in_norm_all,
-                              double *__restrict__ cand, double *__restrict__ part_step, double *__restrict__ part_x) {
-  __shared__ double sh[8];
-  double ds = 0, xs = 0;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-    const int blk = i / stride, k = i % stride;
-    const unsigned m = block_mask ? block_mask[blk] : uniform_mask;
-    const double xv = x[i];
-    double d = 0;
-    if ((m >> k) & 1) d = step[i] * scale[i];
-    cand[i] = xv + d;
-    ds += d * d;
-    if (count_in_norm_all || m != 0) xs += xv * xv;           // constant blocks are not part of the reduced program
-  }
-  const double a = block_sum<256>(ds, sh); const double b = block_sum<256>(xs, sh);
-  if (threadIdx.x == 0) { part_step[blockIdx.x] = a; part_x[blockIdx.x] = b; }
-}
 
 
 // ------------------------------------------------------------------------------ mid-size reduced systems: explicit inverse
@@ -3114,6 +3081,7 @@ __global__ void grad_max3_kernel(Vec3 V, double *__restrict__ part) {          /
 }
 struct Diag3Seg { const double *diag; double *lmD; int n; };
 struct Diag3 { Diag3Seg s[3]; };
+// lmD = sqrt(clamp(diag, lo, hi) / radius)   (levenberg_marquardt_strategy.cc:75-87)
 __global__ void lm_diag3_kernel(Diag3 D, double lo, double hi, double radius) {
   const Diag3Seg &S = D.s[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += gridDim.x * blockDim.x) S.lmD[i] = sqrt(fmin(fmax(S.diag[i], lo), hi) / radius);
