@@ -637,7 +637,20 @@ int omvg_ba_run(omvg_ba_ctx *c, const omvg_ba_options *O, omvg_ba_summary *sum) 
     static const bool schur2 = getenv("OMVG_BA_SCHUR2") != nullptr;      // fused warp-per-landmark kernel (A/B)
     if (m.pts_free && !schur1 && !schur2) {
       if (!c->GE.p) { if ((rc = c->GE.alloc(36 * (size_t)c->no))) return rc; }
-      schur_stage_kernel<<<(unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS), SCHUR_THREADS, 0, c->stream>>>(SA, c->GE.p, c->corner_rep.p); LAUNCH_CHECK();
+      { const unsigned sg = (unsigned)((c->no + SCHUR_THREADS - 1) / SCHUR_THREADS);
+        static const bool minb4 = getenv("OMVG_BA_STAGE_MINB") && atoi(getenv("OMVG_BA_STAGE_MINB")) == 4;   // A/B: 128 registers, 4 CTAs per SM
+#define STAGE(K) do { if (minb4) schur_stage_kernel<K, 4><<<sg, SCHUR_THREADS, 0, c->stream>>>(SA, c->GE.p, c->corner_rep.p); \
+                      else schur_stage_kernel<K, 5><<<sg, SCHUR_THREADS, 0, c->stream>>>(SA, c->GE.p, c->corner_rep.p); } while (0)
+        switch (c->kiu) {        // intrinsic columns in use (as for the column sums)
+          case 3: STAGE(3); break;
+          case 4: STAGE(4); break;
+          case 6: STAGE(6); break;
+          case 7: STAGE(7); break;
+          default: STAGE(8); break;
+        }
+#undef STAGE
+      }
+      LAUNCH_CHECK();
       corner_fold_kernel<<<1, 96, 0, c->stream>>>(c->corner_rep.p, c->obs_intr.p, c->nc, c->ni, c->Sii.p, c->rhs.p); LAUNCH_CHECK(); c->launches++;
       static const int occ2 = [] { int o = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, schur_pair_kernel, 256, 0); return std::max(1, o); }();   // (thread-safe: Adjust may run on several host threads)
       schur_pair_kernel<<<c->n_sms * occ2, 256, 0, c->stream>>>(SA, c->GE.p); LAUNCH_CHECK(); c->launches += 2;

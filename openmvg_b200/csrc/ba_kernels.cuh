@@ -953,14 +953,23 @@ __global__ void __launch_bounds__(32 * SCHUR2_WARPS, MINB) schur_point_kernel(Sc
 //   schur_stage_kernel : thread per observation (coalesced component-major loads), per-observation border / rhs
 //                        terms, writes GE[obs] = { Einv E'Fc (18), E'Fc (18) }  (288 B per observation)
 //   schur_pair_kernel  : warp per landmark, lane e adds element e of block (cam_t, cam_u) reading GE through L1
-__global__ void __launch_bounds__(SCHUR_THREADS) schur_stage_kernel(SchurArgs A, double *__restrict__ GE, double *__restrict__ corner_rep) {
+// KIU = intrinsic columns in use (3 pinhole .. 8 Brown): the generic 8-column body kept 16 Jacobian and 24 EtFi values
+// live per thread (162 registers, 3 CTAs per SM, 17 % of the warps active, 5x off its DRAM time).  The 36 doubles of an
+// observation's {E^-1 E'F, E'F} record go through shared memory so that a warp writes its 32 records (9 KB, contiguous)
+// with full 256-byte stores instead of 36 scattered 8-byte stores per lane.
+constexpr int GE_LD = 37;                            // padded record stride in shared memory (conflict-free for both phases)
+template <int KIU, int MINB>
+__global__ void __launch_bounds__(SCHUR_THREADS, MINB) schur_stage_kernel(SchurArgs A, double *__restrict__ GE, double *__restrict__ corner_rep) {
   // The intrinsics corner (and its rhs) of group q0 is hit once per landmark: accumulate into CORNER_REPS replicas
   // with native FP64 REDs (shared-memory double atomics are CAS loops: they cost 0.3 ms here) and fold them after.
+  __shared__ double ge_s[SCHUR_THREADS / 32][32 * GE_LD];
   const long long t = (long long)blockIdx.x * SCHUR_THREADS + threadIdx.x;
   const long long n = A.n;
   const int nred_c = 6 * A.n_poses, ni8 = KI * A.n_intr;
   const int q0 = A.obs_intr[0];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *s_ii = corner_rep + (size_t)(blockIdx.x % CORNER_REPS) * (KI * KI + KI);
+  double *gs = ge_s[warp] + lane * GE_LD;
   bool mine = t < n;
   int j = 0;
   if (mine) { j = A.obs_pt[t]; const int K = A.pt_start[j + 1] - A.pt_start[j]; mine = A.pt_single[j] != 0 && K <= 32; }
@@ -976,50 +985,64 @@ __global__ void __launch_bounds__(SCHUR_THREADS) schur_stage_kernel(SchurArgs A,
       for (int a = 0; a < 3; ++a) ie[a] = inv[a * 3] * eb[0] + inv[a * 3 + 1] * eb[1] + inv[a * 3 + 2] * eb[2]; }
     const bool first = t == A.pt_start[j];
     if (first) { for (int a = 0; a < 9; ++a) A.Einv[9 * (size_t)j + a] = inv[a]; }
-    double jc[12], ji[2 * KI], jp[6];
+    double jc[12], jp[6];
     #pragma unroll
     for (int k = 0; k < 12; ++k) jc[k] = A.Jc[k * n + t];
     #pragma unroll
-    for (int k = 0; k < 2 * KI; ++k) ji[k] = (k % KI) < A.kiu ? A.Ji[k * n + t] : 0.0;
-    #pragma unroll
     for (int k = 0; k < 6; ++k) jp[k] = A.Jp[k * n + t];
-    double efc[18];
-    #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    // E'F (3 x 6) and E^-1 E'F: the record for the pair walk.  Staged in shared memory (written to GE below) and read
+    // back from there by the border terms, so that the 18 + 18 values are not live in registers next to jc / inv.
+    { double efc[18];
       #pragma unroll
-      for (int c = 0; c < 6; ++c) efc[a * 6 + c] = jp[a] * jc[c] + jp[3 + a] * jc[6 + c];
+      for (int a = 0; a < 3; ++a)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) efc[a * 6 + c] = jp[a] * jc[c] + jp[3 + a] * jc[6 + c];
+      #pragma unroll
+      for (int a = 0; a < 3; ++a)
+        #pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          gs[a * 6 + c] = inv[a * 3] * efc[c] + inv[a * 3 + 1] * efc[6 + c] + inv[a * 3 + 2] * efc[12 + c];
+          gs[18 + a * 6 + c] = efc[a * 6 + c];
+        } }
+    __syncwarp(__activemask());
+    const double *ef = gs + 18;
     #pragma unroll
-    for (int c = 0; c < 6; ++c) atomicAdd(&A.rhs[6 * ct + c], -(efc[c] * ie[0] + efc[6 + c] * ie[1] + efc[12 + c] * ie[2]));
+    for (int c = 0; c < 6; ++c) atomicAdd(&A.rhs[6 * ct + c], -(ef[c] * ie[0] + ef[6 + c] * ie[1] + ef[12 + c] * ie[2]));
     double *sci_row0 = A.Sci + (size_t)(KI * qt) * nred_c + 6 * ct;
     const double *fi = A.EtFi + (size_t)j * 3 * KI;
     #pragma unroll
-    for (int a = 0; a < KI; ++a) {
+    for (int a = 0; a < KIU; ++a) {
       const double f0 = fi[a], f1 = fi[KI + a], f2 = fi[2 * KI + a];
-      if (f0 == 0.0 && f1 == 0.0 && f2 == 0.0 && ji[a] == 0.0 && ji[KI + a] == 0.0) continue;   // constant parameter
+      const double ji0 = A.Ji[a * n + t], ji1 = A.Ji[(KI + a) * n + t];
+      if (f0 == 0.0 && f1 == 0.0 && f2 == 0.0 && ji0 == 0.0 && ji1 == 0.0) continue;   // constant parameter
       const double g0 = inv[0] * f0 + inv[1] * f1 + inv[2] * f2, g1 = inv[3] * f0 + inv[4] * f1 + inv[5] * f2, g2 = inv[6] * f0 + inv[7] * f1 + inv[8] * f2;
       #pragma unroll
       for (int b = 0; b < 6; ++b)
-        atomicAdd(&sci_row0[(size_t)a * nred_c + b], ji[a] * jc[b] + ji[KI + a] * jc[6 + b] - (g0 * efc[b] + g1 * efc[6 + b] + g2 * efc[12 + b]));
+        atomicAdd(&sci_row0[(size_t)a * nred_c + b], ji0 * jc[b] + ji1 * jc[6 + b] - (g0 * ef[b] + g1 * ef[6 + b] + g2 * ef[12 + b]));
       if (first) {
         const double rv = -(f0 * ie[0] + f1 * ie[1] + f2 * ie[2]);
         if (qt == q0) atomicAdd(&s_ii[KI * KI + a], rv); else atomicAdd(&A.rhs[nred_c + KI * qt + a], rv);
         #pragma unroll
-        for (int b = 0; b < KI; ++b) {
+        for (int b = 0; b < KIU; ++b) {
           const double v = -(g0 * fi[b] + g1 * fi[KI + b] + g2 * fi[2 * KI + b]);
           if (v == 0.0) continue;
           if (qt == q0) atomicAdd(&s_ii[a * KI + b], v); else atomicAdd(&A.Sii[(size_t)(KI * qt + a) * ni8 + KI * qt + b], v);
         }
       }
     }
-    double *ge = GE + 36 * (size_t)t;
+  } else {
     #pragma unroll
-    for (int a = 0; a < 3; ++a)
-      #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        ge[a * 6 + c] = inv[a * 3] * efc[c] + inv[a * 3 + 1] * efc[6 + c] + inv[a * 3 + 2] * efc[12 + c];
-        ge[18 + a * 6 + c] = efc[a * 6 + c];
-      }
+    for (int k = 0; k < 36; ++k) gs[k] = 0.0;         // (records of landmarks the general kernel handles are not read)
   }
+  __syncwarp();
+  // the warp's 32 records are contiguous in GE: 36 coalesced 256-byte stores
+  { const long long t0 = (long long)blockIdx.x * SCHUR_THREADS + 32 * warp;
+    const long long nrec = n - t0 < 32 ? n - t0 : 32;
+    if (nrec > 0) {
+      double *dst = GE + 36 * (size_t)t0;
+      #pragma unroll 4
+      for (int e = lane; e < 36 * (int)nrec; e += 32) dst[e] = ge_s[warp][(e / 36) * GE_LD + e % 36];
+    } }
 }
 // folds the corner replicas of schur_stage_kernel into Sii / rhs of group q0 (fixed order)
 __global__ void corner_fold_kernel(const double *__restrict__ corner_rep, const int *__restrict__ obs_intr, int n_poses, int n_intr, double *__restrict__ Sii, double *__restrict__ rhs) {
