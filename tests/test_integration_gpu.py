@@ -84,10 +84,13 @@ def test_patched_bundle_adjustment_ceres_routes_to_the_gpu():
     unit: GPU by default, Ceres with OPENMVG_B200_DISABLE=1; same final cost within 1e-6."""
     exe = os.path.join(REF, "patched_ba_test")
     env = dict(os.environ); env.pop("OPENMVG_B200_DISABLE", None)
+    env["OMVG_BA_TIMING"] = "1"                             # the library prints its host phases to stderr: proof of which solver ran
     g = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
     env["OPENMVG_B200_DISABLE"] = "1"
     c = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
     assert g.returncode == 0 and c.returncode == 0, g.stdout + g.stderr + c.stdout + c.stderr
     assert "falling back" not in g.stdout + g.stderr
+    assert "[omvg_ba timing] solve/run" in g.stderr and "[omvg_ba timing]" not in c.stderr
     cg = float(g.stdout.split("cost")[-1]); cc = float(c.stdout.split("cost")[-1])
-    assert abs(cg - cc) <= 1e-6 * cc and cg != cc          # two different solvers, one answer
+    assert abs(cg - cc) <= 1e-6 * cc                        # two different solvers, one answer (the small scene is solved
+                                                            # directly on the GPU too, so the costs may agree to every printed digit)
